@@ -1,0 +1,138 @@
+/*
+ * okb200.h -- C ABI of libokb200.so: the B200 (sm_100a) implementation of ORBKIT's grid-based
+ * hot path  AO -> MO -> rho / grad rho / second derivatives of rho.
+ *
+ * Plain C, pointers and sizes only; no exceptions cross this boundary.  Every function returns an
+ * int status (OKB_OK == 0) and leaves a message retrievable with okb_last_error() on failure --
+ * the reference's C layer has no error channel at all (c_support.c:169-172 just prints), its
+ * Python layer raises ValueError; the Python shim in orbkit_b200/ turns non-zero statuses back
+ * into the reference's exceptions.
+ *
+ * Two levels are exported:
+ *
+ *  (1) drop-ins for the reference's compiled module `orbkit.cy_core` (cy_core.pyx:21-101) and the C
+ *      routine under it (c_grid-based.h:1-3), HOST buffers in, HOST buffers out:
+ *        okb_aocreator  <- cy_core.aocreator   (cy_core.pyx:51-78)  -> c_lcreator per contraction
+ *        okb_lcreator   <- cy_core.lcreator / c_lcreator (cy_core.pyx:29-47, c_grid-based.c:9-79)
+ *        okb_mocreator  <- cy_core.mocreator   (cy_core.pyx:82-101)
+ *        okb_aonorm     <- cy_core.aonorm / ao_norm     (cy_core.pyx:21, c_support.c:177-188)
+ *        okb_aoxyz      <- cy_core.aoxyz  / get_ao_xyz  (cy_core.pyx:24, c_support.c:28-175)
+ *
+ *  (2) the fused path behind core.rho_compute / rho_compute_no_slice / slice_rho
+ *      (core.py:179-308, 314-605, 607-839): persistent handles for the basis tables, the MO
+ *      coefficients and the grid, and one evaluation call per request that never materialises AO
+ *      or MO arrays in HBM unless they are the requested output.
+ *
+ * All arrays are C-contiguous; doubles are IEEE binary64; index arrays are C int -- exactly the
+ * dtypes tools.require() enforces in the reference (tools.py:290-295).  Pointers are borrowed for
+ * the duration of the call.  A context is bound to one CUDA device and owns one stream; it is
+ * thread-compatible (use one context per host thread), not re-entrant.
+ */
+#ifndef OKB200_H
+#define OKB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct okb_ctx   okb_ctx;
+typedef struct okb_basis okb_basis;
+typedef struct okb_mo    okb_mo;
+typedef struct okb_grid  okb_grid;
+
+enum {
+    OKB_OK = 0,
+    OKB_ERR_ARG = 1,     /* invalid argument (maps to ValueError) */
+    OKB_ERR_CUDA = 2,    /* CUDA runtime / launch failure, or no usable device */
+    OKB_ERR_NOMEM = 3,   /* host or device allocation failed */
+    OKB_ERR_UNSUPPORTED = 4
+};
+
+/* flags */
+#define OKB_FLAG_EXACT_MIXED 1u  /* analytically correct xy/xz/yz AO derivatives instead of the
+                                    reference's incomplete ones (c_support.c:121-168) */
+#define OKB_FLAG_OUT_DEVICE  2u  /* output pointers are DEVICE pointers; the call is asynchronous
+                                    on the context stream (okb_ctx_sync to wait) */
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char *okb_last_error(void);
+int  okb_version(void);
+int  okb_device_count(int *n);
+int  okb_ctx_create(int device, okb_ctx **out);
+int  okb_ctx_destroy(okb_ctx *ctx);
+int  okb_ctx_sync(okb_ctx *ctx);
+void *okb_ctx_stream(okb_ctx *ctx);                       /* cudaStream_t of the context */
+int  okb_ctx_launch_count(okb_ctx *ctx, long long *n);    /* kernels launched by this context */
+int  okb_ctx_last_kernel(okb_ctx *ctx, char *buf, int buflen); /* name of the last variant launched */
+
+/* ---- (1) cy_core drop-ins, host buffers ------------------------------------------------- */
+/* out[n_cart][npts] (row-major).  Arguments as cy_core.aocreator (cy_core.pyx:51-61):
+ * lxlylz[n_cart][3], assign[n_cont] (functions per contraction), ao_coeffs[n_prim][2] (alpha,c),
+ * pnum_list[n_cont], geo_spec[n_atoms][3], atom_indices[n_cont], x/y/z[npts], drv 0..9. */
+int okb_aocreator(okb_ctx *ctx, const int *lxlylz, const int *assign, const double *ao_coeffs,
+                  const int *pnum_list, const double *geo_spec, const int *atom_indices,
+                  int n_cont, int n_cart, int n_prim, int n_atoms,
+                  const double *x, const double *y, const double *z, long long npts,
+                  int drv, int is_normalized, unsigned flags, double *out);
+/* one contraction, written in place at row stride `row_stride` (>= npts) -- c_lcreator's layout
+ * (c_grid-based.c:69). */
+int okb_lcreator(okb_ctx *ctx, double *ao_list, long long row_stride, const int *lxlylz,
+                 const double *coeff_list, const double *at_pos,
+                 const double *x, const double *y, const double *z, long long npts,
+                 int ao_num, int pnum, int drv, int is_normalized, unsigned flags);
+/* mo[n_mo][npts] = coeffs[n_mo][n_ao] * ao[n_ao][npts]  (cy_core.pyx:82-101) */
+int okb_mocreator(okb_ctx *ctx, const double *ao, const double *coeffs,
+                  int n_ao, long long npts, int n_mo, double *mo);
+double okb_aonorm(int lx, int ly, int lz, double alpha, int is_normalized);
+double okb_aoxyz(double x, double y, double z, int lx, int ly, int lz, double alpha, int drv);
+
+/* ---- (2) fused path: handles ------------------------------------------------------------- */
+/* Basis tables.  Same arrays as okb_aocreator plus an optional per-Cartesian-function factor
+ * `renorm[n_cart]` (ao_spec[0]['N'], core.py:98-100; NULL for none). */
+int okb_basis_create(okb_ctx *ctx, const int *lxlylz, const int *assign, const double *ao_coeffs,
+                     const int *pnum_list, const double *geo_spec, const int *atom_indices,
+                     int n_cont, int n_cart, int n_prim, int n_atoms, int is_normalized,
+                     const double *renorm, okb_basis **out);
+/* Cartesian -> real-spherical transform as CSR over Cartesian rows (core.py:135-176):
+ * sph[j] = sum_{t in [row_ptr[j],row_ptr[j+1])} val[t] * cart[col[t]].  After this call the AO
+ * basis of `basis` has n_sph functions. */
+int okb_basis_set_cart2sph(okb_basis *basis, int n_sph, const int *row_ptr, const int *col,
+                           const double *val);
+int okb_basis_info(okb_basis *basis, int *n_cart, int *n_ao, int *n_dev_shells, int *n_chunks);
+int okb_basis_destroy(okb_basis *basis);
+
+/* MO coefficients coeffs[n_mo][n_ao] (MOClass.get_coeffs, orbitals.py:760-771) and occupations
+ * occ[n_mo] (get_occ :786) in the AO basis of `basis`. */
+int okb_mo_create(okb_ctx *ctx, okb_basis *basis, int n_mo, const double *coeffs,
+                  const double *occ, okb_mo **out);
+int okb_mo_destroy(okb_mo *mo);
+
+/* Grids.  Regular: axis vectors; the point index runs x slowest, z fastest (cy_grid.pyx:22-29) and
+ * coordinates are generated in-kernel.  Vector: explicit coordinates (host, or device when
+ * coords_on_device != 0; device arrays must stay alive while the grid is used). */
+int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const double *y, int ny,
+                     const double *z, int nz, okb_grid **out);
+int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, const double *z,
+                    long long npts, int coords_on_device, okb_grid **out);
+int okb_grid_size(okb_grid *grid, long long *npts);
+int okb_grid_destroy(okb_grid *grid);
+
+/* ---- (2) fused path: evaluation over the point range [p0, p1) ---------------------------- */
+/* AOs (calc_ao): out[n_drv][n_ao][p1-p0]; drv_codes[i] in 0..9 (tools.validate_drv). */
+int okb_eval_ao(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
+                const int *drv_codes, int n_drv, double *out, unsigned flags);
+/* MOs (calc_mo): out[n_drv][n_mo][p1-p0]. */
+int okb_eval_mo(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                const int *drv_codes, int n_drv, double *out, unsigned flags);
+/* Density: rho[p1-p0]; delta_rho[n_drv][p1-p0] with, per code d,
+ *   sum_i occ_i * 2 * d_d(phi_i) * phi_i  (+ sum_i occ_i * 2 * d_a(phi_i) d_b(phi_i) for the
+ *   second-derivative codes 4..9, (a,b) the two letters) -- core.py:265-304.
+ * mo_norm[n_mo] (may be NULL) receives sum_points phi_i^2 (core.py:273); always a HOST pointer. */
+int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                 const int *drv_codes, int n_drv, double *rho, double *delta_rho,
+                 double *mo_norm, unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OKB200_H */

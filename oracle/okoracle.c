@@ -1,0 +1,237 @@
+/*
+ * okoracle.c -- CPU ORACLE for the ORBKIT grid-based hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library, and only as the checker or
+ * as the timed CPU baseline.  The product path (orbkit_b200/) never links,
+ * imports or calls it and fails loudly without its CUDA library.
+ *
+ * This is a plain-C restatement (not a copy) of the arithmetic the reference
+ * performs in
+ *     orbkit/c_support.c:8-195      (ipow, xyz, get_ao_xyz, ao_norm, doublefactorial)
+ *     orbkit/c_grid-based.c:9-79    (c_lcreator: one contraction on all points)
+ *     orbkit/cy_core.pyx:51-101     (aocreator shell loop, mocreator triple loop)
+ *     orbkit/cy_grid.pyx:14-55      (grid2vector / vector2grid)
+ * The operation ORDER of every floating-point expression follows the
+ * reference so that this port is bit-identical to the reference's own
+ * objects compiled with the same compiler (checked by
+ * tests/test_oracle.py against oracle/_ref/libokref.so, which is built from
+ * the reference's untouched sources).  Parity is pinned: see
+ * tests/golden/ (reference golden .npz + Gaussian cubegen KATs).
+ *
+ * Known reference bugs are reproduced on purpose (parity mode):
+ *   - mixed second derivatives (codes 7,8,9) drop the -2*alpha cross terms
+ *     (c_support.c:121-168).  okor_poly(..., exact_mixed=1) gives the
+ *     analytically correct value for documentation/tests of the opt-in flag.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ---- scalar helpers ------------------------------------------------- */
+
+/* base**e by binary exponentiation, e >= 0 (c_support.c:8-20). Negative
+ * exponents return 1.0 exactly like the reference's while(exp>0) loop. */
+double okor_ipow(double base, int e)
+{
+    double acc = 1.0;
+    for (; e > 0; e >>= 1) {
+        if (e & 1) acc *= base;
+        base *= base;
+    }
+    return acc;
+}
+
+/* x^lx * y^ly * z^lz (c_support.c:22-26) */
+double okor_mono(double x, double y, double z, int lx, int ly, int lz)
+{
+    return okor_ipow(x, lx) * okor_ipow(y, ly) * okor_ipow(z, lz);
+}
+
+static int okor_dfact(int n) /* n!! with (<=0)!! = 1 (c_support.c:190-195) */
+{
+    int r = 1;
+    for (; n > 0; n -= 2) r *= n;
+    return r;
+}
+
+/* primitive normalisation (c_support.c:177-188) */
+double okor_ao_norm(int l, int m, int n, double alpha, int is_normalized)
+{
+    if (is_normalized > 0) return 1.0;
+    double pref = pow(2. / M_PI, 3. / 4.);
+    double rad  = pow(2., (double)(l + m + n)) *
+                  pow(alpha, (2. * l + 2. * m + 2. * n + 3.) / 4.);
+    double den  = pow((double)(okor_dfact(2 * l - 1) * okor_dfact(2 * m - 1) *
+                               okor_dfact(2 * n - 1)), 0.5);
+    return pref * rad / den;
+}
+
+/*
+ * Polynomial prefactor of d^drv [x^lx y^ly z^lz exp(-alpha r^2)] / exp(-alpha r^2)
+ * (c_support.c:28-175).  drv: 0 value; 1,2,3 = d/dx,d/dy,d/dz;
+ * 4,5,6 = d2/dx2,d2/dy2,d2/dz2; 7,8,9 = dxdy, dxdz, dydz.
+ * exact_mixed=0 reproduces the reference's (incomplete) codes 7-9.
+ */
+double okor_poly(double X, double Y, double Z, int lx, int ly, int lz,
+                 double alpha, int drv, int exact_mixed)
+{
+    double r[3] = {X, Y, Z};
+    int    l[3] = {lx, ly, lz};
+    if (drv == 0) return okor_mono(X, Y, Z, lx, ly, lz);
+
+    if (drv >= 1 && drv <= 3) {            /* first derivatives (:58-93) */
+        int a = drv - 1;
+        int up[3] = {lx, ly, lz}, dn[3] = {lx, ly, lz};
+        up[a] += 1; dn[a] -= 1;
+        if (l[a] == 0)
+            return -2 * alpha * okor_mono(X, Y, Z, up[0], up[1], up[2]);
+        return l[a] * okor_mono(X, Y, Z, dn[0], dn[1], dn[2])
+             - 2 * alpha * okor_mono(X, Y, Z, up[0], up[1], up[2]);
+    }
+    if (drv >= 4 && drv <= 6) {            /* pure second derivatives (:94-120) */
+        int a = drv - 4;
+        double v = 2 * alpha * okor_mono(X, Y, Z, lx, ly, lz)
+                 * (2 * alpha * (r[a] * r[a]) - (2 * l[a] + 1));
+        if (l[a] >= 2) {
+            int dn[3] = {lx, ly, lz};
+            dn[a] -= 2;
+            v += (double)(l[a] * l[a] - l[a]) * okor_mono(X, Y, Z, dn[0], dn[1], dn[2]);
+        }
+        return v;
+    }
+    if (drv >= 7 && drv <= 9) {            /* mixed second derivatives (:121-168) */
+        static const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+        int a = pa[drv - 7], b = pb[drv - 7];
+        int up[3] = {lx, ly, lz};
+        up[a] += 1; up[b] += 1;
+        if (exact_mixed) {
+            /* (l_a r^{l_a-1} - 2 alpha r^{l_a+1}) (l_b r^{l_b-1} - 2 alpha r^{l_b+1}) * rest */
+            int c = 3 - a - b;
+            double fa = (l[a] ? l[a] * okor_ipow(r[a], l[a] - 1) : 0.0)
+                      - 2 * alpha * okor_ipow(r[a], l[a] + 1);
+            double fb = (l[b] ? l[b] * okor_ipow(r[b], l[b] - 1) : 0.0)
+                      - 2 * alpha * okor_ipow(r[b], l[b] + 1);
+            return fa * fb * okor_ipow(r[c], l[c]);
+        }
+        double v = 4 * (alpha * alpha) * okor_mono(X, Y, Z, up[0], up[1], up[2]);
+        int dn[3] = {lx, ly, lz};
+        if (l[a] == 0 && l[b] > 0) {
+            dn[b] -= 1;
+            v += l[b] * okor_mono(X, Y, Z, dn[0], dn[1], dn[2]);
+        } else if (l[a] > 0 && l[b] == 0) {
+            dn[a] -= 1;
+            v += l[a] * okor_mono(X, Y, Z, dn[0], dn[1], dn[2]);
+        } else if (l[a] > 0 && l[b] > 0) {
+            dn[a] -= 1; dn[b] -= 1;
+            v += l[a] * l[b] * okor_mono(X, Y, Z, dn[0], dn[1], dn[2]);
+        }
+        return v;
+    }
+    return 0.0;                            /* invalid code: reference yields 0 (:169-172) */
+}
+
+/* ---- one contraction on npts points (c_grid-based.c:9-79) ------------ */
+/*
+ * out      [ao_num][row_stride]  (row_stride >= npts; the reference passes a
+ *                                 row-offset view of the big array, stride npts)
+ * lxlylz   [ao_num][3] int
+ * coeffs   [pnum][2]   (alpha, c)
+ */
+void okor_lcreator(double *out, long row_stride, const int *lxlylz,
+                   const double *coeffs, const double *centre,
+                   const double *x, const double *y, const double *z,
+                   long npts, int ao_num, int pnum, int drv,
+                   int is_normalized, int exact_mixed)
+{
+    double *nrm = (double *)malloc(sizeof(double) * (size_t)ao_num * (size_t)pnum);
+    double *rad = (double *)malloc(sizeof(double) * (size_t)pnum);
+    for (int f = 0; f < ao_num; ++f)
+        for (int p = 0; p < pnum; ++p)
+            nrm[f * pnum + p] = okor_ao_norm(lxlylz[3 * f], lxlylz[3 * f + 1],
+                                             lxlylz[3 * f + 2], coeffs[2 * p],
+                                             is_normalized);
+    for (long i = 0; i < npts; ++i) {
+        double X = x[i] - centre[0], Y = y[i] - centre[1], Z = z[i] - centre[2];
+        double rr = X * X + Y * Y + Z * Z;
+        for (int p = 0; p < pnum; ++p)
+            rad[p] = coeffs[2 * p + 1] * exp(-coeffs[2 * p] * rr);
+        for (int f = 0; f < ao_num; ++f) {
+            const int lx = lxlylz[3 * f], ly = lxlylz[3 * f + 1], lz = lxlylz[3 * f + 2];
+            double s = 0.;
+            if (drv == 0) {
+                for (int p = 0; p < pnum; ++p) s += nrm[f * pnum + p] * rad[p];
+                s *= okor_mono(X, Y, Z, lx, ly, lz);
+            } else {
+                for (int p = 0; p < pnum; ++p)
+                    s += nrm[f * pnum + p] * rad[p] *
+                         okor_poly(X, Y, Z, lx, ly, lz, coeffs[2 * p], drv, exact_mixed);
+            }
+            out[(long)f * row_stride + i] = s;
+        }
+    }
+    free(nrm);
+    free(rad);
+}
+
+/* ---- all contractions (cy_core.pyx:51-78) ---------------------------- */
+/*
+ * out [n_cart][npts] zero-initialised by the caller (numpy.zeros in the
+ * reference, :67).  assign[s] = number of Cartesian functions of contraction
+ * s; pnum_list[s] = number of primitives; atom_idx[s] indexes geo[n_at][3].
+ */
+void okor_aocreator(double *out, const int *lxlylz, const int *assign,
+                    const double *ao_coeffs, const int *pnum_list,
+                    const double *geo, const int *atom_idx, int n_cont,
+                    const double *x, const double *y, const double *z,
+                    long npts, int drv, int is_normalized, int exact_mixed)
+{
+    long c_ao = 0, c_p = 0;
+    for (int s = 0; s < n_cont; ++s) {
+        okor_lcreator(out + c_ao * npts, npts, lxlylz + 3 * c_ao,
+                      ao_coeffs + 2 * c_p, geo + 3 * atom_idx[s], x, y, z,
+                      npts, assign[s], pnum_list[s], drv, is_normalized,
+                      exact_mixed);
+        c_ao += assign[s];
+        c_p  += pnum_list[s];
+    }
+}
+
+/* ---- MO contraction (cy_core.pyx:82-101): mo[i,j] = sum_k C[i,k] ao[k,j],
+ * k ascending, plain += starting from 0.0 ------------------------------ */
+void okor_mocreator(double *mo, const double *ao, const double *C,
+                    int n_mo, int n_ao, long npts)
+{
+    for (int i = 0; i < n_mo; ++i)
+        for (long j = 0; j < npts; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < n_ao; ++k) v += C[(long)i * n_ao + k] * ao[(long)k * npts + j];
+            mo[(long)i * npts + j] = v;
+        }
+}
+
+/* ---- regular grid <-> vector grid (cy_grid.pyx:14-55): x slowest, z fastest */
+void okor_grid2vector(double *xyz, const double *x, const double *y, const double *z,
+                      long nx, long ny, long nz)
+{
+    long n = nx * ny * nz, c = 0;
+    for (long i = 0; i < nx; ++i)
+        for (long j = 0; j < ny; ++j)
+            for (long k = 0; k < nz; ++k, ++c) {
+                xyz[c] = x[i]; xyz[n + c] = y[j]; xyz[2 * n + c] = z[k];
+            }
+}
+
+void okor_vector2grid(double *xn, double *yn, double *zn,
+                      const double *x, const double *y, const double *z,
+                      long nx, long ny, long nz)
+{
+    for (long i = 0; i < nx; ++i) xn[i] = x[i * ny * nz];
+    for (long j = 0; j < ny; ++j) yn[j] = y[j * nz];
+    for (long k = 0; k < nz; ++k) zn[k] = z[k];
+}

@@ -1,0 +1,139 @@
+"""ctypes binding of libokb200.so (include/okb200.h) -- the only door to the CUDA kernels.
+
+There is NO CPU fallback: if the shared library is missing or no sm_100 device is present every
+compute entry point raises.  The library is built in-tree by `__graft_entry__.build()` /
+`orbkit_b200._lib.build()` with
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libokb200.so')
+SRC = os.path.join(_HERE, 'csrc', 'okb200.cu')
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-shared']
+
+OKB_FLAG_EXACT_MIXED = 1
+OKB_FLAG_OUT_DEVICE = 2
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+ll = ctypes.c_longlong
+
+# name -> (restype, argtypes); every symbol include/okb200.h declares
+SIGNATURES = {
+    'okb_last_error': (ctypes.c_char_p, []),
+    'okb_version': (ctypes.c_int, []),
+    'okb_device_count': (ctypes.c_int, [c_int_p]),
+    'okb_ctx_create': (ctypes.c_int, [ctypes.c_int, c_void_pp]),
+    'okb_ctx_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'okb_ctx_sync': (ctypes.c_int, [ctypes.c_void_p]),
+    'okb_ctx_stream': (ctypes.c_void_p, [ctypes.c_void_p]),
+    'okb_ctx_launch_count': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ll)]),
+    'okb_ctx_last_kernel': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    'okb_aocreator': (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p, c_int_p, c_double_p,
+                                     c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     c_double_p, c_double_p, c_double_p, ll, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_uint, c_double_p]),
+    'okb_lcreator': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ll, c_int_p, c_double_p, c_double_p,
+                                    c_double_p, c_double_p, c_double_p, ll, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_uint]),
+    'okb_mocreator': (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int, ll,
+                                     ctypes.c_int, c_double_p]),
+    'okb_aonorm': (ctypes.c_double, [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.c_int]),
+    'okb_aoxyz': (ctypes.c_double, [ctypes.c_double] * 3 + [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.c_int]),
+    'okb_basis_create': (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p, c_int_p, c_double_p,
+                                        c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, c_double_p, c_void_pp]),
+    'okb_basis_set_cart2sph': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int_p, c_int_p, c_double_p]),
+    'okb_basis_info': (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'okb_basis_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'okb_mo_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p,
+                                     c_void_pp]),
+    'okb_mo_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'okb_grid_regular': (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int, c_double_p, ctypes.c_int,
+                                        c_double_p, ctypes.c_int, c_void_pp]),
+    'okb_grid_vector': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll,
+                                       ctypes.c_int, c_void_pp]),
+    'okb_grid_size': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ll)]),
+    'okb_grid_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'okb_eval_ao': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_uint]),
+    'okb_eval_mo': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_uint]),
+    'okb_eval_rho': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_uint]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class OkbError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/okb200.cu for sm_100a into orbkit_b200/libokb200.so (works without a GPU)."""
+    deps = [SRC, os.path.join(_HERE, 'csrc', 'okb_kernels.cuh'),
+            os.path.join(os.path.dirname(_HERE), 'include', 'okb200.h')]
+    if (not force and os.path.exists(LIB_PATH) and
+            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, SRC]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def load():
+    """Load libokb200.so; raise (loudly) if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise OkbError('orbkit_b200: %s is missing -- run `python -c "import __graft_entry__ as g; '
+                           'g.build()"` (nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().okb_last_error().decode('utf-8', 'replace')
+        if status == 1:
+            raise ValueError(msg)
+        if status == 3:
+            raise MemoryError(msg)
+        raise OkbError(msg)
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def f64(a):
+    return numpy.require(a, dtype=numpy.float64, requirements='CA')
+
+
+def i32(a):
+    return numpy.require(a, dtype=numpy.intc, requirements='CA')

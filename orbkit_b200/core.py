@@ -1,0 +1,360 @@
+"""Grid-path operators and drivers with the reference's signatures (orbkit/core.py).
+
+    ao_creator            core.py:38-105     contracted (Cartesian / real spherical) AOs or one derivative
+    mo_creator            core.py:107-132    MO contraction of a given AO array
+    cartesian2spherical   core.py:135-176    Cartesian -> spherical rows
+    rho_compute           core.py:314-605    density / MOs / AOs and derivatives on the module grid
+    rho_compute_no_slice  core.py:607-839    same with explicit coordinates and optional components
+    calc_mo_matrix        core.py:841-941    MO products on the grid
+
+Differences in mechanism (never in results): the reference expands a regular grid to a vector grid
+in place, slices it, forks `numproc` workers and runs one full AO pass + one naive triple-loop MO
+contraction per derivative code (slice_rho, core.py:179-308).  Here one fused kernel launch
+evaluates every needed derivative set of the AOs tile by tile in shared memory, contracts them in
+registers and reduces to rho / delta_rho on chip; regular-grid coordinates are generated in-kernel;
+`numproc` and `slice_length` are accepted and ignored; when torch.distributed is initialised the
+point range is sharded over the ranks (one GPU each) and gathered at the end.
+"""
+import numpy
+
+from . import cy_core, cy_grid, grid, options
+from . import dist as okdist
+from ._lib import OKB_FLAG_EXACT_MIXED, OKB_FLAG_OUT_DEVICE
+from .display import display
+from .engine import get_engine, build_cart2sph_csr
+from .qcinfo import QCinfo
+from .tools import require, validate_drv, convert, zeros, reshape
+
+
+def _flags():
+    return OKB_FLAG_EXACT_MIXED if options.exact_mixed_derivatives else 0
+
+
+def _drv_list(drv):
+    """normalise `drv` to a list or None (core.py:401-408): 'xyz' -> ['x','y','z']."""
+    if drv is None:
+        return None
+    if isinstance(drv, (int, numpy.integer)):
+        return [int(drv)]
+    try:
+        return list(drv)
+    except TypeError:
+        return [drv]
+
+
+def _grid_handle(eng, x, y, z, is_vector):
+    return eng.grid_vector(x, y, z) if is_vector else eng.grid_regular(x, y, z)
+
+
+def _resolve_grid(x, y, z, is_vector, init_vector=False):
+    """the explicit coordinates or, by default, the module-global grid (core.py:64-71,702-709)"""
+    if all(v is None for v in [x, y, z, is_vector]) and not grid.is_initialized:
+        display('\nSetting up the grid...')
+        grid.grid_init(is_vector=init_vector)
+        display(grid.get_grid())
+    x = grid.x if x is None else x
+    y = grid.y if y is None else y
+    z = grid.z if z is None else z
+    is_vector = grid.is_vector if is_vector is None else is_vector
+    x, y, z = require(x, dtype='f'), require(y, dtype='f'), require(z, dtype='f')
+    if is_vector:
+        if len(x) != len(y) or len(x) != len(z):
+            raise ValueError('Dimensions of x-, y-, and z- coordinate differ!')
+        N = (len(x),)
+    else:
+        N = (len(x), len(y), len(z))
+    return x, y, z, bool(is_vector), N
+
+
+# ---------------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------------
+def ao_creator(geo_spec, ao_spec, drv=None, x=None, y=None, z=None, is_vector=None):
+    """All contracted atomic orbitals, or their derivative w.r.t. `drv`, on the grid.
+
+    Returns ao_list with shape ((NAO,) + N), N = (Nx,Ny,Nz) for a regular grid, (Npts,) for a vector
+    grid (core.py:38-105).  Spherical bases are transformed in-kernel."""
+    x, y, z, is_vector, N = _resolve_grid(x, y, z, is_vector, init_vector=True)
+    code = validate_drv(drv)
+    geo_spec = require(geo_spec, dtype='f')
+    eng = get_engine()
+    basis = eng.basis(geo_spec, ao_spec)
+    if int(numpy.prod(N)) == 0:
+        return numpy.zeros((basis[2],) + N)
+    g = _grid_handle(eng, x, y, z, is_vector)
+    out = eng.eval_ao(basis, g, [code], flags=_flags())
+    return out[0].reshape((basis[2],) + N)
+
+
+def mo_creator(ao_list, mo_spec):
+    """Molecular orbitals from a given AO array: ((NMO,) + N) (core.py:107-132)."""
+    ao_list = require(ao_list, dtype='f')
+    shape = ao_list.shape
+    mo_coeffs = require(mo_spec.get_coeffs(), dtype='f')
+    mo = cy_core.mocreator(ao_list.reshape((shape[0], -1)), mo_coeffs)
+    return mo.reshape((len(mo_coeffs),) + shape[1:])
+
+
+def cartesian2spherical(ao_list, ao_spec):
+    """Cartesian -> real spherical AOs for a given AO array (core.py:135-176; table tools.cart2sph).
+    Runs as T[n_sph,n_cart] x ao[n_cart,N] on the device GEMM."""
+    ao_list = require(ao_list, dtype='f')
+    ptr, col, val = build_cart2sph_csr(ao_spec)
+    T = numpy.zeros((len(ptr) - 1, ao_list.shape[0]))
+    for j in range(len(ptr) - 1):
+        for t in range(ptr[j], ptr[j + 1]):
+            T[j, col[t]] += val[t]
+    out = cy_core.mocreator(ao_list.reshape((ao_list.shape[0], -1)), T)
+    return out.reshape((T.shape[0],) + ao_list.shape[1:])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the driver
+# ---------------------------------------------------------------------------------------------------
+def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
+    """Shared back end of rho_compute / rho_compute_no_slice.  Returns
+         calc_ao/calc_mo:  array (n_sets, n_rows, npts)
+         else:             (rho (npts,), delta (len(drv), npts) or None, mo_norm or None)"""
+    eng = get_engine()
+    geo_spec = require(qc.geo_spec, dtype='f')
+    basis = eng.basis(geo_spec, qc.ao_spec)
+    npts = int(numpy.prod(N))
+    codes = [0] if drv is None else [validate_drv(d) for d in drv]
+    if not calc_ao:
+        mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    n_rows = basis[2] if calc_ao else (mo.n_mo if calc_mo else 1)
+    if npts == 0:
+        if calc_mo or calc_ao:
+            return numpy.zeros((len(codes), n_rows, 0))
+        return numpy.zeros(0), (numpy.zeros((len(codes), 0)) if drv is not None else None), \
+            (numpy.zeros(mo.n_mo) if want_norm else None)
+    g = _grid_handle(eng, x, y, z, is_vector)
+    flags = _flags()
+
+    if not okdist.is_distributed():
+        if calc_ao:
+            return eng.eval_ao(basis, g, codes, flags=flags)
+        if calc_mo:
+            return eng.eval_mo(mo, g, codes, flags=flags)
+        ucodes = [] if drv is None else sorted(set(codes))
+        rho, delta, norm = eng.eval_rho(mo, g, ucodes, want_norm=want_norm, flags=flags)
+        if drv is not None and ucodes != codes:
+            delta = delta[[ucodes.index(c) for c in codes]]
+        return rho, delta, norm
+
+    # ---- one rank per GPU: contiguous point shards, device outputs, NCCL gather -------------------
+    import torch
+    rank, world = okdist.rank_world()
+    p0, p1 = okdist.shard_range(npts, rank, world)
+    dev = torch.device('cuda', eng.device)
+    n_loc = p1 - p0
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    fl = flags | OKB_FLAG_OUT_DEVICE
+    with torch.cuda.device(dev):
+        if calc_ao or calc_mo:
+            loc = torch.empty((len(codes), n_rows, max(n_loc, 1)), dtype=torch.float64, device=dev)[..., :n_loc]
+            loc = loc.contiguous()
+            if n_loc:
+                if calc_ao:
+                    eng.eval_ao(basis, g, codes, p0, p1, out=loc.data_ptr(), flags=fl)
+                else:
+                    eng.eval_mo(mo, g, codes, p0, p1, out=loc.data_ptr(), flags=fl)
+            eng.sync()
+            return okdist.gather_points(loc, npts).cpu().numpy()
+        ucodes = [] if drv is None else sorted(set(codes))
+        loc = torch.zeros((1 + len(ucodes), max(n_loc, 1)), dtype=torch.float64, device=dev)
+        norm = None
+        if n_loc:
+            _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=loc[0].data_ptr(),
+                                      delta=loc[1:].data_ptr() if ucodes else None,
+                                      want_norm=want_norm, flags=fl)
+        eng.sync()
+        full = okdist.gather_points(loc[:, :n_loc].contiguous(), npts).cpu().numpy()
+        if want_norm:
+            norm = okdist.all_reduce_sum(norm if norm is not None else numpy.zeros(mo.n_mo), eng.device)
+        delta = None
+        if drv is not None:
+            delta = full[1:][[ucodes.index(c) for c in codes]]
+        return full[0], delta, norm
+
+
+def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, numproc=1,
+                slice_length=1e4, vector=None, save_hdf5=False, **kwargs):
+    r"""Density, molecular orbitals, atomic orbitals or derivatives thereof on `orbkit_b200.grid`.
+
+    Same arguments and return values as the reference (core.py:314-605):
+      calc_mo (or calc_ao), drv is None      -> mo_list        ((NMO,)+N)
+      calc_mo (or calc_ao), drv not None     -> delta_mo_list  ((NDRV,NMO)+N)
+      else, drv is None                      -> rho            (N)
+      else, drv not None                     -> rho, delta_rho ((NDRV,)+N)
+      else, laplacian                        -> rho, delta_rho, laplacian_rho
+    `numproc`, `slice_length`, `vector` are accepted for compatibility and ignored, except that
+    numproc <= 0 routes to rho_compute_no_slice like the reference does.
+    """
+    if calc_ao and calc_mo:
+        raise ValueError('Choose either calc_ao=True or calc_mo=True')
+    elif calc_ao:
+        calc_mo = True
+    if numproc <= 0:
+        return rho_compute_no_slice(qc, calc_ao=calc_ao, calc_mo=calc_mo and not calc_ao, drv=drv,
+                                    laplacian=laplacian, **kwargs)
+    if laplacian:
+        if not (drv is None or drv == ['xx', 'yy', 'zz'] or drv == ['x2', 'y2', 'z2']):
+            display('Note: You have set the option `laplacian` and specified values\nfor `drv`. '
+                    'Both options are not compatible.\nThe option `drv` has been changed to '
+                    '`drv=["xx","yy","zz"]`.')
+        drv = ['xx', 'yy', 'zz']
+    drv = _drv_list(drv)
+    is_drv = drv is not None
+    if isinstance(qc, dict):
+        qc = QCinfo(qc)
+    if not grid.is_initialized:
+        display('\nSetting up the grid...')
+        grid.grid_init()
+        display(grid.get_grid())
+    was_vector = grid.is_vector
+    x, y, z, _, N = _resolve_grid(grid.x, grid.y, grid.z, was_vector)
+    mo_num = qc.ao_spec.get_ao_num() if calc_ao else len(qc.mo_spec)
+    display('\nStarting the calculation of the %s...' % ('molecular orbitals' if calc_mo else 'density'))
+    display('\nThere are %d contracted %s AOs' % (qc.ao_spec.get_ao_num(),
+            'Cartesian' if not qc.ao_spec.spherical else 'spherical') +
+            ('' if calc_ao else ' and %d MOs to be calculated.' % mo_num))
+
+    show_norm = (not was_vector) and drv is None and not options.quiet
+    res = _compute(qc, x, y, z, was_vector, N, calc_ao, calc_mo, drv, want_norm=show_norm and not calc_mo)
+
+    hdf5_file = None
+    if save_hdf5:
+        import h5py
+        hdf5_file = h5py.File(str(save_hdf5), 'w')
+        for k, v in (('x', grid.x), ('y', grid.y), ('z', grid.z)):
+            hdf5_file['grid/' + k] = v
+        hdf5_file['grid/is_vector'] = False
+        hdf5_file['grid/is_regular'] = was_vector
+
+    if calc_mo:
+        mo_list = res[0] if drv is None else res
+        if show_norm:
+            display('\nNorm of the MOs:')
+            labels = qc.ao_spec.get_labels() if calc_ao else qc.mo_spec.get_labels(format='print')
+            for i in range(mo_num):
+                display('\t%.6f\t%s %s' % (numpy.sum(numpy.square(mo_list[i])) * grid.d3r,
+                                             'AO' if calc_ao else 'MO', labels[i]))
+        mo_list = mo_list.reshape(((mo_num,) if drv is None else (len(drv), mo_num,)) + N)
+        if hdf5_file is not None:
+            hdf5_file['ao_list' if calc_ao else 'mo_list'] = mo_list
+            hdf5_file.close()
+        return mo_list
+
+    rho, delta_rho, mo_norm = res
+    if show_norm:
+        display('\nNorm of the MOs:')
+        labels = qc.mo_spec.get_labels(format='print')
+        for i in range(mo_num):
+            display('\t%.6f\tMO %s' % (mo_norm[i] * grid.d3r, labels[i]))
+    if not was_vector:
+        display('We have ' + str(numpy.sum(rho) * grid.d3r) + ' electrons.')
+    rho = rho.reshape(N)
+    if hdf5_file is not None:
+        hdf5_file['rho'] = rho
+    if not is_drv:
+        if hdf5_file is not None:
+            hdf5_file.close()
+        return rho
+    delta_rho = delta_rho.reshape((len(drv),) + N)
+    if hdf5_file is not None:
+        hdf5_file['delta_rho'] = delta_rho
+        hdf5_file.close()
+    if laplacian:
+        return rho, delta_rho, delta_rho.sum(axis=0)
+    return rho, delta_rho
+
+
+def rho_compute_no_slice(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False,
+                         return_components=False, x=None, y=None, z=None, is_vector=None, **kwargs):
+    r"""As rho_compute but with explicit coordinates and, if `return_components`, the AO and MO
+    arrays as well (core.py:607-839):
+      calc_mo, drv None       -> ao_list, mo_list
+      calc_mo, drv            -> delta_ao_list, delta_mo_list
+      else, drv None          -> ao_list, mo_list, rho
+      else, drv               -> ao_list, mo_list, rho, delta_ao_list, delta_mo_list, delta_rho[, laplacian_rho]
+    """
+    if calc_ao and calc_mo:
+        raise ValueError('calc_ao and calc_mo are mutually exclusive arguments.'
+                         'Use calc_mo and return_components instead!')
+    x, y, z, is_vector, N = _resolve_grid(x, y, z, is_vector)
+    was_vector = is_vector
+    d3r = 1.0
+    if not is_vector:
+        for i in (x, y, z):
+            if len(i) > 1:
+                d3r *= (i[1] - i[0])
+    if laplacian:
+        drv = ['xx', 'yy', 'zz']
+    if isinstance(qc, dict):
+        qc = QCinfo(qc)
+    drv = _drv_list(drv)
+    n_ao = qc.ao_spec.get_ao_num()
+
+    def shaped(a, lead):
+        return a.reshape(lead + N)
+
+    delta_ao_list = delta_mo_list = None
+    if drv is not None:
+        if calc_ao or return_components:
+            delta_ao_list = shaped(_compute(qc, x, y, z, is_vector, N, True, True, drv, False), (len(drv), n_ao))
+        if calc_ao:
+            return delta_ao_list
+        if calc_mo or return_components:
+            delta_mo_list = shaped(_compute(qc, x, y, z, is_vector, N, False, True, drv, False),
+                                   (len(drv), len(qc.mo_spec)))
+        if calc_mo:
+            return (delta_ao_list, delta_mo_list) if return_components else delta_mo_list
+    ao_list = mo_list = None
+    if calc_ao or return_components:
+        ao_list = shaped(_compute(qc, x, y, z, is_vector, N, True, True, None, False)[0], (n_ao,))
+    if calc_ao:
+        return ao_list
+    if calc_mo or return_components:
+        mo_list = shaped(_compute(qc, x, y, z, is_vector, N, False, True, None, False)[0], (len(qc.mo_spec),))
+        if not was_vector and not options.quiet:
+            display('\nNorm of the MOs:')
+            for i in range(len(mo_list)):
+                display('\t%.6f\tMO %s' % (numpy.sum(mo_list[i] ** 2) * d3r, qc.mo_spec[i].get('sym', '')))
+    if calc_mo:
+        return (ao_list, mo_list) if return_components else mo_list
+
+    rho, delta_rho, _ = _compute(qc, x, y, z, is_vector, N, False, False, drv, False)
+    rho = rho.reshape(N)
+    if not was_vector:
+        display('We have ' + str(numpy.sum(rho) * d3r) + ' electrons.')
+    if drv is None:
+        return (ao_list, mo_list, rho) if return_components else rho
+    delta_rho = delta_rho.reshape((len(drv),) + N)
+    delta = (delta_rho, delta_rho.sum(axis=0)) if laplacian else (delta_rho,)
+    return ((ao_list, mo_list, rho, delta_ao_list, delta_mo_list,) + delta
+            if return_components else (rho,) + delta)
+
+
+def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_hdf5=False, **kwargs):
+    """Products mo_bra[n] * d_drv mo_ket[m] on the grid (core.py:841-941); host-side outer product of
+    the device-computed MO arrays."""
+    if drv is None:
+        dl, iket = [None], [0]
+    elif not isinstance(drv, list):
+        dl, iket = [None, drv], [1]
+    else:
+        dl, iket = [None] + drv, list(range(1, len(drv) + 1))
+    if qc_b is None or qc_a == qc_b:
+        mo = rho_compute(qc_a, calc_mo=True, drv=dl, numproc=numproc, slice_length=slice_length)
+        mo_bra, mo_ket = mo[[0]], mo[iket]
+    else:
+        mo_bra = rho_compute(qc_a, calc_mo=True, drv=[None], numproc=numproc, slice_length=slice_length)
+        mo_ket = rho_compute(qc_b, calc_mo=True, drv=[dl[i] for i in iket], numproc=numproc,
+                             slice_length=slice_length)
+    nmo_a, nmo_b = mo_bra.shape[1], mo_ket.shape[1]
+    out = numpy.zeros((mo_ket.shape[0], nmo_a) + mo_ket.shape[1:])
+    for n in range(nmo_a):
+        for m in range(nmo_b):
+            out[:, n, m] = mo_bra[:, n] * mo_ket[:, m]
+    return out

@@ -1,0 +1,967 @@
+// okb200.cu -- C ABI (include/okb200.h) + host runtime of the B200 grid path.
+//
+// Host responsibilities (all O(basis), never O(points)):
+//   * flatten the reference's basis arrays (the argument list of cy_core.aocreator,
+//     cy_core.pyx:51-61) into shell-sorted device tables: per shell the centre, per primitive
+//     (alpha, c * N_L(alpha)) with the primitive norm of c_support.c:177-188 hoisted out of the point
+//     loop, per Cartesian function (lx,ly,lz) and its angular norm 1/sqrt((2lx-1)!!(2ly-1)!!(2lz-1)!!);
+//   * cut the shells into chunks of <= KC functions and pack one fixed-stride table blob per chunk
+//     (a single bulk-async copy per chunk in the kernel);
+//   * fold the Cartesian->spherical rows into the MO coefficients (C' = C T, the transform is linear)
+//     and lay C' out as [mo-tile][chunk][KC][MC] so that each (tile, chunk) is one contiguous TMA copy;
+//   * slab the point range, launch, and stream results back to host buffers.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/okb200.h"
+#include "okb_kernels.cuh"
+
+using namespace okb;
+
+// ---- error channel ------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? OKB_ERR_NOMEM : OKB_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *okb_last_error(void) { return g_err; }
+extern "C" int okb_version(void) { return 100; }
+extern "C" int okb_device_count(int *n) {
+    if (!n) return fail(OKB_ERR_ARG, "okb_device_count: null pointer");
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(OKB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return OKB_OK;
+}
+
+// ---- handles ----------------------------------------------------------------------------------------
+struct okb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    long long launches = 0;
+    std::string last_kernel;
+    void *slab[2] = {nullptr, nullptr};      // device staging for host outputs
+    size_t slab_bytes = 0;
+    double *norm_dev = nullptr;              // mo_norm accumulation
+    size_t norm_cap = 0;
+};
+
+struct DevShell {
+    double c[3];
+    int L;
+    std::vector<int> prims;                  // indices into prim arrays
+    std::vector<double> alpha, cn;
+    std::vector<int> fn_row;                 // Cartesian row of each function
+    std::vector<int> lx, ly, lz;
+    std::vector<double> f;
+};
+
+struct okb_basis {
+    okb_ctx *ctx = nullptr;
+    int n_cart = 0, n_ao = 0;
+    bool spherical = false;
+    std::vector<DevShell> shells;
+    // chunking
+    struct Chunk { int s0, s1, k0, nfn, nprim; };
+    std::vector<Chunk> chunks;
+    std::vector<int> fn_row;                 // device function index -> Cartesian row
+    std::vector<int> fn_chunk, fn_klocal;    // Cartesian row -> chunk / chunk-local k
+    // cart -> sph CSR
+    std::vector<int> t_ptr, t_col;
+    std::vector<double> t_val;
+    // device blob
+    BlobLayout lay{};
+    unsigned char *meta_dev = nullptr;
+    bool dirty = true;
+};
+
+struct okb_mo {
+    okb_ctx *ctx = nullptr;
+    okb_basis *basis = nullptr;
+    int n_mo = 0;
+    std::vector<double> ccart;               // [n_mo][n_cart] in Cartesian rows (C' = C T)
+    std::vector<double> occ;
+    struct Blob { double *c = nullptr; double *occ = nullptr; int n_mtile = 0; };
+    std::map<int, Blob> blobs;               // keyed by MC
+};
+
+struct okb_grid {
+    okb_ctx *ctx = nullptr;
+    int kind = 0;                            // 0 regular, 1 vector
+    int nx = 0, ny = 0, nz = 0;
+    long long npts = 0;
+    double *gx = nullptr, *gy = nullptr, *gz = nullptr;
+    bool owns = true;
+};
+
+// ---- context ------------------------------------------------------------------------------------------
+extern "C" int okb_ctx_create(int device, okb_ctx **out) {
+    if (!out) return fail(OKB_ERR_ARG, "okb_ctx_create: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(OKB_ERR_CUDA, "no CUDA device available (%s): orbkit_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(OKB_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(OKB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    okb_ctx *c = new okb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return OKB_OK;
+}
+
+extern "C" int okb_ctx_destroy(okb_ctx *c) {
+    if (!c) return OKB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->slab[i]) cudaFree(c->slab[i]);
+        if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]);
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    }
+    if (c->norm_dev) cudaFree(c->norm_dev);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return OKB_OK;
+}
+
+extern "C" int okb_ctx_sync(okb_ctx *c) {
+    if (!c) return fail(OKB_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    return OKB_OK;
+}
+extern "C" void *okb_ctx_stream(okb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int okb_ctx_launch_count(okb_ctx *c, long long *n) {
+    if (!c || !n) return fail(OKB_ERR_ARG, "null pointer");
+    *n = c->launches;
+    return OKB_OK;
+}
+extern "C" int okb_ctx_last_kernel(okb_ctx *c, char *buf, int buflen) {
+    if (!c || !buf || buflen <= 0) return fail(OKB_ERR_ARG, "null pointer");
+    snprintf(buf, buflen, "%s", c->last_kernel.c_str());
+    return OKB_OK;
+}
+
+// ---- scalar helpers (host; the reference exposes them through cy_core.aonorm / aoxyz) ------------------
+static int dfact(int n) {
+    int r = 1;
+    for (; n > 0; n -= 2) r *= n;
+    return r;
+}
+static double radial_norm(int L, double alpha) {   // (2/pi)^(3/4) 2^L alpha^((2L+3)/4)
+    return pow(2. / M_PI, 0.75) * (pow(2., (double)L) * pow(alpha, (2. * L + 3.) / 4.));
+}
+static double angular_norm(int lx, int ly, int lz) {
+    return 1.0 / sqrt((double)(dfact(2 * lx - 1) * dfact(2 * ly - 1) * dfact(2 * lz - 1)));
+}
+extern "C" double okb_aonorm(int lx, int ly, int lz, double alpha, int is_normalized) {
+    if (is_normalized > 0) return 1.0;
+    return radial_norm(lx + ly + lz, alpha) /
+           sqrt((double)(dfact(2 * lx - 1) * dfact(2 * ly - 1) * dfact(2 * lz - 1)));
+}
+static double hpow(double r, int l) {
+    double a = 1.0;
+    for (; l > 0; l >>= 1) {
+        if (l & 1) a *= r;
+        r *= r;
+    }
+    return a;
+}
+extern "C" double okb_aoxyz(double x, double y, double z, int lx, int ly, int lz, double alpha, int drv) {
+    // derivative prefactor of x^lx y^ly z^lz exp(-alpha r^2), reference semantics (c_support.c:28-175),
+    // written with the per-axis quantities the kernels use.
+    const double r[3] = {x, y, z};
+    const int l[3] = {lx, ly, lz};
+    double q0[3], qm1[3], qp1[3], qm2[3];
+    for (int a = 0; a < 3; ++a) {
+        q0[a] = hpow(r[a], l[a]);
+        qm1[a] = l[a] > 0 ? l[a] * hpow(r[a], l[a] - 1) : 0.0;
+        qp1[a] = q0[a] * r[a];
+        qm2[a] = l[a] > 1 ? (double)(l[a] * (l[a] - 1)) * hpow(r[a], l[a] - 2) : 0.0;
+    }
+    if (drv == 0) return q0[0] * q0[1] * q0[2];
+    if (drv >= 1 && drv <= 3) {
+        const int a = drv - 1, b = (a + 1) % 3, c = (a + 2) % 3;
+        return q0[b] * q0[c] * (qm1[a] - 2.0 * alpha * qp1[a]);
+    }
+    if (drv >= 4 && drv <= 6) {
+        const int a = drv - 4, b = (a + 1) % 3, c = (a + 2) % 3;
+        return q0[b] * q0[c] *
+               (q0[a] * (4.0 * alpha * alpha * r[a] * r[a] - 2.0 * alpha * (2 * l[a] + 1)) + qm2[a]);
+    }
+    if (drv >= 7 && drv <= 9) {
+        const int a = drv == 9 ? 1 : 0, b = drv == 7 ? 1 : 2, c = 3 - a - b;
+        double B = 0.0;
+        if (l[a] > 0 || l[b] > 0) B = (l[a] > 0 ? qm1[a] : 1.0) * (l[b] > 0 ? qm1[b] : 1.0);
+        return q0[c] * (4.0 * alpha * alpha * qp1[a] * qp1[b] + B);
+    }
+    return 0.0;
+}
+
+// ---- basis ----------------------------------------------------------------------------------------------
+static int basis_build_chunks(okb_basis *b) {
+    b->chunks.clear();
+    b->fn_row.clear();
+    const int MAXS = 32, MAXP = 96;
+    okb_basis::Chunk cur{0, 0, 0, 0, 0};
+    int k = 0;
+    for (int s = 0; s < (int)b->shells.size(); ++s) {
+        const DevShell &sh = b->shells[s];
+        const int nf = (int)sh.fn_row.size(), np = (int)sh.alpha.size();
+        if (nf > KC) return fail(OKB_ERR_UNSUPPORTED, "shell with %d functions exceeds the chunk size %d", nf, KC);
+        const bool full = (cur.s1 > cur.s0) &&
+                          (cur.nfn + nf > KC || cur.s1 - cur.s0 >= MAXS || cur.nprim + np > MAXP);
+        if (full) {
+            b->chunks.push_back(cur);
+            cur = okb_basis::Chunk{s, s, k, 0, 0};
+        }
+        cur.s1 = s + 1;
+        cur.nfn += nf;
+        cur.nprim += np;
+        for (int r : sh.fn_row) b->fn_row.push_back(r);
+        k += nf;
+    }
+    if (cur.s1 > cur.s0) b->chunks.push_back(cur);
+    b->fn_chunk.assign(b->n_cart, -1);
+    b->fn_klocal.assign(b->n_cart, -1);
+    for (int c = 0; c < (int)b->chunks.size(); ++c)
+        for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
+            const int row = b->fn_row[b->chunks[c].k0 + kk];
+            b->fn_chunk[row] = c;
+            b->fn_klocal[row] = kk;
+        }
+    return OKB_OK;
+}
+
+static int basis_upload(okb_basis *b) {
+    // output rows per chunk (SINK_AO): Cartesian identity rows or the spherical CSR rows
+    const int nchunk = (int)b->chunks.size();
+    std::vector<std::vector<RowMeta>> rows(nchunk);
+    std::vector<std::vector<TermMeta>> terms(nchunk);
+    if (!b->spherical) {
+        for (int c = 0; c < nchunk; ++c)
+            for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
+                rows[c].push_back(RowMeta{b->fn_row[b->chunks[c].k0 + kk], (int)terms[c].size(), 1, 0});
+                terms[c].push_back(TermMeta{kk, 0, 1.0});
+            }
+    } else {
+        for (int j = 0; j < b->n_ao; ++j) {
+            const int t0 = b->t_ptr[j], t1 = b->t_ptr[j + 1];
+            if (t1 <= t0) return fail(OKB_ERR_ARG, "spherical function %d has no Cartesian terms", j);
+            const int c = b->fn_chunk[b->t_col[t0]];
+            rows[c].push_back(RowMeta{j, (int)terms[c].size(), t1 - t0, 0});
+            for (int t = t0; t < t1; ++t) {
+                if (b->fn_chunk[b->t_col[t]] != c)
+                    return fail(OKB_ERR_UNSUPPORTED,
+                                "spherical function %d mixes Cartesian functions of different shells", j);
+                terms[c].push_back(TermMeta{b->fn_klocal[b->t_col[t]], 0, b->t_val[t]});
+            }
+        }
+    }
+    int maxS = 1, maxP = 1, maxR = 1, maxT = 1;
+    for (int c = 0; c < nchunk; ++c) {
+        maxS = std::max(maxS, b->chunks[c].s1 - b->chunks[c].s0);
+        maxP = std::max(maxP, b->chunks[c].nprim);
+        maxR = std::max(maxR, (int)rows[c].size());
+        maxT = std::max(maxT, (int)terms[c].size());
+    }
+    BlobLayout &L = b->lay;
+    L.off_shell = 16;
+    L.off_prim = L.off_shell + maxS * (int)sizeof(ShellMeta);
+    L.off_fn = L.off_prim + maxP * 16;
+    L.off_row = L.off_fn + KC * (int)sizeof(FnMeta);
+    L.off_term = L.off_row + maxR * (int)sizeof(RowMeta);
+    L.stride = (L.off_term + maxT * (int)sizeof(TermMeta) + 127) / 128 * 128;
+    if (L.stride > 24 * 1024)
+        return fail(OKB_ERR_UNSUPPORTED, "chunk table of %d bytes is too large", L.stride);
+    std::vector<unsigned char> blob((size_t)L.stride * std::max(nchunk, 1), 0);
+    for (int c = 0; c < nchunk; ++c) {
+        unsigned char *mb = blob.data() + (size_t)c * L.stride;
+        const okb_basis::Chunk &ch = b->chunks[c];
+        ChunkHdr hdr{ch.s1 - ch.s0, ch.nprim, ch.nfn, (int)rows[c].size()};
+        memcpy(mb, &hdr, sizeof(hdr));
+        ShellMeta *sm = reinterpret_cast<ShellMeta *>(mb + L.off_shell);
+        double2 *pm = reinterpret_cast<double2 *>(mb + L.off_prim);
+        FnMeta *fm = reinterpret_cast<FnMeta *>(mb + L.off_fn);
+        int po = 0, fo = 0;
+        for (int s = ch.s0; s < ch.s1; ++s) {
+            const DevShell &sh = b->shells[s];
+            ShellMeta m{};
+            m.cx = sh.c[0]; m.cy = sh.c[1]; m.cz = sh.c[2];
+            m.prim_off = po; m.nprim = (int)sh.alpha.size();
+            m.fn_off = fo; m.nfn = (int)sh.fn_row.size();
+            m.L = sh.L;
+            sm[s - ch.s0] = m;
+            for (size_t i = 0; i < sh.alpha.size(); ++i) pm[po++] = make_double2(sh.alpha[i], sh.cn[i]);
+            for (size_t j = 0; j < sh.fn_row.size(); ++j)
+                fm[fo++] = FnMeta{sh.lx[j] | (sh.ly[j] << 8) | (sh.lz[j] << 16), 0, sh.f[j]};
+        }
+        if (!rows[c].empty()) memcpy(mb + L.off_row, rows[c].data(), rows[c].size() * sizeof(RowMeta));
+        if (!terms[c].empty()) memcpy(mb + L.off_term, terms[c].data(), terms[c].size() * sizeof(TermMeta));
+    }
+    CU(cudaSetDevice(b->ctx->device));
+    if (b->meta_dev) CU(cudaFree(b->meta_dev));
+    b->meta_dev = nullptr;
+    CU(cudaMalloc(&b->meta_dev, blob.size()));
+    CU(cudaMemcpy(b->meta_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    b->dirty = false;
+    return OKB_OK;
+}
+
+extern "C" int okb_basis_create(okb_ctx *ctx, const int *lxlylz, const int *assign, const double *ao_coeffs,
+                                const int *pnum_list, const double *geo_spec, const int *atom_indices,
+                                int n_cont, int n_cart, int n_prim, int n_atoms, int is_normalized,
+                                const double *renorm, okb_basis **out) {
+    if (!ctx || !out) return fail(OKB_ERR_ARG, "okb_basis_create: null context/output");
+    *out = nullptr;
+    if (n_cont <= 0 || n_cart <= 0 || n_prim <= 0 || n_atoms <= 0)
+        return fail(OKB_ERR_ARG, "okb_basis_create: empty basis");
+    if (!lxlylz || !assign || !ao_coeffs || !pnum_list || !geo_spec || !atom_indices)
+        return fail(OKB_ERR_ARG, "okb_basis_create: null array");
+    okb_basis *b = new okb_basis();
+    b->ctx = ctx;
+    b->n_cart = n_cart;
+    b->n_ao = n_cart;
+    int c_ao = 0, c_p = 0;
+    for (int s = 0; s < n_cont; ++s) {
+        const int nf = assign[s], np = pnum_list[s], at = atom_indices[s];
+        if (nf < 0 || np < 0 || c_ao + nf > n_cart || c_p + np > n_prim || at < 0 || at >= n_atoms) {
+            delete b;
+            return fail(OKB_ERR_ARG, "okb_basis_create: contraction %d inconsistent with array sizes", s);
+        }
+        // split a contraction with mixed angular momentum into pure-L device shells
+        std::vector<int> Ls;
+        for (int j = 0; j < nf; ++j) {
+            const int *l = lxlylz + 3 * (c_ao + j);
+            if (l[0] < 0 || l[1] < 0 || l[2] < 0 || l[0] > 15 || l[1] > 15 || l[2] > 15) {
+                delete b;
+                return fail(OKB_ERR_ARG, "okb_basis_create: exponent out of range at function %d", c_ao + j);
+            }
+            const int L = l[0] + l[1] + l[2];
+            if (std::find(Ls.begin(), Ls.end(), L) == Ls.end()) Ls.push_back(L);
+        }
+        for (int L : Ls) {
+            DevShell sh;
+            sh.L = L;
+            for (int a = 0; a < 3; ++a) sh.c[a] = geo_spec[3 * at + a];
+            for (int i = 0; i < np; ++i) {
+                const double alpha = ao_coeffs[2 * (c_p + i)], coef = ao_coeffs[2 * (c_p + i) + 1];
+                sh.alpha.push_back(alpha);
+                sh.cn.push_back(is_normalized > 0 ? coef : coef * radial_norm(L, alpha));
+            }
+            for (int j = 0; j < nf; ++j) {
+                const int *l = lxlylz + 3 * (c_ao + j);
+                if (l[0] + l[1] + l[2] != L) continue;
+                sh.fn_row.push_back(c_ao + j);
+                sh.lx.push_back(l[0]); sh.ly.push_back(l[1]); sh.lz.push_back(l[2]);
+                double f = is_normalized > 0 ? 1.0 : angular_norm(l[0], l[1], l[2]);
+                if (renorm) f *= renorm[c_ao + j];
+                sh.f.push_back(f);
+            }
+            b->shells.push_back(std::move(sh));
+        }
+        c_ao += nf;
+        c_p += np;
+    }
+    if (c_ao != n_cart) {
+        delete b;
+        return fail(OKB_ERR_ARG, "okb_basis_create: sum(assign)=%d != n_cart=%d", c_ao, n_cart);
+    }
+    int rc = basis_build_chunks(b);
+    if (rc == OKB_OK) rc = basis_upload(b);
+    if (rc != OKB_OK) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return OKB_OK;
+}
+
+extern "C" int okb_basis_set_cart2sph(okb_basis *b, int n_sph, const int *row_ptr, const int *col,
+                                      const double *val) {
+    if (!b || !row_ptr || !col || !val || n_sph <= 0) return fail(OKB_ERR_ARG, "okb_basis_set_cart2sph: bad argument");
+    const int nnz = row_ptr[n_sph];
+    for (int t = 0; t < nnz; ++t)
+        if (col[t] < 0 || col[t] >= b->n_cart)
+            return fail(OKB_ERR_ARG, "okb_basis_set_cart2sph: column %d out of range", col[t]);
+    b->t_ptr.assign(row_ptr, row_ptr + n_sph + 1);
+    b->t_col.assign(col, col + nnz);
+    b->t_val.assign(val, val + nnz);
+    b->n_ao = n_sph;
+    b->spherical = true;
+    return basis_upload(b);
+}
+
+extern "C" int okb_basis_info(okb_basis *b, int *n_cart, int *n_ao, int *n_dev_shells, int *n_chunks) {
+    if (!b) return fail(OKB_ERR_ARG, "null basis");
+    if (n_cart) *n_cart = b->n_cart;
+    if (n_ao) *n_ao = b->n_ao;
+    if (n_dev_shells) *n_dev_shells = (int)b->shells.size();
+    if (n_chunks) *n_chunks = (int)b->chunks.size();
+    return OKB_OK;
+}
+
+extern "C" int okb_basis_destroy(okb_basis *b) {
+    if (!b) return OKB_OK;
+    cudaSetDevice(b->ctx->device);
+    if (b->meta_dev) cudaFree(b->meta_dev);
+    delete b;
+    return OKB_OK;
+}
+
+// ---- MO coefficients ------------------------------------------------------------------------------------
+extern "C" int okb_mo_create(okb_ctx *ctx, okb_basis *b, int n_mo, const double *coeffs, const double *occ,
+                             okb_mo **out) {
+    if (!ctx || !b || !out || !coeffs) return fail(OKB_ERR_ARG, "okb_mo_create: null argument");
+    *out = nullptr;
+    if (n_mo <= 0) return fail(OKB_ERR_ARG, "okb_mo_create: n_mo must be positive");
+    okb_mo *m = new okb_mo();
+    m->ctx = ctx;
+    m->basis = b;
+    m->n_mo = n_mo;
+    m->occ.assign(n_mo, 0.0);
+    if (occ) m->occ.assign(occ, occ + n_mo);
+    m->ccart.assign((size_t)n_mo * b->n_cart, 0.0);
+    if (!b->spherical) {
+        memcpy(m->ccart.data(), coeffs, sizeof(double) * (size_t)n_mo * b->n_cart);
+    } else {
+        // C'[i][cart] = sum_j C[i][j] * T[j][cart]; accumulated in (j, term) order like the
+        // row axpys of core.py:168-174
+        for (int i = 0; i < n_mo; ++i) {
+            double *dst = m->ccart.data() + (size_t)i * b->n_cart;
+            const double *src = coeffs + (size_t)i * b->n_ao;
+            for (int j = 0; j < b->n_ao; ++j)
+                for (int t = b->t_ptr[j]; t < b->t_ptr[j + 1]; ++t) dst[b->t_col[t]] += src[j] * b->t_val[t];
+        }
+    }
+    *out = m;
+    return OKB_OK;
+}
+
+static int mo_blob(okb_mo *m, int MC, okb_mo::Blob **out) {
+    auto it = m->blobs.find(MC);
+    if (it != m->blobs.end()) {
+        *out = &it->second;
+        return OKB_OK;
+    }
+    okb_basis *b = m->basis;
+    const int nchunk = (int)b->chunks.size();
+    const int n_mtile = (m->n_mo + MC - 1) / MC;
+    std::vector<double> blob((size_t)n_mtile * nchunk * KC * MC, 0.0);
+    for (int mt = 0; mt < n_mtile; ++mt)
+        for (int c = 0; c < nchunk; ++c) {
+            double *dst = blob.data() + ((size_t)mt * nchunk + c) * KC * MC;
+            for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
+                const int row = b->fn_row[b->chunks[c].k0 + kk];
+                for (int i = 0; i < MC; ++i) {
+                    const int mo = mt * MC + i;
+                    if (mo < m->n_mo) dst[(size_t)kk * MC + i] = m->ccart[(size_t)mo * b->n_cart + row];
+                }
+            }
+        }
+    std::vector<double> occ((size_t)n_mtile * MC, 0.0);
+    std::copy(m->occ.begin(), m->occ.end(), occ.begin());
+    okb_mo::Blob bl;
+    bl.n_mtile = n_mtile;
+    CU(cudaSetDevice(m->ctx->device));
+    CU(cudaMalloc(&bl.c, blob.size() * sizeof(double)));
+    CU(cudaMalloc(&bl.occ, occ.size() * sizeof(double)));
+    CU(cudaMemcpy(bl.c, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(bl.occ, occ.data(), occ.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m->blobs[MC] = bl;
+    *out = &m->blobs[MC];
+    return OKB_OK;
+}
+
+extern "C" int okb_mo_destroy(okb_mo *m) {
+    if (!m) return OKB_OK;
+    cudaSetDevice(m->ctx->device);
+    for (auto &kv : m->blobs) {
+        if (kv.second.c) cudaFree(kv.second.c);
+        if (kv.second.occ) cudaFree(kv.second.occ);
+    }
+    delete m;
+    return OKB_OK;
+}
+
+// ---- grids -----------------------------------------------------------------------------------------------
+extern "C" int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const double *y, int ny,
+                                const double *z, int nz, okb_grid **out) {
+    if (!ctx || !out || !x || !y || !z) return fail(OKB_ERR_ARG, "okb_grid_regular: null argument");
+    *out = nullptr;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(OKB_ERR_ARG, "okb_grid_regular: empty axis");
+    okb_grid *g = new okb_grid();
+    g->ctx = ctx;
+    g->kind = 0;
+    g->nx = nx; g->ny = ny; g->nz = nz;
+    g->npts = (long long)nx * ny * nz;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(&g->gx, sizeof(double) * nx));
+    CU(cudaMalloc(&g->gy, sizeof(double) * ny));
+    CU(cudaMalloc(&g->gz, sizeof(double) * nz));
+    CU(cudaMemcpy(g->gx, x, sizeof(double) * nx, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->gy, y, sizeof(double) * ny, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->gz, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
+    *out = g;
+    return OKB_OK;
+}
+
+extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, const double *z,
+                               long long npts, int coords_on_device, okb_grid **out) {
+    if (!ctx || !out || !x || !y || !z) return fail(OKB_ERR_ARG, "okb_grid_vector: null argument");
+    *out = nullptr;
+    if (npts <= 0) return fail(OKB_ERR_ARG, "okb_grid_vector: empty grid");
+    okb_grid *g = new okb_grid();
+    g->ctx = ctx;
+    g->kind = 1;
+    g->npts = npts;
+    CU(cudaSetDevice(ctx->device));
+    if (coords_on_device) {
+        g->gx = const_cast<double *>(x);
+        g->gy = const_cast<double *>(y);
+        g->gz = const_cast<double *>(z);
+        g->owns = false;
+    } else {
+        CU(cudaMalloc(&g->gx, sizeof(double) * npts));
+        CU(cudaMalloc(&g->gy, sizeof(double) * npts));
+        CU(cudaMalloc(&g->gz, sizeof(double) * npts));
+        CU(cudaMemcpyAsync(g->gx, x, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(g->gy, y, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(g->gz, z, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = g;
+    return OKB_OK;
+}
+
+extern "C" int okb_grid_size(okb_grid *g, long long *npts) {
+    if (!g || !npts) return fail(OKB_ERR_ARG, "null pointer");
+    *npts = g->npts;
+    return OKB_OK;
+}
+
+extern "C" int okb_grid_destroy(okb_grid *g) {
+    if (!g) return OKB_OK;
+    cudaSetDevice(g->ctx->device);
+    if (g->owns) {
+        if (g->gx) cudaFree(g->gx);
+        if (g->gy) cudaFree(g->gy);
+        if (g->gz) cudaFree(g->gz);
+    }
+    delete g;
+    return OKB_OK;
+}
+
+// ---- launch machinery ---------------------------------------------------------------------------------------
+struct Variant {
+    const char *name;
+    int set, sink, MW, PT, NW;
+    int P, MC;
+    size_t (*smem)(int meta_stride);
+    cudaError_t (*launch)(const KParams &, int grid, size_t smem, cudaStream_t);
+};
+
+template <int SET, int MW, int PT, int NW, int SINK>
+static cudaError_t launch_variant(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = okb_grid_kernel<SET, MW, PT, NW, SINK>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NW * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int SET, int MW, int PT, int NW, int SINK>
+static size_t smem_variant(int meta_stride) {
+    return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
+}
+#define OKB_VARIANT(SET, MW, PT, NW, SINK)                                                         \
+    Variant { #SET "/" #SINK "/MW" #MW "xPT" #PT "xNW" #NW, SET, SINK, MW, PT, NW, 32 * PT, NW * MW, \
+              smem_variant<SET, MW, PT, NW, SINK>, launch_variant<SET, MW, PT, NW, SINK> }
+
+// MO-tile widths per derivative set: a wide tile (MC=96), the 84-wide tile that fits the 82
+// occupied MOs of the ~1000-function benchmark molecule with 2% padding, and narrow tiles for
+// small MO counts.  (acc registers per thread = MW*PT*D doubles.)
+static const Variant g_variants[] = {
+    // AO sinks (no contraction): P = 128 points
+    OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
+    OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
+    OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
+    // value only (D=1)
+    OKB_VARIANT(SET_VAL, 8, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 8, 4, 12, SINK_RHO),
+    OKB_VARIANT(SET_VAL, 7, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 7, 4, 12, SINK_RHO),
+    OKB_VARIANT(SET_VAL, 2, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 2, 4, 12, SINK_RHO),
+    OKB_VARIANT(SET_ONE, 8, 4, 12, SINK_MO), OKB_VARIANT(SET_ONE, 2, 4, 12, SINK_MO),
+    // value + gradient (D=4)
+    OKB_VARIANT(SET_GRAD, 8, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 8, 2, 12, SINK_RHO),
+    OKB_VARIANT(SET_GRAD, 7, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 7, 2, 12, SINK_RHO),
+    OKB_VARIANT(SET_GRAD, 2, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 2, 2, 12, SINK_RHO),
+    // value + gradient + pure second derivatives (D=7)
+    OKB_VARIANT(SET_LAP, 8, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 8, 1, 12, SINK_RHO),
+    OKB_VARIANT(SET_LAP, 7, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 7, 1, 12, SINK_RHO),
+    OKB_VARIANT(SET_LAP, 2, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 2, 1, 12, SINK_RHO),
+    // all ten codes (D=10)
+    OKB_VARIANT(SET_ALL, 4, 1, 12, SINK_MO), OKB_VARIANT(SET_ALL, 4, 1, 12, SINK_RHO),
+    OKB_VARIANT(SET_ALL, 2, 1, 12, SINK_MO), OKB_VARIANT(SET_ALL, 2, 1, 12, SINK_RHO),
+};
+
+static const Variant *pick_variant(int set, int sink, int n_mo) {
+    const Variant *best = nullptr;
+    long long best_cost = 0;
+    for (const Variant &v : g_variants) {
+        if (v.set != set || v.sink != sink) continue;
+        if (sink == SINK_AO) return &v;
+        const long long padded = (long long)((n_mo + v.MC - 1) / v.MC) * v.MC;
+        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations)
+        const long long cost = padded * 1000 - v.MC;
+        if (!best || cost < best_cost) {
+            best = &v;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+static int codes_to_set(const int *codes, int n, int *set) {
+    int mx = 0;
+    for (int i = 0; i < n; ++i) {
+        if (codes[i] < 0 || codes[i] > 9) return fail(OKB_ERR_ARG, "derivative code %d not in 0..9", codes[i]);
+        mx = std::max(mx, codes[i]);
+    }
+    *set = mx == 0 ? SET_VAL : mx <= 3 ? SET_GRAD : mx <= 6 ? SET_LAP : SET_ALL;
+    return OKB_OK;
+}
+
+static int ensure_slabs(okb_ctx *c, size_t bytes) {
+    if (c->slab_bytes >= bytes) return OKB_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (c->slab[i]) CU(cudaFree(c->slab[i]));
+        c->slab[i] = nullptr;
+    }
+    c->slab_bytes = 0;
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->slab[i], bytes));
+    c->slab_bytes = bytes;
+    return OKB_OK;
+}
+
+struct EvalReq {
+    int sink;
+    okb_basis *basis;
+    okb_mo *mo;
+    okb_grid *grid;
+    long long p0, p1;
+    const int *codes;
+    int n_codes;
+    double *out;        // AO/MO
+    double *rho, *delta;
+    double *mo_norm;
+    unsigned flags;
+};
+
+static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
+    okb_basis *b = rq.basis;
+    okb_grid *g = rq.grid;
+    if (!ctx || !b || !g) return fail(OKB_ERR_ARG, "eval: null handle");
+    if (b->ctx != ctx || g->ctx != ctx) return fail(OKB_ERR_ARG, "eval: handles belong to another context");
+    if (rq.p0 < 0 || rq.p1 > g->npts || rq.p1 < rq.p0)
+        return fail(OKB_ERR_ARG, "eval: point range [%lld,%lld) outside the grid (%lld points)", rq.p0, rq.p1, g->npts);
+    if (rq.n_codes < 0 || rq.n_codes > 64) return fail(OKB_ERR_ARG, "eval: bad number of derivative codes");
+    if (rq.n_codes > 0 && !rq.codes) return fail(OKB_ERR_ARG, "eval: null derivative code list");
+    const long long ntot = rq.p1 - rq.p0;
+    if (ntot == 0) return OKB_OK;
+    CU(cudaSetDevice(ctx->device));
+
+    // which derivative sets must be evaluated, and where does each requested code go
+    int set = SET_VAL;
+    int rc = codes_to_set(rq.codes, rq.n_codes, &set);
+    if (rc != OKB_OK) return rc;
+    const bool dev_out = (rq.flags & OKB_FLAG_OUT_DEVICE) != 0;
+    const int n_rows = rq.sink == SINK_AO ? b->n_ao : (rq.sink == SINK_MO ? rq.mo->n_mo : 1);
+
+    // Passes: normally one pass with the smallest covering set.  AO/MO requests whose code list has
+    // duplicates or is a single code use one SET_ONE pass per requested slot.
+    struct Pass { int set; int one_code; int slot[10]; };
+    std::vector<Pass> passes;
+    bool dup = false;
+    {
+        int seen[10] = {0};
+        for (int i = 0; i < rq.n_codes; ++i) dup |= (seen[rq.codes[i]]++ > 0);
+    }
+    if (rq.sink == SINK_RHO) {
+        if (dup) return fail(OKB_ERR_ARG, "eval_rho: duplicate derivative codes");
+        for (int i = 0; i < rq.n_codes; ++i)
+            if (rq.codes[i] == 0) return fail(OKB_ERR_ARG, "eval_rho: derivative code 0 is not a derivative");
+        Pass ps;
+        ps.set = set; ps.one_code = 0;
+        for (int k = 0; k < 10; ++k) ps.slot[k] = -1;
+        for (int i = 0; i < rq.n_codes; ++i) ps.slot[rq.codes[i]] = i;
+        passes.push_back(ps);
+    } else if (rq.n_codes == 1 || dup) {
+        for (int i = 0; i < rq.n_codes; ++i) {
+            Pass ps;
+            ps.set = rq.codes[i] == 0 ? SET_VAL : SET_ONE;
+            ps.one_code = rq.codes[i];
+            for (int k = 0; k < 10; ++k) ps.slot[k] = -1;
+            ps.slot[rq.codes[i]] = i;
+            passes.push_back(ps);
+        }
+    } else {
+        Pass ps;
+        ps.set = set; ps.one_code = 0;
+        for (int k = 0; k < 10; ++k) ps.slot[k] = -1;
+        for (int i = 0; i < rq.n_codes; ++i) ps.slot[rq.codes[i]] = i;
+        passes.push_back(ps);
+    }
+
+    // output geometry: rows of `ntot` points; host outputs are produced slab by slab
+    const size_t n_out_rows = rq.sink == SINK_RHO ? (size_t)(1 + rq.n_codes) : (size_t)rq.n_codes * n_rows;
+    long long slab_pts = ntot;
+    if (!dev_out) {
+        const size_t budget = (size_t)192 << 20;     // bytes per staging slab
+        long long fit = (long long)(budget / (n_out_rows * sizeof(double)));
+        fit = std::max<long long>(fit / 1024 * 1024, 1024);
+        slab_pts = std::min(ntot, fit);
+        rc = ensure_slabs(ctx, (size_t)slab_pts * n_out_rows * sizeof(double));
+        if (rc != OKB_OK) return rc;
+    }
+    slab_pts = std::min<long long>(slab_pts, (long long)1 << 30);
+
+    double *norm_dev = nullptr;
+    if (rq.sink == SINK_RHO && rq.mo_norm) {
+        if (ctx->norm_cap < (size_t)rq.mo->n_mo) {
+            if (ctx->norm_dev) CU(cudaFree(ctx->norm_dev));
+            ctx->norm_dev = nullptr;
+            CU(cudaMalloc(&ctx->norm_dev, sizeof(double) * rq.mo->n_mo));
+            ctx->norm_cap = rq.mo->n_mo;
+        }
+        norm_dev = ctx->norm_dev;
+        CU(cudaMemsetAsync(norm_dev, 0, sizeof(double) * rq.mo->n_mo, ctx->stream));
+    }
+
+    int slab_idx = 0;
+    for (long long s0 = 0; s0 < ntot; s0 += slab_pts, ++slab_idx) {
+        const long long sn = std::min(slab_pts, ntot - s0);
+        const int buf = slab_idx & 1;
+        double *dbase;          // device output base for this slab
+        long long ld;
+        if (dev_out) {
+            ld = ntot;
+            dbase = nullptr;
+        } else {
+            ld = sn;
+            dbase = reinterpret_cast<double *>(ctx->slab[buf]);
+            if (slab_idx >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        }
+        for (const Pass &ps : passes) {
+            const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo);
+            if (!v) return fail(OKB_ERR_UNSUPPORTED, "no kernel variant for set %d sink %d", ps.set, rq.sink);
+            KParams p{};
+            p.grid_kind = g->kind;
+            p.gx = g->gx; p.gy = g->gy; p.gz = g->gz;
+            p.ny = g->ny; p.nz = g->nz;
+            p.p0 = rq.p0 + s0;
+            p.npts = (int)sn;
+            p.ntiles = (int)((sn + v->P - 1) / v->P);
+            p.meta = b->meta_dev;
+            p.lay = b->lay;
+            p.nchunk = (int)b->chunks.size();
+            p.n_mtile = 1;
+            p.n_mo = 0;
+            if (rq.sink != SINK_AO) {
+                okb_mo::Blob *bl = nullptr;
+                rc = mo_blob(rq.mo, v->MC, &bl);
+                if (rc != OKB_OK) return rc;
+                p.cblob = bl->c;
+                p.occ = bl->occ;
+                p.n_mtile = bl->n_mtile;
+                p.n_mo = rq.mo->n_mo;
+            }
+            p.ld = ld;
+            p.slot_stride = (long long)n_rows * ld;
+            for (int k = 0; k < 10; ++k) p.slot[k] = ps.slot[k];
+            p.one_code = ps.one_code;
+            p.exact_mixed = (rq.flags & OKB_FLAG_EXACT_MIXED) ? 1 : 0;
+            if (rq.sink == SINK_RHO) {
+                p.rho = dev_out ? rq.rho + s0 : dbase;
+                p.delta = dev_out ? (rq.delta ? rq.delta + s0 : nullptr) : dbase + ld;
+                p.mo_norm = norm_dev;
+            } else {
+                p.out = dev_out ? rq.out + s0 : dbase;
+            }
+            const size_t smem = v->smem(b->lay.stride);
+            if (smem > 227 * 1024) return fail(OKB_ERR_UNSUPPORTED, "variant %s needs %zu bytes of shared memory", v->name, smem);
+            const int grid = std::min(p.ntiles, ctx->sm_count);
+            cudaError_t e = v->launch(p, grid, smem, ctx->stream);
+            if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", v->name, cudaGetErrorString(e));
+            ctx->launches++;
+            ctx->last_kernel = v->name;
+        }
+        if (!dev_out) {
+            CU(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));
+            const size_t wbytes = (size_t)sn * sizeof(double);
+            if (rq.sink == SINK_RHO) {
+                if (rq.rho) CU(cudaMemcpyAsync(rq.rho + s0, dbase, wbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (rq.n_codes > 0)
+                    CU(cudaMemcpy2DAsync(rq.delta + s0, (size_t)ntot * sizeof(double), dbase + ld,
+                                         (size_t)ld * sizeof(double), wbytes, rq.n_codes,
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+            } else {
+                CU(cudaMemcpy2DAsync(rq.out + s0, (size_t)ntot * sizeof(double), dbase, (size_t)ld * sizeof(double),
+                                     wbytes, n_out_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+            CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+        }
+    }
+    if (norm_dev) {
+        CU(cudaMemcpyAsync(rq.mo_norm, norm_dev, sizeof(double) * rq.mo->n_mo, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (!dev_out) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    return OKB_OK;
+}
+
+extern "C" int okb_eval_ao(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
+                           const int *drv_codes, int n_drv, double *out, unsigned flags) {
+    if (!out) return fail(OKB_ERR_ARG, "okb_eval_ao: null output");
+    if (n_drv <= 0) return fail(OKB_ERR_ARG, "okb_eval_ao: need at least one derivative code");
+    EvalReq rq{SINK_AO, basis, nullptr, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags};
+    return run_eval(ctx, rq);
+}
+
+extern "C" int okb_eval_mo(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                           const int *drv_codes, int n_drv, double *out, unsigned flags) {
+    if (!mo) return fail(OKB_ERR_ARG, "okb_eval_mo: null MO handle");
+    if (!out) return fail(OKB_ERR_ARG, "okb_eval_mo: null output");
+    if (n_drv <= 0) return fail(OKB_ERR_ARG, "okb_eval_mo: need at least one derivative code");
+    EvalReq rq{SINK_MO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags};
+    return run_eval(ctx, rq);
+}
+
+extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                            const int *drv_codes, int n_drv, double *rho, double *delta_rho, double *mo_norm,
+                            unsigned flags) {
+    if (!mo) return fail(OKB_ERR_ARG, "okb_eval_rho: null MO handle");
+    if (!rho) return fail(OKB_ERR_ARG, "okb_eval_rho: null rho output");
+    if (n_drv > 0 && !delta_rho) return fail(OKB_ERR_ARG, "okb_eval_rho: null delta_rho output");
+    EvalReq rq{SINK_RHO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, nullptr, rho, delta_rho, mo_norm, flags};
+    return run_eval(ctx, rq);
+}
+
+// ---- cy_core drop-ins -----------------------------------------------------------------------------------------
+extern "C" int okb_aocreator(okb_ctx *ctx, const int *lxlylz, const int *assign, const double *ao_coeffs,
+                             const int *pnum_list, const double *geo_spec, const int *atom_indices,
+                             int n_cont, int n_cart, int n_prim, int n_atoms, const double *x,
+                             const double *y, const double *z, long long npts, int drv, int is_normalized,
+                             unsigned flags, double *out) {
+    if (drv < 0 || drv > 9) return fail(OKB_ERR_ARG, "okb_aocreator: drv=%d not in 0..9", drv);
+    if (!out) return fail(OKB_ERR_ARG, "okb_aocreator: null output");
+    if (flags & OKB_FLAG_OUT_DEVICE) return fail(OKB_ERR_ARG, "okb_aocreator works on host buffers");
+    okb_basis *b = nullptr;
+    okb_grid *g = nullptr;
+    int rc = okb_basis_create(ctx, lxlylz, assign, ao_coeffs, pnum_list, geo_spec, atom_indices, n_cont, n_cart,
+                              n_prim, n_atoms, is_normalized, nullptr, &b);
+    if (rc == OKB_OK) rc = okb_grid_vector(ctx, x, y, z, npts, 0, &g);
+    if (rc == OKB_OK) rc = okb_eval_ao(ctx, b, g, 0, npts, &drv, 1, out, flags);
+    okb_grid_destroy(g);
+    okb_basis_destroy(b);
+    return rc;
+}
+
+extern "C" int okb_lcreator(okb_ctx *ctx, double *ao_list, long long row_stride, const int *lxlylz,
+                            const double *coeff_list, const double *at_pos, const double *x, const double *y,
+                            const double *z, long long npts, int ao_num, int pnum, int drv, int is_normalized,
+                            unsigned flags) {
+    if (!ao_list) return fail(OKB_ERR_ARG, "okb_lcreator: null output");
+    if (row_stride < npts) return fail(OKB_ERR_ARG, "okb_lcreator: row stride smaller than npts");
+    const int atom = 0;
+    std::vector<double> tmp((size_t)ao_num * npts);
+    int rc = okb_aocreator(ctx, lxlylz, &ao_num, coeff_list, &pnum, at_pos, &atom, 1, ao_num, pnum, 1, x, y, z,
+                           npts, drv, is_normalized, flags, tmp.data());
+    if (rc != OKB_OK) return rc;
+    for (int r = 0; r < ao_num; ++r)
+        memcpy(ao_list + (size_t)r * row_stride, tmp.data() + (size_t)r * npts, sizeof(double) * npts);
+    return OKB_OK;
+}
+
+extern "C" int okb_mocreator(okb_ctx *ctx, const double *ao, const double *coeffs, int n_ao, long long npts,
+                             int n_mo, double *mo) {
+    if (!ctx || !ao || !coeffs || !mo) return fail(OKB_ERR_ARG, "okb_mocreator: null argument");
+    if (n_ao <= 0 || n_mo <= 0 || npts <= 0) return fail(OKB_ERR_ARG, "okb_mocreator: empty operand");
+    CU(cudaSetDevice(ctx->device));
+    double *d_c = nullptr, *d_ao = nullptr, *d_mo = nullptr;
+    CU(cudaMalloc(&d_c, sizeof(double) * (size_t)n_mo * n_ao));
+    CU(cudaMemcpyAsync(d_c, coeffs, sizeof(double) * (size_t)n_mo * n_ao, cudaMemcpyHostToDevice, ctx->stream));
+    // stream the point dimension through the device in slabs
+    const long long per_pt = (long long)(n_ao + n_mo) * sizeof(double);
+    long long slab = std::max<long long>(((long long)(512ll << 20) / per_pt) / 64 * 64, 64);
+    slab = std::min(slab, npts);
+    cudaError_t e1 = cudaMalloc(&d_ao, sizeof(double) * (size_t)n_ao * slab);
+    cudaError_t e2 = cudaMalloc(&d_mo, sizeof(double) * (size_t)n_mo * slab);
+    int rc = OKB_OK;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(OKB_ERR_NOMEM, "okb_mocreator: device allocation failed");
+    for (long long s0 = 0; rc == OKB_OK && s0 < npts; s0 += slab) {
+        const long long sn = std::min(slab, npts - s0);
+        cudaError_t e = cudaMemcpy2DAsync(d_ao, sizeof(double) * sn, ao + s0, sizeof(double) * npts,
+                                          sizeof(double) * sn, n_ao, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            dim3 grid((unsigned)((sn + 63) / 64), (unsigned)((n_mo + 63) / 64));
+            okb_mocreator_kernel<<<grid, 256, 0, ctx->stream>>>(d_ao, d_c, d_mo, n_mo, n_ao, sn);
+            e = cudaGetLastError();
+            ctx->launches++;
+            ctx->last_kernel = "okb_mocreator_kernel";
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(mo + s0, sizeof(double) * npts, d_mo, sizeof(double) * sn, sizeof(double) * sn,
+                                  n_mo, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(OKB_ERR_CUDA, "okb_mocreator: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_c);
+    if (d_ao) cudaFree(d_ao);
+    if (d_mo) cudaFree(d_mo);
+    return rc;
+}

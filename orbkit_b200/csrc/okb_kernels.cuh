@@ -1,0 +1,562 @@
+// okb_kernels.cuh -- sm_100a kernels of the ORBKIT grid path (AO -> MO -> rho and derivatives).
+//
+// One persistent kernel template does all three jobs; what differs is the SINK:
+//   SINK_AO   evaluate the AO tile of a chunk of shells in shared memory, apply the (optional)
+//             Cartesian -> spherical rows, store [n_drv][n_ao][pts]        (replaces c_lcreator +
+//             cy_core.aocreator + core.cartesian2spherical: c_grid-based.c:9-79,
+//             cy_core.pyx:51-78, core.py:135-176).  HBM-store bound.
+//   SINK_MO   same AO tile, contracted against the MO coefficient tile that a bulk-async (TMA)
+//             copy lands in shared memory; accumulators live in registers; stores
+//             [n_drv][n_mo][pts]                                             (cy_core.pyx:82-101)
+//   SINK_RHO  same contraction; epilogue squares / cross-multiplies, weights by occupation and
+//             reduces over MOs: rho, delta_rho, mo_norm -- MO values never reach HBM
+//                                                                            (core.py:265-304)
+//
+// Work decomposition (FP64 DFMA tile GEMM, no tensor cores: tcgen05 has no FP64 kind):
+//   CTA tile  = P = 32*PT grid points x MC = NW*MW molecular orbitals, K looped in chunks of
+//               <= KC Cartesian functions (whole shells).
+//   phase A   every warp evaluates (shell, 32 points) items of chunk c+1 into tile[(c+1)&1]
+//             (one thread = one point: exp once per primitive, powers by multiplication,
+//             all D derivative sets from the same radial sums R0,R1,R2).
+//   phase B   warp w owns MOs [w*MW, (w+1)*MW); lane owns points lane+32*j.  Per k: D*PT
+//             conflict-free LDS.64 of AO values + MW/2 broadcast LDS.128 of coefficients feed
+//             MW*PT*D DFMAs.
+//   One __syncthreads per chunk; AO tiles double-buffered; coefficient tiles (2 buffers) and
+//   chunk tables (3 buffers) arrive by cp.async.bulk + mbarrier issued by thread 0.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace okb {
+
+constexpr int KC = 32;            // max Cartesian functions per chunk
+constexpr int NMETA = 3;          // chunk-table buffers in flight
+enum { SET_VAL = 0, SET_GRAD = 1, SET_LAP = 2, SET_ALL = 3, SET_ONE = 4 };
+enum { SINK_AO = 0, SINK_MO = 1, SINK_RHO = 2 };
+
+__host__ __device__ constexpr int set_ncodes(int set) {
+    return set == SET_VAL ? 1 : set == SET_GRAD ? 4 : set == SET_LAP ? 7 : set == SET_ALL ? 10 : 1;
+}
+
+// ---- chunk tables (one fixed-stride blob per chunk, 16-byte aligned sections) ---------------
+struct ChunkHdr { int nshell, nprim, nfn, nrow; };
+struct ShellMeta {                 // 48 B
+    double cx, cy, cz;
+    int prim_off, nprim, fn_off, nfn;   // offsets are chunk-local
+    int L, pad;
+};
+struct FnMeta { int lxyz; int pad; double f; };          // lx | ly<<8 | lz<<16 ; f = angular norm * renorm
+struct RowMeta { int out_row, term_off, nterm, pad; };   // SINK_AO output rows of this chunk
+struct TermMeta { int k; int pad; double coef; };
+
+struct BlobLayout { int off_shell, off_prim, off_fn, off_row, off_term, stride; };
+
+struct KParams {
+    // grid
+    int grid_kind;                 // 0 regular (axes), 1 vector (coordinates)
+    const double *gx, *gy, *gz;
+    int ny, nz;
+    long long p0;                  // global index of the first point of this launch
+    int npts;                      // points in this launch
+    int ntiles;
+    // basis
+    const unsigned char *meta;
+    BlobLayout lay;
+    int nchunk;
+    // MO
+    const double *cblob;           // [n_mtile][nchunk][KC][MC]
+    const double *occ;             // [n_mtile*MC], zero padded
+    int n_mtile, n_mo;
+    // outputs
+    double *out;                   // AO/MO: out[slot][row][ld]
+    double *rho, *delta;           // RHO: rho[ld-indexed], delta[slot][ld]
+    double *mo_norm;               // RHO: [n_mo] or null (device, atomically accumulated)
+    long long ld;                  // leading dimension (points) of an output row
+    long long slot_stride;         // n_rows * ld
+    int slot[10];                  // code -> output slot, -1 = not requested
+    int one_code, exact_mixed;
+};
+
+// ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OKB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OKB_DONE_%=;\n"
+        "bra OKB_WAIT_%=;\n"
+        "OKB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- angular part -----------------------------------------------------------------------------
+// r^l by square-and-multiply; l is warp-uniform (all lanes evaluate the same function).
+__device__ __forceinline__ double upow(double r, int l) {
+    double acc = 1.0;
+    while (l > 0) {
+        if (l & 1) acc *= r;
+        r *= r;
+        l >>= 1;
+    }
+    return acc;
+}
+// Per axis:  q0 = r^l, qm1 = l r^(l-1), qp1 = r^(l+1), qm2 = l(l-1) r^(l-2)
+struct AxisQ { double q0, qm1, qp1, qm2; };
+template <int LEVEL>
+__device__ __forceinline__ AxisQ axis_q(double r, int l) {
+    AxisQ a;
+    if (LEVEL == 0) {
+        a.q0 = upow(r, l);
+        a.qm1 = a.qp1 = a.qm2 = 0.0;
+        return a;
+    }
+    double pm2 = 0.0, pm1 = 0.0, p0 = 1.0;
+    if (l >= 2) {
+        pm2 = upow(r, l - 2);
+        pm1 = pm2 * r;
+        p0 = pm1 * r;
+    } else if (l == 1) {
+        pm1 = 1.0;
+        p0 = r;
+    }
+    a.q0 = p0;
+    a.qm1 = (double)l * pm1;
+    a.qp1 = p0 * r;
+    a.qm2 = (LEVEL >= 2) ? (double)(l * (l - 1)) * pm2 : 0.0;
+    return a;
+}
+
+// Mixed second derivative d_a d_b of one Cartesian Gaussian shell function (without the common
+// angular norm f and the third axis factor).  exact=0 reproduces c_support.c:121-168, which drops
+// the -2*alpha cross terms; exact=1 is the analytic form.
+__device__ __forceinline__ double mixed2(const AxisQ &a, const AxisQ &b, int la, int lb, double R0,
+                                         double R1, double R2, int exact) {
+    if (exact)
+        return a.qm1 * b.qm1 * R0 - 2.0 * (a.qm1 * b.qp1 + a.qp1 * b.qm1) * R1 +
+               4.0 * a.qp1 * b.qp1 * R2;
+    double B = 0.0;
+    if (la > 0 || lb > 0) B = (la > 0 ? a.qm1 : 1.0) * (lb > 0 ? b.qm1 : 1.0);
+    return 4.0 * R2 * a.qp1 * b.qp1 + R0 * B;
+}
+
+// ---- phase A: one (shell, point) item -------------------------------------------------------------
+// tp points at tile[0][0][pt]; element (d, k) lives at tp[(d*KC + k) * P].
+template <int SET, int P>
+__device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__restrict__ prims,
+                                          const FnMeta *__restrict__ fns, double x, double y, double z,
+                                          double *__restrict__ tp, int one_code, int exact) {
+    constexpr bool N1 = (SET != SET_VAL);
+    constexpr bool N2 = (SET == SET_LAP || SET == SET_ALL || SET == SET_ONE);
+    constexpr int LEVEL = N2 ? 2 : (N1 ? 1 : 0);
+    const double X = x - sh.cx, Y = y - sh.cy, Z = z - sh.cz;
+    const double rr = X * X + Y * Y + Z * Z;
+    double R0 = 0.0, R1 = 0.0, R2 = 0.0;   // sum cN e, sum cN alpha e, sum cN alpha^2 e
+    const double2 *pp = prims + sh.prim_off;
+    for (int i = 0; i < sh.nprim; ++i) {
+        const double2 ac = pp[i];
+        const double arg = ac.x * rr;
+        // exp(-arg) == 0.0 exactly in binary64 for arg > 745.14: skipping is bit-exact w.r.t. libm.
+        if (__any_sync(0xffffffffu, arg < 746.0)) {
+            const double t = ac.y * exp(-arg);
+            R0 += t;
+            if (N1) {
+                const double ta = t * ac.x;
+                R1 += ta;
+                if (N2) R2 += ta * ac.x;
+            }
+        }
+    }
+    const FnMeta *ff = fns + sh.fn_off;
+    for (int j = 0; j < sh.nfn; ++j) {
+        const FnMeta fm = ff[j];
+        const int lx = fm.lxyz & 0xff, ly = (fm.lxyz >> 8) & 0xff, lz = (fm.lxyz >> 16) & 0xff;
+        const AxisQ ax = axis_q<LEVEL>(X, lx), ay = axis_q<LEVEL>(Y, ly), az = axis_q<LEVEL>(Z, lz);
+        double *o = tp + (size_t)(sh.fn_off + j) * P;
+        const double f = fm.f;
+        if (SET == SET_ONE) {
+            double v;
+            switch (one_code) {
+                case 0: v = R0 * ax.q0 * ay.q0 * az.q0; break;
+                case 1: v = ay.q0 * az.q0 * (ax.qm1 * R0 - 2.0 * ax.qp1 * R1); break;
+                case 2: v = ax.q0 * az.q0 * (ay.qm1 * R0 - 2.0 * ay.qp1 * R1); break;
+                case 3: v = ax.q0 * ay.q0 * (az.qm1 * R0 - 2.0 * az.qp1 * R1); break;
+                case 4: v = ay.q0 * az.q0 * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0); break;
+                case 5: v = ax.q0 * az.q0 * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0); break;
+                case 6: v = ax.q0 * ay.q0 * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0); break;
+                case 7: v = az.q0 * mixed2(ax, ay, lx, ly, R0, R1, R2, exact); break;
+                case 8: v = ay.q0 * mixed2(ax, az, lx, lz, R0, R1, R2, exact); break;
+                default: v = ax.q0 * mixed2(ay, az, ly, lz, R0, R1, R2, exact); break;
+            }
+            o[0] = f * v;
+            continue;
+        }
+        const double yz = ay.q0 * az.q0, xz = ax.q0 * az.q0, xy = ax.q0 * ay.q0;
+        o[0] = f * (R0 * ax.q0 * yz);
+        if (N1) {
+            o[(size_t)1 * KC * P] = f * (yz * (ax.qm1 * R0 - 2.0 * ax.qp1 * R1));
+            o[(size_t)2 * KC * P] = f * (xz * (ay.qm1 * R0 - 2.0 * ay.qp1 * R1));
+            o[(size_t)3 * KC * P] = f * (xy * (az.qm1 * R0 - 2.0 * az.qp1 * R1));
+        }
+        if (SET == SET_LAP || SET == SET_ALL) {
+            o[(size_t)4 * KC * P] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
+            o[(size_t)5 * KC * P] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
+            o[(size_t)6 * KC * P] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
+        }
+        if (SET == SET_ALL) {
+            o[(size_t)7 * KC * P] = f * (az.q0 * mixed2(ax, ay, lx, ly, R0, R1, R2, exact));
+            o[(size_t)8 * KC * P] = f * (ay.q0 * mixed2(ax, az, lx, lz, R0, R1, R2, exact));
+            o[(size_t)9 * KC * P] = f * (ax.q0 * mixed2(ay, az, ly, lz, R0, R1, R2, exact));
+        }
+    }
+}
+
+// ---- shared memory carve-up (host and device agree through this struct) -----------------------
+template <int SET, int MW, int PT, int NW, int SINK>
+struct Cfg {
+    static constexpr int D = set_ncodes(SET);
+    static constexpr int P = 32 * PT;
+    static constexpr int MC = NW * MW;
+    static constexpr int NT = NW * 32;
+    static constexpr int TILE_DOUBLES = D * KC * P;
+    static constexpr int CBUF_DOUBLES = (SINK == SINK_AO) ? 0 : KC * MC;
+    static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;      // rho + (D-1) derivative sums
+    static constexpr size_t OFF_BAR = 0;                          // 5 mbarriers (3 meta + 2 coef)
+    static constexpr size_t OFF_XYZ = 128;
+    static constexpr size_t OFF_META = OFF_XYZ + (size_t)3 * P * 8;
+    __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
+        return (OFF_META + (size_t)NMETA * meta_stride + 127) / 128 * 128;
+    }
+    __host__ __device__ static constexpr size_t off_tile(int meta_stride) {
+        return off_cbuf(meta_stride) + (size_t)2 * CBUF_DOUBLES * 8;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
+        return off_tile(meta_stride) + (size_t)2 * TILE_DOUBLES * 8;
+    }
+    // the cross-warp reduction scratch of SINK_RHO aliases the AO tiles: NW*NOUT*P doubles
+    static_assert(SINK != SINK_RHO || (size_t)NW * D * P <= (size_t)2 * TILE_DOUBLES, "reduction scratch");
+};
+
+// ---- the kernel -------------------------------------------------------------------------------------
+template <int SET, int MW, int PT, int NW, int SINK>
+__global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
+    using C = Cfg<SET, MW, PT, NW, SINK>;
+    constexpr int D = C::D, P = C::P, MC = C::MC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);   // [0..2] meta, [3..4] coef
+    double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
+    double *ys = xs + P, *zs = ys + P;
+    unsigned char *mbase = smem + C::OFF_META;
+    double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
+    double *tbase = reinterpret_cast<double *>(smem + C::off_tile(p.lay.stride));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NMETA + 2; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t meta_bytes = (uint32_t)p.lay.stride;
+    constexpr uint32_t cbuf_bytes = (uint32_t)C::CBUF_DOUBLES * 8u;
+    uint32_t g = 0;   // running chunk sequence number (uniform across the CTA)
+
+    auto issue_meta = [&](int c, uint32_t gc) {
+        uint64_t *bar = &bars[gc % NMETA];
+        mbar_expect_tx(bar, meta_bytes);
+        bulk_g2s(mbase + (size_t)(gc % NMETA) * meta_bytes, p.meta + (size_t)c * meta_bytes, meta_bytes, bar);
+    };
+    auto issue_coef = [&](int mt, int c, uint32_t gc) {
+        if (SINK == SINK_AO) return;
+        uint64_t *bar = &bars[NMETA + (gc & 1)];
+        mbar_expect_tx(bar, cbuf_bytes);
+        bulk_g2s(cbase + (size_t)(gc & 1) * C::CBUF_DOUBLES,
+                 p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES, cbuf_bytes, bar);
+    };
+    auto phase_a = [&](uint32_t gc) {
+        const unsigned char *mb = mbase + (size_t)(gc % NMETA) * meta_bytes;
+        const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
+        const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
+        const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
+        const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+        double *tile = tbase + (size_t)(gc & 1) * C::TILE_DOUBLES;
+        const int nitems = hdr.nshell * PT;
+        for (int item = warp; item < nitems; item += NW) {
+            const int s = item / PT, pt = (item % PT) * 32 + lane;
+            gen_shell<SET, P>(shells[s], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt, p.one_code,
+                              p.exact_mixed);
+        }
+    };
+
+    for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
+        const int q0 = tile_id * P;               // launch-local index of the tile's first point
+        // stage the coordinates of the tile (previous tile ended with a __syncthreads)
+        if (tid < P) {
+            int q = q0 + tid;
+            if (q >= p.npts) q = p.npts - 1;
+            const long long n = p.p0 + q;
+            if (p.grid_kind == 0) {
+                const long long nyz = (long long)p.ny * p.nz;
+                const long long i = n / nyz, rem = n - i * nyz;
+                const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
+                xs[tid] = p.gx[i]; ys[tid] = p.gy[j]; zs[tid] = p.gz[k];
+            } else {
+                xs[tid] = p.gx[n]; ys[tid] = p.gy[n]; zs[tid] = p.gz[n];
+            }
+        }
+        double osum[C::NOUT > 0 ? C::NOUT : 1][PT];
+        if (SINK == SINK_RHO) {
+#pragma unroll
+            for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                for (int j = 0; j < PT; ++j) osum[o][j] = 0.0;
+        }
+
+        for (int mt = 0; mt < p.n_mtile; ++mt) {
+            double acc[MW][PT][D];
+            if (SINK != SINK_AO) {
+#pragma unroll
+                for (int i = 0; i < MW; ++i)
+#pragma unroll
+                    for (int j = 0; j < PT; ++j)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc[i][j][d] = 0.0;
+            }
+            const uint32_t g0 = g;
+            if (tid == 0) {
+                issue_meta(0, g0);
+                if (p.nchunk > 1) issue_meta(1, g0 + 1);
+                issue_coef(mt, 0, g0);
+            }
+            __syncthreads();                       // coordinates staged
+            mbar_wait(&bars[g0 % NMETA], (g0 / NMETA) & 1);
+            phase_a(g0);
+
+            for (int c = 0; c < p.nchunk; ++c) {
+                const uint32_t gc = g0 + c;
+                __syncthreads();                   // A(c) done, B(c-1) done
+                if (tid == 0) {
+                    if (c + 1 < p.nchunk) issue_coef(mt, c + 1, gc + 1);
+                    if (c + 2 < p.nchunk) issue_meta(c + 2, gc + 2);
+                }
+                const unsigned char *mb = mbase + (size_t)(gc % NMETA) * meta_bytes;
+                const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
+                const double *tile = tbase + (size_t)(gc & 1) * C::TILE_DOUBLES;
+
+                if (SINK == SINK_AO) {
+                    // ---- phase B (store): optional cart->sph rows, coalesced row stores ----
+                    const RowMeta *rows = reinterpret_cast<const RowMeta *>(mb + p.lay.off_row);
+                    const TermMeta *terms = reinterpret_cast<const TermMeta *>(mb + p.lay.off_term);
+                    for (int r = warp; r < hdr.nrow; r += NW) {
+                        const RowMeta rm = rows[r];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const int code = (SET == SET_ONE) ? p.one_code : d;
+                            const int sl = p.slot[code];
+                            if (sl < 0) continue;
+                            double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)rm.out_row * p.ld + q0;
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) {
+                                const int pt = j * 32 + lane;
+                                double v = 0.0;
+                                for (int t = 0; t < rm.nterm; ++t) {
+                                    const TermMeta tm = terms[rm.term_off + t];
+                                    v += tm.coef * tile[((size_t)d * KC + tm.k) * P + pt];
+                                }
+                                if (q0 + pt < p.npts) orow[pt] = v;
+                            }
+                        }
+                    }
+                } else {
+                    // ---- phase B (contract): acc[i][j][d] += C[k][w*MW+i] * ao[d][k][pt_j] ----
+                    mbar_wait(&bars[NMETA + (gc & 1)], (gc >> 1) & 1);
+                    const double *cs = cbase + (size_t)(gc & 1) * C::CBUF_DOUBLES + warp * MW;
+                    const double *tl = tile + lane;
+                    const int nfn = hdr.nfn;
+#pragma unroll 2
+                    for (int k = 0; k < nfn; ++k) {
+                        double cv[MW];
+                        if (MW % 2 == 0) {
+#pragma unroll
+                            for (int i = 0; i < MW; i += 2) {
+                                const double2 c2 = *reinterpret_cast<const double2 *>(cs + (size_t)k * MC + i);
+                                cv[i] = c2.x;
+                                cv[i + 1] = c2.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < MW; ++i) cv[i] = cs[(size_t)k * MC + i];
+                        }
+#pragma unroll
+                        for (int d = 0; d < D; ++d)
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) {
+                                const double a = tl[((size_t)d * KC + k) * P + j * 32];
+#pragma unroll
+                                for (int i = 0; i < MW; ++i) acc[i][j][d] = fma(cv[i], a, acc[i][j][d]);
+                            }
+                    }
+                }
+                if (c + 1 < p.nchunk) {
+                    mbar_wait(&bars[(gc + 1) % NMETA], ((gc + 1) / NMETA) & 1);
+                    phase_a(gc + 1);
+                }
+            }
+            g = g0 + p.nchunk;
+            __syncthreads();                       // every buffer is free again
+
+            // ---- per-MO-tile epilogues -----------------------------------------------------------
+            if (SINK == SINK_MO) {
+#pragma unroll
+                for (int i = 0; i < MW; ++i) {
+                    const int mo = mt * MC + warp * MW + i;
+                    if (mo >= p.n_mo) continue;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const int code = (SET == SET_ONE) ? p.one_code : d;
+                        const int sl = p.slot[code];
+                        if (sl < 0) continue;
+                        double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)mo * p.ld + q0;
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) {
+                            const int pt = j * 32 + lane;
+                            if (q0 + pt < p.npts) orow[pt] = acc[i][j][d];
+                        }
+                    }
+                }
+            }
+            if (SINK == SINK_RHO) {
+#pragma unroll
+                for (int i = 0; i < MW; ++i) {
+                    const int mo = mt * MC + warp * MW + i;
+                    const double oc = p.occ[mo];          // zero for padding MOs
+                    double nrm = 0.0;
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) {
+                        const double phi = acc[i][j][0];
+                        const bool valid = (q0 + j * 32 + lane) < p.npts;
+                        if (valid) nrm += phi * phi;
+                        osum[0][j] += oc * (phi * phi);
+                        if (D >= 4) {
+                            const double o2 = oc * 2.0;
+                            osum[1][j] += o2 * (acc[i][j][1] * phi);
+                            osum[2][j] += o2 * (acc[i][j][2] * phi);
+                            osum[3][j] += o2 * (acc[i][j][3] * phi);
+                            if (D >= 7) {
+                                osum[4][j] += o2 * (acc[i][j][4] * phi + acc[i][j][1] * acc[i][j][1]);
+                                osum[5][j] += o2 * (acc[i][j][5] * phi + acc[i][j][2] * acc[i][j][2]);
+                                osum[6][j] += o2 * (acc[i][j][6] * phi + acc[i][j][3] * acc[i][j][3]);
+                            }
+                            if (D >= 10) {
+                                osum[7][j] += o2 * (acc[i][j][7] * phi + acc[i][j][1] * acc[i][j][2]);
+                                osum[8][j] += o2 * (acc[i][j][8] * phi + acc[i][j][1] * acc[i][j][3]);
+                                osum[9][j] += o2 * (acc[i][j][9] * phi + acc[i][j][2] * acc[i][j][3]);
+                            }
+                        }
+                    }
+                    if (p.mo_norm != nullptr && mo < p.n_mo) {
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+                        if (lane == 0) atomicAdd(p.mo_norm + mo, nrm);
+                    }
+                }
+            }
+        }   // mt
+
+        if (SINK == SINK_RHO) {
+            // cross-warp reduction through shared memory (aliases the AO tiles; all warps passed
+            // the post-loop __syncthreads, so the tiles are dead)
+            double *red = tbase;                   // [NW][NOUT][P]
+#pragma unroll
+            for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                for (int j = 0; j < PT; ++j) red[((size_t)warp * C::NOUT + o) * P + j * 32 + lane] = osum[o][j];
+            __syncthreads();
+            for (int e = tid; e < C::NOUT * P; e += C::NT) {
+                const int o = e / P, pt = e - o * P;
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += red[((size_t)w * C::NOUT + o) * P + pt];
+                if (q0 + pt < p.npts) {
+                    if (o == 0) {
+                        if (p.rho != nullptr) p.rho[q0 + pt] = s;
+                    } else {
+                        const int sl = p.slot[o];
+                        if (sl >= 0) p.delta[(size_t)sl * p.ld + q0 + pt] = s;
+                    }
+                }
+            }
+            __syncthreads();                       // scratch free before the next tile's phase A
+        }
+    }
+}
+
+// ---- plain FP64 GEMM for the cy_core.mocreator drop-in: mo[M][N] = Cm[M][K] * ao[K][N] -----------
+// 64 x 64 output tile per CTA (256 threads, 4x4 register tile), K stepped by 16 through smem.
+__global__ void __launch_bounds__(256) okb_mocreator_kernel(const double *__restrict__ ao,
+                                                            const double *__restrict__ cm,
+                                                            double *__restrict__ mo, int M, int K,
+                                                            long long N) {
+    __shared__ double sa[16][64 + 1];   // ao tile  [k][n]
+    __shared__ double sc[16][64 + 1];   // coef tile [k][m]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long n0 = (long long)blockIdx.x * 64;
+    const int m0 = blockIdx.y * 64;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e >> 6, nn = e & 63;
+            const long long n = n0 + nn;
+            sa[kk][nn] = (k0 + kk < K && n < N) ? ao[(size_t)(k0 + kk) * N + n] : 0.0;
+            const int mm = e >> 4, k2 = e & 15;
+            sc[k2][mm] = (m0 + mm < M && k0 + k2 < K) ? cm[(size_t)(m0 + mm) * K + k0 + k2] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = sa[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = sc[kk][ty + 16 * i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(c[i], a[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long n = n0 + tx + 16 * j;
+            if (n < N) mo[(size_t)m * N + n] = acc[i][j];
+        }
+    }
+}
+
+}  // namespace okb

@@ -1,0 +1,278 @@
+"""Host runtime above the C ABI: one context per process/device, cached device handles for the
+basis tables, MO coefficients and grids, and pinned host outputs.
+
+PyTorch is used for plumbing only (device selection, pinned host buffers, device output tensors,
+streams for timing); every number is produced by libokb200.so.
+"""
+import ctypes
+import hashlib
+import os
+from collections import OrderedDict
+
+import numpy
+
+from . import _lib
+from .tools import get_cart2sph
+
+SINK_AO, SINK_MO, SINK_RHO = 0, 1, 2
+
+
+def _digest(*arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b'\x00none')
+            continue
+        a = numpy.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.view(numpy.uint8).reshape(-1).data)
+    return h.digest()
+
+
+def build_cart2sph_csr(ao_spec):
+    """CSR form of core.cartesian2spherical (orbkit/core.py:157-174): for every spherical function
+    (contraction j0, (l,m)) the Cartesian rows of contraction j0 whose exponent triple matches each
+    table term, with value coef*factor.  A table term without a matching Cartesian function raises
+    (the reference would silently reuse the previous row index)."""
+    lxlylz = ao_spec.get_lxlylz()
+    assign = ao_spec.get_assign_lxlylz_to_cont()
+    rows_of = {}
+    for i, j in enumerate(assign):
+        rows_of.setdefault(int(j), []).append(i)
+    ptr, col, val = [0], [], []
+    for j0, lm in ao_spec.get_old_ao_spherical():
+        exps, coefs, factor = get_cart2sph(int(lm[0]), int(lm[1]))
+        rows = rows_of[int(j0)]
+        for e, c in zip(exps, coefs):
+            hit = None
+            for i in rows:
+                if tuple(int(v) for v in lxlylz[i]) == tuple(e):
+                    hit = i
+            if hit is None:
+                raise ValueError('cartesian2spherical: contraction %d has no Cartesian function %s '
+                                 'needed by (l,m)=%s' % (j0, e, tuple(lm)))
+            col.append(hit)
+            val.append(c * factor)
+        ptr.append(len(col))
+    return (numpy.asarray(ptr, dtype=numpy.intc), numpy.asarray(col, dtype=numpy.intc),
+            numpy.asarray(val, dtype=numpy.float64))
+
+
+class _Handle:
+    def __init__(self, ptr, destroy):
+        self.ptr, self._destroy = ptr, destroy
+
+    def close(self):
+        if self.ptr:
+            self._destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """Owns the okb_ctx of one CUDA device and small LRU caches of device handles."""
+    CACHE = 8
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    n = torch.cuda.device_count()
+                    device = device % max(n, 1)
+            except Exception:
+                pass
+        self.device = device
+        ctx = ctypes.c_void_p()
+        _lib.check(self.lib.okb_ctx_create(device, ctypes.byref(ctx)))
+        self.ctx = ctx
+        self._basis = OrderedDict()
+        self._mo = OrderedDict()
+        self._grid = OrderedDict()
+
+    # ---- caches ---------------------------------------------------------------------------------
+    def _put(self, cache, key, handle):
+        cache[key] = handle
+        while len(cache) > self.CACHE:
+            cache.popitem(last=False)     # the C handle is destroyed when its last Python ref dies
+        return handle
+
+    def basis(self, geo_spec, ao_spec):
+        """Device basis tables for (geo_spec, ao_spec); returns (handle, n_cart, n_ao)."""
+        lxlylz = _lib.i32(ao_spec.get_lxlylz())
+        assign = _lib.i32(ao_spec.get_nlxlylz_per_cont())
+        coeffs = _lib.f64(ao_spec.get_prim_coeffs())
+        pnum = _lib.i32(ao_spec.get_nprim_per_cont())
+        geo = _lib.f64(geo_spec)
+        atoms = _lib.i32(ao_spec.get_assign_cont_to_atoms())
+        normalized = int(ao_spec.get_normalized())
+        renorm = getattr(ao_spec, 'get_renorm', lambda: None)()
+        if renorm is None and len(ao_spec) and isinstance(ao_spec[0], dict) and 'N' in ao_spec[0]:
+            renorm = ao_spec[0]['N']
+        if renorm is not None:
+            renorm = _lib.f64(numpy.asarray(renorm, dtype=float).reshape(-1))
+            if renorm.shape[0] != lxlylz.shape[0]:
+                raise ValueError("ao_spec[0]['N'] must hold one factor per Cartesian function")
+        spherical = bool(ao_spec.spherical)
+        lm = None
+        if spherical:
+            lm = numpy.array([[j, l, m] for j, (l, m) in ao_spec.get_old_ao_spherical()], dtype=numpy.intc)
+        key = _digest(lxlylz, assign, coeffs, pnum, geo, atoms, numpy.array([normalized]), renorm, lm)
+        if key in self._basis:
+            self._basis.move_to_end(key)
+            return self._basis[key]
+        if geo.ndim != 2 or geo.shape[1] != 3:
+            raise ValueError('geo_spec must have shape (n_atoms, 3)')
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.okb_basis_create(
+            self.ctx, _lib.iptr(lxlylz), _lib.iptr(assign), _lib.dptr(coeffs), _lib.iptr(pnum),
+            _lib.dptr(geo), _lib.iptr(atoms), len(assign), lxlylz.shape[0], coeffs.shape[0], geo.shape[0],
+            normalized, _lib.dptr(renorm) if renorm is not None else None, ctypes.byref(h)))
+        handle = _Handle(h, self.lib.okb_basis_destroy)
+        n_cart = n_ao = lxlylz.shape[0]
+        if spherical:
+            ptr, col, val = build_cart2sph_csr(ao_spec)
+            n_ao = len(ptr) - 1
+            _lib.check(self.lib.okb_basis_set_cart2sph(h, n_ao, _lib.iptr(ptr), _lib.iptr(col), _lib.dptr(val)))
+        return self._put(self._basis, key, (handle, n_cart, n_ao, key))
+
+    def mos(self, basis_entry, coeffs, occ):
+        handle_b, _, n_ao, bkey = basis_entry
+        coeffs = _lib.f64(coeffs)
+        occ = _lib.f64(occ)
+        if coeffs.ndim != 2 or coeffs.shape[1] != n_ao:
+            raise ValueError('MO coefficients have shape %s but the basis has %d AOs' % (coeffs.shape, n_ao))
+        if occ.shape != (coeffs.shape[0],):
+            raise ValueError('occupation numbers and MO coefficients differ in length')
+        key = bkey + _digest(coeffs, occ)
+        if key in self._mo:
+            self._mo.move_to_end(key)
+            return self._mo[key]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.okb_mo_create(self.ctx, handle_b.ptr, coeffs.shape[0], _lib.dptr(coeffs),
+                                          _lib.dptr(occ), ctypes.byref(h)))
+        handle = _Handle(h, self.lib.okb_mo_destroy)
+        handle.keepalive = handle_b           # the MO handle borrows the basis
+        handle.n_mo = coeffs.shape[0]
+        return self._put(self._mo, key, handle)
+
+    def grid_regular(self, x, y, z):
+        x, y, z = _lib.f64(x), _lib.f64(y), _lib.f64(z)
+        key = b'r' + _digest(x, y, z)
+        if key in self._grid:
+            self._grid.move_to_end(key)
+            return self._grid[key]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.okb_grid_regular(self.ctx, _lib.dptr(x), len(x), _lib.dptr(y), len(y),
+                                             _lib.dptr(z), len(z), ctypes.byref(h)))
+        handle = _Handle(h, self.lib.okb_grid_destroy)
+        handle.npts = len(x) * len(y) * len(z)
+        return self._put(self._grid, key, handle)
+
+    def grid_vector(self, x, y, z, cache=True):
+        x, y, z = _lib.f64(x), _lib.f64(y), _lib.f64(z)
+        if not (len(x) == len(y) == len(z)):
+            raise ValueError('Dimensions of x-, y-, and z- coordinate differ!')
+        key = b'v' + _digest(x, y, z) if cache else None
+        if cache and key in self._grid:
+            self._grid.move_to_end(key)
+            return self._grid[key]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.okb_grid_vector(self.ctx, x.ctypes.data, y.ctypes.data, z.ctypes.data, len(x), 0,
+                                            ctypes.byref(h)))
+        handle = _Handle(h, self.lib.okb_grid_destroy)
+        handle.npts = len(x)
+        return self._put(self._grid, key, handle) if cache else handle
+
+    # ---- host output buffers -------------------------------------------------------------------------
+    @staticmethod
+    def host_array(shape):
+        """float64 host array for results; page-locked (via torch's caching host allocator) so that
+        device->host copies overlap compute.  Falls back to pageable memory if pinning fails."""
+        try:
+            import torch
+            t = torch.empty(tuple(int(s) for s in shape), dtype=torch.float64, pin_memory=True)
+            return t.numpy()
+        except Exception:
+            return numpy.empty(shape, dtype=numpy.float64)
+
+    # ---- evaluation ---------------------------------------------------------------------------------------
+    def eval_ao(self, basis_entry, grid, codes, p0=0, p1=None, out=None, flags=0):
+        handle_b, _, n_ao, _ = basis_entry
+        p1 = grid.npts if p1 is None else p1
+        codes = _lib.i32(codes)
+        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        if out is None:
+            out = self.host_array((len(codes), n_ao, p1 - p0))
+        ptr = out if dev else out.ctypes.data
+        _lib.check(self.lib.okb_eval_ao(self.ctx, handle_b.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes),
+                                        ptr, flags))
+        return out
+
+    def eval_mo(self, mo, grid, codes, p0=0, p1=None, out=None, flags=0):
+        p1 = grid.npts if p1 is None else p1
+        codes = _lib.i32(codes)
+        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        if out is None:
+            out = self.host_array((len(codes), mo.n_mo, p1 - p0))
+        ptr = out if dev else out.ctypes.data
+        _lib.check(self.lib.okb_eval_mo(self.ctx, mo.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes), ptr,
+                                        flags))
+        return out
+
+    def eval_rho(self, mo, grid, codes, p0=0, p1=None, rho=None, delta=None, want_norm=False, flags=0):
+        """returns (rho, delta_rho or None, mo_norm or None)"""
+        p1 = grid.npts if p1 is None else p1
+        codes = _lib.i32(codes)
+        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        n = p1 - p0
+        if rho is None:
+            rho = self.host_array((n,))
+        if delta is None and len(codes):
+            delta = self.host_array((len(codes), n))
+        norm = numpy.zeros(mo.n_mo) if want_norm else None
+        _lib.check(self.lib.okb_eval_rho(
+            self.ctx, mo.ptr, grid.ptr, p0, p1, _lib.iptr(codes) if len(codes) else None, len(codes),
+            rho if dev else rho.ctypes.data,
+            (delta if dev else delta.ctypes.data) if len(codes) else None,
+            norm.ctypes.data if want_norm else None, flags))
+        return rho, (delta if len(codes) else None), norm
+
+    def sync(self):
+        _lib.check(self.lib.okb_ctx_sync(self.ctx))
+
+    def stream_ptr(self):
+        return self.lib.okb_ctx_stream(self.ctx)
+
+    def launch_count(self):
+        n = _lib.ll()
+        _lib.check(self.lib.okb_ctx_launch_count(self.ctx, ctypes.byref(n)))
+        return n.value
+
+    def last_kernel(self):
+        buf = ctypes.create_string_buffer(256)
+        _lib.check(self.lib.okb_ctx_last_kernel(self.ctx, buf, 256))
+        return buf.value.decode()
+
+
+_engine = None
+
+
+def get_engine():
+    """Process-wide engine (device = LOCAL_RANK when launched by torchrun, else 0)."""
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+def reset_engine():
+    global _engine
+    _engine = None

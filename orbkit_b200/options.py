@@ -1,0 +1,14 @@
+"""Module-level option globals, mirroring the subset of orbkit/options.py:495-525 that the
+grid-based hot path reads (library users set these attributes directly, e.g. options.quiet=True).
+
+`numproc` and `slice_length` are kept for drop-in compatibility; on B200 they are advisory:
+the point range is tiled on-chip and sharded over torch.distributed ranks instead of over a
+process pool (orbkit/core.py:437-447,503-536).
+"""
+quiet = False        #: suppress terminal output (display.py:27-42)
+no_log = True        #: no .oklog file (the CLI/logging layer is out of scope)
+numproc = 1          #: advisory
+slice_length = 1e4   #: advisory: upper bound of points per device launch when > 0
+outputname = 'orbkit_b200'
+exact_mixed_derivatives = False  #: opt-in analytically correct xy/xz/yz AO derivatives
+                                 #  (the reference drops cross terms, c_support.c:121-168)
