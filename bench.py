@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- grid points/s of the ORBKIT grid path (rho + grad rho, FP64) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json north_star target, configs[2] molecule): synthetic C24H20-like molecule
+with cc-pVTZ-shaped shells (360 contractions, 784 primitives, 1140 Cartesian -> 1000 spherical AOs,
+82 doubly occupied MOs, numpy default_rng(0)); rho and (d/dx,d/dy,d/dz) rho on a regular grid of
+200 x 200 x 200 points over [-12,12]^3 bohr PER GPU.  A step is one pass of the hot path over that
+grid.  N > 1: weak scaling -- the x axis carries 200*N points over the same box and every rank
+owns a contiguous x-slab of 8e6 points; there is no data-path collective.
+
+One JSON line is printed by rank 0:
+  value         whole-job points/s, outputs left in HBM, CUDA-event timed on the launch stream
+  e2e           the same through orbkit_b200.rho_compute (QCinfo in, NumPy out): per step the
+                basis tables, MO coefficients and grid axes are re-uploaded (handle caches dropped)
+                and the result comes back to host memory inside the timed region
+  roofline      the fused kernel against the FP64 DFMA peak MEASURED in this run (MEASURED_PEAKS.json
+                has no FP64 entry); algorithmic flops = 2*n_mo*n_ao*4 per point
+  cpu_baseline  the reference's CPU path (oracle/_ref objects) on the box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+GRID_N = 200
+BOX = 12.0
+DRV = ['x', 'y', 'z']
+N_AO, N_MO, D_SETS = 1000, 82, 4
+ALG_FLOPS_PER_POINT = 2.0 * N_MO * N_AO * D_SETS          # 656 kFLOP
+ALG_BYTES_PER_POINT = 8.0 * (1 + 3)                        # rho + 3 derivatives out, 0 in
+WORKLOAD = ('synthetic 1000-AO/82-MO molecule (BASELINE configs[2] generator, seed 0), rho+grad rho, '
+            '200^3 regular grid on [-12,12]^3 per GPU')
+
+
+def molecule():
+    from orbkit_b200 import synth
+    return synth.make_molecule(n_heavy=24, n_light=20, n_mo=N_MO, seed=0, spherical=True)
+
+
+def axes(n_gpus):
+    ax = numpy.linspace(-BOX, BOX, GRID_N)
+    return numpy.linspace(-BOX, BOX, GRID_N * n_gpus), ax, ax
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx, pw = [], set(), None, []
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2]); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(numpy.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(pw) if pw else None)
+        return out
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank, world, local = 0, 1, 0
+    if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch.distributed as dist
+        rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback')
+    rank, world, local = dist_setup(args.gpus)
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    import orbkit_b200 as ok
+    from orbkit_b200 import synth, dist as okdist
+    from orbkit_b200._lib import OKB_FLAG_OUT_DEVICE
+    from orbkit_b200.engine import get_engine
+    ok.options.quiet = True
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    spec = molecule()
+    qc = synth.to_qcinfo(spec)
+    gx, gy, gz = axes(world)
+    npts_total = len(gx) * len(gy) * len(gz)
+    eng = get_engine()
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+
+    # ---- resident inputs: tables, coefficients, axes on the device; outputs stay in HBM -------------
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    g = eng.grid_regular(gx, gy, gz)
+    p0, p1 = okdist.shard_range(npts_total, rank, world)
+    n_loc = p1 - p0
+    out = torch.zeros((4, n_loc), dtype=torch.float64, device=dev)
+    codes = [1, 2, 3]
+
+    def step():
+        eng.eval_rho(mo, g, codes, p0, p1, rho=out[0].data_ptr(), delta=out[1:].data_ptr(), flags=OKB_FLAG_OUT_DEVICE)
+
+    # FP64 roofline denominator, measured here (burst + sustained), rank 0 only prints it
+    dfma_burst, _ = eng.measure_fp64(0, 0.0)
+    dmma_burst, _ = eng.measure_fp64(1, 0.0)
+    dfma_sust, _ = eng.measure_fp64(0, 1.0)
+
+    for _ in range(args.warmup):
+        step()
+    eng.sync()
+    sampler = ClockSampler(local)
+    barrier(world)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for i in range(args.steps):
+            step()
+            evs[i + 1].record(stream)
+    eng.sync()
+    barrier(world)
+    launches = eng.launch_count() - launches0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    total_ms = max_over_ranks(total_ms, world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = npts_total / (ms_per_step * 1e-3)
+    kernel_name = eng.last_kernel()
+    electrons = float(out[0].sum().item()) * (gx[1] - gx[0]) * (gy[1] - gy[0]) * (gz[1] - gz[0])
+    if world > 1:
+        electrons = float(okdist.all_reduce_sum([electrons], local)[0])
+
+    # ---- end to end through the public API: QCinfo + grid in, NumPy out, every step ------------------
+    ok.grid.set_grid(gx, gy, gz, is_vector=False)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        eng.clear_caches()                  # tables / coefficients / axes are uploaded again
+        return ok.rho_compute(qc, drv=DRV)
+
+    if args.no_e2e:
+        e2e_steps = 0
+    for _ in range(2 if e2e_steps else 0):
+        r = e2e_step()
+    barrier(world)
+    h0, d0 = eng.traffic()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier(world)
+    h1, d1 = eng.traffic()
+    t_e2e = max_over_ranks(t_e2e, world, dev)
+    if not e2e_steps:
+        r = [numpy.zeros((len(gx), len(gy), len(gz)))]
+    e2e_value = npts_total * e2e_steps / t_e2e
+    d2h = (d1 - d0) / max(e2e_steps, 1)
+    if world > 1:                           # gathered result is read back by torch (.cpu()) on every rank
+        d2h += 8.0 * 4 * npts_total
+    e2e_ok = bool(numpy.isfinite(r[0]).all() and r[0].shape == (len(gx), len(gy), len(gz)))
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant (only) kernel of the step -----------------------------------------
+    kern_ms = float(numpy.mean(per_step))
+    achieved = ALG_FLOPS_PER_POINT * n_loc / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(REPO, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(kernel_name)
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'fp64', 'achieved': round(achieved, 3), 'peak': round(dfma_sust, 3), 'unit': 'TFLOP/s',
+                'frac': round(achieved / dfma_sust, 4), 'traffic': traffic,
+                'kernel': kernel_name, 'kernel_ms': round(kern_ms, 3),
+                'peak_source': 'FP64 DFMA issue-bound microbenchmark measured in this run, sustained 1 s '
+                               '(MEASURED_PEAKS.json has no FP64 entry; tcgen05 has no FP64 kind)',
+                'peak_dfma_burst': round(dfma_burst, 3), 'peak_dmma_m8n8k4_burst': round(dmma_burst, 3),
+                'alg_flops_per_point': ALG_FLOPS_PER_POINT,
+                'hbm': {'alg_bytes_per_point': ALG_BYTES_PER_POINT,
+                        'achieved_gbs': round(ALG_BYTES_PER_POINT * n_loc / (kern_ms * 1e-3) / 1e9, 2),
+                        'peak_gbs': _peaks().get('hbm_gbs')}}
+    cpu = None if args.no_cpu else cpu_baseline(spec, args)
+    line = {'metric': 'grid points/s, rho + grad rho (FP64)', 'value': value, 'unit': 'points/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic (seeded random molecule and MO coefficients)',
+            'config': {'workload': WORKLOAD, 'points_per_gpu': n_loc, 'points_total': npts_total,
+                       'n_ao': N_AO, 'n_cart': 1140, 'n_mo': N_MO, 'derivative_sets': D_SETS,
+                       'parallelism': 'points sharded over %d rank(s), no data-path collective' % world,
+                       'l2': 'outputs 256 MB/step/GPU exceed the 126 MB L2; inputs are 1 MB of tables by design'},
+            'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': (h1 - h0) / max(e2e_steps, 1),
+                    'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'api': 'orbkit_b200.rho_compute(qc, drv=["x","y","z"])',
+                    'ok': e2e_ok},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+            'electrons': electrons}
+    print(json.dumps(line))
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def cpu_sample(n_gpus, npts):
+    """contiguous run of grid points from the middle of the benchmark grid (vector form)"""
+    gx, gy, gz = axes(1)
+    start = (GRID_N // 2) * GRID_N * GRID_N
+    idx = numpy.arange(start, start + npts)
+    i, rem = numpy.divmod(idx, GRID_N * GRID_N)
+    j, k = numpy.divmod(rem, GRID_N)
+    return gx[i], gy[j], gz[k]
+
+
+def cpu_baseline(spec, args, steps=1):
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import cpu_bench
+    cores = os.cpu_count() or 1
+    workers = min(cores, 64)
+    npts = workers * 4000 if args.cpu_points <= 0 else args.cpu_points
+    x, y, z = cpu_sample(1, npts)
+    res = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=2000, repeats=steps)
+    return {'value': res['points_per_s'], 'unit': 'points/s', 'cores': res['cores'], 'kind': res['kind'],
+            'sample': '%d contiguous points from the middle x-plane of the 200^3 grid, %d worker processes, '
+                      'slices of 2000 points (reference Pool driver, core.py:503-536); %.1f s'
+                      % (res['npts'], res['cores'], res['seconds']), 'host_cores': cores}
+
+
+def run_reference(args):
+    """the reference's own CPU implementation of the path on the host cores (oracle/_ref)"""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    spec = molecule()
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import cpu_bench
+    cores = os.cpu_count() or 1
+    workers = min(cores, 64)
+    npts = workers * 4000 if args.cpu_points <= 0 else args.cpu_points
+    x, y, z = cpu_sample(1, npts)
+    kind = cpu_bench.default_kind()
+    times = []
+    for s in range(args.warmup + args.steps):
+        res = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=2000, kind=kind)
+        if s >= args.warmup:
+            times.append(res['seconds'])
+    sec = float(numpy.mean(times))
+    value = npts / sec
+    sample = ('%d contiguous points of the 200^3 grid per step, %d worker processes, slices of 2000 points'
+              % (npts, res['cores']))
+    line = {'impl': 'reference', 'metric': 'grid points/s, rho + grad rho (FP64)', 'value': value, 'unit': 'points/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic (seeded random molecule and MO coefficients)',
+            'config': {'workload': WORKLOAD, 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': res['cores'], 'kind': res['kind'],
+                             'sample': sample, 'host_cores': cores},
+            'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-points', type=int, default=0, help='size of the CPU sample (0: 4000 per worker)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -63,7 +63,14 @@ int  okb_ctx_destroy(okb_ctx *ctx);
 int  okb_ctx_sync(okb_ctx *ctx);
 void *okb_ctx_stream(okb_ctx *ctx);                       /* cudaStream_t of the context */
 int  okb_ctx_launch_count(okb_ctx *ctx, long long *n);    /* kernels launched by this context */
+int  okb_ctx_traffic(okb_ctx *ctx, long long *h2d_bytes, long long *d2h_bytes); /* PCIe bytes so far */
 int  okb_ctx_last_kernel(okb_ctx *ctx, char *buf, int buflen); /* name of the last variant launched */
+
+/* FP64 roofline denominator measured on the device: kind 0 = DFMA issue-bound loop, 1 = DMMA
+ * (mma.sync.m8n8k4.f64), 2 = half the warps each.  min_seconds <= 0: burst (best single launch of 4);
+ * > 0: launches back to back for at least that long (sustained, under the power cap).  Returns dense
+ * TFLOP/s and the measured time. */
+int  okb_measure_fp64(okb_ctx *ctx, int kind, double min_seconds, double *tflops, double *ms);
 
 /* ---- (1) cy_core drop-ins, host buffers ------------------------------------------------- */
 /* out[n_cart][npts] (row-major).  Arguments as cy_core.aocreator (cy_core.pyx:51-61):

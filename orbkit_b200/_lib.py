@@ -36,7 +36,9 @@ SIGNATURES = {
     'okb_ctx_sync': (ctypes.c_int, [ctypes.c_void_p]),
     'okb_ctx_stream': (ctypes.c_void_p, [ctypes.c_void_p]),
     'okb_ctx_launch_count': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ll)]),
+    'okb_ctx_traffic': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ll), ctypes.POINTER(ll)]),
     'okb_ctx_last_kernel': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    'okb_measure_fp64': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p]),
     'okb_aocreator': (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p, c_int_p, c_double_p,
                                      c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      c_double_p, c_double_p, c_double_p, ll, ctypes.c_int, ctypes.c_int,

@@ -63,6 +63,7 @@ struct okb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     long long launches = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context
     std::string last_kernel;
     void *slab[2] = {nullptr, nullptr};      // device staging for host outputs
     size_t slab_bytes = 0;
@@ -176,6 +177,12 @@ extern "C" void *okb_ctx_stream(okb_ctx *c) { return c ? (void *)c->stream : nul
 extern "C" int okb_ctx_launch_count(okb_ctx *c, long long *n) {
     if (!c || !n) return fail(OKB_ERR_ARG, "null pointer");
     *n = c->launches;
+    return OKB_OK;
+}
+extern "C" int okb_ctx_traffic(okb_ctx *c, long long *h2d, long long *d2h) {
+    if (!c) return fail(OKB_ERR_ARG, "null context");
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
     return OKB_OK;
 }
 extern "C" int okb_ctx_last_kernel(okb_ctx *c, char *buf, int buflen) {
@@ -346,6 +353,7 @@ static int basis_upload(okb_basis *b) {
     b->meta_dev = nullptr;
     CU(cudaMalloc(&b->meta_dev, blob.size()));
     CU(cudaMemcpy(b->meta_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    b->ctx->h2d_bytes += (long long)blob.size();
     b->dirty = false;
     return OKB_OK;
 }
@@ -510,6 +518,7 @@ static int mo_blob(okb_mo *m, int MC, okb_mo::Blob **out) {
     CU(cudaMalloc(&bl.occ, occ.size() * sizeof(double)));
     CU(cudaMemcpy(bl.c, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(bl.occ, occ.data(), occ.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m->ctx->h2d_bytes += (long long)((blob.size() + occ.size()) * sizeof(double));
     m->blobs[MC] = bl;
     *out = &m->blobs[MC];
     return OKB_OK;
@@ -544,6 +553,7 @@ extern "C" int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const dou
     CU(cudaMemcpy(g->gx, x, sizeof(double) * nx, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->gy, y, sizeof(double) * ny, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->gz, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
+    ctx->h2d_bytes += (long long)sizeof(double) * (nx + ny + nz);
     *out = g;
     return OKB_OK;
 }
@@ -571,6 +581,7 @@ extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, c
         CU(cudaMemcpyAsync(g->gy, y, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(g->gz, z, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        ctx->h2d_bytes += 3ll * (long long)sizeof(double) * npts;
     }
     *out = g;
     return OKB_OK;
@@ -851,10 +862,12 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                                      wbytes, n_out_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
             }
             CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+            ctx->d2h_bytes += (long long)(wbytes * n_out_rows);
         }
     }
     if (norm_dev) {
         CU(cudaMemcpyAsync(rq.mo_norm, norm_dev, sizeof(double) * rq.mo->n_mo, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (long long)sizeof(double) * rq.mo->n_mo;
         CU(cudaStreamSynchronize(ctx->stream));
     }
     if (!dev_out) {
@@ -958,10 +971,71 @@ extern "C" int okb_mocreator(okb_ctx *ctx, const double *ao, const double *coeff
             e = cudaMemcpy2DAsync(mo + s0, sizeof(double) * npts, d_mo, sizeof(double) * sn, sizeof(double) * sn,
                                   n_mo, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        ctx->h2d_bytes += (long long)sizeof(double) * sn * n_ao;
+        ctx->d2h_bytes += (long long)sizeof(double) * sn * n_mo;
         if (e != cudaSuccess) rc = fail(OKB_ERR_CUDA, "okb_mocreator: %s", cudaGetErrorString(e));
     }
     cudaFree(d_c);
     if (d_ao) cudaFree(d_ao);
     if (d_mo) cudaFree(d_mo);
     return rc;
+}
+
+// ---- FP64 peak measurement (the roofline denominator MEASURED_PEAKS.json does not carry) --------------
+extern "C" int okb_measure_fp64(okb_ctx *ctx, int kind, double min_seconds, double *tflops, double *ms_out) {
+    if (!ctx || !tflops) return fail(OKB_ERR_ARG, "okb_measure_fp64: null argument");
+    if (kind < 0 || kind > 2) return fail(OKB_ERR_ARG, "okb_measure_fp64: kind must be 0 (DFMA), 1 (DMMA) or 2 (mixed)");
+    CU(cudaSetDevice(ctx->device));
+    double *sink = nullptr;
+    CU(cudaMalloc(&sink, 8));
+    const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
+    // flops per warp-iteration: DFMA 16 chains x 2 x 32 lanes; DMMA 8 mma x (8*8*4*2)
+    const double per_warp_iter_dfma = 16.0 * 2.0 * 32.0, per_warp_iter_dmma = 8.0 * 512.0;
+    const double warps = (double)grid * block / 32.0;
+    double flops;
+    if (kind == 0) flops = warps * iters * per_warp_iter_dfma;
+    else if (kind == 1) flops = warps * iters * per_warp_iter_dmma;
+    else flops = 0.5 * warps * iters * (per_warp_iter_dfma + per_warp_iter_dmma);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    okb_fp64_peak_kernel<<<grid, block, 0, ctx->stream>>>(sink, iters, kind);   // warm-up
+    CU(cudaStreamSynchronize(ctx->stream));
+    double result_ms = 0.0, result_flops = 0.0;
+    if (min_seconds <= 0.0) {           // burst: best single launch of 4
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            okb_fp64_peak_kernel<<<grid, block, 0, ctx->stream>>>(sink, iters, kind);
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+            ctx->launches++;
+        }
+        result_ms = best;
+        result_flops = flops;
+    } else {                            // sustained: back-to-back launches for >= min_seconds
+        int n = 0;
+        CU(cudaEventRecord(e0, ctx->stream));
+        float ms = 0.f;
+        do {
+            for (int k = 0; k < 8; ++k) okb_fp64_peak_kernel<<<grid, block, 0, ctx->stream>>>(sink, iters, kind);
+            n += 8;
+            ctx->launches += 8;
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaEventSynchronize(e1));
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+        } while (ms < min_seconds * 1e3 && n < 100000);
+        result_ms = ms;
+        result_flops = flops * n;
+    }
+    CU(cudaGetLastError());
+    *tflops = result_flops / (result_ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = result_ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return OKB_OK;
 }

@@ -245,6 +245,13 @@ class Engine:
             norm.ctypes.data if want_norm else None, flags))
         return rho, (delta if len(codes) else None), norm
 
+    def measure_fp64(self, kind=0, min_seconds=0.0):
+        """dense FP64 TFLOP/s of this device: kind 0 DFMA, 1 DMMA m8n8k4, 2 mixed; burst when
+        min_seconds <= 0, else sustained over back-to-back launches"""
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self.lib.okb_measure_fp64(self.ctx, kind, float(min_seconds), ctypes.byref(tf), ctypes.byref(ms)))
+        return tf.value, ms.value
+
     def sync(self):
         _lib.check(self.lib.okb_ctx_sync(self.ctx))
 
@@ -255,6 +262,18 @@ class Engine:
         n = _lib.ll()
         _lib.check(self.lib.okb_ctx_launch_count(self.ctx, ctypes.byref(n)))
         return n.value
+
+    def traffic(self):
+        """(host->device, device->host) bytes moved by this context so far"""
+        a, b = _lib.ll(), _lib.ll()
+        _lib.check(self.lib.okb_ctx_traffic(self.ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def clear_caches(self):
+        """drop the cached device handles (basis tables, MO coefficients, grids)"""
+        self._mo.clear()
+        self._basis.clear()
+        self._grid.clear()
 
     def last_kernel(self):
         buf = ctypes.create_string_buffer(256)

@@ -26,13 +26,15 @@ def grid_init(is_vector=False, force=False):
             delta_[i] = 1
             N_[i] = 1
         elif delta_[i]:
-            axes[i] = numpy.arange(min_[i], max_[i] + delta_[i], delta_[i], dtype=numpy.float64)
+            step = float(numpy.asarray(delta_[i]).reshape(-1)[0])
+            axes[i] = numpy.arange(min_[i], max_[i] + step, step, dtype=numpy.float64)
+            delta_[i] = step
             N_[i] = len(axes[i])
         else:
             axes[i] = numpy.array(numpy.linspace(min_[i], max_[i], N_[i]), dtype=numpy.float64)
             delta_[i] = axes[i][1] - axes[i][0]
     x, y, z = axes
-    d3r = numpy.prod(delta_)
+    d3r = float(numpy.prod([float(numpy.asarray(d).reshape(-1)[0]) for d in delta_]))
     is_initialized = True
     is_regular = True
     if is_vector:

@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the public API and the C ABI) against
+   (1) the outputs the reference itself wrote into tests/golden/ (make_golden.py),
+   (2) the reference's own golden refdata_rho_compute.npz and the Gaussian cubegen KATs,
+   (3) the pinned CPU oracle on seeded random inputs and edge-case sizes,
+   (4) size-independent properties at large sizes.
+Tolerance (FP64 path): |d| <= 1e-10*|ref| + 1e-14*max|ref|; electron counts to 1e-8."""
+import numpy
+import pytest
+
+from conftest import DRV10, FIXTURES, assert_close, golden_qc, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ok():
+    import orbkit_b200
+    orbkit_b200.options.quiet = True
+    return orbkit_b200
+
+
+def set_regular(ok, x, y, z):
+    ok.grid.set_grid(numpy.array(x), numpy.array(y), numpy.array(z), is_vector=False)
+
+
+def set_vector(ok, x, y, z):
+    ok.grid.set_grid(numpy.array(x), numpy.array(y), numpy.array(z), is_vector=True)
+
+
+def test_reference_golden_refdata(ok):
+    """orbkit/test/grid_based/rho_compute.py: rho, laplacian, 24 MOs x 10 derivative codes"""
+    qc, _ = golden_qc('h2o_molpro_cart')
+    g = load_golden('ref_rho_compute')
+    for vector in (False, True):
+        set_regular(ok, g['x'], g['y'], g['z'])
+        if vector:
+            ok.grid.grid2vector()
+        shp = (-1,) if vector else (5, 9, 7)
+        assert_close(ok.rho_compute(qc, slice_length=0), g['zero'].reshape(shp), 'rho')
+        assert_close(ok.rho_compute(qc, numproc=2), g['zero'].reshape(shp), 'rho numproc')
+        assert_close(ok.rho_compute(qc, laplacian=True)[-1], g['two'].reshape(shp), 'laplacian')
+        mo = ok.rho_compute(qc, calc_mo=True, drv=DRV10)
+        assert_close(mo, g['four'].reshape((10, 24) + ((315,) if vector else (5, 9, 7))), 'mo10')
+    # the grid module state is restored like the reference does (core.py:433,569)
+    assert ok.grid.is_vector
+
+
+def test_gaussian_cubegen_kat(ok):
+    """orbkit/test/grid_based/cube_files.py with the reference's own tolerances"""
+    k = load_golden('cube_kat')
+    qc, _ = golden_qc('h2o_gaussian_sph_occ')
+    eq = lambda a, b, tol=1e-5: numpy.allclose(a, b, rtol=tol * 1e2, atol=tol)
+    set_regular(ok, k['x'], k['y'], k['z'])
+    rho, drho = ok.rho_compute(qc, drv='xyz')
+    rho2, d2, lap = ok.rho_compute(qc, laplacian=True)
+    assert eq(rho, rho2) and eq(rho, k['rho']) and eq(drho, k['drho'], 1e-3) and eq(lap, k['laplacian'])
+    qc.mo_spec = qc.mo_spec[1:]
+    assert eq(ok.rho_compute(qc), k['rho_valence'])
+    qc.mo_spec = qc.mo_spec['homo']
+    assert eq(ok.rho_compute(qc, calc_mo=True), k['homo'])
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_fixture_molecules_vs_reference_outputs(ok, name):
+    qc, a = golden_qc(name)
+    set_regular(ok, a['rx'], a['ry'], a['rz'])
+    assert_close(ok.rho_compute(qc), a['reg.rho'], name + ' reg.rho')
+    r, d = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert_close(r, a['reg.rho'], name + ' reg.rho(drv)')
+    assert_close(d, a['reg.drho'], name + ' reg.drho')
+    r, d, l = ok.rho_compute(qc, laplacian=True)
+    assert_close(d, a['reg.d2rho'], name + ' reg.d2rho')
+    assert_close(l, a['reg.lap'], name + ' reg.lap', afloor=3e-14)
+    set_vector(ok, a['vx'], a['vy'], a['vz'])
+    assert_close(ok.rho_compute(qc), a['vec.rho'], name + ' vec.rho')
+    r, d = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert_close(d, a['vec.drho'], name + ' vec.drho')
+    r, d, l = ok.rho_compute(qc, laplacian=True)
+    assert_close(d, a['vec.d2rho'], name + ' vec.d2rho')
+    r, d = ok.rho_compute(qc, drv=['xy', 'z', 'yz', 'x2'])
+    assert_close(d, a['vec.dmixed'], name + ' vec.dmixed')
+    if 'vec.mo10' in a.files:
+        assert_close(ok.rho_compute(qc, calc_mo=True, drv=DRV10), a['vec.mo10'], name + ' mo10')
+        assert_close(ok.rho_compute(qc, calc_ao=True, drv=DRV10), a['vec.ao10'], name + ' ao10')
+        assert_close(ok.extras.calc_ao(qc, drv=['z', 'xy']), a['vec.ao10'][[3, 5]], name + ' calc_ao')
+    else:
+        assert_close(ok.rho_compute(qc, calc_mo=True), a['vec.mo'], name + ' mo')
+        assert_close(ok.rho_compute(qc, calc_ao=True), a['vec.ao'], name + ' ao')
+        assert_close(ok.rho_compute(qc, calc_mo=True, drv=['z'])[0], a['vec.mo_z'], name + ' mo_z')
+        assert_close(ok.rho_compute(qc, calc_ao=True, drv=['yy'])[0], a['vec.ao_yy'], name + ' ao_yy')
+
+
+@pytest.mark.parametrize('name', ['h2o_gaussian_sph', 'lih_psi4_sph_f', 'water_gamess_wfn'])
+def test_operators_and_components(ok, oracle_mod, name):
+    """core.ao_creator / mo_creator / cartesian2spherical / rho_compute_no_slice(return_components)"""
+    qc, a = golden_qc(name)
+    x, y, z = a['vx'], a['vy'], a['vz']
+    for drv in (None, 'x', 'zz', 'xz', 2, 9):
+        got = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, drv=drv, x=x, y=y, z=z, is_vector=True)
+        ref = oracle_mod.ao_creator(qc.geo_spec, qc.ao_spec, drv=drv, x=x, y=y, z=z, is_vector=True)
+        assert_close(got, ref, '%s ao_creator drv=%s' % (name, drv))
+    ao = oracle_mod.ao_creator(qc.geo_spec, qc.ao_spec, x=a['rx'], y=a['ry'], z=a['rz'], is_vector=False)
+    got = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, x=a['rx'], y=a['ry'], z=a['rz'], is_vector=False)
+    assert got.shape == ao.shape == (qc.ao_spec.get_ao_num(), 4, 5, 3)
+    assert_close(got, ao, name + ' ao_creator regular')
+    assert_close(ok.core.mo_creator(ao, qc.mo_spec), oracle_mod.mo_creator(ao, qc.mo_spec), name + ' mo_creator')
+    if qc.ao_spec.spherical:
+        import copy
+        cart_spec = copy.deepcopy(qc.ao_spec)
+        cart_spec.spherical = False
+        cart = oracle_mod.ao_creator(qc.geo_spec, cart_spec, x=x, y=y, z=z, is_vector=True)
+        assert_close(ok.core.cartesian2spherical(cart, qc.ao_spec),
+                     oracle_mod.cartesian2spherical(cart, qc.ao_spec), name + ' cart2sph')
+    res = ok.rho_compute_no_slice(qc, drv=['x', 'y', 'z'], return_components=True, x=x, y=y, z=z, is_vector=True)
+    ao_l, mo_l, rho, dao, dmo, drho = res
+    assert_close(rho, a['vec.rho'], name + ' no_slice rho')
+    assert_close(drho, a['vec.drho'], name + ' no_slice drho')
+    assert_close(mo_l, a['vec.mo10'][0], name + ' no_slice mo')
+    assert_close(dao, a['vec.ao10'][1:4], name + ' no_slice dao')
+    assert_close(dmo, a['vec.mo10'][1:4], name + ' no_slice dmo')
+    r, d, l = ok.rho_compute(qc, laplacian=True, numproc=0, x=x, y=y, z=z, is_vector=True)
+    assert_close(d, a['vec.d2rho'], name + ' numproc=0 route')
+
+
+def test_cy_core_dropins_random_shells(ok, oracle_mod):
+    rng = numpy.random.default_rng(11)
+    from orbkit_b200.tools import exp, exp_wfn
+    port = oracle_mod.backend('port')
+    for trial in range(6):
+        L = list(rng.integers(0, 5, size=5))
+        table = exp_wfn if trial % 2 else exp
+        lxlylz = numpy.array(sum([table[l] for l in L], []), dtype=numpy.intc)
+        assign = numpy.array([len(table[l]) for l in L], dtype=numpy.intc)
+        pnum = numpy.array(rng.integers(1, 7, size=5), dtype=numpy.intc)
+        coeffs = numpy.stack([10 ** rng.uniform(-1, 3.5, pnum.sum()), rng.uniform(-1, 1, pnum.sum())], axis=1)
+        geo = rng.uniform(-2, 2, size=(3, 3))
+        atoms = numpy.array(rng.integers(0, 3, size=5), dtype=numpy.intc)
+        npts = [1, 31, 33, 127, 129, 1000][trial]
+        x, y, z = rng.uniform(-3, 3, size=(3, npts))
+        for normalized in (0, 1):
+            for drv in range(10):
+                got = ok.cy_core.aocreator(lxlylz, assign, coeffs, pnum, geo, atoms, x, y, z, drv, normalized)
+                ref = port.aocreator(lxlylz, assign, coeffs, pnum, geo, atoms, x, y, z, drv, normalized)
+                assert_close(got, ref, 'aocreator trial %d norm %d drv %d' % (trial, normalized, drv))
+        for drv in (7, 8, 9):
+            got = ok.cy_core.aocreator(lxlylz, assign, coeffs, pnum, geo, atoms, x, y, z, drv, 0, exact_mixed=True)
+            ref = port.aocreator(lxlylz, assign, coeffs, pnum, geo, atoms, x, y, z, drv, 0, exact_mixed=1)
+            assert_close(got, ref, 'aocreator exact mixed drv %d' % drv)
+        C = rng.standard_normal((int(rng.integers(1, 70)), lxlylz.shape[0]))
+        assert_close(ok.cy_core.mocreator(ref, C), port.mocreator(ref, C), 'mocreator')
+        # lcreator writes the first ao_num rows in place at the array's own row stride
+        big = numpy.full((assign[0] + 2, npts), -7.0)
+        ok.cy_core.lcreator(big, lxlylz, coeffs, geo[atoms[0]].copy(), x, y, z, int(assign[0]), int(pnum[0]), 3, 0)
+        one = port.aocreator(lxlylz[:assign[0]], assign[:1], coeffs[:pnum[0]], pnum[:1], geo, atoms[:1], x, y, z, 3, 0)
+        assert_close(big[:assign[0]], one, 'lcreator')
+        assert (big[assign[0]:] == -7.0).all()
+    for (lx, ly, lz) in [(0, 0, 0), (1, 0, 0), (2, 1, 0), (1, 1, 1), (0, 0, 4)]:
+        assert abs(ok.cy_core.aonorm(lx, ly, lz, 0.8, 0) / port.aonorm(lx, ly, lz, 0.8, 0) - 1) < 1e-15
+        assert ok.cy_core.aonorm(lx, ly, lz, 0.8, 1) == 1.0
+        for drv in range(10):
+            r = port.aoxyz(0.3, -1.1, 0.6, lx, ly, lz, 1.3, drv)
+            assert abs(ok.cy_core.aoxyz(0.3, -1.1, 0.6, lx, ly, lz, 1.3, drv) - r) <= 1e-13 * max(1, abs(r))
+
+
+def test_edge_sizes_and_point_ranges(ok, oracle_mod):
+    """empty grid, single point, ragged tails, regular == vector, results independent of ranges"""
+    from orbkit_b200.engine import get_engine
+    qc, a = golden_qc('synth_small_sph')
+    rng = numpy.random.default_rng(5)
+    set_vector(ok, numpy.zeros(0), numpy.zeros(0), numpy.zeros(0))
+    assert ok.rho_compute(qc).shape == (0,)
+    assert ok.rho_compute(qc, calc_mo=True).shape == (9, 0)
+    for n in (1, 2, 63, 64, 65, 257, 4099):
+        x, y, z = rng.uniform(-6, 6, size=(3, n))
+        set_vector(ok, x, y, z)
+        r, d = ok.rho_compute(qc, drv='xyz')
+        rr, dr = oracle_mod.rho_compute(qc, x, y, z, is_vector=True, drv='xyz')
+        assert_close(r, rr, 'rho n=%d' % n)
+        assert_close(d, dr, 'drho n=%d' % n)
+    ax, ay, az = numpy.linspace(-5, 5, 7), numpy.linspace(-4, 4, 6), numpy.linspace(-3, 3, 11)
+    set_regular(ok, ax, ay, az)
+    reg = ok.rho_compute(qc, laplacian=True)
+    ok.grid.grid2vector()
+    vec = ok.rho_compute(qc, laplacian=True)
+    for p, q in zip(reg, vec):
+        assert numpy.array_equal(p.reshape(q.shape), q)       # same kernels, same values
+    # explicit sub-ranges through the engine == the full evaluation
+    eng = get_engine()
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    g = eng.grid_regular(ax, ay, az)
+    full, dfull, nrm = eng.eval_rho(mo, g, [1, 2, 3], want_norm=True)
+    parts = [eng.eval_rho(mo, g, [1, 2, 3], p0, p1, want_norm=True) for p0, p1 in ((0, 100), (100, 101), (101, 462))]
+    assert numpy.array_equal(numpy.concatenate([p[0] for p in parts]), full)
+    assert numpy.array_equal(numpy.concatenate([p[1] for p in parts], axis=1), dfull)
+    assert_close(sum(p[2] for p in parts), nrm, 'mo_norm parts')
+    mo_ref = oracle_mod.rho_compute(qc, ax, ay, az, is_vector=False, calc_mo=True)
+    assert_close(nrm, (mo_ref.reshape(9, -1) ** 2).sum(axis=1), 'mo_norm', rtol=1e-12)
+
+
+def test_many_mos_multiple_mo_tiles(ok, oracle_mod):
+    """n_mo larger than one MO tile (MC<=96): AO tiles are regenerated per MO tile"""
+    from orbkit_b200 import synth
+    spec = synth.make_molecule(n_heavy=2, n_light=3, n_mo=230, seed=21, spherical=True)
+    qc = synth.to_qcinfo(spec)
+    rng = numpy.random.default_rng(2)
+    x, y, z = rng.uniform(-9, 9, size=(3, 300))
+    set_vector(ok, x, y, z)
+    r, d, l = ok.rho_compute(qc, laplacian=True)
+    rr, dr, lr = oracle_mod.rho_compute(qc, x, y, z, is_vector=True, laplacian=True)
+    assert_close(r, rr, 'rho 230 MOs')
+    assert_close(d, dr, 'd2rho 230 MOs')
+    mo = ok.rho_compute(qc, calc_mo=True, drv=['y'])
+    assert_close(mo, oracle_mod.rho_compute(qc, x, y, z, is_vector=True, calc_mo=True, drv=['y']), 'mo_y 230')
+
+
+def test_errors_match_reference_conventions(ok):
+    qc, a = golden_qc('nh3_molpro')
+    set_vector(ok, a['vx'], a['vy'], a['vz'])
+    with pytest.raises(ValueError):
+        ok.rho_compute(qc, calc_ao=True, calc_mo=True)
+    with pytest.raises(ValueError):
+        ok.rho_compute(qc, drv=['q'])
+    with pytest.raises(ValueError):
+        ok.core.ao_creator(qc.geo_spec, qc.ao_spec, x=a['vx'], y=a['vy'][:-1], z=a['vz'], is_vector=True)
+    with pytest.raises(ValueError):
+        ok.cy_core.mocreator(numpy.zeros((3, 4)), numpy.zeros((2, 5)))
+    with pytest.raises(ValueError):
+        ok.cy_core.mocreator(numpy.zeros((3, 4), dtype=numpy.float32), numpy.zeros((2, 3)))
+    with pytest.raises(TypeError):
+        ok.cy_core.mocreator(None, numpy.zeros((2, 3)))
+
+
+def test_full_size_properties_config3(ok, oracle_mod):
+    """BASELINE config 3 molecule (1000 AOs, 82 MOs) on a 48^3 cut of the benchmark box:
+       subsample parity vs the oracle, additivity over MO subsets, gradient vs central differences,
+       electron count consistency between independent evaluations."""
+    qc, a = golden_qc('synth_c3')
+    ax = numpy.linspace(-12, 12, 48)
+    set_regular(ok, ax, ax, ax)
+    rho, drho = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert rho.shape == (48, 48, 48) and (rho >= 0).all()
+    # parity on a strided subsample (the oracle needs seconds per 1e3 points at this size)
+    idx = numpy.arange(0, 48 ** 3, 48 ** 3 // 96)[:96]
+    X, Y, Z = numpy.meshgrid(ax, ax, ax, indexing='ij')
+    xs, ys, zs = X.ravel()[idx], Y.ravel()[idx], Z.ravel()[idx]
+    rr, dr = oracle_mod.rho_compute(qc, xs, ys, zs, is_vector=True, drv=['x', 'y', 'z'],
+                                    kind='ref' if oracle_mod.have_ref() else 'port')
+    assert_close(rho.ravel()[idx], rr, 'c3 rho subsample')
+    assert_close(drho.reshape(3, -1)[:, idx], dr, 'c3 drho subsample')
+    # additivity: rho(all MOs) = rho(first 40) + rho(rest)
+    qa, qb = qc.copy(), qc.copy()
+    qa.mo_spec = qc.mo_spec[:40]
+    qb.mo_spec = qc.mo_spec[40:]
+    ra, rb = ok.rho_compute(qa), ok.rho_compute(qb)
+    assert_close(ra + rb, rho, 'additivity', rtol=1e-12)
+    d3r = (ax[1] - ax[0]) ** 3
+    assert abs((ra.sum() + rb.sum() - rho.sum()) * d3r) < 1e-8
+    # gradient vs central differences of rho on the vector grid around a few points
+    h = 1e-4
+    p = numpy.stack([xs[:12], ys[:12], zs[:12]])
+    for ax_i in range(3):
+        e = numpy.zeros((3, 1)); e[ax_i] = h
+        set_vector(ok, *(p + e))
+        rp = ok.rho_compute(qc)
+        set_vector(ok, *(p - e))
+        rm = ok.rho_compute(qc)
+        fd = (rp - rm) / (2 * h)
+        assert numpy.allclose(fd, dr[ax_i, :12], rtol=1e-5, atol=1e-7 * numpy.abs(dr).max())

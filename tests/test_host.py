@@ -1,0 +1,236 @@
+"""CPU-only checks of the host side: data-model mirror, grid state, drv parsing, the cart->sph CSR,
+the C ABI surface (library loads and exports every symbol of include/okb200.h; no compute without
+a GPU, and it says so loudly), and the multi-rank sharding logic on gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from conftest import FIXTURES, REPO, golden_qc, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from orbkit_b200 import _lib
+    _lib.build()
+    lib = _lib.load()
+    header = open(os.path.join(REPO, 'include', 'okb200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(okb_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.okb_version() >= 100
+    # scalar helpers are host code and work without a GPU
+    assert lib.okb_aonorm(0, 0, 0, 1.0, 1) == 1.0
+    assert abs(lib.okb_aonorm(0, 0, 0, 1.0, 0) - (2 / numpy.pi) ** 0.75) < 1e-15
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from orbkit_b200 import _lib
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    rc = lib.okb_ctx_create(0, ctypes.byref(ctx))
+    assert rc != 0 and not ctx.value
+    assert b'no CPU fallback' in lib.okb_last_error() or b'CUDA' in lib.okb_last_error()
+    import orbkit_b200 as ok
+    from orbkit_b200 import engine
+    engine.reset_engine()
+    qc, a = golden_qc('nh3_molpro')
+    ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
+    with pytest.raises(RuntimeError):
+        ok.rho_compute(qc)
+    with pytest.raises(RuntimeError):
+        ok.cy_core.mocreator(numpy.zeros((3, 4)), numpy.zeros((2, 3)))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, 'orbkit_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(root, f)).read()
+                assert 'import oracle' not in src and 'okoracle' not in src and 'oracle/' not in src, f
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_data_model_roundtrip(name):
+    """AOClass / MOClass getters reproduce the flat arrays the reference's own classes produced"""
+    qc, a = golden_qc(name)
+    ao = qc.ao_spec
+    for key, getter in [('_assign_cont_to_atoms', ao.get_assign_cont_to_atoms), ('_nprim_per_cont', ao.get_nprim_per_cont),
+                        ('_prim_coeffs', ao.get_prim_coeffs), ('_assign_prim_to_cont', ao.get_assign_prim_to_cont),
+                        ('_lxlylz', ao.get_lxlylz), ('_assign_lxlylz_to_cont', ao.get_assign_lxlylz_to_cont),
+                        ('_nlxlylz_per_cont', ao.get_nlxlylz_per_cont)]:
+        got = getter()
+        assert numpy.array_equal(got, a['ao.' + key]), key
+        assert got.flags['C_CONTIGUOUS'] and got.dtype in (numpy.intc, numpy.float64)
+    assert ao.get_normalized() == int(a['ao.normalized'])
+    assert ao.spherical == bool(a['ao.spherical'])
+    if ao.spherical:
+        assert numpy.array_equal(numpy.array(ao.get_lm()), a['ao._lm'])
+        assert numpy.array_equal(ao.get_assign_lm_to_cont(), a['ao._assign_lm_to_cont'])
+        assert ao.get_ao_num() == len(a['ao._lm'])
+    assert numpy.array_equal(qc.mo_spec.get_coeffs(), a['mo.coeffs'])
+    assert numpy.array_equal(qc.mo_spec.get_occ(), a['mo.occ'])
+    assert qc.mo_spec.get_coeffs().shape[1] == ao.get_ao_num()
+    # list-of-dict <-> flat round trip, copy semantics, equality
+    qc2 = qc.copy()
+    assert qc2 == qc
+    qc2.mo_spec[0]['occ_num'] = 7.5
+    qc2.mo_spec.update()
+    assert qc2.mo_spec.get_occ()[0] == 7.5 and qc.mo_spec.get_occ()[0] != 7.5
+    ao2 = type(ao)(restart=ao.todict())
+    assert ao2 == ao
+
+
+def test_set_lm_dict_order_and_mo_selection():
+    from orbkit_b200 import synth
+    qc = synth.to_qcinfo(synth.make_molecule(n_heavy=1, n_light=0, n_mo=6, seed=1))
+    lm = qc.ao_spec.get_lm()
+    # s, s, s, s, p(1,1),(1,-1),(1,0) ... d: 0,+1,-1,+2,-2  (orbitals.py:303-316)
+    assert lm[:4] == [(0, 0)] * 4 and lm[4:7] == [(1, 1), (1, -1), (1, 0)]
+    d0 = [i for i, t in enumerate(lm) if t[0] == 2][0]
+    assert lm[d0:d0 + 5] == [(2, 0), (2, 1), (2, -1), (2, 2), (2, -2)]
+    mo = qc.mo_spec
+    for i in range(3, 6):
+        mo[i]['occ_num'] = 0.0
+    mo.update()
+    assert mo.get_homo() == 2 and mo.get_lumo() == 3
+    assert list(mo.select('homo-1:lumo+1').get_indices()) == [1, 2, 3]
+    assert len(mo[[0, 5]]) == 2 and len(mo[1:]) == 5 and len(mo.select('all_mo')) == 6
+    assert list(mo['lumo'].get_indices()) == [3]
+    with pytest.raises(ValueError):
+        bad = qc.ao_spec[:]
+        bad[0]['pnum'] = -abs(bad[0]['pnum'])
+        bad.update()
+
+
+def test_validate_drv_and_tables():
+    from orbkit_b200.tools import validate_drv, exp, cart2sph, get_cart2sph, l_deg
+    expect = {None: 0, 'None': 0, '': 0, 'x': 1, 'y': 2, 'z': 3, 'xx': 4, 'x2': 4, 'yy': 5, 'y2': 5, 'zz': 6,
+              'z2': 6, 'xy': 7, 'yx': 7, 'xz': 8, 'zx': 8, 'yz': 9, 'zy': 9}
+    for k, v in expect.items():
+        assert validate_drv(k) == v
+    for i in range(10):
+        assert validate_drv(i) == i        # ints pass through: drv=0 means "no derivative"
+    for bad in ('q', 'xyz', 10, -1, 1.5):
+        with pytest.raises(ValueError):
+            validate_drv(bad)
+    for l in range(5):
+        assert len(exp[l]) == l_deg(l) == (l + 1) * (l + 2) // 2
+        assert len(cart2sph[l]) == l_deg(l, cartesian_basis=False) == 2 * l + 1
+        assert all(sum(t) == l for t in exp[l])
+    assert get_cart2sph(2, 0)[1] == [1., -0.5, -0.5]
+
+
+def test_cart2sph_csr_equals_reference_loop(oracle_mod):
+    """the CSR handed to the device reproduces core.cartesian2spherical on random data"""
+    from orbkit_b200.engine import build_cart2sph_csr
+    rng = numpy.random.default_rng(3)
+    for name in ('h2o_gaussian_sph', 'lih_psi4_sph_f', 'synth_small_sph'):
+        qc, _ = golden_qc(name)
+        ptr, col, val = build_cart2sph_csr(qc.ao_spec)
+        cart = rng.standard_normal((len(qc.ao_spec.get_lxlylz()), 13))
+        ref = oracle_mod.cartesian2spherical(cart, qc.ao_spec)
+        got = numpy.zeros_like(ref)
+        for j in range(len(ptr) - 1):
+            for t in range(ptr[j], ptr[j + 1]):
+                got[j] += val[t] * cart[col[t]]
+        assert numpy.array_equal(got, ref)
+
+
+def test_grid_module_state():
+    from orbkit_b200 import grid, cy_grid
+    grid.reset_grid()
+    grid.min_, grid.max_, grid.N_ = [-1., -2., 0.], [1., 2., 0.], [3, 5, 1]
+    grid.delta_ = numpy.zeros((3, 1))
+    grid.grid_init(force=True)
+    assert grid.get_shape() == (3, 5, 1) and not grid.is_vector and grid.is_regular
+    assert numpy.allclose(grid.x, [-1, 0, 1]) and numpy.allclose(grid.y, [-2, -1, 0, 1, 2]) and grid.z.tolist() == [0.]
+    assert abs(grid.d3r - 1.0) < 1e-15
+    x0, y0, z0 = grid.tolist()
+    grid.grid2vector()
+    assert grid.is_vector and len(grid.x) == 15
+    # x slowest, z fastest (cy_grid.pyx:22-29)
+    assert numpy.array_equal(grid.x, numpy.repeat(x0, 5)) and numpy.array_equal(grid.y, numpy.tile(y0, 3))
+    v = numpy.arange(15.0)
+    assert numpy.array_equal(grid.mv2g(d=v), v.reshape(3, 5, 1))
+    grid.vector2grid(3, 5, 1)
+    assert numpy.array_equal(grid.x, x0) and numpy.array_equal(grid.y, y0) and numpy.array_equal(grid.z, z0)
+    with pytest.raises(ValueError):
+        grid.grid2vector(); grid.vector2grid(2, 5, 1)
+    qc, _ = golden_qc('h2o_molpro_cart')
+    grid.adjust_to_geo(qc, extend=2.0, step=1)
+    grid.grid_init(is_vector=False, force=True)
+    g = load_golden('ref_rho_compute')
+    assert numpy.allclose(grid.x, g['x']) and numpy.allclose(grid.y, g['y']) and numpy.allclose(grid.z, g['z'])
+    out = cy_grid.grid2vector(g['x'], g['y'], g['z'])
+    assert out.shape == (3, 315)
+    back = cy_grid.vector2grid(out[0], out[1], out[2], 5, 9, 7)
+    assert all(numpy.array_equal(p, q) for p, q in zip(back, (g['x'], g['y'], g['z'])))
+    grid.set_grid([0., 1.], [0., 1.], [0., 1.], is_vector=True)
+    assert grid.is_vector and not grid.is_regular and grid.get_shape() == (2,)
+
+
+def test_oracle_grid2vector_matches(oracle_mod):
+    from orbkit_b200 import cy_grid
+    x, y, z = numpy.linspace(0, 1, 3), numpy.linspace(2, 3, 4), numpy.linspace(-1, 0, 5)
+    assert numpy.array_equal(cy_grid.grid2vector(x, y, z), oracle_mod.backend('port').grid2vector(x, y, z))
+
+
+def test_shard_ranges_cover_and_balance():
+    from orbkit_b200.dist import shard_range, shard_sizes, ALIGN
+    for npts in (0, 1, 127, 128, 129, 1000, 200 ** 3, 256 ** 3 + 17):
+        for world in (1, 2, 3, 4, 8):
+            r = shard_sizes(npts, world)
+            assert r[0][0] == 0 and r[-1][1] == npts
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) < 2 * ALIGN
+            assert all(a % ALIGN == 0 for a, _ in r if a < npts)
+
+
+_GLOO_SCRIPT = r'''
+import os, sys, numpy, torch
+import torch.distributed as dist
+sys.path.insert(0, %(repo)r)
+from orbkit_b200 import dist as okdist
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=int(sys.argv[1]), world_size=2)
+rank, world = okdist.rank_world()
+assert okdist.is_distributed() and world == 2
+npts = 1000
+full = numpy.arange(4 * npts, dtype=numpy.float64).reshape(4, npts)
+p0, p1 = okdist.shard_range(npts, rank, world)
+local = torch.from_numpy(full[:, p0:p1].copy())
+got = okdist.gather_points(local, npts).numpy()
+assert numpy.array_equal(got, full), 'gather'
+norm = okdist.all_reduce_sum(numpy.array([1.0 + rank, 2.0]))
+assert numpy.allclose(norm, [3.0, 4.0]), norm
+# one shard empty
+p0, p1 = okdist.shard_range(100, rank, world)
+local = torch.from_numpy(numpy.arange(100.0)[None, p0:p1].copy())
+assert numpy.array_equal(okdist.gather_points(local, 100).numpy()[0], numpy.arange(100.0))
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_world_size_2_gloo_gather_and_allreduce(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / 'gloo_worker.py'
+    script.write_text(_GLOO_SCRIPT % {'repo': REPO, 'port': port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
