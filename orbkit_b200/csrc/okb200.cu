@@ -626,6 +626,21 @@ template <int SET, int MW, int PT, int NW, int SINK>
 static size_t smem_variant(int meta_stride) {
     return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
 }
+template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+static cudaError_t launch_ws(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = okb_ws_kernel<SET, MW, PT, NCW, NST, SINK>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (NCW + 4) * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+static size_t smem_ws(int meta_stride) {
+    return WsCfg<SET, MW, PT, NCW, NST, SINK>::smem_bytes(meta_stride);
+}
+#define OKB_WS(SET, MW, PT, NCW, NST, SINK)                                                              \
+    Variant { "ws/" #SET "/" #SINK "/MW" #MW "xPT" #PT "xNCW" #NCW "xNST" #NST, SET, SINK, MW, PT, NCW, 32 * PT, \
+              NCW * MW, smem_ws<SET, MW, PT, NCW, NST, SINK>, launch_ws<SET, MW, PT, NCW, NST, SINK> }
 #define OKB_VARIANT(SET, MW, PT, NW, SINK)                                                         \
     Variant { #SET "/" #SINK "/MW" #MW "xPT" #PT "xNW" #NW, SET, SINK, MW, PT, NW, 32 * PT, NW * MW, \
               smem_variant<SET, MW, PT, NW, SINK>, launch_variant<SET, MW, PT, NW, SINK> }
@@ -638,22 +653,23 @@ static const Variant g_variants[] = {
     OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
     OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
     OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
-    // value only (D=1)
-    OKB_VARIANT(SET_VAL, 8, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 8, 4, 12, SINK_RHO),
-    OKB_VARIANT(SET_VAL, 7, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 7, 4, 12, SINK_RHO),
-    OKB_VARIANT(SET_VAL, 2, 4, 12, SINK_MO), OKB_VARIANT(SET_VAL, 2, 4, 12, SINK_RHO),
-    OKB_VARIANT(SET_ONE, 8, 4, 12, SINK_MO), OKB_VARIANT(SET_ONE, 2, 4, 12, SINK_MO),
-    // value + gradient (D=4)
-    OKB_VARIANT(SET_GRAD, 8, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 8, 2, 12, SINK_RHO),
-    OKB_VARIANT(SET_GRAD, 7, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 7, 2, 12, SINK_RHO),
-    OKB_VARIANT(SET_GRAD, 2, 2, 12, SINK_MO), OKB_VARIANT(SET_GRAD, 2, 2, 12, SINK_RHO),
-    // value + gradient + pure second derivatives (D=7)
-    OKB_VARIANT(SET_LAP, 8, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 8, 1, 12, SINK_RHO),
-    OKB_VARIANT(SET_LAP, 7, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 7, 1, 12, SINK_RHO),
-    OKB_VARIANT(SET_LAP, 2, 1, 12, SINK_MO), OKB_VARIANT(SET_LAP, 2, 1, 12, SINK_RHO),
-    // all ten codes (D=10)
-    OKB_VARIANT(SET_ALL, 4, 1, 12, SINK_MO), OKB_VARIANT(SET_ALL, 4, 1, 12, SINK_RHO),
-    OKB_VARIANT(SET_ALL, 2, 1, 12, SINK_MO), OKB_VARIANT(SET_ALL, 2, 1, 12, SINK_RHO),
+    // warp-specialised contraction kernels: 8 consumer warps + 4 producer warps, 2 stages
+    // value only (D=1): P = 256 points
+    OKB_WS(SET_VAL, 12, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 12, 8, 8, 2, SINK_RHO),
+    OKB_WS(SET_VAL, 11, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 11, 8, 8, 2, SINK_RHO),
+    OKB_WS(SET_VAL, 3, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 3, 8, 8, 2, SINK_RHO),
+    OKB_WS(SET_ONE, 12, 8, 8, 2, SINK_MO), OKB_WS(SET_ONE, 3, 8, 8, 2, SINK_MO),
+    // value + gradient (D=4): P = 64
+    OKB_WS(SET_GRAD, 12, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 12, 2, 8, 2, SINK_RHO),
+    OKB_WS(SET_GRAD, 11, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 11, 2, 8, 2, SINK_RHO),
+    OKB_WS(SET_GRAD, 3, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 3, 2, 8, 2, SINK_RHO),
+    // value + gradient + pure second derivatives (D=7): P = 32
+    OKB_WS(SET_LAP, 12, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_LAP, 11, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_LAP, 3, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 3, 1, 8, 2, SINK_RHO),
+    // all ten codes (D=10): P = 32
+    OKB_WS(SET_ALL, 6, 1, 8, 2, SINK_MO), OKB_WS(SET_ALL, 6, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_ALL, 3, 1, 8, 2, SINK_MO), OKB_WS(SET_ALL, 3, 1, 8, 2, SINK_RHO),
 };
 
 static const Variant *pick_variant(int set, int sink, int n_mo) {

@@ -508,6 +508,296 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
     }
 }
 
+// ====================================================================================================
+// Warp-specialised variant of the fused kernel (SINK_MO / SINK_RHO).
+//
+// ncu on the first version (profiles/r01_fused_v1.md) showed the FP64 pipe 56% active: all warps ran
+// phase A (latency-bound: exp chains, little ILP) and phase B (pipe-bound) in lock step, so the pipe
+// idled during A and 13% of the stall samples sat on the per-chunk __syncthreads.  Here the two
+// phases run CONCURRENTLY on different warps:
+//   * 4 producer warps (one warpgroup, registers cut to 72 by setmaxnreg) generate AO tiles into a
+//     ring of NST stages and issue the bulk-async copies (chunk tables, coefficient tiles);
+//   * NCW consumer warps (registers raised to 216) contract stage after stage into MW*PT*D register
+//     accumulators and run the epilogues.
+// Stages are handed over with mbarriers (full: 128 producer arrivals; empty: one arrival per
+// consumer warp; cfull: TMA transaction bytes).  There is no CTA-wide barrier in the main loop.
+// ====================================================================================================
+template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+struct WsCfg {
+    static constexpr int D = set_ncodes(SET);
+    static constexpr int P = 32 * PT;
+    static constexpr int MC = NCW * MW;
+    static constexpr int NPW = 4;                              // producer warps
+    static constexpr int NT = (NCW + NPW) * 32;
+    static constexpr int TILE_DOUBLES = D * KC * P;
+    static constexpr int CBUF_DOUBLES = KC * MC;
+    static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;
+    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] cfull[NST] mfull[NMETA]
+    static constexpr size_t OFF_NFN = 256;                     // int nfn[NST]
+    static constexpr size_t OFF_XYZ = 384;
+    static constexpr size_t OFF_RED = OFF_XYZ + (size_t)3 * P * 8;
+    static constexpr size_t OFF_META = OFF_RED + (size_t)(NOUT > 0 ? NCW * NOUT * P * 8 : 0);
+    __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
+        return (OFF_META + (size_t)NMETA * meta_stride + 127) / 128 * 128;
+    }
+    __host__ __device__ static constexpr size_t off_tile(int meta_stride) {
+        return off_cbuf(meta_stride) + (size_t)NST * CBUF_DOUBLES * 8;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
+        return off_tile(meta_stride) + (size_t)NST * TILE_DOUBLES * 8;
+    }
+    static_assert(3 * NST + NMETA <= 32, "barrier area");
+    static_assert(NCW % 4 == 0, "consumer warps must form whole warpgroups (setmaxnreg)");
+};
+
+// register split between the producer warpgroup and the consumer warpgroups (launch: 168/thread at
+// 384 threads; 128*PREG + 256*CREG <= 384*168)
+__host__ __device__ constexpr int ws_preg(int set) {
+    return set == SET_VAL ? 56 : set == SET_GRAD ? 72 : set == SET_LAP ? 104 : set == SET_ALL ? 128 : 88;
+}
+__host__ __device__ constexpr int ws_creg(int set) { return (504 - ws_preg(set)) / 2 / 8 * 8; }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+__global__ void __launch_bounds__((NCW + 4) * 32, 1) okb_ws_kernel(const KParams p) {
+    using C = WsCfg<SET, MW, PT, NCW, NST, SINK>;
+    constexpr int D = C::D, P = C::P, MC = C::MC, NPT = C::NPW * 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint64_t *bar_empty = bar_full + NST;
+    uint64_t *bar_cfull = bar_empty + NST;
+    uint64_t *bar_mfull = bar_cfull + NST;
+    int *nfn_s = reinterpret_cast<int *>(smem + C::OFF_NFN);
+    double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
+    double *ys = xs + P, *zs = ys + P;
+    double *red = reinterpret_cast<double *>(smem + C::OFF_RED);
+    unsigned char *mbase = smem + C::OFF_META;
+    double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
+    double *tbase = reinterpret_cast<double *>(smem + C::off_tile(p.lay.stride));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&bar_full[i], NPT);
+            mbar_init(&bar_empty[i], NCW);
+            mbar_init(&bar_cfull[i], 1);
+        }
+        for (int i = 0; i < NMETA; ++i) mbar_init(&bar_mfull[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t meta_bytes = (uint32_t)p.lay.stride;
+    constexpr uint32_t cbuf_bytes = (uint32_t)C::CBUF_DOUBLES * 8u;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t per_tile = (uint32_t)p.n_mtile * (uint32_t)p.nchunk;
+    const uint32_t total = (uint32_t)my_tiles * per_tile;       // chunk passes of this CTA
+
+    if (warp >= NCW) {
+        // ================================ producers =================================================
+        reg_dec<ws_preg(SET)>();
+        const int ptid = tid - NCW * 32, pwarp = warp - NCW;
+        auto issue_meta = [&](uint32_t gc) {
+            uint64_t *bar = &bar_mfull[gc % NMETA];
+            mbar_expect_tx(bar, meta_bytes);
+            bulk_g2s(mbase + (size_t)(gc % NMETA) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes,
+                     meta_bytes, bar);
+        };
+        if (ptid == 0)
+            for (uint32_t i = 0; i < NMETA && i < total; ++i) issue_meta(i);
+        uint32_t g = 0;
+        for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
+            const int q0 = tile_id * P;
+            named_bar(1, NPT);                        // previous tile's items no longer read xs/ys/zs
+            for (int e = ptid; e < P; e += NPT) {
+                int q = q0 + e;
+                if (q >= p.npts) q = p.npts - 1;
+                const long long n = p.p0 + q;
+                if (p.grid_kind == 0) {
+                    const long long nyz = (long long)p.ny * p.nz;
+                    const long long i = n / nyz, rem = n - i * nyz;
+                    const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
+                    xs[e] = p.gx[i]; ys[e] = p.gy[j]; zs[e] = p.gz[k];
+                } else {
+                    xs[e] = p.gx[n]; ys[e] = p.gy[n]; zs[e] = p.gz[n];
+                }
+            }
+            named_bar(1, NPT);
+            for (int mt = 0; mt < p.n_mtile; ++mt)
+                for (int c = 0; c < p.nchunk; ++c, ++g) {
+                    const int s = g % NST;
+                    const uint32_t round = g / NST;
+                    mbar_wait(&bar_mfull[g % NMETA], (g / NMETA) & 1);
+                    mbar_wait(&bar_empty[s], (round & 1) ^ 1);          // consumers released the stage
+                    if (ptid == 0) {
+                        mbar_expect_tx(&bar_cfull[s], cbuf_bytes);
+                        bulk_g2s(cbase + (size_t)s * C::CBUF_DOUBLES,
+                                 p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES, cbuf_bytes, &bar_cfull[s]);
+                    }
+                    const unsigned char *mb = mbase + (size_t)(g % NMETA) * meta_bytes;
+                    const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
+                    const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
+                    const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
+                    const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+                    double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
+                    const int nitems = hdr.nshell * PT;
+                    for (int item = pwarp; item < nitems; item += C::NPW) {
+                        const int sh = item / PT, pt = (item % PT) * 32 + lane;
+                        gen_shell<SET, P>(shells[sh], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt, p.one_code,
+                                          p.exact_mixed);
+                    }
+                    if (ptid == 0) nfn_s[s] = hdr.nfn;
+                    mbar_arrive(&bar_full[s]);                           // release: tile + nfn visible
+                    named_bar(1, NPT);                                   // chunk table no longer read
+                    if (ptid == 0 && g + NMETA < total) issue_meta(g + NMETA);
+                }
+        }
+    } else {
+        // ================================ consumers =================================================
+        reg_inc<ws_creg(SET)>();
+        uint32_t g = 0;
+        for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
+            const int q0 = tile_id * P;
+            double osum[C::NOUT > 0 ? C::NOUT : 1][PT];
+            if (SINK == SINK_RHO) {
+#pragma unroll
+                for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) osum[o][j] = 0.0;
+            }
+            for (int mt = 0; mt < p.n_mtile; ++mt) {
+                double acc[MW][PT][D];
+#pragma unroll
+                for (int i = 0; i < MW; ++i)
+#pragma unroll
+                    for (int j = 0; j < PT; ++j)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc[i][j][d] = 0.0;
+                for (int c = 0; c < p.nchunk; ++c, ++g) {
+                    const int s = g % NST;
+                    const uint32_t par = (g / NST) & 1;
+                    mbar_wait(&bar_full[s], par);
+                    mbar_wait(&bar_cfull[s], par);
+                    const int nfn = nfn_s[s];
+                    const double *cs = cbase + (size_t)s * C::CBUF_DOUBLES + warp * MW;
+                    const double *tl = tbase + (size_t)s * C::TILE_DOUBLES + lane;
+#pragma unroll 2
+                    for (int k = 0; k < nfn; ++k) {
+                        double cv[MW];
+                        if (MW % 2 == 0) {
+#pragma unroll
+                            for (int i = 0; i < MW; i += 2) {
+                                const double2 c2 = *reinterpret_cast<const double2 *>(cs + (size_t)k * MC + i);
+                                cv[i] = c2.x;
+                                cv[i + 1] = c2.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < MW; ++i) cv[i] = cs[(size_t)k * MC + i];
+                        }
+#pragma unroll
+                        for (int d = 0; d < D; ++d)
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) {
+                                const double a = tl[((size_t)d * KC + k) * P + j * 32];
+#pragma unroll
+                                for (int i = 0; i < MW; ++i) acc[i][j][d] = fma(cv[i], a, acc[i][j][d]);
+                            }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_empty[s]);
+                }
+                // ---- per-MO-tile epilogues ---------------------------------------------------------
+                if (SINK == SINK_MO) {
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        const int mo = mt * MC + warp * MW + i;
+                        if (mo >= p.n_mo) continue;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const int code = (SET == SET_ONE) ? p.one_code : d;
+                            const int sl = p.slot[code];
+                            if (sl < 0) continue;
+                            double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)mo * p.ld + q0;
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) {
+                                const int pt = j * 32 + lane;
+                                if (q0 + pt < p.npts) orow[pt] = acc[i][j][d];
+                            }
+                        }
+                    }
+                }
+                if (SINK == SINK_RHO) {
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        const int mo = mt * MC + warp * MW + i;
+                        const double oc = p.occ[mo];
+                        double nrm = 0.0;
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) {
+                            const double phi = acc[i][j][0];
+                            if ((q0 + j * 32 + lane) < p.npts) nrm += phi * phi;
+                            osum[0][j] += oc * (phi * phi);
+                            if (D >= 4) {
+                                const double o2 = oc * 2.0;
+                                osum[1][j] += o2 * (acc[i][j][1] * phi);
+                                osum[2][j] += o2 * (acc[i][j][2] * phi);
+                                osum[3][j] += o2 * (acc[i][j][3] * phi);
+                                if (D >= 7) {
+                                    osum[4][j] += o2 * (acc[i][j][4] * phi + acc[i][j][1] * acc[i][j][1]);
+                                    osum[5][j] += o2 * (acc[i][j][5] * phi + acc[i][j][2] * acc[i][j][2]);
+                                    osum[6][j] += o2 * (acc[i][j][6] * phi + acc[i][j][3] * acc[i][j][3]);
+                                }
+                                if (D >= 10) {
+                                    osum[7][j] += o2 * (acc[i][j][7] * phi + acc[i][j][1] * acc[i][j][2]);
+                                    osum[8][j] += o2 * (acc[i][j][8] * phi + acc[i][j][1] * acc[i][j][3]);
+                                    osum[9][j] += o2 * (acc[i][j][9] * phi + acc[i][j][2] * acc[i][j][3]);
+                                }
+                            }
+                        }
+                        if (p.mo_norm != nullptr && mo < p.n_mo) {
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, off);
+                            if (lane == 0) atomicAdd(p.mo_norm + mo, nrm);
+                        }
+                    }
+                }
+            }   // mt
+            if (SINK == SINK_RHO) {
+                // cross-warp reduction among the consumer warps (own scratch; producers run ahead)
+#pragma unroll
+                for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) red[((size_t)warp * C::NOUT + o) * P + j * 32 + lane] = osum[o][j];
+                named_bar(2, NCW * 32);
+                for (int e = tid; e < C::NOUT * P; e += NCW * 32) {
+                    const int o = e / P, pt = e - o * P;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NCW; ++w) sum += red[((size_t)w * C::NOUT + o) * P + pt];
+                    if (q0 + pt < p.npts) {
+                        if (o == 0) {
+                            if (p.rho != nullptr) p.rho[q0 + pt] = sum;
+                        } else {
+                            const int sl = p.slot[o];
+                            if (sl >= 0) p.delta[(size_t)sl * p.ld + q0 + pt] = sum;
+                        }
+                    }
+                }
+                named_bar(2, NCW * 32);
+            }
+        }
+    }
+}
+
 // ---- plain FP64 GEMM for the cy_core.mocreator drop-in: mo[M][N] = Cm[M][K] * ao[K][N] -----------
 // 64 x 64 output tile per CTA (256 threads, 4x4 register tile), K stepped by 16 through smem.
 __global__ void __launch_bounds__(256) okb_mocreator_kernel(const double *__restrict__ ao,

@@ -95,8 +95,8 @@ def set_grid(xnew, ynew, znew, is_vector):
 
 def set_boundaries(is_regular, Nx=None, Ny=None, Nz=None):
     global min_, max_, delta_, N_
-    min_ = [x.min(), y.min(), z.min()]
-    max_ = [x.max(), y.max(), z.max()]
+    min_ = [v.min() if len(v) else 0.0 for v in (x, y, z)]
+    max_ = [v.max() if len(v) else 0.0 for v in (x, y, z)]
     N_ = [len(x), len(y), len(z)]
     if is_regular:
         f = lambda v: 1.0 if len(v) <= 1 else v[1] - v[0]
