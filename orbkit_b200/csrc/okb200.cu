@@ -8,12 +8,14 @@
 //   * cut the shells into chunks of <= KC functions and pack one fixed-stride table blob per chunk
 //     (a single bulk-async copy per chunk in the kernel);
 //   * fold the Cartesian->spherical rows into the MO coefficients (C' = C T, the transform is linear)
-//     and lay C' out as [mo-tile][chunk][KC][MC] so that each (tile, chunk) is one contiguous TMA copy;
+//     and lay C' out as [mo-tile][chunk][KC][CS] (CS = MC padded to 4 mod 16) so that each (tile, chunk) is
+//     one contiguous TMA copy and the DMMA fragment loads are bank-conflict free;
 //   * slab the point range, launch, and stream results back to host buffers.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -22,7 +24,10 @@
 #include <vector>
 
 #include "../../include/okb200.h"
-#include "okb_kernels.cuh"
+#include "okb_common.cuh"
+#include "okb_tile_kernel.cuh"
+#include "okb_ws.cuh"
+#include "okb_misc.cuh"
 
 using namespace okb;
 
@@ -282,6 +287,16 @@ static int basis_build_chunks(okb_basis *b) {
     return OKB_OK;
 }
 
+// functions in the default (Molden) order of tools.exp[L]?  Those shells take the straight-line AO code.
+static bool shell_is_standard(const DevShell &sh) {
+    if (sh.L < 0 || sh.L > 4 || (int)sh.fn_row.size() != std_nfn(sh.L)) return false;
+    for (int j = 0; j < std_nfn(sh.L); ++j) {
+        const int e = std_lxyz(sh.L, j);
+        if (sh.lx[j] != (e & 15) || sh.ly[j] != ((e >> 4) & 15) || sh.lz[j] != ((e >> 8) & 15)) return false;
+    }
+    return true;
+}
+
 static int basis_upload(okb_basis *b) {
     // output rows per chunk (SINK_AO): Cartesian identity rows or the spherical CSR rows
     const int nchunk = (int)b->chunks.size();
@@ -340,6 +355,7 @@ static int basis_upload(okb_basis *b) {
             m.prim_off = po; m.nprim = (int)sh.alpha.size();
             m.fn_off = fo; m.nfn = (int)sh.fn_row.size();
             m.L = sh.L;
+            m.kind = shell_is_standard(sh) ? 1 : 0;
             sm[s - ch.s0] = m;
             for (size_t i = 0; i < sh.alpha.size(); ++i) pm[po++] = make_double2(sh.alpha[i], sh.cn[i]);
             for (size_t j = 0; j < sh.fn_row.size(); ++j)
@@ -497,15 +513,16 @@ static int mo_blob(okb_mo *m, int MC, okb_mo::Blob **out) {
     okb_basis *b = m->basis;
     const int nchunk = (int)b->chunks.size();
     const int n_mtile = (m->n_mo + MC - 1) / MC;
-    std::vector<double> blob((size_t)n_mtile * nchunk * KC * MC, 0.0);
+    const int CS = pad_stride(MC);           // row stride = 4 (mod 16) doubles: conflict-free MMA fragment loads
+    std::vector<double> blob((size_t)n_mtile * nchunk * KC * CS, 0.0);
     for (int mt = 0; mt < n_mtile; ++mt)
         for (int c = 0; c < nchunk; ++c) {
-            double *dst = blob.data() + ((size_t)mt * nchunk + c) * KC * MC;
+            double *dst = blob.data() + ((size_t)mt * nchunk + c) * KC * CS;
             for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
                 const int row = b->fn_row[b->chunks[c].k0 + kk];
                 for (int i = 0; i < MC; ++i) {
                     const int mo = mt * MC + i;
-                    if (mo < m->n_mo) dst[(size_t)kk * MC + i] = m->ccart[(size_t)mo * b->n_cart + row];
+                    if (mo < m->n_mo) dst[(size_t)kk * CS + i] = m->ccart[(size_t)mo * b->n_cart + row];
                 }
             }
         }
@@ -626,21 +643,22 @@ template <int SET, int MW, int PT, int NW, int SINK>
 static size_t smem_variant(int meta_stride) {
     return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
 }
-template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
 static cudaError_t launch_ws(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = okb_ws_kernel<SET, MW, PT, NCW, NST, SINK>;
+    auto kern = okb_ws_kernel<SET, AM, BN, WM, WN, NST, SINK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, (NCW + 4) * 32, smem, st>>>(p);
+    kern<<<grid, 384, smem, st>>>(p);
     return cudaGetLastError();
 }
-template <int SET, int MW, int PT, int NCW, int NST, int SINK>
+template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
 static size_t smem_ws(int meta_stride) {
-    return WsCfg<SET, MW, PT, NCW, NST, SINK>::smem_bytes(meta_stride);
+    return WsCfg<SET, AM, BN, WM, WN, NST, SINK>::smem_bytes(meta_stride);
 }
-#define OKB_WS(SET, MW, PT, NCW, NST, SINK)                                                              \
-    Variant { "ws/" #SET "/" #SINK "/MW" #MW "xPT" #PT "xNCW" #NCW "xNST" #NST, SET, SINK, MW, PT, NCW, 32 * PT, \
-              NCW * MW, smem_ws<SET, MW, PT, NCW, NST, SINK>, launch_ws<SET, MW, PT, NCW, NST, SINK> }
+#define OKB_WS(SET, AM, BN, WM, WN, NST, SINK)                                                              \
+    Variant { "ws-dmma/" #SET "/" #SINK "/AM" #AM "xBN" #BN "xWM" #WM "xWN" #WN "xNST" #NST, SET, SINK, AM, BN, WM * WN, \
+              8 * BN * WN, 8 * AM * WM, smem_ws<SET, AM, BN, WM, WN, NST, SINK>,                             \
+              launch_ws<SET, AM, BN, WM, WN, NST, SINK> }
 #define OKB_VARIANT(SET, MW, PT, NW, SINK)                                                         \
     Variant { #SET "/" #SINK "/MW" #MW "xPT" #PT "xNW" #NW, SET, SINK, MW, PT, NW, 32 * PT, NW * MW, \
               smem_variant<SET, MW, PT, NW, SINK>, launch_variant<SET, MW, PT, NW, SINK> }
@@ -653,23 +671,25 @@ static const Variant g_variants[] = {
     OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
     OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
     OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
-    // warp-specialised contraction kernels: 8 consumer warps + 4 producer warps, 2 stages
-    // value only (D=1): P = 256 points
-    OKB_WS(SET_VAL, 12, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 12, 8, 8, 2, SINK_RHO),
-    OKB_WS(SET_VAL, 11, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 11, 8, 8, 2, SINK_RHO),
-    OKB_WS(SET_VAL, 3, 8, 8, 2, SINK_MO), OKB_WS(SET_VAL, 3, 8, 8, 2, SINK_RHO),
-    OKB_WS(SET_ONE, 12, 8, 8, 2, SINK_MO), OKB_WS(SET_ONE, 3, 8, 8, 2, SINK_MO),
+    // warp-specialised DMMA contraction kernels: 4 producer warps + 8 consumer warps (WM x WN), NST stages.
+    // MO tile MC = 8*AM*WM, point tile P = 8*BN*WN, accumulators per thread 2*AM*BN*D doubles.
+    // value only (D=1): P = 256
+    OKB_WS(SET_VAL, 11, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 11, 4, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_VAL, 12, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 12, 4, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_VAL, 3, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 3, 4, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_ONE, 12, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_ONE, 3, 4, 1, 8, 2, SINK_MO),
     // value + gradient (D=4): P = 64
-    OKB_WS(SET_GRAD, 12, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 12, 2, 8, 2, SINK_RHO),
-    OKB_WS(SET_GRAD, 11, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 11, 2, 8, 2, SINK_RHO),
-    OKB_WS(SET_GRAD, 3, 2, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 3, 2, 8, 2, SINK_RHO),
-    // value + gradient + pure second derivatives (D=7): P = 32
-    OKB_WS(SET_LAP, 12, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_LAP, 11, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_LAP, 3, 1, 8, 2, SINK_MO), OKB_WS(SET_LAP, 3, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_GRAD, 11, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_GRAD, 12, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_GRAD, 3, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 8, 2, SINK_RHO),
+    // one consumer warpgroup + two producer warpgroups: P = 32, 3 stages
+    OKB_WS(SET_GRAD, 11, 1, 1, 4, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 3, SINK_RHO),
+    // value + gradient + pure second derivatives (D=7): P = 32, two warp rows of MOs
+    OKB_WS(SET_LAP, 6, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_LAP, 6, 1, 2, 4, 2, SINK_RHO),
+    OKB_WS(SET_LAP, 2, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_LAP, 2, 1, 2, 4, 2, SINK_RHO),
     // all ten codes (D=10): P = 32
-    OKB_WS(SET_ALL, 6, 1, 8, 2, SINK_MO), OKB_WS(SET_ALL, 6, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_ALL, 3, 1, 8, 2, SINK_MO), OKB_WS(SET_ALL, 3, 1, 8, 2, SINK_RHO),
+    OKB_WS(SET_ALL, 4, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_ALL, 4, 1, 2, 4, 2, SINK_RHO),
+    OKB_WS(SET_ALL, 1, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_ALL, 1, 1, 2, 4, 2, SINK_RHO),
 };
 
 static const Variant *pick_variant(int set, int sink, int n_mo) {
@@ -679,8 +699,10 @@ static const Variant *pick_variant(int set, int sink, int n_mo) {
         if (v.set != set || v.sink != sink) continue;
         if (sink == SINK_AO) return &v;
         const long long padded = (long long)((n_mo + v.MC - 1) / v.MC) * v.MC;
-        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations)
-        const long long cost = padded * 1000 - v.MC;
+        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations); the number
+        // of consumer warps (4 by default) can be forced with OKB_WS_NCW for A/B measurements
+        static const int want_ncw = getenv("OKB_WS_NCW") ? atoi(getenv("OKB_WS_NCW")) : 4;
+        const long long cost = padded * 1000 - v.MC + (v.NW == want_ncw ? 0 : 500);
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;

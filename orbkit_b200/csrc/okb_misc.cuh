@@ -1,0 +1,92 @@
+// okb_misc.cuh -- FP64 GEMM behind the cy_core.mocreator drop-in and the FP64 peak microbenchmarks.
+#pragma once
+#include "okb_common.cuh"
+
+namespace okb {
+
+// ---- plain FP64 GEMM for the cy_core.mocreator drop-in: mo[M][N] = Cm[M][K] * ao[K][N] -----------
+// 64 x 64 output tile per CTA (256 threads, 4x4 register tile), K stepped by 16 through smem.
+__global__ void __launch_bounds__(256) okb_mocreator_kernel(const double *__restrict__ ao,
+                                                            const double *__restrict__ cm,
+                                                            double *__restrict__ mo, int M, int K,
+                                                            long long N) {
+    __shared__ double sa[16][64 + 1];   // ao tile  [k][n]
+    __shared__ double sc[16][64 + 1];   // coef tile [k][m]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long n0 = (long long)blockIdx.x * 64;
+    const int m0 = blockIdx.y * 64;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e >> 6, nn = e & 63;
+            const long long n = n0 + nn;
+            sa[kk][nn] = (k0 + kk < K && n < N) ? ao[(size_t)(k0 + kk) * N + n] : 0.0;
+            const int mm = e >> 4, k2 = e & 15;
+            sc[k2][mm] = (m0 + mm < M && k0 + k2 < K) ? cm[(size_t)(m0 + mm) * K + k0 + k2] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = sa[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = sc[kk][ty + 16 * i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(c[i], a[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long n = n0 + tx + 16 * j;
+            if (n < N) mo[(size_t)m * N + n] = acc[i][j];
+        }
+    }
+}
+
+
+// ---- FP64 peak microbenchmarks (roofline denominators measured on the box) ------------
+// kind 0: DFMA issue-bound (8 independent chains per thread)
+// kind 1: DMMA mma.sync.m8n8k4.f64 (8 independent accumulator tiles per warp)
+// kind 2: even warps DFMA, odd warps DMMA (do the two share the FP64 datapath?)
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256) okb_fp64_peak_kernel(double *sink, int iters, int kind) {
+    const int warp = threadIdx.x >> 5;
+    double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 1e-3 * i;
+    const bool use_mma = (kind == 1) || (kind == 2 && (warp & 1));
+    if (!use_mma) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) dmma884(acc[i], acc[i + 1], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 12345.678) sink[0] = s;   // keep the chains alive
+}
+
+}  // namespace okb

@@ -1,0 +1,172 @@
+// okb_shell.cuh -- fast AO generation for shells in the standard (Molden) Cartesian order.
+//
+// The generic gen_shell (okb_common.cuh) decodes (lx,ly,lz) at run time and rebuilds every power per
+// function: ncu showed ~390 warp instructions per (shell, 32 points) item, 70% of them integer /
+// branch overhead.  Almost every shell of every input uses the default order of tools.exp[L]
+// (orbkit/tools.py:118-135); for those the exponents are compile-time constants and the item becomes
+// straight-line code: powers by multiplication once per shell, per-axis factor tables
+//     g0[l] = r^l
+//     g1[l] = l r^(l-1) R0 - 2 r^(l+1) R1                           (d/dr of r^l e^{-a r^2}, summed over primitives)
+//     g2[l] = r^l (4 r^2 R2 - (4l+2) R1) + l(l-1) r^(l-2) R0        (d2/dr2)
+// and 3..9 multiplications per function.  Shells with any other ordering (wfn f order, explicit
+// lxlylz) and the SET_ALL / SET_ONE requests keep the generic path.
+//
+// exp(-t) is evaluated by exp_neg(): k = round(-t*4/ln2), Cody-Waite reduction to |r| <= ln2/8,
+// degree-9 Taylor polynomial (truncation 6.5e-18), 2^(k/4) by selects + exponent add.  Relative error
+// ~3e-16; results below the normal range (t > 708, values < 3.3e-308) are flushed to 0.
+#pragma once
+#include "okb_common.cuh"
+
+namespace okb {
+
+__device__ __forceinline__ double exp_neg(double t) {
+    // e^{-t}, 0 <= t < 708
+    const double x = -t;
+    const double MAGIC = 6755399441055744.0;                 // 2^52 + 2^51: round-to-nearest-integer
+    double kd = fma(x, 5.7707801635558535, MAGIC);           // 4/ln2
+    const int ki = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -1.7328679509228095e-01, x);          // ln2/4 high part (fdlibm ln2_hi / 4)
+    r = fma(kd, -4.7705373231764692e-11, r);                 // ln2/4 low part
+    double p = 2.7557319223985893e-06;                       // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);
+    p = fma(p, r, 1.9841269841269841e-04);
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int j = ki & 3;
+    const double s = (j & 2) ? ((j & 1) ? 1.6817928305074290 : 1.4142135623730951)
+                             : ((j & 1) ? 1.1892071150027210 : 1.0);
+    p *= s;
+    const int m = ki >> 2;                                   // arithmetic shift: floor(k/4)
+    return __hiloint2double(__double2hiint(p) + (m << 20), __double2loint(p));
+}
+
+// Molden order of the Cartesian exponents, packed lx | ly<<4 | lz<<8 (tools.py:118-135)
+__host__ __device__ constexpr int std_lxyz(int L, int j) {
+    constexpr int T0[1] = {0x000};
+    constexpr int T1[3] = {0x001, 0x010, 0x100};
+    constexpr int T2[6] = {0x002, 0x020, 0x200, 0x011, 0x101, 0x110};
+    constexpr int T3[10] = {0x003, 0x030, 0x300, 0x021, 0x012, 0x102, 0x201, 0x210, 0x120, 0x111};
+    constexpr int T4[15] = {0x004, 0x040, 0x400, 0x013, 0x103, 0x031, 0x130, 0x301, 0x310,
+                            0x022, 0x202, 0x220, 0x112, 0x121, 0x211};
+    return L == 0 ? T0[j] : L == 1 ? T1[j] : L == 2 ? T2[j] : L == 3 ? T3[j] : T4[j];
+}
+__host__ __device__ constexpr int std_nfn(int L) { return (L + 1) * (L + 2) / 2; }
+
+// radial sums over the primitives of one shell: R0 = sum cN e, R1 = sum cN a e, R2 = sum cN a^2 e
+template <bool N1, bool N2, bool FAST_EXP>
+__device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *__restrict__ prims, double rr,
+                                            double &R0, double &R1, double &R2) {
+    R0 = R1 = R2 = 0.0;
+    const double2 *pp = prims + sh.prim_off;
+    for (int i = 0; i < sh.nprim; ++i) {
+        const double2 ac = pp[i];
+        const double arg = ac.x * rr;
+        if (FAST_EXP) {
+            if (__any_sync(0xffffffffu, arg < 708.0)) {
+                const double t = (arg < 708.0) ? ac.y * exp_neg(arg) : 0.0;
+                R0 += t;
+                if (N1) {
+                    const double ta = t * ac.x;
+                    R1 += ta;
+                    if (N2) R2 = fma(ta, ac.x, R2);
+                }
+            }
+        } else if (__any_sync(0xffffffffu, arg < 746.0)) {   // exp(-arg) == 0.0 exactly beyond 745.14
+            const double t = ac.y * exp(-arg);
+            R0 += t;
+            if (N1) {
+                const double ta = t * ac.x;
+                R1 += ta;
+                if (N2) R2 += ta * ac.x;
+            }
+        }
+    }
+}
+
+template <int SET, int L, int STRIDE>
+__device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
+                                              const FnMeta *__restrict__ fns, double x, double y, double z,
+                                              double *__restrict__ tp) {
+    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP, "specialised sets");
+    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP);
+    const double r[3] = {x - sh.cx, y - sh.cy, z - sh.cz};
+    const double rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double R0, R1, R2;
+    radial_sums<N1, N2, true>(sh, prims, rr, R0, R1, R2);
+    // per-axis factor tables (all indices are compile-time constants after unrolling)
+    double g0[3][L + 2], g1[3][L + 1], g2[3][L + 1];
+    const double m2R1 = -2.0 * R1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        g0[a][0] = 1.0;
+#pragma unroll
+        for (int l = 1; l <= L + 1; ++l) g0[a][l] = g0[a][l - 1] * r[a];
+        if (N1) {
+#pragma unroll
+            for (int l = 0; l <= L; ++l)
+                g1[a][l] = (l == 0) ? g0[a][1] * m2R1 : fma(g0[a][l + 1], m2R1, g0[a][l - 1] * ((double)l * R0));
+        }
+        if (N2) {
+            const double r2R2 = 4.0 * (r[a] * r[a]) * R2;
+#pragma unroll
+            for (int l = 0; l <= L; ++l) {
+                const double t = g0[a][l] * fma((double)(-(4 * l + 2)), R1, r2R2);
+                g2[a][l] = (l < 2) ? t : fma(g0[a][l - 2], (double)(l * (l - 1)) * R0, t);
+            }
+        }
+    }
+    const FnMeta *ff = fns + sh.fn_off;
+    double *o = tp + (size_t)sh.fn_off * STRIDE;
+#pragma unroll
+    for (int j = 0; j < std_nfn(L); ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int e = std_lxyz(L, j);
+        const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
+        const double f = ff[j].f;
+        const double fz = f * g0[2][lz];
+        const double fyz = fz * g0[1][ly];
+        o[(size_t)j * STRIDE] = fyz * (R0 * g0[0][lx]);
+        if (N1) {
+            const double fxz = fz * g0[0][lx];
+            const double fxy = f * (g0[0][lx] * g0[1][ly]);
+            o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
+            o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
+            o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
+            if (N2) {
+                o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
+                o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
+                o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+            }
+        }
+    }
+}
+
+// dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one
+template <int SET, int STRIDE>
+__device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2 *__restrict__ prims,
+                                              const FnMeta *__restrict__ fns, double x, double y, double z,
+                                              double *__restrict__ tp, int one_code, int exact) {
+    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) {
+        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) ? SET : SET_VAL;
+        if (sh.kind == 1) {                  // warp-uniform
+            switch (sh.L) {
+                case 0: gen_shell_std<S, 0, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                case 1: gen_shell_std<S, 1, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                case 2: gen_shell_std<S, 2, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                case 3: gen_shell_std<S, 3, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                case 4: gen_shell_std<S, 4, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                default: break;
+            }
+        }
+    }
+    gen_shell<SET, STRIDE>(sh, prims, fns, x, y, z, tp, one_code, exact);
+}
+
+}  // namespace okb

@@ -1,0 +1,340 @@
+// okb_ws.cuh -- warp-specialised fused kernel for SINK_MO / SINK_RHO: AO generation and the FP64
+// contraction run CONCURRENTLY on different warps of one persistent CTA per SM.
+//
+// Why (measured, profiles/r01_*): in the phase-serial kernel the FP64 pipe was 56% active -- all warps
+// did the latency-bound AO generation together, then the pipe-bound contraction together.  With
+// DFMA consumers the pipe reached 67%: DFMA with varying operands issues at 2.44 cycles/instruction
+// (30 TFLOP/s) and the MW x PT x D register tile needed an LDS per 4.6 DFMA.  scripts/fp64_micro.cu
+// shows DMMA (mma.sync.m8n8k4.f64) sustaining 37.1 TFLOP/s = 16.0 cycles per instruction per SM
+// sub-partition with two warps, 8x fewer issue slots than DFMA and the same 64 lanes/SM datapath.
+// So the contraction uses DMMA; the FP64 tensor path of sm_100a is mma.sync (tcgen05 has no f64 kind).
+//
+//   producers  4 warps (one warpgroup, registers cut by setmaxnreg): evaluate (shell, 32 points) items
+//              of chunk g into stage g % NST of the AO tile ring, zero the k-padding rows, issue the
+//              bulk-async (TMA) copies of the chunk tables and of the coefficient tile of the stage.
+//   consumers  8 warps (registers raised by setmaxnreg) arranged WM x WN: warp (wm, wn) owns MO blocks
+//              [wm*AM, (wm+1)*AM) x point blocks [wn*BN, (wn+1)*BN) (blocks of 8), i.e. an
+//              (8 AM) x (8 BN) x D register tile of 2*AM*BN*D doubles per thread.  Per k-step of 4:
+//              AM + D*BN conflict-free LDS.64 feed AM*BN*D DMMAs.
+//   hand-over  mbarriers: full[s] (128 producer arrivals), cfull[s] (TMA bytes), empty[s] (one arrival
+//              per consumer warp).  No CTA-wide barrier in the main loop.
+//
+// mma.m8n8k4 operand mapping (lane T):  A[m][k] = C'[mo0 + T/4][k0 + T%4]   (row-major 8x4)
+//                                       B[k][n] = ao[d][k0 + T%4][pt0 + T/4] (col-major 4x8)
+//                                       C[m][n] : m = T/4, n = 2*(T%4) + {0,1}
+// Shared-memory rows are padded to a stride = 4 (mod 16) doubles so that both fragment loads touch
+// 32 distinct 8-byte words per half-warp (2 wavefronts per LDS.64, the minimum).
+#pragma once
+#include "okb_shell.cuh"
+
+namespace okb {
+
+__host__ __device__ constexpr int pad_stride(int n) { return n + ((4 - (n % 16)) + 16) % 16; }
+
+template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
+struct WsCfg {
+    static constexpr int D = set_ncodes(SET);
+    static constexpr int NCW = WM * WN;                        // consumer warps
+    static constexpr int NPW = 12 - WM * WN;                   // producer warps (4 or 8; 12 warps per CTA)
+    static constexpr int P = 8 * BN * WN;                      // points per CTA tile
+    static constexpr int PT = P / 32;
+    static constexpr int MC = 8 * AM * WM;                     // MOs per CTA tile
+    static constexpr int PS = pad_stride(P);                   // AO tile row stride (doubles)
+    static constexpr int CS = pad_stride(MC);                  // coefficient tile row stride (doubles)
+    static constexpr int NT = (NCW + NPW) * 32;
+    static constexpr int TILE_DOUBLES = D * KC * PS;
+    static constexpr int CBUF_DOUBLES = KC * CS;
+    static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;
+    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] cfull[NST] mfull[NMETA]
+    static constexpr size_t OFF_NFN = 256;                     // int nfn[NST]
+    static constexpr size_t OFF_XYZ = 384;
+    static constexpr size_t OFF_RED = OFF_XYZ + (size_t)3 * P * 8;
+    static constexpr size_t OFF_META = OFF_RED + (size_t)(NOUT > 0 ? WM * NOUT * P * 8 : 0);
+    __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
+        return (OFF_META + (size_t)NMETA * meta_stride + 127) / 128 * 128;
+    }
+    __host__ __device__ static constexpr size_t off_tile(int meta_stride) {
+        return off_cbuf(meta_stride) + (size_t)NST * CBUF_DOUBLES * 8;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
+        return off_tile(meta_stride) + (size_t)NST * TILE_DOUBLES * 8;
+    }
+    static_assert(3 * NST + NMETA <= 32, "barrier area");
+    static_assert(NCW == 8 || NCW == 4, "one or two consumer warpgroups");
+    static_assert(P % 32 == 0, "whole warps of points for the producers");
+};
+
+// register split between producer and consumer warpgroups (launch: 168/thread at 384 threads, i.e.
+// 504 registers per thread-triple): NCW = 8: 1 producer + 2 consumer warpgroups, PREG + 2 CREG <= 504;
+// NCW = 4: 2 producer + 1 consumer warpgroups, 2 PREG + CREG <= 504.
+__host__ __device__ constexpr int ws_preg(int set, int ncw) {
+    return ncw == 4 ? 136
+                    : (set == SET_VAL ? 56 : set == SET_GRAD ? 72 : set == SET_LAP ? 104 : set == SET_ALL ? 128 : 88);
+}
+__host__ __device__ constexpr int ws_creg(int set, int ncw) {
+    return ncw == 4 ? 232 : (504 - ws_preg(set, ncw)) / 2 / 8 * 8;
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
+__global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
+    using C = WsCfg<SET, AM, BN, WM, WN, NST, SINK>;
+    constexpr int D = C::D, P = C::P, PT = C::PT, PS = C::PS, CS = C::CS, MC = C::MC, NCW = C::NCW;
+    constexpr int NPT = C::NPW * 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint64_t *bar_empty = bar_full + NST;
+    uint64_t *bar_cfull = bar_empty + NST;
+    uint64_t *bar_mfull = bar_cfull + NST;
+    int *nfn_s = reinterpret_cast<int *>(smem + C::OFF_NFN);
+    double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
+    double *ys = xs + P, *zs = ys + P;
+    double *red = reinterpret_cast<double *>(smem + C::OFF_RED);
+    unsigned char *mbase = smem + C::OFF_META;
+    double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
+    double *tbase = reinterpret_cast<double *>(smem + C::off_tile(p.lay.stride));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&bar_full[i], NPT);
+            mbar_init(&bar_empty[i], NCW);
+            mbar_init(&bar_cfull[i], 1);
+        }
+        for (int i = 0; i < NMETA; ++i) mbar_init(&bar_mfull[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t meta_bytes = (uint32_t)p.lay.stride;
+    constexpr uint32_t cbuf_bytes = (uint32_t)C::CBUF_DOUBLES * 8u;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.n_mtile * (uint32_t)p.nchunk;
+
+    if (warp >= NCW) {
+        // ====================================== producers ==========================================
+        reg_dec<ws_preg(SET, NCW)>();
+        const int ptid = tid - NCW * 32, pwarp = warp - NCW;
+        auto issue_meta = [&](uint32_t gc) {
+            uint64_t *bar = &bar_mfull[gc % NMETA];
+            mbar_expect_tx(bar, meta_bytes);
+            bulk_g2s(mbase + (size_t)(gc % NMETA) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes,
+                     meta_bytes, bar);
+        };
+        if (ptid == 0)
+            for (uint32_t i = 0; i < NMETA && i < total; ++i) issue_meta(i);
+        uint32_t g = 0;
+        for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
+            const int q0 = tile_id * P;
+            named_bar(1, NPT);                        // previous tile's items no longer read xs/ys/zs
+            for (int e = ptid; e < P; e += NPT) {
+                int q = q0 + e;
+                if (q >= p.npts) q = p.npts - 1;
+                const long long n = p.p0 + q;
+                if (p.grid_kind == 0) {
+                    const long long nyz = (long long)p.ny * p.nz;
+                    const long long i = n / nyz, rem = n - i * nyz;
+                    const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
+                    xs[e] = p.gx[i]; ys[e] = p.gy[j]; zs[e] = p.gz[k];
+                } else {
+                    xs[e] = p.gx[n]; ys[e] = p.gy[n]; zs[e] = p.gz[n];
+                }
+            }
+            named_bar(1, NPT);
+            for (int mt = 0; mt < p.n_mtile; ++mt)
+                for (int c = 0; c < p.nchunk; ++c, ++g) {
+                    const int s = g % NST;
+                    mbar_wait(&bar_mfull[g % NMETA], (g / NMETA) & 1);
+                    mbar_wait(&bar_empty[s], ((g / NST) & 1) ^ 1);      // consumers released the stage
+                    if (ptid == 0) {
+                        mbar_expect_tx(&bar_cfull[s], cbuf_bytes);
+                        bulk_g2s(cbase + (size_t)s * C::CBUF_DOUBLES,
+                                 p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES, cbuf_bytes, &bar_cfull[s]);
+                    }
+                    const unsigned char *mb = mbase + (size_t)(g % NMETA) * meta_bytes;
+                    const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
+                    const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
+                    const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
+                    const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+                    double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
+                    const int nitems = hdr.nshell * PT;
+                    for (int item = pwarp; item < nitems; item += C::NPW) {
+                        const int sh = item / PT, pt = (item % PT) * 32 + lane;
+                        gen_shell_any<SET, PS>(shells[sh], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt,
+                                               p.one_code, p.exact_mixed);
+                    }
+                    // zero the rows that pad nfn up to the k-step of the MMA (coefficients there are 0,
+                    // but stale shared memory could hold NaN/Inf bit patterns)
+                    const int kpad = (hdr.nfn + 3) & ~3;
+                    for (int e = ptid; e < (kpad - hdr.nfn) * D * P; e += NPT) {
+                        const int pt = e % P, r = e / P, d = r % D, k = hdr.nfn + r / D;
+                        tile[((size_t)d * KC + k) * PS + pt] = 0.0;
+                    }
+                    if (ptid == 0) nfn_s[s] = kpad;
+                    mbar_arrive(&bar_full[s]);                           // release: tile + nfn visible
+                    named_bar(1, NPT);                                   // chunk table no longer read
+                    if (ptid == 0 && g + NMETA < total) issue_meta(g + NMETA);
+                }
+        }
+    } else {
+        // ====================================== consumers ==========================================
+        reg_inc<ws_creg(SET, NCW)>();
+        const int wm = warp / WN, wn = warp % WN;
+        const int tr = lane >> 2, tc = lane & 3;            // fragment row (T/4) and column (T%4)
+        const int mo_w = wm * AM * 8;                       // first MO of this warp inside the tile
+        const int pt_w = wn * BN * 8;                       // first point of this warp inside the tile
+        uint32_t g = 0;
+        for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
+            const int q0 = tile_id * P;
+            double osum[C::NOUT > 0 ? C::NOUT : 1][BN][2];
+            if (SINK == SINK_RHO) {
+#pragma unroll
+                for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib) osum[o][ib][0] = osum[o][ib][1] = 0.0;
+            }
+            for (int mt = 0; mt < p.n_mtile; ++mt) {
+                double acc[AM][BN][D][2];
+#pragma unroll
+                for (int ia = 0; ia < AM; ++ia)
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc[ia][ib][d][0] = acc[ia][ib][d][1] = 0.0;
+                for (int c = 0; c < p.nchunk; ++c, ++g) {
+                    const int s = g % NST;
+                    const uint32_t par = (g / NST) & 1;
+                    mbar_wait(&bar_full[s], par);
+                    mbar_wait(&bar_cfull[s], par);
+                    const int nk = nfn_s[s];                             // multiple of 4
+                    const double *ap = cbase + (size_t)s * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr;
+                    const double *bp = tbase + (size_t)s * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr;
+#pragma unroll 2
+                    for (int k0 = 0; k0 < nk; k0 += 4) {
+                        double afr[AM];
+#pragma unroll
+                        for (int ia = 0; ia < AM; ++ia) afr[ia] = ap[(size_t)k0 * CS + ia * 8];
+#pragma unroll
+                        for (int d = 0; d < D; ++d)
+#pragma unroll
+                            for (int ib = 0; ib < BN; ++ib) {
+                                const double bfr = bp[((size_t)d * KC + k0) * PS + ib * 8];
+#pragma unroll
+                                for (int ia = 0; ia < AM; ++ia)
+                                    dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr);
+                            }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_empty[s]);
+                }
+                // ---- per-MO-tile epilogues: lane holds MO row tr of each block, points 2*tc + {0,1} -----
+                if (SINK == SINK_MO) {
+#pragma unroll
+                    for (int ia = 0; ia < AM; ++ia) {
+                        const int mo = mt * MC + mo_w + ia * 8 + tr;
+                        if (mo >= p.n_mo) continue;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const int code = (SET == SET_ONE) ? p.one_code : d;
+                            const int sl = p.slot[code];
+                            if (sl < 0) continue;
+                            double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)mo * p.ld + q0;
+#pragma unroll
+                            for (int ib = 0; ib < BN; ++ib) {
+                                const int pt = pt_w + ib * 8 + 2 * tc;
+                                if (q0 + pt < p.npts) orow[pt] = acc[ia][ib][d][0];
+                                if (q0 + pt + 1 < p.npts) orow[pt + 1] = acc[ia][ib][d][1];
+                            }
+                        }
+                    }
+                }
+                if (SINK == SINK_RHO) {
+#pragma unroll
+                    for (int ia = 0; ia < AM; ++ia) {
+                        const int mo = mt * MC + mo_w + ia * 8 + tr;
+                        const double oc = p.occ[mo];                     // zero for padding MOs
+                        const double o2 = oc * 2.0;
+                        double nrm = 0.0;
+#pragma unroll
+                        for (int ib = 0; ib < BN; ++ib)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const double phi = acc[ia][ib][0][e];
+                                if ((q0 + pt_w + ib * 8 + 2 * tc + e) < p.npts) nrm += phi * phi;
+                                osum[0][ib][e] += oc * (phi * phi);
+                                if (D >= 4) {
+                                    const double gx = acc[ia][ib][1][e], gy = acc[ia][ib][2][e], gz = acc[ia][ib][3][e];
+                                    osum[1][ib][e] += o2 * (gx * phi);
+                                    osum[2][ib][e] += o2 * (gy * phi);
+                                    osum[3][ib][e] += o2 * (gz * phi);
+                                    if (D >= 7) {
+                                        osum[4][ib][e] += o2 * (acc[ia][ib][4][e] * phi + gx * gx);
+                                        osum[5][ib][e] += o2 * (acc[ia][ib][5][e] * phi + gy * gy);
+                                        osum[6][ib][e] += o2 * (acc[ia][ib][6][e] * phi + gz * gz);
+                                    }
+                                    if (D >= 10) {
+                                        osum[7][ib][e] += o2 * (acc[ia][ib][7][e] * phi + gx * gy);
+                                        osum[8][ib][e] += o2 * (acc[ia][ib][8][e] * phi + gx * gz);
+                                        osum[9][ib][e] += o2 * (acc[ia][ib][9][e] * phi + gy * gz);
+                                    }
+                                }
+                            }
+                        if (p.mo_norm != nullptr) {
+                            nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);     // over the 4 lanes of a row
+                            nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
+                            if (tc == 0 && mo < p.n_mo) atomicAdd(p.mo_norm + mo, nrm);
+                        }
+                    }
+                }
+            }   // mt
+            if (SINK == SINK_RHO) {
+                // sum over the 8 MO rows held by different lanes (xor 4, 8, 16), then over the WM warp
+                // rows through shared memory (own scratch: the producers are already filling stages of
+                // the next tile)
+#pragma unroll
+                for (int o = 0; o < C::NOUT; ++o)
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double v = osum[o][ib][e];
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (tr == 0) red[((size_t)wm * C::NOUT + o) * P + pt_w + ib * 8 + 2 * tc + e] = v;
+                        }
+                named_bar(2, NCW * 32);
+                for (int e = tid; e < C::NOUT * P; e += NCW * 32) {
+                    const int o = e / P, pt = e - o * P;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < WM; ++w) sum += red[((size_t)w * C::NOUT + o) * P + pt];
+                    if (q0 + pt < p.npts) {
+                        if (o == 0) {
+                            if (p.rho != nullptr) p.rho[q0 + pt] = sum;
+                        } else {
+                            const int sl = p.slot[o];
+                            if (sl >= 0) p.delta[(size_t)sl * p.ld + q0 + pt] = sum;
+                        }
+                    }
+                }
+                named_bar(2, NCW * 32);
+            }
+        }
+    }
+}
+
+}  // namespace okb
