@@ -643,22 +643,22 @@ template <int SET, int MW, int PT, int NW, int SINK>
 static size_t smem_variant(int meta_stride) {
     return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
 }
-template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
 static cudaError_t launch_ws(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = okb_ws_kernel<SET, AM, BN, WM, WN, NST, SINK>;
+    auto kern = okb_ws_kernel<SET, MB, BN, WM, WN, NPW, NST, SINK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 384, smem, st>>>(p);
+    kern<<<grid, (WM * WN + NPW) * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
-template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
 static size_t smem_ws(int meta_stride) {
-    return WsCfg<SET, AM, BN, WM, WN, NST, SINK>::smem_bytes(meta_stride);
+    return WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK>::smem_bytes(meta_stride);
 }
-#define OKB_WS(SET, AM, BN, WM, WN, NST, SINK)                                                              \
-    Variant { "ws-dmma/" #SET "/" #SINK "/AM" #AM "xBN" #BN "xWM" #WM "xWN" #WN "xNST" #NST, SET, SINK, AM, BN, WM * WN, \
-              8 * BN * WN, 8 * AM * WM, smem_ws<SET, AM, BN, WM, WN, NST, SINK>,                             \
-              launch_ws<SET, AM, BN, WM, WN, NST, SINK> }
+#define OKB_WS(SET, MB, BN, WM, WN, NPW, NST, SINK)                                                           \
+    Variant { "ws-dmma/" #SET "/" #SINK "/MB" #MB "xBN" #BN "xWM" #WM "xWN" #WN "xNPW" #NPW "xNST" #NST, SET, SINK, \
+              MB, BN, WM * WN, 8 * BN * WN, 8 * MB, smem_ws<SET, MB, BN, WM, WN, NPW, NST, SINK>,               \
+              launch_ws<SET, MB, BN, WM, WN, NPW, NST, SINK> }
 #define OKB_VARIANT(SET, MW, PT, NW, SINK)                                                         \
     Variant { #SET "/" #SINK "/MW" #MW "xPT" #PT "xNW" #NW, SET, SINK, MW, PT, NW, 32 * PT, NW * MW, \
               smem_variant<SET, MW, PT, NW, SINK>, launch_variant<SET, MW, PT, NW, SINK> }
@@ -671,25 +671,26 @@ static const Variant g_variants[] = {
     OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
     OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
     OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
-    // warp-specialised DMMA contraction kernels: 4 producer warps + 8 consumer warps (WM x WN), NST stages.
-    // MO tile MC = 8*AM*WM, point tile P = 8*BN*WN, accumulators per thread 2*AM*BN*D doubles.
-    // value only (D=1): P = 256
-    OKB_WS(SET_VAL, 11, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 11, 4, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_VAL, 12, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 12, 4, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_VAL, 3, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_VAL, 3, 4, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_ONE, 12, 4, 1, 8, 2, SINK_MO), OKB_WS(SET_ONE, 3, 4, 1, 8, 2, SINK_MO),
-    // value + gradient (D=4): P = 64
-    OKB_WS(SET_GRAD, 11, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_GRAD, 12, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 8, 2, SINK_RHO),
-    OKB_WS(SET_GRAD, 3, 1, 1, 8, 2, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 8, 2, SINK_RHO),
-    // one consumer warpgroup + two producer warpgroups: P = 32, 3 stages
-    OKB_WS(SET_GRAD, 11, 1, 1, 4, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 3, SINK_RHO),
-    // value + gradient + pure second derivatives (D=7): P = 32, two warp rows of MOs
-    OKB_WS(SET_LAP, 6, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_LAP, 6, 1, 2, 4, 2, SINK_RHO),
-    OKB_WS(SET_LAP, 2, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_LAP, 2, 1, 2, 4, 2, SINK_RHO),
-    // all ten codes (D=10): P = 32
-    OKB_WS(SET_ALL, 4, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_ALL, 4, 1, 2, 4, 2, SINK_RHO),
-    OKB_WS(SET_ALL, 1, 1, 2, 4, 2, SINK_MO), OKB_WS(SET_ALL, 1, 1, 2, 4, 2, SINK_RHO),
+    // warp-specialised DMMA contraction kernels: NPW producer warps + WM x WN consumer warps, NST stages.
+    // MO tile MC = 8*MB (MB blocks split over the WM warp rows), point tile P = 8*BN*WN.
+    // value only (D=1): 8 + 8 warps, P = 128
+    OKB_WS(SET_VAL, 11, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 11, 4, 2, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_VAL, 12, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 12, 4, 2, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_VAL, 3, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 3, 4, 2, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_ONE, 12, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_ONE, 3, 4, 2, 4, 8, 3, SINK_MO),
+    // value + gradient (D=4): 8 + 8 warps, P = 32
+    OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_RHO),   // 4 + 8 warps
+    OKB_WS(SET_GRAD, 12, 1, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 2, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_GRAD, 3, 1, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 2, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_GRAD, 11, 1, 1, 4, 12, 3, SINK_RHO),   // 4 + 12 warps (A/B)
+    OKB_WS(SET_GRAD, 11, 1, 2, 4, 4, 3, SINK_RHO),    // 8 + 4 warps (A/B)
+    // value + gradient + pure second derivatives (D=7): 8 consumer + 4 producer warps, P = 32
+    OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_RHO),
+    OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_RHO),
+    OKB_WS(SET_LAP, 3, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 3, 1, 2, 4, 4, 2, SINK_RHO),
+    // all ten codes (D=10): 8 consumer + 4 producer warps, P = 32
+    OKB_WS(SET_ALL, 6, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_ALL, 6, 1, 2, 4, 4, 2, SINK_RHO),
+    OKB_WS(SET_ALL, 2, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_ALL, 2, 1, 2, 4, 4, 2, SINK_RHO),
 };
 
 static const Variant *pick_variant(int set, int sink, int n_mo) {
@@ -698,11 +699,12 @@ static const Variant *pick_variant(int set, int sink, int n_mo) {
     for (const Variant &v : g_variants) {
         if (v.set != set || v.sink != sink) continue;
         if (sink == SINK_AO) return &v;
+        // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
+        static const char *force = getenv("OKB_VARIANT");
+        if (force && force[0] && strstr(v.name, force)) return &v;
         const long long padded = (long long)((n_mo + v.MC - 1) / v.MC) * v.MC;
-        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations); the number
-        // of consumer warps (4 by default) can be forced with OKB_WS_NCW for A/B measurements
-        static const int want_ncw = getenv("OKB_WS_NCW") ? atoi(getenv("OKB_WS_NCW")) : 4;
-        const long long cost = padded * 1000 - v.MC + (v.NW == want_ncw ? 0 : 500);
+        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations)
+        const long long cost = padded * 1000 - v.MC;
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;

@@ -4,20 +4,23 @@
 // Why (measured, profiles/r01_*): in the phase-serial kernel the FP64 pipe was 56% active -- all warps
 // did the latency-bound AO generation together, then the pipe-bound contraction together.  With
 // DFMA consumers the pipe reached 67%: DFMA with varying operands issues at 2.44 cycles/instruction
-// (30 TFLOP/s) and the MW x PT x D register tile needed an LDS per 4.6 DFMA.  scripts/fp64_micro.cu
-// shows DMMA (mma.sync.m8n8k4.f64) sustaining 37.1 TFLOP/s = 16.0 cycles per instruction per SM
-// sub-partition with two warps, 8x fewer issue slots than DFMA and the same 64 lanes/SM datapath.
-// So the contraction uses DMMA; the FP64 tensor path of sm_100a is mma.sync (tcgen05 has no f64 kind).
+// (30 TFLOP/s) and the register tile needed an LDS per 4.6 DFMA.  scripts/fp64_micro.cu shows DMMA
+// (mma.sync.m8n8k4.f64) sustaining 37.1 TFLOP/s = 16.0 cycles per instruction per SM sub-partition,
+// 8x fewer issue slots than DFMA on the same 64 lanes/SM datapath (DMMA wins arbitration against
+// DFMA).  So the contraction uses DMMA; the FP64 tensor path of sm_100a is mma.sync (tcgen05 has no
+// f64 kind).
 //
-//   producers  4 warps (one warpgroup, registers cut by setmaxnreg): evaluate (shell, 32 points) items
-//              of chunk g into stage g % NST of the AO tile ring, zero the k-padding rows, issue the
-//              bulk-async (TMA) copies of the chunk tables and of the coefficient tile of the stage.
-//   consumers  8 warps (registers raised by setmaxnreg) arranged WM x WN: warp (wm, wn) owns MO blocks
-//              [wm*AM, (wm+1)*AM) x point blocks [wn*BN, (wn+1)*BN) (blocks of 8), i.e. an
+//   producers  NPW warps (registers cut by setmaxnreg): evaluate (shell, 32 points) items of chunk g
+//              into stage g % NST of the AO tile ring, zero the k-padding rows, issue the bulk-async
+//              (TMA) copies of the chunk tables and of the coefficient tile of the stage.
+//   consumers  NCW = WM x WN warps (registers raised by setmaxnreg): warp (wm, wn) owns the MO blocks
+//              [wm*AM, min((wm+1)*AM, MB)) x point blocks [wn*BN, (wn+1)*BN) (blocks of 8), an
 //              (8 AM) x (8 BN) x D register tile of 2*AM*BN*D doubles per thread.  Per k-step of 4:
-//              AM + D*BN conflict-free LDS.64 feed AM*BN*D DMMAs.
-//   hand-over  mbarriers: full[s] (128 producer arrivals), cfull[s] (TMA bytes), empty[s] (one arrival
-//              per consumer warp).  No CTA-wide barrier in the main loop.
+//              AM + D*BN conflict-free LDS.64 feed AM*BN*D DMMAs.  Warps wm = 0..WM-1 of one wn share
+//              an SM sub-partition (warp % 4 == wn for WN == 4), so while one waits on a barrier or a
+//              fragment load the other keeps the pipe busy.
+//   hand-over  mbarriers: full[s] (one arrival per producer thread + the TMA bytes of the coefficient
+//              tile), empty[s] (one arrival per consumer warp).  No CTA-wide barrier in the main loop.
 //
 // mma.m8n8k4 operand mapping (lane T):  A[m][k] = C'[mo0 + T/4][k0 + T%4]   (row-major 8x4)
 //                                       B[k][n] = ao[d][k0 + T%4][pt0 + T/4] (col-major 4x8)
@@ -25,27 +28,41 @@
 // Shared-memory rows are padded to a stride = 4 (mod 16) doubles so that both fragment loads touch
 // 32 distinct 8-byte words per half-warp (2 wavefronts per LDS.64, the minimum).
 #pragma once
+#include <type_traits>
+
 #include "okb_shell.cuh"
 
 namespace okb {
 
 __host__ __device__ constexpr int pad_stride(int n) { return n + ((4 - (n % 16)) + 16) % 16; }
 
-template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
+// MB: MO blocks of 8 per CTA tile; WM x WN consumer warps; BN point blocks per warp; NPW producer warps
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
 struct WsCfg {
     static constexpr int D = set_ncodes(SET);
-    static constexpr int NCW = WM * WN;                        // consumer warps
-    static constexpr int NPW = 12 - WM * WN;                   // producer warps (4 or 8; 12 warps per CTA)
+    static constexpr int NCW = WM * WN;
+    static constexpr int AM = (MB + WM - 1) / WM;              // MO blocks per consumer warp
     static constexpr int P = 8 * BN * WN;                      // points per CTA tile
     static constexpr int PT = P / 32;
-    static constexpr int MC = 8 * AM * WM;                     // MOs per CTA tile
+    static constexpr int MC = 8 * MB;                          // MOs per CTA tile
     static constexpr int PS = pad_stride(P);                   // AO tile row stride (doubles)
     static constexpr int CS = pad_stride(MC);                  // coefficient tile row stride (doubles)
     static constexpr int NT = (NCW + NPW) * 32;
     static constexpr int TILE_DOUBLES = D * KC * PS;
     static constexpr int CBUF_DOUBLES = KC * CS;
     static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;
-    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] cfull[NST] mfull[NMETA]
+    // register budget: NT threads are launched with 65536/NT registers each; after setmaxnreg
+    // NCW*32*CREG + NPW*32*PREG must not exceed what the launch reserved
+    static constexpr int LAUNCH_REGS = (65536 / NT) / 8 * 8;
+    static constexpr int ACC_REGS = 4 * AM * BN * D;
+    static constexpr int CREG_WANT = ((ACC_REGS + 40 + 7) / 8 * 8 > 248) ? 248 : (ACC_REGS + 40 + 7) / 8 * 8;
+    static constexpr int PREG_MAX = ((NT * LAUNCH_REGS - NCW * 32 * CREG_WANT) / (NPW * 32)) / 8 * 8;
+    static constexpr int PREG_CAP = LAUNCH_REGS < 152 ? LAUNCH_REGS : 152;   // setmaxnreg.dec may only lower
+    static constexpr int PREG = PREG_MAX > PREG_CAP ? PREG_CAP : PREG_MAX;
+    static constexpr int CREG = ((NT * LAUNCH_REGS - NPW * 32 * PREG) / (NCW * 32)) / 8 * 8 > 248
+                                    ? 248
+                                    : ((NT * LAUNCH_REGS - NPW * 32 * PREG) / (NCW * 32)) / 8 * 8;
+    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] mfull[NMETA]
     static constexpr size_t OFF_NFN = 256;                     // int nfn[NST]
     static constexpr size_t OFF_XYZ = 384;
     static constexpr size_t OFF_RED = OFF_XYZ + (size_t)3 * P * 8;
@@ -59,29 +76,50 @@ struct WsCfg {
     __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
         return off_tile(meta_stride) + (size_t)NST * TILE_DOUBLES * 8;
     }
-    static_assert(3 * NST + NMETA <= 32, "barrier area");
-    static_assert(NCW == 8 || NCW == 4, "one or two consumer warpgroups");
+    static_assert(2 * NST + NMETA <= 32, "barrier area");
+    static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
     static_assert(P % 32 == 0, "whole warps of points for the producers");
+    static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
 };
 
-// register split between producer and consumer warpgroups (launch: 168/thread at 384 threads, i.e.
-// 504 registers per thread-triple): NCW = 8: 1 producer + 2 consumer warpgroups, PREG + 2 CREG <= 504;
-// NCW = 4: 2 producer + 1 consumer warpgroups, 2 PREG + CREG <= 504.
-__host__ __device__ constexpr int ws_preg(int set, int ncw) {
-    return ncw == 4 ? 136
-                    : (set == SET_VAL ? 56 : set == SET_GRAD ? 72 : set == SET_LAP ? 104 : set == SET_ALL ? 128 : 88);
-}
-__host__ __device__ constexpr int ws_creg(int set, int ncw) {
-    return ncw == 4 ? 232 : (504 - ws_preg(set, ncw)) / 2 / 8 * 8;
-}
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// barrier helpers on precomputed shared-space addresses (no generic->shared conversion in the loops)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only_a(uint32_t bar, uint32_t bytes) {   // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OKB_WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OKB_DONEA_%=;\n"
+        "bra OKB_WAITA_%=;\n"
+        "OKB_DONEA_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// volatile shared load: keeps its place in the hand-scheduled DMMA stream
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -89,16 +127,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-template <int SET, int AM, int BN, int WM, int WN, int NST, int SINK>
-__global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
-    using C = WsCfg<SET, AM, BN, WM, WN, NST, SINK>;
-    constexpr int D = C::D, P = C::P, PT = C::PT, PS = C::PS, CS = C::CS, MC = C::MC, NCW = C::NCW;
-    constexpr int NPT = C::NPW * 32;
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
+__global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const KParams p) {
+    using C = WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK>;
+    constexpr int D = C::D, P = C::P, PT = C::PT, PS = C::PS, CS = C::CS, MC = C::MC, NCW = C::NCW, AM = C::AM;
+    constexpr int NPT = NPW * 32;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-    uint64_t *bar_empty = bar_full + NST;
-    uint64_t *bar_cfull = bar_empty + NST;
-    uint64_t *bar_mfull = bar_cfull + NST;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_full = sbase + (uint32_t)C::OFF_BAR, a_empty = a_full + 8 * NST, a_mfull = a_empty + 8 * NST;
     int *nfn_s = reinterpret_cast<int *>(smem + C::OFF_NFN);
     double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
     double *ys = xs + P, *zs = ys + P;
@@ -109,12 +145,12 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
         for (int i = 0; i < NST; ++i) {
-            mbar_init(&bar_full[i], NPT);
-            mbar_init(&bar_empty[i], NCW);
-            mbar_init(&bar_cfull[i], 1);
+            mbar_init(&bars[i], NPT);                 // + TMA bytes of the coefficient tile
+            mbar_init(&bars[NST + i], NCW);
         }
-        for (int i = 0; i < NMETA; ++i) mbar_init(&bar_mfull[i], 1);
+        for (int i = 0; i < NMETA; ++i) mbar_init(&bars[2 * NST + i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -126,13 +162,13 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
 
     if (warp >= NCW) {
         // ====================================== producers ==========================================
-        reg_dec<ws_preg(SET, NCW)>();
+        reg_dec<C::PREG>();
         const int ptid = tid - NCW * 32, pwarp = warp - NCW;
+        const uint32_t a_meta = smem_u32(mbase), a_cbuf = smem_u32(cbase);
         auto issue_meta = [&](uint32_t gc) {
-            uint64_t *bar = &bar_mfull[gc % NMETA];
-            mbar_expect_tx(bar, meta_bytes);
-            bulk_g2s(mbase + (size_t)(gc % NMETA) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes,
-                     meta_bytes, bar);
+            const uint32_t bar = a_mfull + 8 * (gc % NMETA);
+            mbar_arrive_expect_tx_a(bar, meta_bytes);
+            bulk_g2s_a(a_meta + (gc % NMETA) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes, meta_bytes, bar);
         };
         if (ptid == 0)
             for (uint32_t i = 0; i < NMETA && i < total; ++i) issue_meta(i);
@@ -157,12 +193,12 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
             for (int mt = 0; mt < p.n_mtile; ++mt)
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
-                    mbar_wait(&bar_mfull[g % NMETA], (g / NMETA) & 1);
-                    mbar_wait(&bar_empty[s], ((g / NST) & 1) ^ 1);      // consumers released the stage
+                    mbar_wait_a(a_mfull + 8 * (g % NMETA), (g / NMETA) & 1);
+                    mbar_wait_a(a_empty + 8 * s, ((g / NST) & 1) ^ 1);   // consumers released the stage
                     if (ptid == 0) {
-                        mbar_expect_tx(&bar_cfull[s], cbuf_bytes);
-                        bulk_g2s(cbase + (size_t)s * C::CBUF_DOUBLES,
-                                 p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES, cbuf_bytes, &bar_cfull[s]);
+                        mbar_expect_tx_only_a(a_full + 8 * s, cbuf_bytes);
+                        bulk_g2s_a(a_cbuf + s * cbuf_bytes, p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES,
+                                   cbuf_bytes, a_full + 8 * s);
                     }
                     const unsigned char *mb = mbase + (size_t)(g % NMETA) * meta_bytes;
                     const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
@@ -171,7 +207,9 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
                     const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
                     double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
                     const int nitems = hdr.nshell * PT;
-                    for (int item = pwarp; item < nitems; item += C::NPW) {
+                    // heavy shells first is the host's job (chunk order); warps take items round-robin,
+                    // rotated per chunk so that the same warp is not always the one with the extra item
+                    for (int item = (pwarp + g) % NPW; item < nitems; item += NPW) {
                         const int sh = item / PT, pt = (item % PT) * 32 + lane;
                         gen_shell_any<SET, PS>(shells[sh], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt,
                                                p.one_code, p.exact_mixed);
@@ -184,18 +222,20 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
                         tile[((size_t)d * KC + k) * PS + pt] = 0.0;
                     }
                     if (ptid == 0) nfn_s[s] = kpad;
-                    mbar_arrive(&bar_full[s]);                           // release: tile + nfn visible
+                    mbar_arrive_a(a_full + 8 * s);                       // release: tile + nfn visible
                     named_bar(1, NPT);                                   // chunk table no longer read
                     if (ptid == 0 && g + NMETA < total) issue_meta(g + NMETA);
                 }
         }
     } else {
         // ====================================== consumers ==========================================
-        reg_inc<ws_creg(SET, NCW)>();
+        reg_inc<C::CREG>();
         const int wm = warp / WN, wn = warp % WN;
         const int tr = lane >> 2, tc = lane & 3;            // fragment row (T/4) and column (T%4)
         const int mo_w = wm * AM * 8;                       // first MO of this warp inside the tile
         const int pt_w = wn * BN * 8;                       // first point of this warp inside the tile
+        // number of MO blocks this warp really owns (the last warp row may own fewer: MB % WM != 0)
+        const int nblk = (MB - wm * AM) < AM ? (MB - wm * AM) : AM;
         uint32_t g = 0;
         for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
             const int q0 = tile_id * P;
@@ -216,36 +256,63 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
                         for (int d = 0; d < D; ++d) acc[ia][ib][d][0] = acc[ia][ib][d][1] = 0.0;
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
-                    const uint32_t par = (g / NST) & 1;
-                    mbar_wait(&bar_full[s], par);
-                    mbar_wait(&bar_cfull[s], par);
+                    mbar_wait_a(a_full + 8 * s, (g / NST) & 1);          // AO tile + coefficient tile landed
                     const int nk = nfn_s[s];                             // multiple of 4
                     const double *ap = cbase + (size_t)s * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr;
                     const double *bp = tbase + (size_t)s * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr;
-#pragma unroll 2
-                    for (int k0 = 0; k0 < nk; k0 += 4) {
-                        double afr[AM];
+                    // Explicitly scheduled k-loop (volatile asm keeps the order): ncu showed every LDS that
+                    // refilled an A fragment right behind the last DMMA reading that register stalling on
+                    // the write-after-read hazard (~6 cycles per 4 DMMAs), plus the exposed LDS latency at
+                    // the head of each step.  Here the fragments of step k0+4 are fetched during step k0:
+                    // B into the other half of a double buffer at the start of the step, A[ia-1] only
+                    // after the DMMAs of block ia have been issued, so no load waits for a reader and no
+                    // DMMA waits for a load.
+                    const uint32_t a_ap = smem_u32(ap), a_bp = smem_u32(bp);
+                    double afr[AM], bfr[2][D][BN];
 #pragma unroll
-                        for (int ia = 0; ia < AM; ++ia) afr[ia] = ap[(size_t)k0 * CS + ia * 8];
+                    for (int d = 0; d < D; ++d)
+#pragma unroll
+                        for (int ib = 0; ib < BN; ++ib) bfr[0][d][ib] = lds64(a_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+#pragma unroll
+                    for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(a_ap + (uint32_t)(ia * 8) * 8u);
+                    auto step = [&](const int k0, auto cur_tag) {
+                        constexpr int CUR = decltype(cur_tag)::value;
+                        // next step (clamped to the last one: a harmless reload at the end of the chunk)
+                        const int kn = (k0 + 4 < nk) ? k0 + 4 : k0;
+                        const uint32_t na = a_ap + (uint32_t)(kn * CS) * 8u, nb = a_bp + (uint32_t)(kn * PS) * 8u;
 #pragma unroll
                         for (int d = 0; d < D; ++d)
 #pragma unroll
-                            for (int ib = 0; ib < BN; ++ib) {
-                                const double bfr = bp[((size_t)d * KC + k0) * PS + ib * 8];
+                            for (int ib = 0; ib < BN; ++ib)
+                                bfr[CUR ^ 1][d][ib] = lds64(nb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
 #pragma unroll
-                                for (int ia = 0; ia < AM; ++ia)
-                                    dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr);
+                        for (int ia = 0; ia < AM; ++ia) {
+                            if (!(MB % WM != 0 && ia == AM - 1 && ia >= nblk)) {     // warp-uniform
+#pragma unroll
+                                for (int d = 0; d < D; ++d)
+#pragma unroll
+                                    for (int ib = 0; ib < BN; ++ib)
+                                        dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr[CUR][d][ib]);
                             }
+                            if (ia >= 1) afr[ia - 1] = lds64(na + (uint32_t)((ia - 1) * 8) * 8u);
+                        }
+                        afr[AM - 1] = lds64(na + (uint32_t)((AM - 1) * 8) * 8u);
+                    };
+                    int k0 = 0;
+                    for (; k0 + 8 <= nk; k0 += 8) {
+                        step(k0, std::integral_constant<int, 0>{});
+                        step(k0 + 4, std::integral_constant<int, 1>{});
                     }
+                    if (k0 < nk) step(k0, std::integral_constant<int, 0>{});
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_empty[s]);
+                    if (lane == 0) mbar_arrive_a(a_empty + 8 * s);
                 }
                 // ---- per-MO-tile epilogues: lane holds MO row tr of each block, points 2*tc + {0,1} -----
                 if (SINK == SINK_MO) {
 #pragma unroll
                     for (int ia = 0; ia < AM; ++ia) {
                         const int mo = mt * MC + mo_w + ia * 8 + tr;
-                        if (mo >= p.n_mo) continue;
+                        if (ia >= nblk || mo >= p.n_mo) continue;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const int code = (SET == SET_ONE) ? p.one_code : d;
@@ -264,6 +331,7 @@ __global__ void __launch_bounds__(384, 1) okb_ws_kernel(const KParams p) {
                 if (SINK == SINK_RHO) {
 #pragma unroll
                     for (int ia = 0; ia < AM; ++ia) {
+                        if (ia >= nblk) continue;                        // warp-uniform
                         const int mo = mt * MC + mo_w + ia * 8 + tr;
                         const double oc = p.occ[mo];                     // zero for padding MOs
                         const double o2 = oc * 2.0;
