@@ -84,8 +84,9 @@ class OkbError(RuntimeError):
 
 def build(force=False, verbose=False):
     """Compile csrc/okb200.cu for sm_100a into orbkit_b200/libokb200.so (works without a GPU)."""
-    deps = [SRC, os.path.join(_HERE, 'csrc', 'okb_kernels.cuh'),
-            os.path.join(os.path.dirname(_HERE), 'include', 'okb200.h')]
+    csrc = os.path.join(_HERE, 'csrc')
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))]
+    deps.append(os.path.join(os.path.dirname(_HERE), 'include', 'okb200.h'))
     if (not force and os.path.exists(LIB_PATH) and
             all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
         return LIB_PATH
