@@ -86,23 +86,34 @@ struct DevShell {
     std::vector<double> f;
 };
 
+// One way of cutting the device shells into chunks, with its packed chunk tables on the device.
+// `cart`: every shell writes its Cartesian rows (SINK_AO applies the spherical rows while storing).
+// `mix` : standard d/f/g shells of a spherical basis write their 2L+1 spherical rows themselves
+//         (kind 2), so the contraction runs over n_sph instead of n_cart functions; all other shells
+//         write Cartesian rows whose transform is folded into the MO coefficients.
+struct KRow { int is_sph; int index; };      // what a tile row holds: spherical AO `index` or Cartesian row `index`
+struct Layout {
+    struct Chunk { int s0, s1, k0, nfn, nprim; };
+    std::vector<Chunk> chunks;
+    std::vector<KRow> krow;                  // device row -> content
+    std::vector<int> shell_sph;              // per device shell: 1 if it writes spherical rows
+    BlobLayout lay{};
+    unsigned char *meta_dev = nullptr;
+    int n_rows = 0;
+};
+
 struct okb_basis {
     okb_ctx *ctx = nullptr;
     int n_cart = 0, n_ao = 0;
     bool spherical = false;
     std::vector<DevShell> shells;
-    // chunking
-    struct Chunk { int s0, s1, k0, nfn, nprim; };
-    std::vector<Chunk> chunks;
-    std::vector<int> fn_row;                 // device function index -> Cartesian row
-    std::vector<int> fn_chunk, fn_klocal;    // Cartesian row -> chunk / chunk-local k
+    std::vector<int> row_shell;              // Cartesian row -> device shell
     // cart -> sph CSR
     std::vector<int> t_ptr, t_col;
     std::vector<double> t_val;
-    // device blob
-    BlobLayout lay{};
-    unsigned char *meta_dev = nullptr;
-    bool dirty = true;
+    Layout cart, mix;
+    bool mix_is_cart = true;                 // Cartesian basis: the two layouts coincide
+    const Layout &contraction_layout() const { return mix_is_cart ? cart : mix; }
 };
 
 struct okb_mo {
@@ -110,9 +121,10 @@ struct okb_mo {
     okb_basis *basis = nullptr;
     int n_mo = 0;
     std::vector<double> ccart;               // [n_mo][n_cart] in Cartesian rows (C' = C T)
+    std::vector<double> csph;                // [n_mo][n_ao] as given (spherical bases only)
     std::vector<double> occ;
     struct Blob { double *c = nullptr; double *occ = nullptr; int n_mtile = 0; };
-    std::map<int, Blob> blobs;               // keyed by MC
+    std::map<int, Blob> blobs;               // keyed by 2*MC + (mix layout ? 1 : 0)
 };
 
 struct okb_grid {
@@ -253,40 +265,6 @@ extern "C" double okb_aoxyz(double x, double y, double z, int lx, int ly, int lz
 }
 
 // ---- basis ----------------------------------------------------------------------------------------------
-static int basis_build_chunks(okb_basis *b) {
-    b->chunks.clear();
-    b->fn_row.clear();
-    const int MAXS = 32, MAXP = 96;
-    okb_basis::Chunk cur{0, 0, 0, 0, 0};
-    int k = 0;
-    for (int s = 0; s < (int)b->shells.size(); ++s) {
-        const DevShell &sh = b->shells[s];
-        const int nf = (int)sh.fn_row.size(), np = (int)sh.alpha.size();
-        if (nf > KC) return fail(OKB_ERR_UNSUPPORTED, "shell with %d functions exceeds the chunk size %d", nf, KC);
-        const bool full = (cur.s1 > cur.s0) &&
-                          (cur.nfn + nf > KC || cur.s1 - cur.s0 >= MAXS || cur.nprim + np > MAXP);
-        if (full) {
-            b->chunks.push_back(cur);
-            cur = okb_basis::Chunk{s, s, k, 0, 0};
-        }
-        cur.s1 = s + 1;
-        cur.nfn += nf;
-        cur.nprim += np;
-        for (int r : sh.fn_row) b->fn_row.push_back(r);
-        k += nf;
-    }
-    if (cur.s1 > cur.s0) b->chunks.push_back(cur);
-    b->fn_chunk.assign(b->n_cart, -1);
-    b->fn_klocal.assign(b->n_cart, -1);
-    for (int c = 0; c < (int)b->chunks.size(); ++c)
-        for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
-            const int row = b->fn_row[b->chunks[c].k0 + kk];
-            b->fn_chunk[row] = c;
-            b->fn_klocal[row] = kk;
-        }
-    return OKB_OK;
-}
-
 // functions in the default (Molden) order of tools.exp[L]?  Those shells take the straight-line AO code.
 static bool shell_is_standard(const DevShell &sh) {
     if (sh.L < 0 || sh.L > 4 || (int)sh.fn_row.size() != std_nfn(sh.L)) return false;
@@ -297,80 +275,221 @@ static bool shell_is_standard(const DevShell &sh) {
     return true;
 }
 
-static int basis_upload(okb_basis *b) {
-    // output rows per chunk (SINK_AO): Cartesian identity rows or the spherical CSR rows
-    const int nchunk = (int)b->chunks.size();
+// Spherical rows of a standard shell: which spherical AOs (CSR rows) are built from exactly this shell's
+// Cartesian functions with the compiled-in term pattern of canonical row r?  Returns false (-> fold the
+// transform into the coefficients instead) unless all 2L+1 canonical rows are matched exactly once.
+static bool match_sph_rows(const okb_basis *b, int s, std::vector<int> &sph_of_canon) {
+    const DevShell &sh = b->shells[s];
+    const int L = sh.L;
+    if (!b->spherical || L < 2 || L > 4 || !shell_is_standard(sh)) return false;
+    sph_of_canon.assign(2 * L + 1, -1);
+    int found = 0;
+    for (int j = 0; j < b->n_ao; ++j) {
+        const int t0 = b->t_ptr[j], t1 = b->t_ptr[j + 1];
+        if (t1 <= t0 || b->row_shell[b->t_col[t0]] != s) continue;
+        int hit = -1;
+        for (int r = 0; r < 2 * L + 1 && hit < 0; ++r) {
+            if (sph_nterm(L, r) != t1 - t0 || sph_of_canon[r] >= 0) continue;
+            bool same = true;
+            for (int t = 0; t < t1 - t0 && same; ++t)
+                same = (b->t_col[t0 + t] == sh.fn_row[sph_cart(L, r, t)]);
+            if (same) hit = r;
+        }
+        if (hit < 0) return false;          // a spherical function of this shell with an unknown pattern
+        sph_of_canon[hit] = j;
+        ++found;
+    }
+    // every Cartesian function of the shell must be used only by these rows
+    for (int j = 0; j < b->n_ao; ++j)
+        for (int t = b->t_ptr[j]; t < b->t_ptr[j + 1]; ++t)
+            if (b->row_shell[b->t_col[t]] == s) {
+                bool mine = false;
+                for (int r = 0; r < 2 * L + 1; ++r) mine |= (sph_of_canon[r] == j);
+                if (!mine) return false;
+            }
+    return found == 2 * L + 1;
+}
+
+static void layout_free(okb_ctx *ctx, Layout &lo) {
+    if (lo.meta_dev) {
+        cudaSetDevice(ctx->device);
+        cudaFree(lo.meta_dev);
+    }
+    lo = Layout();
+}
+
+static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
+    layout_free(b->ctx, lo);
+    const int nshell = (int)b->shells.size();
+    // ---- rows written by every shell -------------------------------------------------------------
+    std::vector<std::vector<int>> canon(nshell);           // kind-2 shells: spherical AO of canonical row r
+    lo.shell_sph.assign(nshell, 0);
+    for (int s = 0; s < nshell; ++s)
+        if (sph_out && match_sph_rows(b, s, canon[s])) lo.shell_sph[s] = 1;
+    // ---- greedy chunking over the rows ------------------------------------------------------------------
+    const int MAXS = 32, MAXP = 96;
+    Layout::Chunk cur{0, 0, 0, 0, 0};
+    int k = 0;
+    std::vector<int> shell_k0(nshell, 0);
+    for (int s = 0; s < nshell; ++s) {
+        const DevShell &sh = b->shells[s];
+        const int nf = lo.shell_sph[s] ? 2 * sh.L + 1 : (int)sh.fn_row.size(), np = (int)sh.alpha.size();
+        if (nf > KC) return fail(OKB_ERR_UNSUPPORTED, "shell with %d functions exceeds the chunk size %d", nf, KC);
+        const bool full = (cur.s1 > cur.s0) &&
+                          (cur.nfn + nf > KC || cur.s1 - cur.s0 >= MAXS || cur.nprim + np > MAXP);
+        if (full) {
+            lo.chunks.push_back(cur);
+            cur = Layout::Chunk{s, s, k, 0, 0};
+        }
+        cur.s1 = s + 1;
+        cur.nfn += nf;
+        cur.nprim += np;
+        shell_k0[s] = k;
+        if (lo.shell_sph[s]) {
+            // rows in ascending spherical AO index (keeps the coefficient rows in the caller's order)
+            std::vector<int> js(canon[s]);
+            std::sort(js.begin(), js.end());
+            for (int j : js) lo.krow.push_back(KRow{1, j});
+        } else {
+            for (int r : sh.fn_row) lo.krow.push_back(KRow{0, r});
+        }
+        k += nf;
+    }
+    if (cur.s1 > cur.s0) lo.chunks.push_back(cur);
+    lo.n_rows = k;
+    const int nchunk = (int)lo.chunks.size();
+    // Cartesian row -> (chunk, chunk-local k) for the SINK_AO output rows (cart layout only)
+    std::vector<int> fn_chunk(b->n_cart, -1), fn_klocal(b->n_cart, -1);
+    for (int c = 0; c < nchunk; ++c)
+        for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
+            const KRow &kr = lo.krow[lo.chunks[c].k0 + kk];
+            if (!kr.is_sph) {
+                fn_chunk[kr.index] = c;
+                fn_klocal[kr.index] = kk;
+            }
+        }
+    // ---- output rows per chunk (used by SINK_AO only; the cart layout) ---------------------------------------
     std::vector<std::vector<RowMeta>> rows(nchunk);
     std::vector<std::vector<TermMeta>> terms(nchunk);
-    if (!b->spherical) {
-        for (int c = 0; c < nchunk; ++c)
-            for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
-                rows[c].push_back(RowMeta{b->fn_row[b->chunks[c].k0 + kk], (int)terms[c].size(), 1, 0});
-                terms[c].push_back(TermMeta{kk, 0, 1.0});
-            }
-    } else {
-        for (int j = 0; j < b->n_ao; ++j) {
-            const int t0 = b->t_ptr[j], t1 = b->t_ptr[j + 1];
-            if (t1 <= t0) return fail(OKB_ERR_ARG, "spherical function %d has no Cartesian terms", j);
-            const int c = b->fn_chunk[b->t_col[t0]];
-            rows[c].push_back(RowMeta{j, (int)terms[c].size(), t1 - t0, 0});
-            for (int t = t0; t < t1; ++t) {
-                if (b->fn_chunk[b->t_col[t]] != c)
-                    return fail(OKB_ERR_UNSUPPORTED,
-                                "spherical function %d mixes Cartesian functions of different shells", j);
-                terms[c].push_back(TermMeta{b->fn_klocal[b->t_col[t]], 0, b->t_val[t]});
+    if (!sph_out) {
+        if (!b->spherical) {
+            for (int c = 0; c < nchunk; ++c)
+                for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
+                    rows[c].push_back(RowMeta{lo.krow[lo.chunks[c].k0 + kk].index, (int)terms[c].size(), 1, 0});
+                    terms[c].push_back(TermMeta{kk, 0, 1.0});
+                }
+        } else {
+            for (int j = 0; j < b->n_ao; ++j) {
+                const int t0 = b->t_ptr[j], t1 = b->t_ptr[j + 1];
+                if (t1 <= t0) return fail(OKB_ERR_ARG, "spherical function %d has no Cartesian terms", j);
+                const int c = fn_chunk[b->t_col[t0]];
+                rows[c].push_back(RowMeta{j, (int)terms[c].size(), t1 - t0, 0});
+                for (int t = t0; t < t1; ++t) {
+                    if (fn_chunk[b->t_col[t]] != c)
+                        return fail(OKB_ERR_UNSUPPORTED,
+                                    "spherical function %d mixes Cartesian functions of different shells", j);
+                    terms[c].push_back(TermMeta{fn_klocal[b->t_col[t]], 0, b->t_val[t]});
+                }
             }
         }
     }
-    int maxS = 1, maxP = 1, maxR = 1, maxT = 1;
+    // ---- aux records of the kind-2 shells ----------------------------------------------------------------------
+    std::vector<std::vector<double>> aux(nchunk);
+    std::vector<int> shell_aux(nshell, 0);
+    for (int c = 0; c < nchunk; ++c)
+        for (int s = lo.chunks[c].s0; s < lo.chunks[c].s1; ++s) {
+            if (!lo.shell_sph[s]) continue;
+            const DevShell &sh = b->shells[s];
+            const int L = sh.L;
+            shell_aux[s] = (int)aux[c].size();
+            for (int j = 0; j < std_nfn(L); ++j) aux[c].push_back(sh.f[j]);
+            std::vector<int> js(canon[s]);
+            std::sort(js.begin(), js.end());
+            for (int r = 0; r < 2 * L + 1; ++r) {
+                const int j = canon[s][r];
+                const int pos = (int)(std::find(js.begin(), js.end(), j) - js.begin());
+                aux[c].push_back((double)pos);
+                for (int t = b->t_ptr[j]; t < b->t_ptr[j + 1]; ++t) aux[c].push_back(b->t_val[t]);
+            }
+        }
+    // ---- pack -------------------------------------------------------------------------------------------------------
+    int maxS = 1, maxP = 1, maxR = 1, maxT = 1, maxA = 2;
     for (int c = 0; c < nchunk; ++c) {
-        maxS = std::max(maxS, b->chunks[c].s1 - b->chunks[c].s0);
-        maxP = std::max(maxP, b->chunks[c].nprim);
+        maxS = std::max(maxS, lo.chunks[c].s1 - lo.chunks[c].s0);
+        maxP = std::max(maxP, lo.chunks[c].nprim);
         maxR = std::max(maxR, (int)rows[c].size());
         maxT = std::max(maxT, (int)terms[c].size());
+        maxA = std::max(maxA, (int)aux[c].size());
     }
-    BlobLayout &L = b->lay;
+    BlobLayout &L = lo.lay;
+    auto up16 = [](int v) { return (v + 15) / 16 * 16; };
     L.off_shell = 16;
-    L.off_prim = L.off_shell + maxS * (int)sizeof(ShellMeta);
+    L.off_prim = up16(L.off_shell + maxS * (int)sizeof(ShellMeta));
     L.off_fn = L.off_prim + maxP * 16;
     L.off_row = L.off_fn + KC * (int)sizeof(FnMeta);
     L.off_term = L.off_row + maxR * (int)sizeof(RowMeta);
-    L.stride = (L.off_term + maxT * (int)sizeof(TermMeta) + 127) / 128 * 128;
+    L.off_aux = L.off_term + maxT * (int)sizeof(TermMeta);
+    L.stride = (L.off_aux + maxA * 8 + 127) / 128 * 128;
     if (L.stride > 24 * 1024)
         return fail(OKB_ERR_UNSUPPORTED, "chunk table of %d bytes is too large", L.stride);
     std::vector<unsigned char> blob((size_t)L.stride * std::max(nchunk, 1), 0);
     for (int c = 0; c < nchunk; ++c) {
         unsigned char *mb = blob.data() + (size_t)c * L.stride;
-        const okb_basis::Chunk &ch = b->chunks[c];
+        const Layout::Chunk &ch = lo.chunks[c];
         ChunkHdr hdr{ch.s1 - ch.s0, ch.nprim, ch.nfn, (int)rows[c].size()};
         memcpy(mb, &hdr, sizeof(hdr));
         ShellMeta *sm = reinterpret_cast<ShellMeta *>(mb + L.off_shell);
         double2 *pm = reinterpret_cast<double2 *>(mb + L.off_prim);
         FnMeta *fm = reinterpret_cast<FnMeta *>(mb + L.off_fn);
-        int po = 0, fo = 0;
+        int po = 0;
         for (int s = ch.s0; s < ch.s1; ++s) {
             const DevShell &sh = b->shells[s];
+            const int fo = shell_k0[s] - ch.k0;
             ShellMeta m{};
             m.cx = sh.c[0]; m.cy = sh.c[1]; m.cz = sh.c[2];
             m.prim_off = po; m.nprim = (int)sh.alpha.size();
-            m.fn_off = fo; m.nfn = (int)sh.fn_row.size();
+            m.fn_off = fo;
             m.L = sh.L;
-            m.kind = shell_is_standard(sh) ? 1 : 0;
+            if (lo.shell_sph[s]) {
+                m.kind = 2;
+                m.nfn = 2 * sh.L + 1;
+                m.aux_off = shell_aux[s];
+            } else {
+                m.kind = shell_is_standard(sh) ? 1 : 0;
+                m.nfn = (int)sh.fn_row.size();
+                for (size_t j = 0; j < sh.fn_row.size(); ++j)
+                    fm[fo + j] = FnMeta{sh.lx[j] | (sh.ly[j] << 8) | (sh.lz[j] << 16), 0, sh.f[j]};
+            }
             sm[s - ch.s0] = m;
             for (size_t i = 0; i < sh.alpha.size(); ++i) pm[po++] = make_double2(sh.alpha[i], sh.cn[i]);
-            for (size_t j = 0; j < sh.fn_row.size(); ++j)
-                fm[fo++] = FnMeta{sh.lx[j] | (sh.ly[j] << 8) | (sh.lz[j] << 16), 0, sh.f[j]};
         }
         if (!rows[c].empty()) memcpy(mb + L.off_row, rows[c].data(), rows[c].size() * sizeof(RowMeta));
         if (!terms[c].empty()) memcpy(mb + L.off_term, terms[c].data(), terms[c].size() * sizeof(TermMeta));
+        if (!aux[c].empty()) memcpy(mb + L.off_aux, aux[c].data(), aux[c].size() * sizeof(double));
     }
     CU(cudaSetDevice(b->ctx->device));
-    if (b->meta_dev) CU(cudaFree(b->meta_dev));
-    b->meta_dev = nullptr;
-    CU(cudaMalloc(&b->meta_dev, blob.size()));
-    CU(cudaMemcpy(b->meta_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&lo.meta_dev, blob.size()));
+    CU(cudaMemcpy(lo.meta_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     b->ctx->h2d_bytes += (long long)blob.size();
-    b->dirty = false;
+    return OKB_OK;
+}
+
+// (re)build both layouts after the basis or its spherical transform changed
+static int basis_upload(okb_basis *b) {
+    b->row_shell.assign(b->n_cart, -1);
+    for (int s = 0; s < (int)b->shells.size(); ++s)
+        for (int r : b->shells[s].fn_row) b->row_shell[r] = s;
+    int rc = layout_build(b, false, b->cart);
+    if (rc != OKB_OK) return rc;
+    b->mix_is_cart = true;
+    if (b->spherical && !getenv("OKB_NO_SPH_ROWS")) {
+        rc = layout_build(b, true, b->mix);
+        if (rc != OKB_OK) return rc;
+        bool any = false;
+        for (int v : b->mix.shell_sph) any |= (v != 0);
+        if (any) b->mix_is_cart = false;
+        else layout_free(b->ctx, b->mix);
+    }
     return OKB_OK;
 }
 
@@ -433,8 +552,7 @@ extern "C" int okb_basis_create(okb_ctx *ctx, const int *lxlylz, const int *assi
         delete b;
         return fail(OKB_ERR_ARG, "okb_basis_create: sum(assign)=%d != n_cart=%d", c_ao, n_cart);
     }
-    int rc = basis_build_chunks(b);
-    if (rc == OKB_OK) rc = basis_upload(b);
+    int rc = basis_upload(b);
     if (rc != OKB_OK) {
         delete b;
         return rc;
@@ -463,14 +581,14 @@ extern "C" int okb_basis_info(okb_basis *b, int *n_cart, int *n_ao, int *n_dev_s
     if (n_cart) *n_cart = b->n_cart;
     if (n_ao) *n_ao = b->n_ao;
     if (n_dev_shells) *n_dev_shells = (int)b->shells.size();
-    if (n_chunks) *n_chunks = (int)b->chunks.size();
+    if (n_chunks) *n_chunks = (int)b->contraction_layout().chunks.size();
     return OKB_OK;
 }
 
 extern "C" int okb_basis_destroy(okb_basis *b) {
     if (!b) return OKB_OK;
-    cudaSetDevice(b->ctx->device);
-    if (b->meta_dev) cudaFree(b->meta_dev);
+    layout_free(b->ctx, b->cart);
+    layout_free(b->ctx, b->mix);
     delete b;
     return OKB_OK;
 }
@@ -491,6 +609,7 @@ extern "C" int okb_mo_create(okb_ctx *ctx, okb_basis *b, int n_mo, const double 
     if (!b->spherical) {
         memcpy(m->ccart.data(), coeffs, sizeof(double) * (size_t)n_mo * b->n_cart);
     } else {
+        m->csph.assign(coeffs, coeffs + (size_t)n_mo * b->n_ao);
         // C'[i][cart] = sum_j C[i][j] * T[j][cart]; accumulated in (j, term) order like the
         // row axpys of core.py:168-174
         for (int i = 0; i < n_mo; ++i) {
@@ -504,25 +623,28 @@ extern "C" int okb_mo_create(okb_ctx *ctx, okb_basis *b, int n_mo, const double 
     return OKB_OK;
 }
 
-static int mo_blob(okb_mo *m, int MC, okb_mo::Blob **out) {
-    auto it = m->blobs.find(MC);
+static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blob **out) {
+    const int key = 2 * MC + (is_mix ? 1 : 0);
+    auto it = m->blobs.find(key);
     if (it != m->blobs.end()) {
         *out = &it->second;
         return OKB_OK;
     }
     okb_basis *b = m->basis;
-    const int nchunk = (int)b->chunks.size();
+    const int nchunk = (int)lo.chunks.size();
     const int n_mtile = (m->n_mo + MC - 1) / MC;
     const int CS = pad_stride(MC);           // row stride = 4 (mod 16) doubles: conflict-free MMA fragment loads
     std::vector<double> blob((size_t)n_mtile * nchunk * KC * CS, 0.0);
     for (int mt = 0; mt < n_mtile; ++mt)
         for (int c = 0; c < nchunk; ++c) {
             double *dst = blob.data() + ((size_t)mt * nchunk + c) * KC * CS;
-            for (int kk = 0; kk < b->chunks[c].nfn; ++kk) {
-                const int row = b->fn_row[b->chunks[c].k0 + kk];
+            for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
+                const KRow &kr = lo.krow[lo.chunks[c].k0 + kk];
                 for (int i = 0; i < MC; ++i) {
                     const int mo = mt * MC + i;
-                    if (mo < m->n_mo) dst[(size_t)kk * CS + i] = m->ccart[(size_t)mo * b->n_cart + row];
+                    if (mo >= m->n_mo) continue;
+                    dst[(size_t)kk * CS + i] = kr.is_sph ? m->csph[(size_t)mo * b->n_ao + kr.index]
+                                                         : m->ccart[(size_t)mo * b->n_cart + kr.index];
                 }
             }
         }
@@ -536,8 +658,8 @@ static int mo_blob(okb_mo *m, int MC, okb_mo::Blob **out) {
     CU(cudaMemcpy(bl.c, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(bl.occ, occ.data(), occ.size() * sizeof(double), cudaMemcpyHostToDevice));
     m->ctx->h2d_bytes += (long long)((blob.size() + occ.size()) * sizeof(double));
-    m->blobs[MC] = bl;
-    *out = &m->blobs[MC];
+    m->blobs[key] = bl;
+    *out = &m->blobs[key];
     return OKB_OK;
 }
 
@@ -853,14 +975,19 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.p0 = rq.p0 + s0;
             p.npts = (int)sn;
             p.ntiles = (int)((sn + v->P - 1) / v->P);
-            p.meta = b->meta_dev;
-            p.lay = b->lay;
-            p.nchunk = (int)b->chunks.size();
+            // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); SINK_AO and the
+            // generic sets work on the all-Cartesian layout
+            const bool use_mix = rq.sink != SINK_AO && !b->mix_is_cart &&
+                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP);
+            const Layout &lo = use_mix ? b->mix : b->cart;
+            p.meta = lo.meta_dev;
+            p.lay = lo.lay;
+            p.nchunk = (int)lo.chunks.size();
             p.n_mtile = 1;
             p.n_mo = 0;
             if (rq.sink != SINK_AO) {
                 okb_mo::Blob *bl = nullptr;
-                rc = mo_blob(rq.mo, v->MC, &bl);
+                rc = mo_blob(rq.mo, v->MC, lo, use_mix, &bl);
                 if (rc != OKB_OK) return rc;
                 p.cblob = bl->c;
                 p.occ = bl->occ;
@@ -879,7 +1006,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             } else {
                 p.out = dev_out ? rq.out + s0 : dbase;
             }
-            const size_t smem = v->smem(b->lay.stride);
+            const size_t smem = v->smem(lo.lay.stride);
             if (smem > 227 * 1024) return fail(OKB_ERR_UNSUPPORTED, "variant %s needs %zu bytes of shared memory", v->name, smem);
             const int grid = std::min(p.ntiles, ctx->sm_count);
             cudaError_t e = v->launch(p, grid, smem, ctx->stream);

@@ -40,16 +40,18 @@ __host__ __device__ constexpr int set_ncodes(int set) {
 
 // ---- chunk tables (one fixed-stride blob per chunk, 16-byte aligned sections) ---------------
 struct ChunkHdr { int nshell, nprim, nfn, nrow; };
-struct ShellMeta {                 // 48 B
+struct ShellMeta {                 // 56 B
     double cx, cy, cz;
-    int prim_off, nprim, fn_off, nfn;   // offsets are chunk-local
-    int L, kind;                        // kind 1: functions in the standard order of std_lxyz(L, .) (okb_shell.cuh)
+    int prim_off, nprim, fn_off, nfn;   // offsets are chunk-local; nfn = rows this shell writes
+    int L, kind;                        // kind 1: Cartesian functions in the standard order of std_lxyz(L, .);
+                                        // kind 2: same, but the shell writes its 2L+1 real-spherical rows
+    int aux_off, pad;                   // kind 2: offset (doubles) of [f[ncart] | per row: position, coefs] in aux
 };
 struct FnMeta { int lxyz; int pad; double f; };          // lx | ly<<8 | lz<<16 ; f = angular norm * renorm
 struct RowMeta { int out_row, term_off, nterm, pad; };   // SINK_AO output rows of this chunk
 struct TermMeta { int k; int pad; double coef; };
 
-struct BlobLayout { int off_shell, off_prim, off_fn, off_row, off_term, stride; };
+struct BlobLayout { int off_shell, off_prim, off_fn, off_row, off_term, off_aux, stride; };
 
 struct KParams {
     // grid

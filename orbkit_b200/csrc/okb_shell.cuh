@@ -15,6 +15,8 @@
 // degree-9 Taylor polynomial (truncation 6.5e-18), 2^(k/4) by selects + exponent add.  Relative error
 // ~3e-16; results below the normal range (t > 708, values < 3.3e-308) are flushed to 0.
 #pragma once
+#include <type_traits>
+
 #include "okb_common.cuh"
 
 namespace okb {
@@ -58,6 +60,43 @@ __host__ __device__ constexpr int std_lxyz(int L, int j) {
 }
 __host__ __device__ constexpr int std_nfn(int L) { return (L + 1) * (L + 2) / 2; }
 
+// Sparsity pattern of the Cartesian -> real-spherical rows in the canonical order m = -L..L of the
+// reference table (orbkit/tools.py:155-191): sph_nterm(L, r) terms, term t combines the Cartesian
+// function number sph_cart(L, r, t) of the standard order above.  Only the PATTERN is compiled in; the
+// coefficient values travel in the chunk tables (the host takes them from the caller's CSR and falls back
+// to folding the transform into the MO coefficients whenever a shell does not match).  The l=4 rows
+// reproduce the reference's table as it is, including the duplicated yyyz term of (4,-1).
+__host__ __device__ constexpr int sph_nterm(int L, int r) {
+    constexpr int N2[5] = {1, 1, 3, 1, 2};
+    constexpr int N3[7] = {2, 1, 3, 3, 3, 2, 2};
+    constexpr int N4[9] = {2, 2, 3, 3, 6, 3, 4, 2, 3};
+    return L == 2 ? N2[r] : L == 3 ? N3[r] : N4[r];
+}
+__host__ __device__ constexpr int sph_cart(int L, int r, int t) {
+    constexpr int C2[5][3] = {{3}, {5}, {2, 0, 1}, {4}, {0, 1}};
+    constexpr int C3[7][3] = {{1, 4}, {9}, {7, 1, 4}, {2, 5, 8}, {6, 0, 3}, {5, 8}, {0, 3}};
+    constexpr int C4[9][6] = {{3, 5}, {6, 12}, {14, 3, 5}, {6, 6, 12}, {2, 0, 1, 10, 11, 9},
+                              {7, 4, 13}, {10, 11, 0, 1}, {4, 13}, {0, 1, 9}};
+    return L == 2 ? C2[r][t] : L == 3 ? C3[r][t] : C4[r][t];
+}
+__host__ __device__ constexpr int sph_nnz(int L) { return L == 2 ? 8 : L == 3 ? 16 : 28; }
+// aux record of a kind-2 shell (doubles): f[std_nfn(L)], then per canonical row r: tile-row position
+// (stored as a double), then its sph_nterm(L, r) coefficients
+__host__ __device__ constexpr int sph_aux_doubles(int L) { return std_nfn(L) + (2 * L + 1) + sph_nnz(L); }
+__host__ __device__ constexpr int sph_aux_row(int L, int r) {      // offset of canonical row r in the record
+    int a = std_nfn(L);
+    for (int q = 0; q < r; ++q) a += 1 + sph_nterm(L, q);
+    return a;
+}
+// compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 // radial sums over the primitives of one shell: R0 = sum cN e, R1 = sum cN a e, R2 = sum cN a^2 e
 template <bool N1, bool N2, bool FAST_EXP>
 __device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *__restrict__ prims, double rr,
@@ -89,10 +128,10 @@ __device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *
     }
 }
 
-template <int SET, int L, int STRIDE>
+template <int SET, int L, int STRIDE, bool SPH>
 __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
-                                              const FnMeta *__restrict__ fns, double x, double y, double z,
-                                              double *__restrict__ tp) {
+                                              const FnMeta *__restrict__ fns, const double *__restrict__ aux,
+                                              double x, double y, double z, double *__restrict__ tp) {
     static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP, "specialised sets");
     constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP);
     const double r[3] = {x - sh.cx, y - sh.cy, z - sh.cz};
@@ -121,48 +160,98 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
             }
         }
     }
-    const FnMeta *ff = fns + sh.fn_off;
+    constexpr int D = set_ncodes(SET);
     double *o = tp + (size_t)sh.fn_off * STRIDE;
+    if constexpr (!SPH) {
+        const FnMeta *ff = fns + sh.fn_off;
 #pragma unroll
-    for (int j = 0; j < std_nfn(L); ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int e = std_lxyz(L, j);
-        const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
-        const double f = ff[j].f;
-        const double fz = f * g0[2][lz];
-        const double fyz = fz * g0[1][ly];
-        o[(size_t)j * STRIDE] = fyz * (R0 * g0[0][lx]);
-        if (N1) {
-            const double fxz = fz * g0[0][lx];
-            const double fxy = f * (g0[0][lx] * g0[1][ly]);
-            o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
-            o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
-            o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
-            if (N2) {
-                o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
-                o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
-                o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+        for (int j = 0; j < std_nfn(L); ++j) {
+            const int e = std_lxyz(L, j);
+            const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
+            const double f = ff[j].f;
+            const double fz = f * g0[2][lz];
+            const double fyz = fz * g0[1][ly];
+            o[(size_t)j * STRIDE] = fyz * (R0 * g0[0][lx]);
+            if (N1) {
+                const double fxz = fz * g0[0][lx];
+                const double fxy = f * (g0[0][lx] * g0[1][ly]);
+                o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
+                o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
+                o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
+                if (N2) {
+                    o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
+                    o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
+                    o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+                }
             }
         }
+    } else {
+        // Cartesian values stay in registers; the 2L+1 real-spherical rows are the only ones written
+        // (core.cartesian2spherical, core.py:135-176, applied per point instead of being folded into the
+        // coefficients: the contraction then runs over n_sph instead of n_cart functions).
+        const double *ax = aux + sh.aux_off;
+        double v[std_nfn(L)][D];
+#pragma unroll
+        for (int j = 0; j < std_nfn(L); ++j) {
+            const int e = std_lxyz(L, j);
+            const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
+            const double f = ax[j];
+            const double fz = f * g0[2][lz];
+            const double fyz = fz * g0[1][ly];
+            v[j][0] = fyz * (R0 * g0[0][lx]);
+            if (N1) {
+                const double fxz = fz * g0[0][lx];
+                const double fxy = f * (g0[0][lx] * g0[1][ly]);
+                v[j][1] = fyz * g1[0][lx];
+                v[j][2] = fxz * g1[1][ly];
+                v[j][3] = fxy * g1[2][lz];
+                if (N2) {
+                    v[j][4] = fyz * g2[0][lx];
+                    v[j][5] = fxz * g2[1][ly];
+                    v[j][6] = fxy * g2[2][lz];
+                }
+            }
+        }
+        static_for<0, 2 * L + 1>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            constexpr int a = sph_aux_row(L, r);
+            const int pos = (int)ax[a];
+            double sacc[D];
+            static_for<0, sph_nterm(L, r)>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                constexpr int cj = sph_cart(L, r, t);
+                const double c = ax[a + 1 + t];
+#pragma unroll
+                for (int d = 0; d < D; ++d) sacc[d] = (t == 0) ? c * v[cj][d] : fma(c, v[cj][d], sacc[d]);
+            });
+#pragma unroll
+            for (int d = 0; d < D; ++d) o[((size_t)d * KC + pos) * STRIDE] = sacc[d];
+        });
     }
 }
 
 // dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one
 template <int SET, int STRIDE>
 __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2 *__restrict__ prims,
-                                              const FnMeta *__restrict__ fns, double x, double y, double z,
-                                              double *__restrict__ tp, int one_code, int exact) {
+                                              const FnMeta *__restrict__ fns, const double *__restrict__ aux,
+                                              double x, double y, double z, double *__restrict__ tp,
+                                              int one_code, int exact) {
     if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) {
         constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) ? SET : SET_VAL;
         if (sh.kind == 1) {                  // warp-uniform
             switch (sh.L) {
-                case 0: gen_shell_std<S, 0, STRIDE>(sh, prims, fns, x, y, z, tp); return;
-                case 1: gen_shell_std<S, 1, STRIDE>(sh, prims, fns, x, y, z, tp); return;
-                case 2: gen_shell_std<S, 2, STRIDE>(sh, prims, fns, x, y, z, tp); return;
-                case 3: gen_shell_std<S, 3, STRIDE>(sh, prims, fns, x, y, z, tp); return;
-                case 4: gen_shell_std<S, 4, STRIDE>(sh, prims, fns, x, y, z, tp); return;
+                case 0: gen_shell_std<S, 0, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 1: gen_shell_std<S, 1, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 2: gen_shell_std<S, 2, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 3: gen_shell_std<S, 3, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 4: gen_shell_std<S, 4, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
                 default: break;
+            }
+        } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
+            switch (sh.L) {
+                case 2: gen_shell_std<S, 2, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 3: gen_shell_std<S, 3, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
+                default: gen_shell_std<S, 4, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
             }
         }
     }

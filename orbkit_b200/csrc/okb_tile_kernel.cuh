@@ -74,11 +74,12 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
         const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
         const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
         const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+        const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
         double *tile = tbase + (size_t)(gc & 1) * C::TILE_DOUBLES;
         const int nitems = hdr.nshell * PT;
         for (int item = warp; item < nitems; item += NW) {
             const int s = item / PT, pt = (item % PT) * 32 + lane;
-            gen_shell_any<SET, P>(shells[s], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt, p.one_code,
+            gen_shell_any<SET, P>(shells[s], prims, fns, aux, xs[pt], ys[pt], zs[pt], tile + pt, p.one_code,
                               p.exact_mixed);
         }
     };

@@ -205,13 +205,14 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
                     const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
                     const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+                    const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
                     double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
                     const int nitems = hdr.nshell * PT;
                     // heavy shells first is the host's job (chunk order); warps take items round-robin,
                     // rotated per chunk so that the same warp is not always the one with the extra item
                     for (int item = (pwarp + g) % NPW; item < nitems; item += NPW) {
                         const int sh = item / PT, pt = (item % PT) * 32 + lane;
-                        gen_shell_any<SET, PS>(shells[sh], prims, fns, xs[pt], ys[pt], zs[pt], tile + pt,
+                        gen_shell_any<SET, PS>(shells[sh], prims, fns, aux, xs[pt], ys[pt], zs[pt], tile + pt,
                                                p.one_code, p.exact_mixed);
                     }
                     // zero the rows that pad nfn up to the k-step of the MMA (coefficients there are 0,
