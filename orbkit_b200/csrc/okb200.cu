@@ -371,7 +371,38 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
     // ---- output rows per chunk (used by SINK_AO only; the cart layout) ---------------------------------------
     std::vector<std::vector<RowMeta>> rows(nchunk);
     std::vector<std::vector<TermMeta>> terms(nchunk);
-    if (!sph_out) {
+    if (sph_out) {
+        // every spherical AO is either a tile row of a kind-2 shell or a combination of the Cartesian rows
+        // of another shell
+        std::vector<int> sph_chunk(b->n_ao, -1), sph_klocal(b->n_ao, -1);
+        for (int c = 0; c < nchunk; ++c)
+            for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
+                const KRow &kr = lo.krow[lo.chunks[c].k0 + kk];
+                if (kr.is_sph) {
+                    sph_chunk[kr.index] = c;
+                    sph_klocal[kr.index] = kk;
+                }
+            }
+        for (int j = 0; j < b->n_ao; ++j) {
+            if (sph_chunk[j] >= 0) {
+                const int c = sph_chunk[j];
+                rows[c].push_back(RowMeta{j, (int)terms[c].size(), 1, 0});
+                terms[c].push_back(TermMeta{sph_klocal[j], 0, 1.0});
+                continue;
+            }
+            const int t0 = b->t_ptr[j], t1 = b->t_ptr[j + 1];
+            if (t1 <= t0) return fail(OKB_ERR_ARG, "spherical function %d has no Cartesian terms", j);
+            const int c = fn_chunk[b->t_col[t0]];
+            if (c < 0) return fail(OKB_ERR_UNSUPPORTED, "spherical function %d refers to a transformed shell", j);
+            rows[c].push_back(RowMeta{j, (int)terms[c].size(), t1 - t0, 0});
+            for (int t = t0; t < t1; ++t) {
+                if (fn_chunk[b->t_col[t]] != c)
+                    return fail(OKB_ERR_UNSUPPORTED,
+                                "spherical function %d mixes Cartesian functions of different shells", j);
+                terms[c].push_back(TermMeta{fn_klocal[b->t_col[t]], 0, b->t_val[t]});
+            }
+        }
+    } else {
         if (!b->spherical) {
             for (int c = 0; c < nchunk; ++c)
                 for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
@@ -975,10 +1006,9 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.p0 = rq.p0 + s0;
             p.npts = (int)sn;
             p.ntiles = (int)((sn + v->P - 1) / v->P);
-            // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); SINK_AO and the
-            // generic sets work on the all-Cartesian layout
-            const bool use_mix = rq.sink != SINK_AO && !b->mix_is_cart &&
-                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP);
+            // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); the generic sets
+            // work on the all-Cartesian layout
+            const bool use_mix = !b->mix_is_cart && (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP);
             const Layout &lo = use_mix ? b->mix : b->cart;
             p.meta = lo.meta_dev;
             p.lay = lo.lay;
@@ -1008,7 +1038,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             }
             const size_t smem = v->smem(lo.lay.stride);
             if (smem > 227 * 1024) return fail(OKB_ERR_UNSUPPORTED, "variant %s needs %zu bytes of shared memory", v->name, smem);
-            const int grid = std::min(p.ntiles, ctx->sm_count);
+            // SINK_AO CTAs are small (8 warps, < 100 KB): two per SM overlap generation and stores
+            const int grid = std::min(p.ntiles, ctx->sm_count * (rq.sink == SINK_AO ? 2 : 1));
             cudaError_t e = v->launch(p, grid, smem, ctx->stream);
             if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", v->name, cudaGetErrorString(e));
             ctx->launches++;

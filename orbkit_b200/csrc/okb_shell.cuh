@@ -98,25 +98,56 @@ __device__ __forceinline__ void static_for(F &&f) {
 }
 
 // radial sums over the primitives of one shell: R0 = sum cN e, R1 = sum cN a e, R2 = sum cN a^2 e
+// G primitives at once: their exp chains are independent, so the ~15 dependent FP64 operations of
+// one exp_neg overlap with those of the others (the producer warps are latency bound: ~10 cycles per
+// dependent FP64 instruction and only two or three warps per sub-partition to hide it).
+template <int G, bool N1, bool N2>
+__device__ __forceinline__ void radial_group(const double2 *__restrict__ pp, double rr, double &R0, double &R1,
+                                             double &R2) {
+    double2 ac[G];
+    double arg[G];
+    bool live = false;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        ac[u] = pp[u];
+        arg[u] = ac[u].x * rr;
+        live |= (arg[u] < 708.0);
+    }
+    if (!__any_sync(0xffffffffu, live)) return;              // every exp of the group underflows
+    double t[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) t[u] = exp_neg(fmin(arg[u], 708.0));
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const double tu = (arg[u] < 708.0) ? ac[u].y * t[u] : 0.0;
+        R0 += tu;
+        if (N1) {
+            const double ta = tu * ac[u].x;
+            R1 += ta;
+            if (N2) R2 = fma(ta, ac[u].x, R2);
+        }
+    }
+}
+
 template <bool N1, bool N2, bool FAST_EXP>
 __device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *__restrict__ prims, double rr,
                                             double &R0, double &R1, double &R2) {
     R0 = R1 = R2 = 0.0;
     const double2 *pp = prims + sh.prim_off;
+    if (FAST_EXP) {
+        int i = 0;
+        for (; i + 4 <= sh.nprim; i += 4) radial_group<4, N1, N2>(pp + i, rr, R0, R1, R2);
+        if (i + 2 <= sh.nprim) {
+            radial_group<2, N1, N2>(pp + i, rr, R0, R1, R2);
+            i += 2;
+        }
+        if (i < sh.nprim) radial_group<1, N1, N2>(pp + i, rr, R0, R1, R2);
+        return;
+    }
     for (int i = 0; i < sh.nprim; ++i) {
         const double2 ac = pp[i];
         const double arg = ac.x * rr;
-        if (FAST_EXP) {
-            if (__any_sync(0xffffffffu, arg < 708.0)) {
-                const double t = (arg < 708.0) ? ac.y * exp_neg(arg) : 0.0;
-                R0 += t;
-                if (N1) {
-                    const double ta = t * ac.x;
-                    R1 += ta;
-                    if (N2) R2 = fma(ta, ac.x, R2);
-                }
-            }
-        } else if (__any_sync(0xffffffffu, arg < 746.0)) {   // exp(-arg) == 0.0 exactly beyond 745.14
+        if (__any_sync(0xffffffffu, arg < 746.0)) {          // exp(-arg) == 0.0 exactly beyond 745.14
             const double t = ac.y * exp(-arg);
             R0 += t;
             if (N1) {

@@ -145,22 +145,28 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
                     const TermMeta *terms = reinterpret_cast<const TermMeta *>(mb + p.lay.off_term);
                     for (int r = warp; r < hdr.nrow; r += NW) {
                         const RowMeta rm = rows[r];
+                        // rows are warp-uniform: the common single-term row (a Cartesian function, a spherical
+                        // row the generator already built, or an s/p function) is a scaled copy with PT*D
+                        // independent load -> multiply -> store chains; multi-term rows keep PT accumulators
+                        const TermMeta t0 = terms[rm.term_off];
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const int code = (SET == SET_ONE) ? p.one_code : d;
                             const int sl = p.slot[code];
                             if (sl < 0) continue;
                             double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)rm.out_row * p.ld + q0;
+                            double v[PT];
 #pragma unroll
-                            for (int j = 0; j < PT; ++j) {
-                                const int pt = j * 32 + lane;
-                                double v = 0.0;
-                                for (int t = 0; t < rm.nterm; ++t) {
-                                    const TermMeta tm = terms[rm.term_off + t];
-                                    v += tm.coef * tile[((size_t)d * KC + tm.k) * P + pt];
-                                }
-                                if (q0 + pt < p.npts) orow[pt] = v;
+                            for (int j = 0; j < PT; ++j) v[j] = t0.coef * tile[((size_t)d * KC + t0.k) * P + j * 32 + lane];
+                            for (int t = 1; t < rm.nterm; ++t) {
+                                const TermMeta tm = terms[rm.term_off + t];
+#pragma unroll
+                                for (int j = 0; j < PT; ++j)
+                                    v[j] = fma(tm.coef, tile[((size_t)d * KC + tm.k) * P + j * 32 + lane], v[j]);
                             }
+#pragma unroll
+                            for (int j = 0; j < PT; ++j)
+                                if (q0 + j * 32 + lane < p.npts) orow[j * 32 + lane] = v[j];
                         }
                     }
                 } else {
