@@ -42,6 +42,18 @@ def _drv_list(drv):
         return [drv]
 
 
+def _to_host(t):
+    """device tensor -> NumPy through page-locked memory (torch's caching host allocator)"""
+    import torch
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except Exception:
+        return t.cpu().numpy()
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
 def _grid_handle(eng, x, y, z, is_vector):
     return eng.grid_vector(x, y, z) if is_vector else eng.grid_regular(x, y, z)
 
@@ -160,7 +172,7 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
                 else:
                     eng.eval_mo(mo, g, codes, p0, p1, out=loc.data_ptr(), flags=fl)
             eng.sync()
-            return okdist.gather_points(loc, npts).cpu().numpy()
+            return _to_host(okdist.gather_points(loc, npts))
         ucodes = [] if drv is None else sorted(set(codes))
         loc = torch.zeros((1 + len(ucodes), max(n_loc, 1)), dtype=torch.float64, device=dev)
         norm = None
@@ -169,7 +181,7 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
                                       delta=loc[1:].data_ptr() if ucodes else None,
                                       want_norm=want_norm, flags=fl)
         eng.sync()
-        full = okdist.gather_points(loc[:, :n_loc].contiguous(), npts).cpu().numpy()
+        full = _to_host(okdist.gather_points(loc[:, :n_loc].contiguous(), npts))
         if want_norm:
             norm = okdist.all_reduce_sum(norm if norm is not None else numpy.zeros(mo.n_mo), eng.device)
         delta = None

@@ -826,17 +826,15 @@ static const Variant g_variants[] = {
     OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
     // warp-specialised DMMA contraction kernels: NPW producer warps + WM x WN consumer warps, NST stages.
     // MO tile MC = 8*MB (MB blocks split over the WM warp rows), point tile P = 8*BN*WN.
-    // value only (D=1): 8 + 8 warps, P = 128
-    OKB_WS(SET_VAL, 11, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 11, 4, 2, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_VAL, 12, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 12, 4, 2, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_VAL, 3, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_VAL, 3, 4, 2, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_ONE, 12, 4, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_ONE, 3, 4, 2, 4, 8, 3, SINK_MO),
-    // value + gradient (D=4): 8 + 8 warps, P = 32
+    // value only (D=1): 4 consumer + 12 producer warps (AO generation dominates), P = 128
+    OKB_WS(SET_VAL, 11, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 11, 4, 1, 4, 12, 3, SINK_RHO),
+    OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_RHO),
+    OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_RHO),
+    OKB_WS(SET_ONE, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_ONE, 3, 4, 1, 4, 12, 3, SINK_MO),
+    // value + gradient (D=4): 4 consumer + 8 producer warps, P = 32
     OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_RHO),   // 4 + 8 warps
-    OKB_WS(SET_GRAD, 12, 1, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 2, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_GRAD, 3, 1, 2, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 2, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_GRAD, 11, 1, 1, 4, 12, 3, SINK_RHO),   // 4 + 12 warps (A/B)
-    OKB_WS(SET_GRAD, 11, 1, 2, 4, 4, 3, SINK_RHO),    // 8 + 4 warps (A/B)
+    OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_RHO),
     // value + gradient + pure second derivatives (D=7): 8 consumer + 4 producer warps, P = 32
     OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_RHO),
     OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_RHO),

@@ -97,196 +97,207 @@ __device__ __forceinline__ void static_for(F &&f) {
     }
 }
 
-// radial sums over the primitives of one shell: R0 = sum cN e, R1 = sum cN a e, R2 = sum cN a^2 e
-// G primitives at once: their exp chains are independent, so the ~15 dependent FP64 operations of
-// one exp_neg overlap with those of the others (the producer warps are latency bound: ~10 cycles per
+// Radial sums over the primitives of one shell for NP points of the same thread:
+// R0 = sum cN e, R1 = sum cN a e, R2 = sum cN a^2 e.
+// G primitives x NP points at once: the exp chains are independent, so the ~15 dependent FP64 operations
+// of one exp_neg overlap with those of the others (the producer warps are latency bound: ~10 cycles per
 // dependent FP64 instruction and only two or three warps per sub-partition to hide it).
-template <int G, bool N1, bool N2>
-__device__ __forceinline__ void radial_group(const double2 *__restrict__ pp, double rr, double &R0, double &R1,
-                                             double &R2) {
+template <int G, int NP, bool N1, bool N2>
+__device__ __forceinline__ void radial_group(const double2 *__restrict__ pp, const double (&rr)[NP], double (&R0)[NP],
+                                             double (&R1)[NP], double (&R2)[NP]) {
     double2 ac[G];
-    double arg[G];
+    double arg[G][NP];
     bool live = false;
 #pragma unroll
     for (int u = 0; u < G; ++u) {
         ac[u] = pp[u];
-        arg[u] = ac[u].x * rr;
-        live |= (arg[u] < 708.0);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            arg[u][q] = ac[u].x * rr[q];
+            live |= (arg[u][q] < 708.0);
+        }
     }
     if (!__any_sync(0xffffffffu, live)) return;              // every exp of the group underflows
-    double t[G];
+    double t[G][NP];
 #pragma unroll
-    for (int u = 0; u < G; ++u) t[u] = exp_neg(fmin(arg[u], 708.0));
+    for (int u = 0; u < G; ++u)
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-        const double tu = (arg[u] < 708.0) ? ac[u].y * t[u] : 0.0;
-        R0 += tu;
-        if (N1) {
-            const double ta = tu * ac[u].x;
-            R1 += ta;
-            if (N2) R2 = fma(ta, ac[u].x, R2);
-        }
-    }
-}
-
-template <bool N1, bool N2, bool FAST_EXP>
-__device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *__restrict__ prims, double rr,
-                                            double &R0, double &R1, double &R2) {
-    R0 = R1 = R2 = 0.0;
-    const double2 *pp = prims + sh.prim_off;
-    if (FAST_EXP) {
-        int i = 0;
-        for (; i + 4 <= sh.nprim; i += 4) radial_group<4, N1, N2>(pp + i, rr, R0, R1, R2);
-        if (i + 2 <= sh.nprim) {
-            radial_group<2, N1, N2>(pp + i, rr, R0, R1, R2);
-            i += 2;
-        }
-        if (i < sh.nprim) radial_group<1, N1, N2>(pp + i, rr, R0, R1, R2);
-        return;
-    }
-    for (int i = 0; i < sh.nprim; ++i) {
-        const double2 ac = pp[i];
-        const double arg = ac.x * rr;
-        if (__any_sync(0xffffffffu, arg < 746.0)) {          // exp(-arg) == 0.0 exactly beyond 745.14
-            const double t = ac.y * exp(-arg);
-            R0 += t;
+        for (int q = 0; q < NP; ++q) t[u][q] = exp_neg(fmin(arg[u][q], 708.0));
+#pragma unroll
+    for (int u = 0; u < G; ++u)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const double tu = (arg[u][q] < 708.0) ? ac[u].y * t[u][q] : 0.0;
+            R0[q] += tu;
             if (N1) {
-                const double ta = t * ac.x;
-                R1 += ta;
-                if (N2) R2 += ta * ac.x;
+                const double ta = tu * ac[u].x;
+                R1[q] += ta;
+                if (N2) R2[q] = fma(ta, ac[u].x, R2[q]);
             }
         }
-    }
 }
 
-template <int SET, int L, int STRIDE, bool SPH>
+template <int NP, bool N1, bool N2>
+__device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *__restrict__ prims,
+                                            const double (&rr)[NP], double (&R0)[NP], double (&R1)[NP],
+                                            double (&R2)[NP]) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) R0[q] = R1[q] = R2[q] = 0.0;
+    const double2 *pp = prims + sh.prim_off;
+    constexpr int G = (NP >= 2) ? 2 : 4;                     // keep G*NP exp chains in flight
+    int i = 0;
+    for (; i + G <= sh.nprim; i += G) radial_group<G, NP, N1, N2>(pp + i, rr, R0, R1, R2);
+    if (G == 4 && i + 2 <= sh.nprim) {
+        radial_group<2, NP, N1, N2>(pp + i, rr, R0, R1, R2);
+        i += 2;
+    }
+    if (i < sh.nprim) radial_group<1, NP, N1, N2>(pp + i, rr, R0, R1, R2);
+}
+
+// One standard shell for NP points of the same thread (points pt, pt+32, ...: tile columns tp[32*q]).
+template <int SET, int L, int STRIDE, bool SPH, int NP>
 __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
-                                              double x, double y, double z, double *__restrict__ tp) {
+                                              const double *__restrict__ xs, const double *__restrict__ ys,
+                                              const double *__restrict__ zs, double *__restrict__ tp) {
     static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP, "specialised sets");
     constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP);
-    const double r[3] = {x - sh.cx, y - sh.cy, z - sh.cz};
-    const double rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    double R0, R1, R2;
-    radial_sums<N1, N2, true>(sh, prims, rr, R0, R1, R2);
-    // per-axis factor tables (all indices are compile-time constants after unrolling)
-    double g0[3][L + 2], g1[3][L + 1], g2[3][L + 1];
-    const double m2R1 = -2.0 * R1;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        g0[a][0] = 1.0;
-#pragma unroll
-        for (int l = 1; l <= L + 1; ++l) g0[a][l] = g0[a][l - 1] * r[a];
-        if (N1) {
-#pragma unroll
-            for (int l = 0; l <= L; ++l)
-                g1[a][l] = (l == 0) ? g0[a][1] * m2R1 : fma(g0[a][l + 1], m2R1, g0[a][l - 1] * ((double)l * R0));
-        }
-        if (N2) {
-            const double r2R2 = 4.0 * (r[a] * r[a]) * R2;
-#pragma unroll
-            for (int l = 0; l <= L; ++l) {
-                const double t = g0[a][l] * fma((double)(-(4 * l + 2)), R1, r2R2);
-                g2[a][l] = (l < 2) ? t : fma(g0[a][l - 2], (double)(l * (l - 1)) * R0, t);
-            }
-        }
-    }
     constexpr int D = set_ncodes(SET);
-    double *o = tp + (size_t)sh.fn_off * STRIDE;
-    if constexpr (!SPH) {
-        const FnMeta *ff = fns + sh.fn_off;
+    double r[NP][3], rr[NP];
 #pragma unroll
-        for (int j = 0; j < std_nfn(L); ++j) {
-            const int e = std_lxyz(L, j);
-            const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
-            const double f = ff[j].f;
-            const double fz = f * g0[2][lz];
-            const double fyz = fz * g0[1][ly];
-            o[(size_t)j * STRIDE] = fyz * (R0 * g0[0][lx]);
+    for (int q = 0; q < NP; ++q) {
+        r[q][0] = xs[32 * q] - sh.cx;
+        r[q][1] = ys[32 * q] - sh.cy;
+        r[q][2] = zs[32 * q] - sh.cz;
+        rr[q] = r[q][0] * r[q][0] + r[q][1] * r[q][1] + r[q][2] * r[q][2];
+    }
+    double R0[NP], R1[NP], R2[NP];
+    radial_sums<NP, N1, N2>(sh, prims, rr, R0, R1, R2);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        // per-axis factor tables (all indices are compile-time constants after unrolling)
+        double g0[3][L + 2], g1[3][L + 1], g2[3][L + 1];
+        const double m2R1 = -2.0 * R1[q];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            g0[a][0] = 1.0;
+#pragma unroll
+            for (int l = 1; l <= L + 1; ++l) g0[a][l] = g0[a][l - 1] * r[q][a];
             if (N1) {
-                const double fxz = fz * g0[0][lx];
-                const double fxy = f * (g0[0][lx] * g0[1][ly]);
-                o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
-                o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
-                o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
-                if (N2) {
-                    o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
-                    o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
-                    o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+#pragma unroll
+                for (int l = 0; l <= L; ++l)
+                    g1[a][l] = (l == 0) ? g0[a][1] * m2R1
+                                        : fma(g0[a][l + 1], m2R1, g0[a][l - 1] * ((double)l * R0[q]));
+            }
+            if (N2) {
+                const double r2R2 = 4.0 * (r[q][a] * r[q][a]) * R2[q];
+#pragma unroll
+                for (int l = 0; l <= L; ++l) {
+                    const double t = g0[a][l] * fma((double)(-(4 * l + 2)), R1[q], r2R2);
+                    g2[a][l] = (l < 2) ? t : fma(g0[a][l - 2], (double)(l * (l - 1)) * R0[q], t);
                 }
             }
         }
-    } else {
-        // Cartesian values stay in registers; the 2L+1 real-spherical rows are the only ones written
-        // (core.cartesian2spherical, core.py:135-176, applied per point instead of being folded into the
-        // coefficients: the contraction then runs over n_sph instead of n_cart functions).
-        const double *ax = aux + sh.aux_off;
-        double v[std_nfn(L)][D];
+        double *o = tp + 32 * q + (size_t)sh.fn_off * STRIDE;
+        if constexpr (!SPH) {
+            const FnMeta *ff = fns + sh.fn_off;
 #pragma unroll
-        for (int j = 0; j < std_nfn(L); ++j) {
-            const int e = std_lxyz(L, j);
-            const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
-            const double f = ax[j];
-            const double fz = f * g0[2][lz];
-            const double fyz = fz * g0[1][ly];
-            v[j][0] = fyz * (R0 * g0[0][lx]);
-            if (N1) {
-                const double fxz = fz * g0[0][lx];
-                const double fxy = f * (g0[0][lx] * g0[1][ly]);
-                v[j][1] = fyz * g1[0][lx];
-                v[j][2] = fxz * g1[1][ly];
-                v[j][3] = fxy * g1[2][lz];
-                if (N2) {
-                    v[j][4] = fyz * g2[0][lx];
-                    v[j][5] = fxz * g2[1][ly];
-                    v[j][6] = fxy * g2[2][lz];
+            for (int j = 0; j < std_nfn(L); ++j) {
+                const int e = std_lxyz(L, j);
+                const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
+                const double f = ff[j].f;
+                const double fz = f * g0[2][lz];
+                const double fyz = fz * g0[1][ly];
+                o[(size_t)j * STRIDE] = fyz * (R0[q] * g0[0][lx]);
+                if (N1) {
+                    const double fxz = fz * g0[0][lx];
+                    const double fxy = f * (g0[0][lx] * g0[1][ly]);
+                    o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
+                    o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
+                    o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
+                    if (N2) {
+                        o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
+                        o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
+                        o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+                    }
                 }
             }
-        }
-        static_for<0, 2 * L + 1>([&](auto rc) {
-            constexpr int r = decltype(rc)::value;
-            constexpr int a = sph_aux_row(L, r);
-            const int pos = (int)ax[a];
-            double sacc[D];
-            static_for<0, sph_nterm(L, r)>([&](auto tc) {
-                constexpr int t = decltype(tc)::value;
-                constexpr int cj = sph_cart(L, r, t);
-                const double c = ax[a + 1 + t];
+        } else {
+            // Cartesian values stay in registers; the 2L+1 real-spherical rows are the only ones written
+            // (core.cartesian2spherical, core.py:135-176, applied per point instead of being folded into the
+            // coefficients: the contraction then runs over n_sph instead of n_cart functions).
+            const double *ax = aux + sh.aux_off;
+            double v[std_nfn(L)][D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) sacc[d] = (t == 0) ? c * v[cj][d] : fma(c, v[cj][d], sacc[d]);
+            for (int j = 0; j < std_nfn(L); ++j) {
+                const int e = std_lxyz(L, j);
+                const int lx = e & 15, ly = (e >> 4) & 15, lz = (e >> 8) & 15;
+                const double f = ax[j];
+                const double fz = f * g0[2][lz];
+                const double fyz = fz * g0[1][ly];
+                v[j][0] = fyz * (R0[q] * g0[0][lx]);
+                if (N1) {
+                    const double fxz = fz * g0[0][lx];
+                    const double fxy = f * (g0[0][lx] * g0[1][ly]);
+                    v[j][1] = fyz * g1[0][lx];
+                    v[j][2] = fxz * g1[1][ly];
+                    v[j][3] = fxy * g1[2][lz];
+                    if (N2) {
+                        v[j][4] = fyz * g2[0][lx];
+                        v[j][5] = fxz * g2[1][ly];
+                        v[j][6] = fxy * g2[2][lz];
+                    }
+                }
+            }
+            static_for<0, 2 * L + 1>([&](auto rc) {
+                constexpr int rw = decltype(rc)::value;
+                constexpr int a = sph_aux_row(L, rw);
+                const int pos = (int)ax[a];
+                double sacc[D];
+                static_for<0, sph_nterm(L, rw)>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    constexpr int cj = sph_cart(L, rw, t);
+                    const double c = ax[a + 1 + t];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) sacc[d] = (t == 0) ? c * v[cj][d] : fma(c, v[cj][d], sacc[d]);
+                });
+#pragma unroll
+                for (int d = 0; d < D; ++d) o[((size_t)d * KC + pos) * STRIDE] = sacc[d];
             });
-#pragma unroll
-            for (int d = 0; d < D; ++d) o[((size_t)d * KC + pos) * STRIDE] = sacc[d];
-        });
+        }
     }
 }
 
-// dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one
-template <int SET, int STRIDE>
+// dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one.
+// xs/ys/zs point at the coordinates of the thread's first point; its NP points are 32 apart.
+template <int SET, int STRIDE, int NP>
 __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
-                                              double x, double y, double z, double *__restrict__ tp,
+                                              const double *__restrict__ xs, const double *__restrict__ ys,
+                                              const double *__restrict__ zs, double *__restrict__ tp,
                                               int one_code, int exact) {
     if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) {
         constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) ? SET : SET_VAL;
         if (sh.kind == 1) {                  // warp-uniform
             switch (sh.L) {
-                case 0: gen_shell_std<S, 0, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
-                case 1: gen_shell_std<S, 1, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
-                case 2: gen_shell_std<S, 2, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
-                case 3: gen_shell_std<S, 3, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
-                case 4: gen_shell_std<S, 4, STRIDE, false>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 1: gen_shell_std<S, 1, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 2: gen_shell_std<S, 2, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 3: gen_shell_std<S, 3, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 4: gen_shell_std<S, 4, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
                 default: break;
             }
         } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
             switch (sh.L) {
-                case 2: gen_shell_std<S, 2, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
-                case 3: gen_shell_std<S, 3, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
-                default: gen_shell_std<S, 4, STRIDE, true>(sh, prims, fns, aux, x, y, z, tp); return;
+                case 2: gen_shell_std<S, 2, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 3: gen_shell_std<S, 3, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                default: gen_shell_std<S, 4, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
             }
         }
     }
-    gen_shell<SET, STRIDE>(sh, prims, fns, x, y, z, tp, one_code, exact);
+#pragma unroll 1
+    for (int q = 0; q < NP; ++q)
+        gen_shell<SET, STRIDE>(sh, prims, fns, xs[32 * q], ys[32 * q], zs[32 * q], tp + 32 * q, one_code, exact);
 }
 
 }  // namespace okb

@@ -76,11 +76,13 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
         const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
         const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
         double *tile = tbase + (size_t)(gc & 1) * C::TILE_DOUBLES;
-        const int nitems = hdr.nshell * PT;
+        // a thread evaluates NP points (32 apart) of one shell at a time: independent dependency chains
+        constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
+        const int nitems = hdr.nshell * PG;
         for (int item = warp; item < nitems; item += NW) {
-            const int s = item / PT, pt = (item % PT) * 32 + lane;
-            gen_shell_any<SET, P>(shells[s], prims, fns, aux, xs[pt], ys[pt], zs[pt], tile + pt, p.one_code,
-                              p.exact_mixed);
+            const int s = item / PG, pt = (item % PG) * (32 * NP) + lane;
+            gen_shell_any<SET, P, NP>(shells[s], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt, p.one_code,
+                                      p.exact_mixed);
         }
     };
 

@@ -207,13 +207,15 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
                     const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
                     double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
-                    const int nitems = hdr.nshell * PT;
-                    // heavy shells first is the host's job (chunk order); warps take items round-robin,
-                    // rotated per chunk so that the same warp is not always the one with the extra item
+                    // a thread evaluates NP points (32 apart) of one shell at a time (independent dependency
+                    // chains); warps take items round-robin, rotated per chunk so that the same warp is not
+                    // always the one with the extra item
+                    constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
+                    const int nitems = hdr.nshell * PG;
                     for (int item = (pwarp + g) % NPW; item < nitems; item += NPW) {
-                        const int sh = item / PT, pt = (item % PT) * 32 + lane;
-                        gen_shell_any<SET, PS>(shells[sh], prims, fns, aux, xs[pt], ys[pt], zs[pt], tile + pt,
-                                               p.one_code, p.exact_mixed);
+                        const int sh = item / PG, pt = (item % PG) * (32 * NP) + lane;
+                        gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
+                                                   p.one_code, p.exact_mixed);
                     }
                     // zero the rows that pad nfn up to the k-step of the MMA (coefficients there are 0,
                     // but stale shared memory could hold NaN/Inf bit patterns)

@@ -1,0 +1,27 @@
+#!/bin/bash
+# A/B of kernel variants for a rho request: args = derivative codes string, then variant substrings
+codes="$1"; shift
+for v in "$@"; do
+  echo "== [$v] codes=[$codes]"
+  OKB_VARIANT="$v" python - <<PY
+import os, sys, numpy, torch
+sys.path.insert(0, '.')
+from orbkit_b200 import synth
+from orbkit_b200._lib import OKB_FLAG_OUT_DEVICE
+from orbkit_b200.engine import get_engine
+eng = get_engine(); dev = torch.device('cuda', eng.device)
+stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+qc = synth.to_qcinfo(synth.make_molecule(n_heavy=24, n_light=20, n_mo=82, seed=0, spherical=True))
+ax = numpy.linspace(-12, 12, 200)
+basis = eng.basis(qc.geo_spec, qc.ao_spec); mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ()); g = eng.grid_regular(ax, ax, ax)
+codes = [int(c) for c in "$codes".split()] if "$codes".strip() else []
+out = torch.zeros((8, 8000000), dtype=torch.float64, device=dev)
+f = lambda: eng.eval_rho(mo, g, codes, rho=out[0].data_ptr(), delta=out[1:].data_ptr() if codes else None, flags=OKB_FLAG_OUT_DEVICE)
+f(); f(); eng.sync()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.cuda.stream(stream):
+    e0.record(stream); [f() for _ in range(3)]; e1.record(stream)
+eng.sync()
+print('%.2f ms  %s  sum %.6f' % (e0.elapsed_time(e1) / 3, eng.last_kernel(), float(out[0].sum())))
+PY
+done
