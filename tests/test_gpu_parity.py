@@ -267,3 +267,58 @@ def test_full_size_properties_config3(ok, oracle_mod):
         rm = ok.rho_compute(qc)
         fd = (rp - rm) / (2 * h)
         assert numpy.allclose(fd, dr[ax_i, :12], rtol=1e-5, atol=1e-7 * numpy.abs(dr).max())
+
+
+def test_config1_h2o_80cube_full_parity(ok, oracle_mod):
+    """BASELINE configs[0] at full size: H2O RHF (Gaussian fchk, spherical d), rho and grad rho on the
+    regular 80^3 grid over [-6,6]^3, every point against the reference's own objects."""
+    qc, _ = golden_qc('h2o_gaussian_sph_occ')
+    ax = numpy.linspace(-6.0, 6.0, 80)
+    set_regular(ok, ax, ax, ax)
+    rho, drho = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    kind = 'ref' if oracle_mod.have_ref() else 'port'
+    r_ref, d_ref = oracle_mod.rho_compute(qc, ax, ax, ax, is_vector=False, drv=['x', 'y', 'z'], numproc=4,
+                                          slice_length=20000, kind=kind)
+    assert rho.shape == (80, 80, 80)
+    assert_close(rho, r_ref, 'C1 rho 80^3')
+    assert_close(drho, d_ref, 'C1 grad rho 80^3')
+    d3r = (ax[1] - ax[0]) ** 3
+    assert abs(rho.sum() * d3r - r_ref.sum() * d3r) < 1e-8          # electron count
+    assert abs(rho.sum() * d3r - 10.0) < 0.05                       # 10 electrons, coarse quadrature
+
+
+def test_benchmark_size_properties_200cube(ok, oracle_mod):
+    """The benchmark workload itself (1000 AOs, 82 MOs, 200^3 points): parity on a random sub-sample
+    against the reference objects, and size-independent properties of the full result."""
+    from orbkit_b200.engine import get_engine
+    qc, _ = golden_qc('synth_c3')
+    ax = numpy.linspace(-12.0, 12.0, 200)
+    set_regular(ok, ax, ax, ax)
+    rho, drho = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert rho.shape == (200, 200, 200) and numpy.isfinite(rho).all() and (rho >= 0).all()
+    rng = numpy.random.default_rng(9)
+    idx = rng.choice(200 ** 3, size=64, replace=False)
+    i, rem = numpy.divmod(idx, 200 * 200)
+    j, k = numpy.divmod(rem, 200)
+    kind = 'ref' if oracle_mod.have_ref() else 'port'
+    rr, dr = oracle_mod.rho_compute(qc, ax[i], ax[j], ax[k], is_vector=True, drv=['x', 'y', 'z'], kind=kind)
+    assert_close(rho.ravel()[idx], rr, 'C3 rho sample')
+    assert_close(drho.reshape(3, -1)[:, idx], dr, 'C3 grad rho sample')
+    # (1) checksum of checksums: eight disjoint point ranges reproduce the full evaluation bit for bit
+    eng = get_engine()
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    g = eng.grid_regular(ax, ax, ax)
+    bounds = numpy.linspace(0, 200 ** 3, 9).astype(int)
+    bounds[1:-1] += [3, -5, 17, 0, 31, -1, 64]                      # ragged, not tile aligned
+    norm_sum = numpy.zeros(82)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        r, d, n = eng.eval_rho(mo, g, [1, 2, 3], int(a), int(b), want_norm=True)
+        assert numpy.array_equal(r, rho.ravel()[a:b])
+        assert numpy.array_equal(d, drho.reshape(3, -1)[:, a:b])
+        norm_sum += n
+    # (2) two independent accumulation paths: sum_i occ_i * (sum_p phi_i^2)  ==  sum_p rho
+    occ = qc.mo_spec.get_occ()
+    assert abs((occ * norm_sum).sum() / rho.sum() - 1.0) < 1e-11
+    # (3) rho decays towards the box faces, so the gradient integrates to (nearly) zero
+    assert numpy.abs(drho.sum(axis=(1, 2, 3))).max() < 1e-6 * numpy.abs(drho).sum()
