@@ -97,6 +97,7 @@ struct Layout {
     std::vector<Chunk> chunks;
     std::vector<KRow> krow;                  // device row -> content
     std::vector<int> shell_sph;              // per device shell: 1 if it writes spherical rows
+    std::vector<int> order;                  // chunk c holds the device shells order[s0..s1)
     BlobLayout lay{};
     unsigned char *meta_dev = nullptr;
     int n_rows = 0;
@@ -326,36 +327,74 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
     lo.shell_sph.assign(nshell, 0);
     for (int s = 0; s < nshell; ++s)
         if (sph_out && match_sph_rows(b, s, canon[s])) lo.shell_sph[s] = 1;
-    // ---- greedy chunking over the rows ------------------------------------------------------------------
+    // ---- chunking -----------------------------------------------------------------------------------------
+    // Shells are taken in the caller's order; when the next one no longer fits, the remaining room of
+    // the chunk is filled with the largest later shells that still fit (`order` records the resulting
+    // permutation; chunk c holds order[s0..s1)).  The contraction pads every chunk to a multiple of 4
+    // rows and pays a fixed hand-over cost per chunk, so full chunks are worth 4-5% on the 1000-AO
+    // molecule (38 chunks / 1045 padded rows in plain order -> 32 chunks / 1000 rows).
     const int MAXS = 32, MAXP = 96;
-    Layout::Chunk cur{0, 0, 0, 0, 0};
-    int k = 0;
-    std::vector<int> shell_k0(nshell, 0);
+    std::vector<int> nf_of(nshell), np_of(nshell);
     for (int s = 0; s < nshell; ++s) {
         const DevShell &sh = b->shells[s];
-        const int nf = lo.shell_sph[s] ? 2 * sh.L + 1 : (int)sh.fn_row.size(), np = (int)sh.alpha.size();
-        if (nf > KC) return fail(OKB_ERR_UNSUPPORTED, "shell with %d functions exceeds the chunk size %d", nf, KC);
-        const bool full = (cur.s1 > cur.s0) &&
-                          (cur.nfn + nf > KC || cur.s1 - cur.s0 >= MAXS || cur.nprim + np > MAXP);
-        if (full) {
-            lo.chunks.push_back(cur);
-            cur = Layout::Chunk{s, s, k, 0, 0};
-        }
-        cur.s1 = s + 1;
-        cur.nfn += nf;
-        cur.nprim += np;
-        shell_k0[s] = k;
-        if (lo.shell_sph[s]) {
-            // rows in ascending spherical AO index (keeps the coefficient rows in the caller's order)
-            std::vector<int> js(canon[s]);
-            std::sort(js.begin(), js.end());
-            for (int j : js) lo.krow.push_back(KRow{1, j});
-        } else {
-            for (int r : sh.fn_row) lo.krow.push_back(KRow{0, r});
-        }
-        k += nf;
+        nf_of[s] = lo.shell_sph[s] ? 2 * sh.L + 1 : (int)sh.fn_row.size();
+        np_of[s] = (int)sh.alpha.size();
+        if (nf_of[s] > KC) return fail(OKB_ERR_UNSUPPORTED, "shell with %d functions exceeds the chunk size %d", nf_of[s], KC);
+        if (np_of[s] > MAXP) return fail(OKB_ERR_UNSUPPORTED, "shell with %d primitives exceeds the chunk limit %d", np_of[s], MAXP);
     }
-    if (cur.s1 > cur.s0) lo.chunks.push_back(cur);
+    static const bool plain_order = getenv("OKB_PLAIN_CHUNKS") != nullptr;
+    lo.order.clear();
+    {
+        std::vector<char> used(nshell, 0);
+        int first = 0;                                   // first unused shell
+        while (first < nshell) {
+            Layout::Chunk cur{(int)lo.order.size(), (int)lo.order.size(), 0, 0, 0};
+            auto fits = [&](int s) {
+                return cur.nfn + nf_of[s] <= KC && cur.s1 - cur.s0 < MAXS && cur.nprim + np_of[s] <= MAXP;
+            };
+            auto take = [&](int s) {
+                used[s] = 1;
+                lo.order.push_back(s);
+                cur.s1++;
+                cur.nfn += nf_of[s];
+                cur.nprim += np_of[s];
+            };
+            int s = first;
+            for (; s < nshell; ++s) {                    // the caller's order while it fits
+                if (used[s]) continue;
+                if (!fits(s)) break;
+                take(s);
+            }
+            while (!plain_order && cur.nfn < KC) {       // fill the remaining room from later shells
+                int best = -1;
+                for (int t = s; t < nshell; ++t)
+                    if (!used[t] && fits(t) && (best < 0 || nf_of[t] > nf_of[best])) best = t;
+                if (best < 0) break;
+                take(best);
+            }
+            while (first < nshell && used[first]) ++first;
+            lo.chunks.push_back(cur);
+        }
+    }
+    int k = 0;
+    std::vector<int> shell_k0(nshell, 0);
+    for (Layout::Chunk &ch : lo.chunks) {
+        ch.k0 = k;
+        for (int o = ch.s0; o < ch.s1; ++o) {
+            const int s = lo.order[o];
+            const DevShell &sh = b->shells[s];
+            shell_k0[s] = k;
+            if (lo.shell_sph[s]) {
+                // rows in ascending spherical AO index (keeps the coefficient rows in the caller's order)
+                std::vector<int> js(canon[s]);
+                std::sort(js.begin(), js.end());
+                for (int j : js) lo.krow.push_back(KRow{1, j});
+            } else {
+                for (int r : sh.fn_row) lo.krow.push_back(KRow{0, r});
+            }
+            k += nf_of[s];
+        }
+    }
     lo.n_rows = k;
     const int nchunk = (int)lo.chunks.size();
     // Cartesian row -> (chunk, chunk-local k) for the SINK_AO output rows (cart layout only)
@@ -428,7 +467,8 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
     std::vector<std::vector<double>> aux(nchunk);
     std::vector<int> shell_aux(nshell, 0);
     for (int c = 0; c < nchunk; ++c)
-        for (int s = lo.chunks[c].s0; s < lo.chunks[c].s1; ++s) {
+        for (int o = lo.chunks[c].s0; o < lo.chunks[c].s1; ++o) {
+            const int s = lo.order[o];
             if (!lo.shell_sph[s]) continue;
             const DevShell &sh = b->shells[s];
             const int L = sh.L;
@@ -473,7 +513,8 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
         double2 *pm = reinterpret_cast<double2 *>(mb + L.off_prim);
         FnMeta *fm = reinterpret_cast<FnMeta *>(mb + L.off_fn);
         int po = 0;
-        for (int s = ch.s0; s < ch.s1; ++s) {
+        for (int o = ch.s0; o < ch.s1; ++o) {
+            const int s = lo.order[o];
             const DevShell &sh = b->shells[s];
             const int fo = shell_k0[s] - ch.k0;
             ShellMeta m{};
@@ -491,7 +532,7 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
                 for (size_t j = 0; j < sh.fn_row.size(); ++j)
                     fm[fo + j] = FnMeta{sh.lx[j] | (sh.ly[j] << 8) | (sh.lz[j] << 16), 0, sh.f[j]};
             }
-            sm[s - ch.s0] = m;
+            sm[o - ch.s0] = m;
             for (size_t i = 0; i < sh.alpha.size(); ++i) pm[po++] = make_double2(sh.alpha[i], sh.cn[i]);
         }
         if (!rows[c].empty()) memcpy(mb + L.off_row, rows[c].data(), rows[c].size() * sizeof(RowMeta));
@@ -835,6 +876,8 @@ static const Variant g_variants[] = {
     OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_RHO),   // 4 + 8 warps
     OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_RHO),
     OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_GRAD, 11, 1, 2, 4, 8, 3, SINK_RHO),     // experiment: two consumer warps per sub-partition
+    OKB_WS(SET_GRAD, 11, 2, 2, 2, 8, 3, SINK_RHO),     // experiment: 2x2 consumer warps, 16 points each
     // value + gradient + pure second derivatives (D=7): 8 consumer + 4 producer warps, P = 32
     OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_RHO),
     OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_RHO),
@@ -853,9 +896,12 @@ static const Variant *pick_variant(int set, int sink, int n_mo) {
         // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
-        const long long padded = (long long)((n_mo + v.MC - 1) / v.MC) * v.MC;
-        // padded MO count dominates; prefer the wider tile on ties (fewer AO regenerations)
-        const long long cost = padded * 1000 - v.MC;
+        // Every MO tile regenerates the AO tiles, and the producers run beside the consumers: a pass over one
+        // MO tile costs max(contraction ~ MC, generation).  Measured on the 1000-AO molecule the two balance at
+        // MC ~ 45-60 for every set (profiles/r01_perf_matrix.txt), so narrow tiles are charged as 48 wide.
+        // Prefer the wider tile on ties (fewer AO regenerations).
+        const long long n_tiles = (n_mo + v.MC - 1) / v.MC;
+        const long long cost = n_tiles * std::max(v.MC, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;

@@ -55,7 +55,9 @@ struct WsCfg {
     // NCW*32*CREG + NPW*32*PREG must not exceed what the launch reserved
     static constexpr int LAUNCH_REGS = (65536 / NT) / 8 * 8;
     static constexpr int ACC_REGS = 4 * AM * BN * D;
-    static constexpr int CREG_WANT = ((ACC_REGS + 40 + 7) / 8 * 8 > 248) ? 248 : (ACC_REGS + 40 + 7) / 8 * 8;
+    static constexpr int CREG_SLACK = (NCW == 8 && ACC_REGS > 160) ? 32 : 40;   // big tiles on two warpgroups:
+                                                                                  // leave the producers > 100 registers
+    static constexpr int CREG_WANT = ((ACC_REGS + CREG_SLACK + 7) / 8 * 8 > 248) ? 248 : (ACC_REGS + CREG_SLACK + 7) / 8 * 8;
     static constexpr int PREG_MAX = ((NT * LAUNCH_REGS - NCW * 32 * CREG_WANT) / (NPW * 32)) / 8 * 8;
     static constexpr int PREG_CAP = LAUNCH_REGS < 152 ? LAUNCH_REGS : 152;   // setmaxnreg.dec may only lower
     static constexpr int PREG = PREG_MAX > PREG_CAP ? PREG_CAP : PREG_MAX;
