@@ -139,6 +139,34 @@ int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long lo
                  const int *drv_codes, int n_drv, double *rho, double *delta_rho,
                  double *mo_norm, unsigned flags);
 
+/* ---- (3) detCI grid contractions --------------------------------------------
+ * Replace the per-slice loops cy_ci.get_rho / get_jab / get_a_nabla_b (orbkit/detci/cy_ci.pyx:70-97,
+ * 156-186, 211-240) behind detci.ci_core.rho / jab / a_nabla_b (ci_core.py:85-267).  The Python lists
+ * `zero` and `sing` arrive flattened into n_terms terms (coef[t], ia[t], ib[t]) in list order; for
+ * OKB_CI_RHO the entries of `zero` are terms with ia == ib.  Results are bit-identical to the
+ * reference loops for identical MO arrays (same expression order, no FMA contraction).
+ *   OKB_CI_RHO        out[npts]          = sum_t coef mo[ia] mo[ib]
+ *   OKB_CI_JAB        out[3][npts]       = sum_t -1/2 coef (mo[ia] dmo[d][ib] - mo[ib] dmo[d][ia])
+ *   OKB_CI_A_NABLA_B  out[3][npts]       = sum_t coef mo[ia] dmo[d][ib]
+ *   OKB_CI_PAIRS      out[n_terms][npts] = mo[ia] mo[ib]       (per-pair products; coef ignored) */
+#define OKB_CI_RHO 0
+#define OKB_CI_JAB 1
+#define OKB_CI_A_NABLA_B 2
+#define OKB_CI_PAIRS 3
+#define OKB_FLAG_IN_DEVICE 4u    /* okb_ci_contract: molist / molistdrv are DEVICE pointers */
+/* Level 1: given MO arrays molist[n_mo][ld_in] and (JAB, A_NABLA_B) molistdrv[3][n_mo][ld_in]; the first
+ * npts points of every row are contracted into the first npts entries of the rows of out[.][ld_out]
+ * (ld_* = row strides in points, >= npts). */
+int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
+                    const double *molist, const double *molistdrv, int n_terms, const double *coef,
+                    const int *ia, const int *ib, double *out, long long ld_out, unsigned flags);
+/* Level 2 (fused): the MOs of `mo` (and, for JAB / A_NABLA_B, the three derivative sets drv_codes[3],
+ * e.g. {1,2,3} or {4,5,6}) are evaluated slab by slab on the device over the points [p0, p1) of `grid`
+ * and contracted there; MO values never cross PCIe.  out as above with npts = p1 - p0. */
+int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1, int mode,
+                const int *drv_codes, int n_terms, const double *coef, const int *ia,
+                const int *ib, double *out, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,71 @@ void okor_vector2grid(double *xn, double *yn, double *zn,
     for (long j = 0; j < ny; ++j) yn[j] = y[j * nz];
     for (long k = 0; k < nz; ++k) zn[k] = z[k];
 }
+
+/* ---- detCI grid contractions (orbkit/detci/cy_ci.pyx) --------------------
+ * The reference walks Python lists `zero = [coefficients, orbital indices]`
+ * (identical determinants) and `sing = [coefficients, orbital pairs]`
+ * (effective single excitations); here they arrive flattened:
+ *   zc[nz], zi[nz]           every (prefactor, orbital) entry of zero, in list order
+ *   sc[ns], sa[ns], sb[ns]   every (product of CI coefficients, orbital a, orbital b) of sing
+ * molist is [n_mo][npts], molistdrv [3][n_mo][npts]; the slice [i0, i1) of the
+ * points is written to out (rho: [i1-i0]; jab / a_nabla_b: [3][i1-i0]).
+ * Operation order follows the reference expression by expression. */
+
+/* get_rho, cy_ci.pyx:70-97:  rho[x] += c*mo[a,x]*mo[a,x]  then  rho[x] += c*mo[a,x]*mo[b,x] */
+void okor_ci_rho(double *out, long i0, long i1, long npts, const double *molist,
+                 long nz, const double *zc, const int *zi,
+                 long ns, const double *sc, const int *sa, const int *sb)
+{
+    long slen = i1 - i0, t, x;
+    for (x = 0; x < slen; ++x) out[x] = 0.0;
+    for (t = 0; t < nz; ++t) {
+        const double c = zc[t];
+        const double *m = molist + (long)zi[t] * npts + i0;
+        for (x = 0; x < slen; ++x) out[x] += c * m[x] * m[x];
+    }
+    for (t = 0; t < ns; ++t) {
+        const double c = sc[t];
+        const double *ma = molist + (long)sa[t] * npts + i0;
+        const double *mb = molist + (long)sb[t] * npts + i0;
+        for (x = 0; x < slen; ++x) out[x] += c * ma[x] * mb[x];
+    }
+}
+
+/* get_jab, cy_ci.pyx:156-186:  jab[d,x] -= 0.5*(c*(mo[a,x]*dmo[d,b,x] - mo[b,x]*dmo[d,a,x])) */
+void okor_ci_jab(double *out, long i0, long i1, long npts, long n_mo, const double *molist,
+                 const double *molistdrv, long ns, const double *sc, const int *sa, const int *sb)
+{
+    long slen = i1 - i0, t, x;
+    int d;
+    for (x = 0; x < 3 * slen; ++x) out[x] = 0.0;
+    for (t = 0; t < ns; ++t) {
+        const double c = sc[t];
+        const double *ma = molist + (long)sa[t] * npts + i0;
+        const double *mb = molist + (long)sb[t] * npts + i0;
+        for (d = 0; d < 3; ++d) {
+            const double *da = molistdrv + ((long)d * n_mo + sa[t]) * npts + i0;
+            const double *db = molistdrv + ((long)d * n_mo + sb[t]) * npts + i0;
+            double *o = out + (long)d * slen;
+            for (x = 0; x < slen; ++x) o[x] -= 0.5 * (c * (ma[x] * db[x] - mb[x] * da[x]));
+        }
+    }
+}
+
+/* get_a_nabla_b, cy_ci.pyx:211-240:  out[d,x] += c*(mo[a,x]*dmo[d,b,x]) */
+void okor_ci_a_nabla_b(double *out, long i0, long i1, long npts, long n_mo, const double *molist,
+                       const double *molistdrv, long ns, const double *sc, const int *sa, const int *sb)
+{
+    long slen = i1 - i0, t, x;
+    int d;
+    for (x = 0; x < 3 * slen; ++x) out[x] = 0.0;
+    for (t = 0; t < ns; ++t) {
+        const double c = sc[t];
+        const double *ma = molist + (long)sa[t] * npts + i0;
+        for (d = 0; d < 3; ++d) {
+            const double *db = molistdrv + ((long)d * n_mo + sb[t]) * npts + i0;
+            double *o = out + (long)d * slen;
+            for (x = 0; x < slen; ++x) o[x] += c * (ma[x] * db[x]);
+        }
+    }
+}

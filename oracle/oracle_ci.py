@@ -1,0 +1,128 @@
+"""CPU ORACLE for the detCI grid contractions (orbkit/detci/ci_core.py:85-267, cy_ci.pyx:70-240).
+
+TEST INFRASTRUCTURE ONLY (see oracle.py): imported by tests/ and bench legs as the checker,
+never by orbkit_b200.
+
+    rho(zero, sing, molist)                  sum_k c_k mo[a_k] mo[b_k]              (ci_core.rho)
+    jab(zero, sing, molist, molistdrv)       -1/2 sum_k c_k (mo[a] d mo[b] - mo[b] d mo[a])   (ci_core.jab)
+    a_nabla_b(zero, sing, molist, molistdrv) sum_k c_k mo[a] d mo[b]                (ci_core.a_nabla_b)
+
+`zero = [[coeffs per determinant], [orbital indices per determinant]]`,
+`sing = [[coeffs], [[a, b], ...]]` exactly as detci.occ_check.compare returns them.
+
+Backends: "port" = libokoracle.so (okor_ci_*, our C restatement in the reference's operation
+order), "ref" = the reference's own cy_ci module compiled into oracle/_ref (pinned bit for bit
+against each other and against the golden refdata_h3+.npz in tests/test_oracle_ci.py).
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+_ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+_lib = None
+
+
+def _port():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(os.path.join(_HERE, 'libokoracle.so'))
+        for name in ('okor_ci_rho', 'okor_ci_jab', 'okor_ci_a_nabla_b'):
+            getattr(_lib, name).restype = None
+    return _lib
+
+
+def have_ref():
+    import glob
+    return bool(glob.glob(os.path.join(_HERE, '_ref', 'cy_ci*.so')))
+
+
+def _ref():
+    d = os.path.join(_HERE, '_ref')
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import cy_ci
+    return cy_ci
+
+
+def flatten(zero, sing):
+    """(zero, sing) lists -> flat arrays (zc, zi, sc, sa, sb) in list order."""
+    zc = [c for cs in zero[0] for c in cs]
+    zi = [i for idx in zero[1] for i in idx]
+    if len(zc) != len(zi):
+        raise ValueError('zero: coefficient and index lists differ in length')
+    sc = list(sing[0])
+    sa = [p[0] for p in sing[1]]
+    sb = [p[1] for p in sing[1]]
+    if not (len(sc) == len(sa) == len(sb)):
+        raise ValueError('sing: coefficient and index lists differ in length')
+    f = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    i = lambda v: np.ascontiguousarray(v, dtype=np.intc)
+    return f(zc), i(zi), f(sc), i(sa), i(sb)
+
+
+def _prep(molist, molistdrv=None):
+    molist = np.require(molist, dtype=np.float64, requirements='CA')
+    shape = molist.shape
+    mo = molist.reshape(shape[0], -1)
+    if molistdrv is None:
+        return mo, None, shape
+    drv = np.require(molistdrv, dtype=np.float64, requirements='CA').reshape(3, shape[0], -1)
+    return mo, drv, shape
+
+
+def slices(n, slice_length):
+    """the slice driver of ci_core.rho / jab / a_nabla_b (ci_core.py:123-125, 184-186, 248-250):
+        slice_length = min(N, slice_length); ij = arange(0, N+1, abs(int(slice_length)))
+    NOTE (reference quirk, pinned by refdata_h3+.npz): the points behind the last full slice,
+    N - (N // slice_length) * slice_length of them, are never visited and stay 0."""
+    sl = abs(int(min(n, slice_length)))
+    ij = np.arange(0, n + 1, sl, dtype=np.intc)
+    return list(zip(ij[:-1], ij[1:]))
+
+
+def rho(zero, sing, molist, slice_length=1e4, kind='port'):
+    mo, _, shape = _prep(molist)
+    n = mo.shape[1]
+    data = np.zeros(n)
+    if kind != 'ref':
+        zc, zi, sc, sa, sb = flatten(zero, sing)
+    for i, j in slices(n, slice_length):
+        if kind == 'ref':
+            data[i:j] = _ref().get_rho(int(i), int(j), zero, sing, mo)
+        else:
+            out = np.zeros(j - i)
+            _port().okor_ci_rho(_dp(out), ctypes.c_long(i), ctypes.c_long(j), ctypes.c_long(n), _dp(mo),
+                                ctypes.c_long(len(zc)), _dp(zc), _ip(zi), ctypes.c_long(len(sc)), _dp(sc), _ip(sa),
+                                _ip(sb))
+            data[i:j] = out
+    return data.reshape(shape[1:])
+
+
+def _vec(fn_ref, fn_port, zero, sing, molist, molistdrv, slice_length, kind):
+    mo, drv, shape = _prep(molist, molistdrv)
+    n = mo.shape[1]
+    data = np.zeros((3, n))
+    if kind != 'ref':
+        _, _, sc, sa, sb = flatten(zero, sing)
+    for i, j in slices(n, slice_length):
+        if kind == 'ref':
+            data[:, i:j] = getattr(_ref(), fn_ref)(int(i), int(j), zero, sing, mo, drv)
+        else:
+            out = np.zeros((3, j - i))
+            getattr(_port(), fn_port)(_dp(out), ctypes.c_long(i), ctypes.c_long(j), ctypes.c_long(n),
+                                      ctypes.c_long(mo.shape[0]), _dp(mo), _dp(drv), ctypes.c_long(len(sc)),
+                                      _dp(sc), _ip(sa), _ip(sb))
+            data[:, i:j] = out
+    return data.reshape((3,) + shape[1:])
+
+
+def jab(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
+    return _vec('get_jab', 'okor_ci_jab', zero, sing, molist, molistdrv, slice_length, kind)
+
+
+def a_nabla_b(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
+    return _vec('get_a_nabla_b', 'okor_ci_a_nabla_b', zero, sing, molist, molistdrv, slice_length, kind)

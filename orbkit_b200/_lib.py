@@ -3,7 +3,8 @@
 There is NO CPU fallback: if the shared library is missing or no sm_100 device is present every
 compute entry point raises.  The library is built in-tree by `__graft_entry__.build()` /
 `orbkit_b200._lib.build()` with
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -c  (one object per csrc/*.cu,
+    compiled in parallel) and nvcc -shared to link
 """
 import ctypes
 import os
@@ -16,10 +17,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libokb200.so')
 SRC = os.path.join(_HERE, 'csrc', 'okb200.cu')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC']
 
 OKB_FLAG_EXACT_MIXED = 1
 OKB_FLAG_OUT_DEVICE = 2
+OKB_FLAG_IN_DEVICE = 4
+OKB_CI_RHO, OKB_CI_JAB, OKB_CI_A_NABLA_B, OKB_CI_PAIRS = 0, 1, 2, 3
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -72,6 +75,12 @@ SIGNATURES = {
     'okb_eval_rho': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_uint]),
+    'okb_ci_contract': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, c_double_p, c_int_p, c_int_p,
+                                       ctypes.c_void_p, ll, ctypes.c_uint]),
+    'okb_eval_ci': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, ctypes.c_int,
+                                   c_int_p, ctypes.c_int, c_double_p, c_int_p, c_int_p, ctypes.c_void_p,
+                                   ctypes.c_uint]),
 }
 
 _lock = threading.Lock()
@@ -82,19 +91,45 @@ class OkbError(RuntimeError):
     pass
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/okb200.cu for sm_100a into orbkit_b200/libokb200.so (works without a GPU)."""
+def build(force=False, verbose=False, jobs=None):
+    """Compile csrc/*.cu for sm_100a into orbkit_b200/libokb200.so (works without a GPU).
+
+    One object per translation unit (okb200.cu = host side + small kernels, inst_*.cu = groups of
+    kernel-template instantiations), compiled in parallel, then linked by nvcc."""
+    from concurrent.futures import ThreadPoolExecutor
     csrc = os.path.join(_HERE, 'csrc')
-    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))]
-    deps.append(os.path.join(os.path.dirname(_HERE), 'include', 'okb200.h'))
-    if (not force and os.path.exists(LIB_PATH) and
-            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
-        return LIB_PATH
+    headers = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cuh', '.h'))]
+    headers.append(os.path.join(os.path.dirname(_HERE), 'include', 'okb200.h'))
+    units = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith('.cu'))
+    objdir = os.path.join(csrc, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(h) for h in headers)
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, SRC]
-    if verbose:
-        print(' '.join(cmd))
-    subprocess.check_call(cmd)
+
+    def obj_of(u):
+        return os.path.join(objdir, os.path.basename(u)[:-3] + '.o')
+
+    def stale(u):
+        o = obj_of(u)
+        return force or not os.path.exists(o) or os.path.getmtime(o) < max(hdr_time, os.path.getmtime(u))
+
+    todo = [u for u in units if stale(u)]
+
+    def compile_one(u):
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', obj_of(u), u]
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.check_call(cmd)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as pool:
+            list(pool.map(compile_one, todo))
+    objs = [obj_of(u) for u in units]
+    if todo or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB_PATH] + objs
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.check_call(cmd)
     return LIB_PATH
 
 

@@ -1,0 +1,18 @@
+// inst_tile.cu -- one group of kernel instantiations (see okb_variant.h).
+// Warp-specialised DMMA kernels: NPW producer warps + WM x WN consumer warps, NST stages; MO tile
+// MC = 8*MB (MB blocks split over the WM warp rows), point tile P = 8*BN*WN.  MO-tile widths per set: a
+// wide tile (96), the 88-wide tile that fits the 82 occupied MOs of the ~1000-function benchmark molecule,
+// and a narrow tile for small MO counts.
+#include "okb_variant_inst.h"
+
+namespace okb {
+
+static const Variant table[] = {
+    // AO sinks (no contraction): P = 128 points for values, fewer for the derivative sets
+    OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
+    OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
+    OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
+};
+OKB_TABLE(okb_variants_tile, table);
+
+}  // namespace okb

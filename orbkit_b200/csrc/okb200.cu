@@ -25,9 +25,11 @@
 
 #include "../../include/okb200.h"
 #include "okb_common.cuh"
-#include "okb_tile_kernel.cuh"
-#include "okb_ws.cuh"
+#include "okb_variant.h"
+#include "okb_shell.cuh"   // constexpr shell tables (templates are instantiated in inst_*.cu only)
+#include "okb_ws.cuh"      // pad_stride
 #include "okb_misc.cuh"
+#include "okb_ci.cuh"
 
 using namespace okb;
 
@@ -74,8 +76,41 @@ struct okb_ctx {
     size_t slab_bytes = 0;
     double *norm_dev = nullptr;              // mo_norm accumulation
     size_t norm_cap = 0;
+    void *ci_buf = nullptr;                  // detCI: term arrays + MO slab + output slab
+    size_t ci_bytes = 0;
+    // Recycled device buffers of destroyed handles (chunk tables, coefficient tiles, axes, axis tables).
+    // cudaFree sporadically takes 5-600 ms next to large page-locked host buffers (measured:
+    // scripts/e2e_probe.py, e2e_probe2.py), so handle churn must not free.
+    std::vector<std::pair<void *, size_t>> pool;
 };
 
+static int pool_get(okb_ctx *ctx, size_t bytes, void **out, size_t *got) {
+    bytes = std::max<size_t>(bytes, 256);
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool.size(); ++i)
+        if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= 2 * bytes + ((size_t)64 << 10) &&
+            (best < 0 || ctx->pool[i].second < ctx->pool[best].second))
+            best = i;
+    if (best >= 0) {
+        *out = ctx->pool[best].first;
+        *got = ctx->pool[best].second;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return OKB_OK;
+    }
+    CU(cudaMalloc(out, bytes));
+    *got = bytes;
+    return OKB_OK;
+}
+// The caller guarantees that no kernel still uses the buffer (the destroy functions drain the stream first:
+// a recycled buffer may be overwritten by a synchronous copy that is not ordered with ctx->stream).
+static void pool_put(okb_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (ctx->pool.size() < 64 && bytes <= ((size_t)256 << 20)) {
+        ctx->pool.emplace_back(ptr, bytes);
+        return;
+    }
+    cudaFree(ptr);
+}
 struct DevShell {
     double c[3];
     int L;
@@ -100,6 +135,7 @@ struct Layout {
     std::vector<int> order;                  // chunk c holds the device shells order[s0..s1)
     BlobLayout lay{};
     unsigned char *meta_dev = nullptr;
+    size_t meta_bytes = 0;                   // pooled size of meta_dev
     int n_rows = 0;
 };
 
@@ -114,6 +150,11 @@ struct okb_basis {
     std::vector<double> t_val;
     Layout cart, mix;
     bool mix_is_cart = true;                 // Cartesian basis: the two layouts coincide
+    unsigned long long serial = 0;           // identifies the primitive set (axis-table cache key)
+    std::vector<int> shell_gprim;            // device shell -> index of its first primitive (basis-wide)
+    int n_prim_dev = 0;
+    double *prim5_dev = nullptr;             // [n_prim_dev][5] = alpha, cN, X, Y, Z
+    size_t prim5_bytes = 0;
     const Layout &contraction_layout() const { return mix_is_cart ? cart : mix; }
 };
 
@@ -124,7 +165,7 @@ struct okb_mo {
     std::vector<double> ccart;               // [n_mo][n_cart] in Cartesian rows (C' = C T)
     std::vector<double> csph;                // [n_mo][n_ao] as given (spherical bases only)
     std::vector<double> occ;
-    struct Blob { double *c = nullptr; double *occ = nullptr; int n_mtile = 0; };
+    struct Blob { double *c = nullptr; double *occ = nullptr; int n_mtile = 0; size_t c_bytes = 0, occ_bytes = 0; };
     std::map<int, Blob> blobs;               // keyed by 2*MC + (mix layout ? 1 : 0)
 };
 
@@ -134,7 +175,11 @@ struct okb_grid {
     int nx = 0, ny = 0, nz = 0;
     long long npts = 0;
     double *gx = nullptr, *gy = nullptr, *gz = nullptr;
+    size_t gbytes[3] = {0, 0, 0};            // pooled sizes of gx, gy, gz
     bool owns = true;
+    // regular grids: separable-exponential tables per basis (key: okb_basis::serial), [3 tables back to back]
+    struct Tab { double *ptr; size_t bytes; };
+    std::map<unsigned long long, Tab> axis_tabs;
 };
 
 // ---- context ------------------------------------------------------------------------------------------
@@ -178,6 +223,8 @@ extern "C" int okb_ctx_destroy(okb_ctx *c) {
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     }
     if (c->norm_dev) cudaFree(c->norm_dev);
+    if (c->ci_buf) cudaFree(c->ci_buf);
+    for (auto &e : c->pool) cudaFree(e.first);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -314,7 +361,8 @@ static bool match_sph_rows(const okb_basis *b, int s, std::vector<int> &sph_of_c
 static void layout_free(okb_ctx *ctx, Layout &lo) {
     if (lo.meta_dev) {
         cudaSetDevice(ctx->device);
-        cudaFree(lo.meta_dev);
+        cudaStreamSynchronize(ctx->stream);
+        pool_put(ctx, lo.meta_dev, lo.meta_bytes);
     }
     lo = Layout();
 }
@@ -373,6 +421,12 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
                 take(best);
             }
             while (first < nshell && used[first]) ++first;
+            // most expensive shells first: the producer warps deal the items of a chunk out in this order
+            // (cost ~ exponentials + per-function polynomial work)
+            auto cost = [&](int t) { return 5 * np_of[t] + 4 * (int)b->shells[t].fn_row.size(); };
+            if (!plain_order)
+                std::stable_sort(lo.order.begin() + cur.s0, lo.order.begin() + cur.s1,
+                                 [&](int a, int c) { return cost(a) > cost(c); });
             lo.chunks.push_back(cur);
         }
     }
@@ -522,6 +576,7 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
             m.prim_off = po; m.nprim = (int)sh.alpha.size();
             m.fn_off = fo;
             m.L = sh.L;
+            m.gprim = b->shell_gprim[s];
             if (lo.shell_sph[s]) {
                 m.kind = 2;
                 m.nfn = 2 * sh.L + 1;
@@ -540,7 +595,12 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
         if (!aux[c].empty()) memcpy(mb + L.off_aux, aux[c].data(), aux[c].size() * sizeof(double));
     }
     CU(cudaSetDevice(b->ctx->device));
-    CU(cudaMalloc(&lo.meta_dev, blob.size()));
+    {
+        void *raw = nullptr;
+        int rcp = pool_get(b->ctx, blob.size(), &raw, &lo.meta_bytes);
+        if (rcp != OKB_OK) return rcp;
+        lo.meta_dev = reinterpret_cast<unsigned char *>(raw);
+    }
     CU(cudaMemcpy(lo.meta_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     b->ctx->h2d_bytes += (long long)blob.size();
     return OKB_OK;
@@ -548,6 +608,32 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
 
 // (re)build both layouts after the basis or its spherical transform changed
 static int basis_upload(okb_basis *b) {
+    static unsigned long long next_serial = 1;
+    b->serial = next_serial++;
+    {
+        std::vector<double> prim5;
+        b->shell_gprim.assign(b->shells.size(), 0);
+        for (size_t s = 0; s < b->shells.size(); ++s) {
+            const DevShell &sh = b->shells[s];
+            b->shell_gprim[s] = (int)(prim5.size() / 5);
+            for (size_t i = 0; i < sh.alpha.size(); ++i) {
+                const double q[5] = {sh.alpha[i], sh.cn[i], sh.c[0], sh.c[1], sh.c[2]};
+                prim5.insert(prim5.end(), q, q + 5);
+            }
+        }
+        b->n_prim_dev = (int)(prim5.size() / 5);
+        CU(cudaSetDevice(b->ctx->device));
+        pool_put(b->ctx, b->prim5_dev, b->prim5_bytes);
+        b->prim5_dev = nullptr;
+        {
+            void *raw = nullptr;
+            int rcp = pool_get(b->ctx, std::max<size_t>(prim5.size(), 1) * sizeof(double), &raw, &b->prim5_bytes);
+            if (rcp != OKB_OK) return rcp;
+            b->prim5_dev = reinterpret_cast<double *>(raw);
+        }
+        CU(cudaMemcpy(b->prim5_dev, prim5.data(), prim5.size() * sizeof(double), cudaMemcpyHostToDevice));
+        b->ctx->h2d_bytes += (long long)(prim5.size() * sizeof(double));
+    }
     b->row_shell.assign(b->n_cart, -1);
     for (int s = 0; s < (int)b->shells.size(); ++s)
         for (int r : b->shells[s].fn_row) b->row_shell[r] = s;
@@ -659,8 +745,11 @@ extern "C" int okb_basis_info(okb_basis *b, int *n_cart, int *n_ao, int *n_dev_s
 
 extern "C" int okb_basis_destroy(okb_basis *b) {
     if (!b) return OKB_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
     layout_free(b->ctx, b->cart);
     layout_free(b->ctx, b->mix);
+    pool_put(b->ctx, b->prim5_dev, b->prim5_bytes);
     delete b;
     return OKB_OK;
 }
@@ -725,8 +814,15 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
     okb_mo::Blob bl;
     bl.n_mtile = n_mtile;
     CU(cudaSetDevice(m->ctx->device));
-    CU(cudaMalloc(&bl.c, blob.size() * sizeof(double)));
-    CU(cudaMalloc(&bl.occ, occ.size() * sizeof(double)));
+    {
+        void *raw = nullptr;
+        int rcp = pool_get(m->ctx, blob.size() * sizeof(double), &raw, &bl.c_bytes);
+        if (rcp != OKB_OK) return rcp;
+        bl.c = reinterpret_cast<double *>(raw);
+        rcp = pool_get(m->ctx, occ.size() * sizeof(double), &raw, &bl.occ_bytes);
+        if (rcp != OKB_OK) return rcp;
+        bl.occ = reinterpret_cast<double *>(raw);
+    }
     CU(cudaMemcpy(bl.c, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(bl.occ, occ.data(), occ.size() * sizeof(double), cudaMemcpyHostToDevice));
     m->ctx->h2d_bytes += (long long)((blob.size() + occ.size()) * sizeof(double));
@@ -738,9 +834,10 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
 extern "C" int okb_mo_destroy(okb_mo *m) {
     if (!m) return OKB_OK;
     cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
     for (auto &kv : m->blobs) {
-        if (kv.second.c) cudaFree(kv.second.c);
-        if (kv.second.occ) cudaFree(kv.second.occ);
+        pool_put(m->ctx, kv.second.c, kv.second.c_bytes);
+        pool_put(m->ctx, kv.second.occ, kv.second.occ_bytes);
     }
     delete m;
     return OKB_OK;
@@ -758,9 +855,16 @@ extern "C" int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const dou
     g->nx = nx; g->ny = ny; g->nz = nz;
     g->npts = (long long)nx * ny * nz;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaMalloc(&g->gx, sizeof(double) * nx));
-    CU(cudaMalloc(&g->gy, sizeof(double) * ny));
-    CU(cudaMalloc(&g->gz, sizeof(double) * nz));
+    {
+        double **dst[3] = {&g->gx, &g->gy, &g->gz};
+        const int n[3] = {nx, ny, nz};
+        for (int a = 0; a < 3; ++a) {
+            void *raw = nullptr;
+            int rcp = pool_get(ctx, sizeof(double) * n[a], &raw, &g->gbytes[a]);
+            if (rcp != OKB_OK) return rcp;
+            *dst[a] = reinterpret_cast<double *>(raw);
+        }
+    }
     CU(cudaMemcpy(g->gx, x, sizeof(double) * nx, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->gy, y, sizeof(double) * ny, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->gz, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
@@ -785,9 +889,13 @@ extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, c
         g->gz = const_cast<double *>(z);
         g->owns = false;
     } else {
-        CU(cudaMalloc(&g->gx, sizeof(double) * npts));
-        CU(cudaMalloc(&g->gy, sizeof(double) * npts));
-        CU(cudaMalloc(&g->gz, sizeof(double) * npts));
+        double **dst[3] = {&g->gx, &g->gy, &g->gz};
+        for (int a = 0; a < 3; ++a) {
+            void *raw = nullptr;
+            int rcp = pool_get(ctx, sizeof(double) * npts, &raw, &g->gbytes[a]);
+            if (rcp != OKB_OK) return rcp;
+            *dst[a] = reinterpret_cast<double *>(raw);
+        }
         CU(cudaMemcpyAsync(g->gx, x, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(g->gy, y, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(g->gz, z, sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
@@ -807,90 +915,28 @@ extern "C" int okb_grid_size(okb_grid *g, long long *npts) {
 extern "C" int okb_grid_destroy(okb_grid *g) {
     if (!g) return OKB_OK;
     cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    for (auto &kv : g->axis_tabs) pool_put(g->ctx, kv.second.ptr, kv.second.bytes);
     if (g->owns) {
-        if (g->gx) cudaFree(g->gx);
-        if (g->gy) cudaFree(g->gy);
-        if (g->gz) cudaFree(g->gz);
+        pool_put(g->ctx, g->gx, g->gbytes[0]);
+        pool_put(g->ctx, g->gy, g->gbytes[1]);
+        pool_put(g->ctx, g->gz, g->gbytes[2]);
     }
     delete g;
     return OKB_OK;
 }
 
 // ---- launch machinery ---------------------------------------------------------------------------------------
-struct Variant {
-    const char *name;
-    int set, sink, MW, PT, NW;
-    int P, MC;
-    size_t (*smem)(int meta_stride);
-    cudaError_t (*launch)(const KParams &, int grid, size_t smem, cudaStream_t);
-};
-
-template <int SET, int MW, int PT, int NW, int SINK>
-static cudaError_t launch_variant(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = okb_grid_kernel<SET, MW, PT, NW, SINK>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-template <int SET, int MW, int PT, int NW, int SINK>
-static size_t smem_variant(int meta_stride) {
-    return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
-}
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
-static cudaError_t launch_ws(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = okb_ws_kernel<SET, MB, BN, WM, WN, NPW, NST, SINK>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, (WM * WN + NPW) * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
-static size_t smem_ws(int meta_stride) {
-    return WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK>::smem_bytes(meta_stride);
-}
-#define OKB_WS(SET, MB, BN, WM, WN, NPW, NST, SINK)                                                           \
-    Variant { "ws-dmma/" #SET "/" #SINK "/MB" #MB "xBN" #BN "xWM" #WM "xWN" #WN "xNPW" #NPW "xNST" #NST, SET, SINK, \
-              MB, BN, WM * WN, 8 * BN * WN, 8 * MB, smem_ws<SET, MB, BN, WM, WN, NPW, NST, SINK>,               \
-              launch_ws<SET, MB, BN, WM, WN, NPW, NST, SINK> }
-#define OKB_VARIANT(SET, MW, PT, NW, SINK)                                                         \
-    Variant { #SET "/" #SINK "/MW" #MW "xPT" #PT "xNW" #NW, SET, SINK, MW, PT, NW, 32 * PT, NW * MW, \
-              smem_variant<SET, MW, PT, NW, SINK>, launch_variant<SET, MW, PT, NW, SINK> }
-
-// MO-tile widths per derivative set: a wide tile (MC=96), the 84-wide tile that fits the 82
-// occupied MOs of the ~1000-function benchmark molecule with 2% padding, and narrow tiles for
-// small MO counts.  (acc registers per thread = MW*PT*D doubles.)
-static const Variant g_variants[] = {
-    // AO sinks (no contraction): P = 128 points
-    OKB_VARIANT(SET_VAL, 1, 4, 8, SINK_AO), OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
-    OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
-    OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
-    // warp-specialised DMMA contraction kernels: NPW producer warps + WM x WN consumer warps, NST stages.
-    // MO tile MC = 8*MB (MB blocks split over the WM warp rows), point tile P = 8*BN*WN.
-    // value only (D=1): 4 consumer + 12 producer warps (AO generation dominates), P = 128
-    OKB_WS(SET_VAL, 11, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 11, 4, 1, 4, 12, 3, SINK_RHO),
-    OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_RHO),
-    OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_RHO),
-    OKB_WS(SET_ONE, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_ONE, 3, 4, 1, 4, 12, 3, SINK_MO),
-    // value + gradient (D=4): 4 consumer + 8 producer warps, P = 32
-    OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_RHO),   // 4 + 8 warps
-    OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_GRAD, 11, 1, 2, 4, 8, 3, SINK_RHO),     // experiment: two consumer warps per sub-partition
-    OKB_WS(SET_GRAD, 11, 2, 2, 2, 8, 3, SINK_RHO),     // experiment: 2x2 consumer warps, 16 points each
-    // value + gradient + pure second derivatives (D=7): 8 consumer + 4 producer warps, P = 32
-    OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 11, 1, 2, 4, 4, 2, SINK_RHO),
-    OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 12, 1, 2, 4, 4, 2, SINK_RHO),
-    OKB_WS(SET_LAP, 3, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_LAP, 3, 1, 2, 4, 4, 2, SINK_RHO),
-    // all ten codes (D=10): 8 consumer + 4 producer warps, P = 32
-    OKB_WS(SET_ALL, 6, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_ALL, 6, 1, 2, 4, 4, 2, SINK_RHO),
-    OKB_WS(SET_ALL, 2, 1, 2, 4, 4, 2, SINK_MO), OKB_WS(SET_ALL, 2, 1, 2, 4, 4, 2, SINK_RHO),
-};
+// the kernel instantiations live in inst_*.cu (compiled in parallel); okb_variant.h declares their tables
+static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_val, &okb_variants_grad,
+                                               &okb_variants_lap, &okb_variants_all};
 
 static const Variant *pick_variant(int set, int sink, int n_mo) {
     const Variant *best = nullptr;
     long long best_cost = 0;
-    for (const Variant &v : g_variants) {
+    for (const VariantTable *tab : g_tables)
+      for (int iv = 0; iv < tab->n; ++iv) {
+        const Variant &v = tab->v[iv];
         if (v.set != set || v.sink != sink) continue;
         if (sink == SINK_AO) return &v;
         // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
@@ -929,6 +975,49 @@ static int ensure_slabs(okb_ctx *c, size_t bytes) {
     c->slab_bytes = 0;
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->slab[i], bytes));
     c->slab_bytes = bytes;
+    return OKB_OK;
+}
+
+// Separable-exponential tables of (basis, regular grid): built on first use, cached in the grid handle.
+static int ensure_axis_tables(okb_ctx *ctx, okb_basis *b, okb_grid *g, const double **tx, const double **ty,
+                              const double **tz) {
+    *tx = *ty = *tz = nullptr;
+    static const bool off = getenv("OKB_NO_AXIS_TABLES") != nullptr;
+    const size_t np = (size_t)b->n_prim_dev;
+    const size_t total = np * ((size_t)g->nx + g->ny + g->nz);
+    // index arithmetic in the kernels is 32-bit
+    if (off || g->kind != 0 || np == 0 || np * (size_t)std::max(g->nx, std::max(g->ny, g->nz)) >= ((size_t)1 << 31))
+        return OKB_OK;
+    auto it = g->axis_tabs.find(b->serial);
+    double *base = nullptr;
+    if (it != g->axis_tabs.end()) {
+        base = it->second.ptr;
+    } else {
+        size_t got = 0;
+        void *raw = nullptr;
+        int rcp = pool_get(ctx, total * sizeof(double), &raw, &got);
+        if (rcp != OKB_OK) return rcp;
+        base = reinterpret_cast<double *>(raw);
+        const double *axes[3] = {g->gx, g->gy, g->gz};
+        const int n[3] = {g->nx, g->ny, g->nz};
+        double *dst = base;
+        for (int a = 0; a < 3; ++a) {
+            const long long cnt = (long long)np * n[a];
+            okb_axis_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(b->prim5_dev, (int)np, axes[a], n[a],
+                                                                                          a, dst);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                pool_put(ctx, base, got);
+                return fail(OKB_ERR_CUDA, "axis table kernel: %s", cudaGetErrorString(e));
+            }
+            ctx->launches++;
+            dst += cnt;
+        }
+        g->axis_tabs[b->serial] = okb_grid::Tab{base, got};
+    }
+    *tx = base;
+    *ty = base + np * g->nx;
+    *tz = *ty + np * g->ny;
     return OKB_OK;
 }
 
@@ -1026,6 +1115,13 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
         CU(cudaMemsetAsync(norm_dev, 0, sizeof(double) * rq.mo->n_mo, ctx->stream));
     }
 
+    const double *tabx = nullptr, *taby = nullptr, *tabz = nullptr;
+    // (not for SINK_AO: its store-bound kernel has too few warps to hide the table loads -- measured 1.6x slower)
+    if (rq.sink != SINK_AO) {
+        rc = ensure_axis_tables(ctx, b, g, &tabx, &taby, &tabz);
+        if (rc != OKB_OK) return rc;
+    }
+
     int slab_idx = 0;
     for (long long s0 = 0; s0 < ntot; s0 += slab_pts, ++slab_idx) {
         const long long sn = std::min(slab_pts, ntot - s0);
@@ -1046,7 +1142,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             KParams p{};
             p.grid_kind = g->kind;
             p.gx = g->gx; p.gy = g->gy; p.gz = g->gz;
-            p.ny = g->ny; p.nz = g->nz;
+            p.nx = g->nx; p.ny = g->ny; p.nz = g->nz;
+            p.tabx = tabx; p.taby = taby; p.tabz = tabz;
             p.p0 = rq.p0 + s0;
             p.npts = (int)sn;
             p.ntiles = (int)((sn + v->P - 1) / v->P);
@@ -1144,6 +1241,193 @@ extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long 
     if (n_drv > 0 && !delta_rho) return fail(OKB_ERR_ARG, "okb_eval_rho: null delta_rho output");
     EvalReq rq{SINK_RHO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, nullptr, rho, delta_rho, mo_norm, flags};
     return run_eval(ctx, rq);
+}
+
+// ---- detCI grid contractions ------------------------------------------------------------------------------------
+static int ci_ncomp(int mode, int n_terms) { return mode == CI_RHO ? 1 : mode == CI_PAIRS ? n_terms : 3; }
+
+static int ci_reserve(okb_ctx *ctx, size_t bytes) {
+    if (ctx->ci_bytes >= bytes) return OKB_OK;
+    if (ctx->ci_buf) CU(cudaFree(ctx->ci_buf));
+    ctx->ci_buf = nullptr;
+    ctx->ci_bytes = 0;
+    CU(cudaMalloc(&ctx->ci_buf, bytes));
+    ctx->ci_bytes = bytes;
+    return OKB_OK;
+}
+
+static int ci_check(okb_ctx *ctx, int mode, int n_mo, int n_terms, const double *coef, const int *ia, const int *ib,
+                    const double *out) {
+    if (!ctx) return fail(OKB_ERR_ARG, "ci: null context");
+    if (mode < CI_RHO || mode > CI_PAIRS) return fail(OKB_ERR_ARG, "ci: unknown mode %d", mode);
+    if (n_mo <= 0) return fail(OKB_ERR_ARG, "ci: n_mo must be positive");
+    if (n_terms < 0) return fail(OKB_ERR_ARG, "ci: negative term count");
+    if (n_terms > 0 && (!ia || !ib || (mode != CI_PAIRS && !coef))) return fail(OKB_ERR_ARG, "ci: null term array");
+    if (!out) return fail(OKB_ERR_ARG, "ci: null output");
+    for (int t = 0; t < n_terms; ++t)
+        if (ia[t] < 0 || ia[t] >= n_mo || ib[t] < 0 || ib[t] >= n_mo)
+            return fail(OKB_ERR_ARG, "ci: term %d refers to orbitals (%d,%d) outside 0..%d", t, ia[t], ib[t], n_mo - 1);
+    return OKB_OK;
+}
+
+// term arrays at the head of ctx->ci_buf: [coef n_terms doubles | ia | ib], padded to 256 bytes
+static size_t ci_terms_bytes(int n_terms) { return (((size_t)n_terms * 16 + 255) / 256 + 1) * 256; }
+static int ci_upload_terms(okb_ctx *ctx, int n_terms, const double *coef, const int *ia, const int *ib, CiParams *p) {
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
+    double *tc = reinterpret_cast<double *>(base);
+    int *ta = reinterpret_cast<int *>(base + (size_t)n_terms * 8), *tb = ta + n_terms;
+    if (n_terms > 0) {
+        if (coef) CU(cudaMemcpyAsync(tc, coef, (size_t)n_terms * 8, cudaMemcpyHostToDevice, ctx->stream));
+        else CU(cudaMemsetAsync(tc, 0, (size_t)n_terms * 8, ctx->stream));
+        CU(cudaMemcpyAsync(ta, ia, (size_t)n_terms * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(tb, ib, (size_t)n_terms * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (long long)n_terms * 16;
+    }
+    p->n_terms = n_terms;
+    p->tc = tc; p->ta = ta; p->tb = tb;
+    return OKB_OK;
+}
+
+static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
+    if (p.npts <= 0) return OKB_OK;
+    const unsigned grid = (unsigned)((p.npts + CI_NT - 1) / CI_NT);
+    switch (mode) {
+        case CI_RHO: okb_ci_kernel<CI_RHO><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        case CI_JAB: okb_ci_kernel<CI_JAB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        case CI_ANB: okb_ci_kernel<CI_ANB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        default: okb_ci_kernel<CI_PAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "ci kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ctx->last_kernel = mode == CI_RHO ? "ci/rho" : mode == CI_JAB ? "ci/jab" : mode == CI_ANB ? "ci/a_nabla_b" : "ci/pairs";
+    return OKB_OK;
+}
+
+extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
+                               const double *molist, const double *molistdrv, int n_terms, const double *coef,
+                               const int *ia, const int *ib, double *out, long long ld_out, unsigned flags) {
+    int rc = ci_check(ctx, mode, n_mo, n_terms, coef, ia, ib, out);
+    if (rc != OKB_OK) return rc;
+    if (npts < 0) return fail(OKB_ERR_ARG, "okb_ci_contract: negative point count");
+    if (ld_in < npts || ld_out < npts) return fail(OKB_ERR_ARG, "okb_ci_contract: row stride smaller than the point count");
+    if (npts == 0) return OKB_OK;
+    const bool need_drv = (mode == CI_JAB || mode == CI_ANB);
+    if (!molist || (need_drv && !molistdrv)) return fail(OKB_ERR_ARG, "okb_ci_contract: null MO array");
+    const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
+    const int nsets = need_drv ? 4 : 1, ncomp = ci_ncomp(mode, n_terms);
+    CU(cudaSetDevice(ctx->device));
+    // slab geometry: device-resident inputs and outputs need no staging at all
+    const size_t per_pt = (in_dev ? 0 : (size_t)nsets * n_mo * 8) + (out_dev ? 0 : (size_t)ncomp * 8);
+    long long slab = npts;
+    if (per_pt > 0) {
+        slab = (long long)(((size_t)1 << 30) / per_pt) / 1024 * 1024;
+        slab = std::max<long long>(1024, std::min(slab, npts));
+    }
+    const size_t tbytes = ci_terms_bytes(n_terms);
+    const size_t in_bytes = in_dev ? 0 : ((size_t)nsets * n_mo * slab * 8 + 255) / 256 * 256;
+    rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
+    if (rc != OKB_OK) return rc;
+    CiParams p{};
+    rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
+    if (rc != OKB_OK) return rc;
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
+    double *d_in = reinterpret_cast<double *>(base + tbytes), *d_out = reinterpret_cast<double *>(base + tbytes + in_bytes);
+    for (long long s0 = 0; s0 < npts; s0 += slab) {
+        const long long sn = std::min(slab, npts - s0);
+        if (in_dev) {
+            p.mo = molist + s0;
+            p.dmo = need_drv ? molistdrv + s0 : nullptr;
+            p.ld = ld_in;
+        } else {
+            CU(cudaMemcpy2DAsync(d_in, (size_t)sn * 8, molist + s0, (size_t)ld_in * 8, (size_t)sn * 8, n_mo,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+            if (need_drv)
+                CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * sn, (size_t)sn * 8, molistdrv + s0, (size_t)ld_in * 8,
+                                     (size_t)sn * 8, (size_t)3 * n_mo, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += (long long)nsets * n_mo * sn * 8;
+            p.mo = d_in;
+            p.dmo = need_drv ? d_in + (size_t)n_mo * sn : nullptr;
+            p.ld = sn;
+        }
+        p.dstride = (long long)n_mo * p.ld;
+        p.npts = sn;
+        p.out = out_dev ? out + s0 : d_out;
+        p.ldo = out_dev ? ld_out : sn;
+        rc = ci_launch(ctx, mode, p);
+        if (rc != OKB_OK) return rc;
+        if (!out_dev) {
+            CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += (long long)ncomp * sn * 8;
+            CU(cudaStreamSynchronize(ctx->stream));          // the staging buffers are reused by the next slab
+        }
+    }
+    if (!out_dev || !in_dev) CU(cudaStreamSynchronize(ctx->stream));
+    return OKB_OK;
+}
+
+extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1, int mode,
+                           const int *drv_codes, int n_terms, const double *coef, const int *ia, const int *ib,
+                           double *out, unsigned flags) {
+    if (!mo) return fail(OKB_ERR_ARG, "okb_eval_ci: null MO handle");
+    if (!grid) return fail(OKB_ERR_ARG, "okb_eval_ci: null grid handle");
+    int rc = ci_check(ctx, mode, mo->n_mo, n_terms, coef, ia, ib, out);
+    if (rc != OKB_OK) return rc;
+    if (p0 < 0 || p1 > grid->npts || p1 < p0) return fail(OKB_ERR_ARG, "okb_eval_ci: point range outside the grid");
+    const long long npts = p1 - p0;
+    if (npts == 0) return OKB_OK;
+    const bool need_drv = (mode == CI_JAB || mode == CI_ANB);
+    int codes[4] = {0, 1, 2, 3};
+    if (need_drv) {
+        if (!drv_codes) return fail(OKB_ERR_ARG, "okb_eval_ci: null derivative codes");
+        for (int d = 0; d < 3; ++d) {
+            if (drv_codes[d] < 1 || drv_codes[d] > 9) return fail(OKB_ERR_ARG, "okb_eval_ci: derivative code %d not in 1..9", drv_codes[d]);
+            for (int e = 0; e < d; ++e)
+                if (drv_codes[e] == drv_codes[d]) return fail(OKB_ERR_ARG, "okb_eval_ci: duplicate derivative code");
+            codes[1 + d] = drv_codes[d];
+        }
+    }
+    const bool out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
+    const int n_mo = mo->n_mo, nsets = need_drv ? 4 : 1, ncomp = ci_ncomp(mode, n_terms);
+    CU(cudaSetDevice(ctx->device));
+    const size_t per_pt = (size_t)nsets * n_mo * 8 + (out_dev ? 0 : (size_t)ncomp * 8);
+    long long slab = (long long)(((size_t)1 << 30) / per_pt) / 1024 * 1024;
+    slab = std::max<long long>(1024, std::min(slab, npts));
+    const size_t tbytes = ci_terms_bytes(n_terms);
+    const size_t in_bytes = ((size_t)nsets * n_mo * slab * 8 + 255) / 256 * 256;
+    rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
+    if (rc != OKB_OK) return rc;
+    CiParams p{};
+    rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
+    if (rc != OKB_OK) return rc;
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
+    double *d_in = reinterpret_cast<double *>(base + tbytes), *d_out = reinterpret_cast<double *>(base + tbytes + in_bytes);
+    for (long long s0 = 0; s0 < npts; s0 += slab) {
+        const long long sn = std::min(slab, npts - s0);
+        // MOs (+ derivative sets) of the slab, device resident: [nsets][n_mo][sn]
+        EvalReq rq{SINK_MO, mo->basis, mo, grid, p0 + s0, p0 + s0 + sn, codes, nsets, d_in, nullptr, nullptr, nullptr,
+                   (flags & OKB_FLAG_EXACT_MIXED) | OKB_FLAG_OUT_DEVICE};
+        rc = run_eval(ctx, rq);
+        if (rc != OKB_OK) return rc;
+        p.mo = d_in;
+        p.dmo = need_drv ? d_in + (size_t)n_mo * sn : nullptr;
+        p.ld = sn;
+        p.dstride = (long long)n_mo * sn;
+        p.npts = sn;
+        p.out = out_dev ? out + s0 : d_out;
+        p.ldo = out_dev ? npts : sn;
+        rc = ci_launch(ctx, mode, p);
+        if (rc != OKB_OK) return rc;
+        if (!out_dev) {
+            CU(cudaMemcpy2DAsync(out + s0, (size_t)npts * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += (long long)ncomp * sn * 8;
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (!out_dev) CU(cudaStreamSynchronize(ctx->stream));
+    return OKB_OK;
 }
 
 // ---- cy_core drop-ins -----------------------------------------------------------------------------------------

@@ -1,0 +1,95 @@
+// okb_ci.cuh -- detCI grid contractions over pairs of molecular orbitals (replaces the loops of
+// orbkit/detci/cy_ci.pyx:70-97 get_rho, 156-186 get_jab, 211-240 get_a_nabla_b):
+//
+//   CI_RHO    out[x]    = sum_t c_t mo[a_t][x] mo[b_t][x]
+//   CI_JAB    out[d][x] = sum_t -1/2 c_t (mo[a_t][x] dmo[d][b_t][x] - mo[b_t][x] dmo[d][a_t][x])
+//   CI_ANB    out[d][x] = sum_t c_t mo[a_t][x] dmo[d][b_t][x]
+//   CI_PAIRS  out[t][x] = mo[a_t][x] mo[b_t][x]                     (per-pair products, store bound)
+//
+// One thread owns one grid point and walks the term list in the caller's order with the reference's
+// expression order and NO fused multiply-add (__dmul_rn / __dadd_rn), so for the same MO arrays the
+// results are bit-identical to the reference's C loops.  The term list streams through shared memory
+// in batches (every lane of a warp needs the same term: broadcast reads); the MO rows are read with
+// fully coalesced, L1/L2-cached loads (a warp reads 32 consecutive doubles of row a_t and of row b_t).
+// HBM-bound: algorithmic traffic = the MO rows once (8 n_mo n_sets bytes per point) + the output.
+#pragma once
+#include "okb_common.cuh"
+
+namespace okb {
+
+enum { CI_RHO = 0, CI_JAB = 1, CI_ANB = 2, CI_PAIRS = 3 };
+
+struct CiParams {
+    const double *mo;          // [n_mo][ld]
+    const double *dmo;         // [3][n_mo][ld] (JAB, ANB) or null
+    long long ld;              // row stride of mo / dmo in points
+    long long dstride;         // n_mo * ld: distance between the three derivative blocks
+    long long npts;
+    int n_terms;
+    const double *tc;          // term coefficients
+    const int *ta, *tb;        // term orbital indices
+    double *out;
+    long long ldo;             // row stride of out in points
+};
+
+constexpr int CI_NT = 128;     // threads per CTA = points per CTA
+constexpr int CI_TB = 1024;    // terms per shared-memory batch
+
+template <int MODE>
+__global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
+    __shared__ double s_c[CI_TB];
+    __shared__ int s_a[CI_TB], s_b[CI_TB];
+    const long long x = (long long)blockIdx.x * CI_NT + threadIdx.x;
+    const bool live = x < p.npts;
+    const long long xc = live ? x : p.npts - 1;              // clamp: every thread takes part in the staging
+    const double *mo = p.mo + xc;
+    const double *d0 = (MODE == CI_JAB || MODE == CI_ANB) ? p.dmo + xc : nullptr;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int t0 = 0; t0 < p.n_terms; t0 += CI_TB) {
+        const int nb = min(CI_TB, p.n_terms - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb; e += CI_NT) {
+            s_c[e] = p.tc[t0 + e];
+            s_a[e] = p.ta[t0 + e];
+            s_b[e] = p.tb[t0 + e];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int e = 0; e < nb; ++e) {
+            const double c = s_c[e];
+            const long long ra = (long long)s_a[e] * p.ld, rb = (long long)s_b[e] * p.ld;
+            if (MODE == CI_RHO) {
+                // rho[x] += citmp*molist[sta,x]*molist[stb,x]        (cy_ci.pyx:88,95)
+                acc0 = __dadd_rn(acc0, __dmul_rn(__dmul_rn(c, __ldg(mo + ra)), __ldg(mo + rb)));
+            } else if (MODE == CI_PAIRS) {
+                if (live) p.out[(long long)(t0 + e) * p.ldo + x] = __dmul_rn(__ldg(mo + ra), __ldg(mo + rb));
+            } else {
+                const double ma = __ldg(mo + ra), mb = (MODE == CI_JAB) ? __ldg(mo + rb) : 0.0;
+                double v[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double db = __ldg(d0 + d * p.dstride + rb);
+                    if (MODE == CI_JAB) {
+                        // jab[d,x] -= 0.5*(citmp*(mo[a]*dmo[d,b] - mo[b]*dmo[d,a]))      (cy_ci.pyx:181-184)
+                        const double da = __ldg(d0 + d * p.dstride + ra);
+                        v[d] = -__dmul_rn(0.5, __dmul_rn(c, __dadd_rn(__dmul_rn(ma, db), -__dmul_rn(mb, da))));
+                    } else {
+                        // out[d,x] += citmp*(mo[a]*dmo[d,b])                             (cy_ci.pyx:236-238)
+                        v[d] = __dmul_rn(c, __dmul_rn(ma, db));
+                    }
+                }
+                acc0 = __dadd_rn(acc0, v[0]);
+                acc1 = __dadd_rn(acc1, v[1]);
+                acc2 = __dadd_rn(acc2, v[2]);
+            }
+        }
+    }
+    if (!live || MODE == CI_PAIRS) return;
+    p.out[x] = acc0;
+    if (MODE != CI_RHO) {
+        p.out[p.ldo + x] = acc1;
+        p.out[2 * p.ldo + x] = acc2;
+    }
+}
+
+}  // namespace okb

@@ -45,7 +45,8 @@ struct ShellMeta {                 // 56 B
     int prim_off, nprim, fn_off, nfn;   // offsets are chunk-local; nfn = rows this shell writes
     int L, kind;                        // kind 1: Cartesian functions in the standard order of std_lxyz(L, .);
                                         // kind 2: same, but the shell writes its 2L+1 real-spherical rows
-    int aux_off, pad;                   // kind 2: offset (doubles) of [f[ncart] | per row: position, coefs] in aux
+    int aux_off;                        // kind 2: offset (doubles) of [f[ncart] | per row: position, coefs] in aux
+    int gprim;                          // index of the shell's first primitive in the basis-wide axis tables
 };
 struct FnMeta { int lxyz; int pad; double f; };          // lx | ly<<8 | lz<<16 ; f = angular norm * renorm
 struct RowMeta { int out_row, term_off, nterm, pad; };   // SINK_AO output rows of this chunk
@@ -57,7 +58,10 @@ struct KParams {
     // grid
     int grid_kind;                 // 0 regular (axes), 1 vector (coordinates)
     const double *gx, *gy, *gz;
-    int ny, nz;
+    int nx, ny, nz;
+    // regular grids: separable exponentials  c N exp(-a (x_i-X)^2), exp(-a (y_j-Y)^2), exp(-a (z_k-Z)^2)
+    // per (primitive, axis point), [n_prim][n_axis] each; null -> evaluate exp(-a r^2) per point
+    const double *tabx, *taby, *tabz;
     long long p0;                  // global index of the first point of this launch
     int npts;                      // points in this launch
     int ntiles;
@@ -77,6 +81,14 @@ struct KParams {
     long long slot_stride;         // n_rows * ld
     int slot[10];                  // code -> output slot, -1 = not requested
     int one_code, exact_mixed;
+};
+
+// Axis tables of a regular grid as the AO generators see them; ii/jj/kk point at the axis indices of the
+// thread's first point in shared memory (its other points are 32 entries apart).
+struct AxTab {
+    const double *ex, *ey, *ez;    // null ex -> no tables (vector grid)
+    int nx, ny, nz;
+    const int *ii, *jj, *kk;
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) -------------------------

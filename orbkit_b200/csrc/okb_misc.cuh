@@ -4,6 +4,21 @@
 
 namespace okb {
 
+// ---- separable exponentials of a regular grid ----------------------------------------------------------------
+// out[p][i] = scale_p * exp(-alpha_p (ax[i] - centre_p)^2) for every primitive p and axis point i; prim5 holds
+// (alpha, cN, X, Y, Z) per primitive, `axis` selects the centre component, the x table carries cN.
+__global__ void __launch_bounds__(256) okb_axis_table_kernel(const double *__restrict__ prim5, int nprim,
+                                                             const double *__restrict__ ax, int n, int axis,
+                                                             double *__restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nprim * n) return;
+    const int pr = (int)(idx / n), i = (int)(idx - (long long)pr * n);
+    const double *q = prim5 + 5 * (size_t)pr;
+    const double d = ax[i] - q[2 + axis];
+    const double e = exp(-(q[0] * (d * d)));
+    out[idx] = axis == 0 ? q[1] * e : e;
+}
+
 // ---- plain FP64 GEMM for the cy_core.mocreator drop-in: mo[M][N] = Cm[M][K] * ao[K][N] -----------
 // 64 x 64 output tile per CTA (256 threads, 4x4 register tile), K stepped by 16 through smem.
 __global__ void __launch_bounds__(256) okb_mocreator_kernel(const double *__restrict__ ao,

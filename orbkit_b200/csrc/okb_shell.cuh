@@ -154,12 +154,64 @@ __device__ __forceinline__ void radial_sums(const ShellMeta &sh, const double2 *
     if (i < sh.nprim) radial_group<1, NP, N1, N2>(pp + i, rr, R0, R1, R2);
 }
 
+// Same sums on a regular grid from the separable axis tables (okb_axis_table_kernel): per primitive and point
+// three cached loads and two multiplications replace the exponential,
+//     cN exp(-a r^2) = [cN exp(-a X^2)] [exp(-a Y^2)] [exp(-a Z^2)].
+// ox/oy/oz: table offsets of the shell's first primitive at each of the thread's points.
+template <int G, int NP, bool N1, bool N2>
+__device__ __forceinline__ void radial_group_tab(const double2 *__restrict__ pp, const AxTab &tab, int u0,
+                                                 const int (&ox)[NP], const int (&oy)[NP], const int (&oz)[NP],
+                                                 double (&R0)[NP], double (&R1)[NP], double (&R2)[NP]) {
+    double t[G][NP];
+#pragma unroll
+    for (int u = 0; u < G; ++u)
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            t[u][q] = (__ldg(tab.ex + ox[q] + (u0 + u) * tab.nx) * __ldg(tab.ey + oy[q] + (u0 + u) * tab.ny)) *
+                      __ldg(tab.ez + oz[q] + (u0 + u) * tab.nz);
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const double a = N1 ? pp[u0 + u].x : 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            R0[q] += t[u][q];
+            if (N1) {
+                const double ta = t[u][q] * a;
+                R1[q] += ta;
+                if (N2) R2[q] = fma(ta, a, R2[q]);
+            }
+        }
+    }
+}
+
+template <int NP, bool N1, bool N2>
+__device__ __forceinline__ void radial_sums_tab(const ShellMeta &sh, const double2 *__restrict__ prims, const AxTab &tab,
+                                                double (&R0)[NP], double (&R1)[NP], double (&R2)[NP]) {
+    int ox[NP], oy[NP], oz[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        R0[q] = R1[q] = R2[q] = 0.0;
+        ox[q] = sh.gprim * tab.nx + tab.ii[32 * q];
+        oy[q] = sh.gprim * tab.ny + tab.jj[32 * q];
+        oz[q] = sh.gprim * tab.nz + tab.kk[32 * q];
+    }
+    const double2 *pp = prims + sh.prim_off;
+    constexpr int G = (NP >= 2) ? 2 : 4;
+    int i = 0;
+    for (; i + G <= sh.nprim; i += G) radial_group_tab<G, NP, N1, N2>(pp, tab, i, ox, oy, oz, R0, R1, R2);
+    if (G == 4 && i + 2 <= sh.nprim) {
+        radial_group_tab<2, NP, N1, N2>(pp, tab, i, ox, oy, oz, R0, R1, R2);
+        i += 2;
+    }
+    if (i < sh.nprim) radial_group_tab<1, NP, N1, N2>(pp, tab, i, ox, oy, oz, R0, R1, R2);
+}
+
 // One standard shell for NP points of the same thread (points pt, pt+32, ...: tile columns tp[32*q]).
 template <int SET, int L, int STRIDE, bool SPH, int NP>
 __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
-                                              const double *__restrict__ zs, double *__restrict__ tp) {
+                                              const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
     static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP, "specialised sets");
     constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP);
     constexpr int D = set_ncodes(SET);
@@ -172,7 +224,8 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
         rr[q] = r[q][0] * r[q][0] + r[q][1] * r[q][1] + r[q][2] * r[q][2];
     }
     double R0[NP], R1[NP], R2[NP];
-    radial_sums<NP, N1, N2>(sh, prims, rr, R0, R1, R2);
+    if (tab.ex != nullptr) radial_sums_tab<NP, N1, N2>(sh, prims, tab, R0, R1, R2);      // warp-uniform
+    else radial_sums<NP, N1, N2>(sh, prims, rr, R0, R1, R2);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         // per-axis factor tables (all indices are compile-time constants after unrolling)
@@ -275,23 +328,23 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp,
-                                              int one_code, int exact) {
+                                              int one_code, int exact, const AxTab &tab) {
     if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) {
         constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) ? SET : SET_VAL;
         if (sh.kind == 1) {                  // warp-uniform
             switch (sh.L) {
-                case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                case 1: gen_shell_std<S, 1, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                case 2: gen_shell_std<S, 2, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                case 3: gen_shell_std<S, 3, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                case 4: gen_shell_std<S, 4, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                case 1: gen_shell_std<S, 1, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                case 2: gen_shell_std<S, 2, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                case 3: gen_shell_std<S, 3, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                case 4: gen_shell_std<S, 4, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
                 default: break;
             }
         } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
             switch (sh.L) {
-                case 2: gen_shell_std<S, 2, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                case 3: gen_shell_std<S, 3, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
-                default: gen_shell_std<S, 4, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp); return;
+                case 2: gen_shell_std<S, 2, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                case 3: gen_shell_std<S, 3, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
+                default: gen_shell_std<S, 4, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
             }
         }
     }

@@ -18,7 +18,8 @@ struct Cfg {
     static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;      // rho + (D-1) derivative sums
     static constexpr size_t OFF_BAR = 0;                          // 5 mbarriers (3 meta + 2 coef)
     static constexpr size_t OFF_XYZ = 128;
-    static constexpr size_t OFF_META = OFF_XYZ + (size_t)3 * P * 8;
+    static constexpr size_t OFF_IJK = OFF_XYZ + (size_t)3 * P * 8;      // axis indices (regular grids)
+    static constexpr size_t OFF_META = OFF_IJK + (size_t)3 * P * 4;
     __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
         return (OFF_META + (size_t)NMETA * meta_stride + 127) / 128 * 128;
     }
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);   // [0..2] meta, [3..4] coef
     double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
     double *ys = xs + P, *zs = ys + P;
+    int *isx = reinterpret_cast<int *>(smem + C::OFF_IJK), *isy = isx + P, *isz = isy + P;
     unsigned char *mbase = smem + C::OFF_META;
     double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
     double *tbase = reinterpret_cast<double *>(smem + C::off_tile(p.lay.stride));
@@ -81,8 +83,9 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
         const int nitems = hdr.nshell * PG;
         for (int item = warp; item < nitems; item += NW) {
             const int s = item / PG, pt = (item % PG) * (32 * NP) + lane;
+            const AxTab tab{p.tabx, p.taby, p.tabz, p.nx, p.ny, p.nz, isx + pt, isy + pt, isz + pt};
             gen_shell_any<SET, P, NP>(shells[s], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt, p.one_code,
-                                      p.exact_mixed);
+                                      p.exact_mixed, tab);
         }
     };
 
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
                 const long long i = n / nyz, rem = n - i * nyz;
                 const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
                 xs[tid] = p.gx[i]; ys[tid] = p.gy[j]; zs[tid] = p.gz[k];
+                isx[tid] = (int)i; isy[tid] = j; isz[tid] = k;
             } else {
                 xs[tid] = p.gx[n]; ys[tid] = p.gy[n]; zs[tid] = p.gz[n];
             }

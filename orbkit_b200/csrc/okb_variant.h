@@ -1,0 +1,21 @@
+// okb_variant.h -- kernel variant records.  The template instantiations are spread over several
+// translation units (inst_*.cu, via okb_variant_inst.h) so that they compile in parallel; okb200.cu only
+// walks the per-unit tables declared here.
+#pragma once
+#include "okb_common.cuh"
+
+namespace okb {
+
+struct Variant {
+    const char *name;
+    int set, sink, MW, PT, NW;
+    int P, MC;
+    size_t (*smem)(int meta_stride);
+    cudaError_t (*launch)(const KParams &, int grid, size_t smem, cudaStream_t);
+};
+struct VariantTable { const Variant *v; int n; };
+
+// defined in inst_tile.cu, inst_ws_val.cu, inst_ws_grad.cu, inst_ws_lap.cu, inst_ws_all.cu
+extern const VariantTable okb_variants_tile, okb_variants_val, okb_variants_grad, okb_variants_lap, okb_variants_all;
+
+}  // namespace okb

@@ -55,8 +55,10 @@ struct WsCfg {
     // NCW*32*CREG + NPW*32*PREG must not exceed what the launch reserved
     static constexpr int LAUNCH_REGS = (65536 / NT) / 8 * 8;
     static constexpr int ACC_REGS = 4 * AM * BN * D;
-    static constexpr int CREG_SLACK = (NCW == 8 && ACC_REGS > 160) ? 32 : 40;   // big tiles on two warpgroups:
-                                                                                  // leave the producers > 100 registers
+    // registers of a consumer thread beyond its accumulators: A/B fragments, addresses, loop state.  One consumer
+    // warpgroup with a full tile gets 56 (ptxas otherwise recycles a B-fragment register as address register and
+    // refills it right in front of its use); big tiles on two warpgroups leave the producers > 100 registers.
+    static constexpr int CREG_SLACK = (NCW == 8 && ACC_REGS > 160) ? 32 : (NCW == 4 && ACC_REGS >= 160) ? 56 : 40;
     static constexpr int CREG_WANT = ((ACC_REGS + CREG_SLACK + 7) / 8 * 8 > 248) ? 248 : (ACC_REGS + CREG_SLACK + 7) / 8 * 8;
     static constexpr int PREG_MAX = ((NT * LAUNCH_REGS - NCW * 32 * CREG_WANT) / (NPW * 32)) / 8 * 8;
     static constexpr int PREG_CAP = LAUNCH_REGS < 152 ? LAUNCH_REGS : 152;   // setmaxnreg.dec may only lower
@@ -64,13 +66,16 @@ struct WsCfg {
     static constexpr int CREG = ((NT * LAUNCH_REGS - NPW * 32 * PREG) / (NCW * 32)) / 8 * 8 > 248
                                     ? 248
                                     : ((NT * LAUNCH_REGS - NPW * 32 * PREG) / (NCW * 32)) / 8 * 8;
-    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] mfull[NMETA]
+    static constexpr int NM = 4;                               // chunk-table ring slots
+    static constexpr int LAG = 2;                              // a slot is refilled LAG chunks after its chunk
+    static constexpr size_t OFF_BAR = 0;                       // full[NST] empty[NST] mfull[NM] mempty[NM]
     static constexpr size_t OFF_NFN = 256;                     // int nfn[NST]
     static constexpr size_t OFF_XYZ = 384;
-    static constexpr size_t OFF_RED = OFF_XYZ + (size_t)3 * P * 8;
+    static constexpr size_t OFF_IJK = OFF_XYZ + (size_t)3 * P * 8;     // axis indices of the tile's points (regular grids)
+    static constexpr size_t OFF_RED = OFF_IJK + (size_t)3 * P * 4;
     static constexpr size_t OFF_META = OFF_RED + (size_t)(NOUT > 0 ? WM * NOUT * P * 8 : 0);
     __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
-        return (OFF_META + (size_t)NMETA * meta_stride + 127) / 128 * 128;
+        return (OFF_META + (size_t)NM * meta_stride + 127) / 128 * 128;
     }
     __host__ __device__ static constexpr size_t off_tile(int meta_stride) {
         return off_cbuf(meta_stride) + (size_t)NST * CBUF_DOUBLES * 8;
@@ -78,7 +83,7 @@ struct WsCfg {
     __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
         return off_tile(meta_stride) + (size_t)NST * TILE_DOUBLES * 8;
     }
-    static_assert(2 * NST + NMETA <= 32, "barrier area");
+    static_assert(2 * NST + 2 * NM <= 32, "barrier area");
     static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
     static_assert(P % 32 == 0, "whole warps of points for the producers");
     static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
@@ -136,10 +141,13 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
     constexpr int NPT = NPW * 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t a_full = sbase + (uint32_t)C::OFF_BAR, a_empty = a_full + 8 * NST, a_mfull = a_empty + 8 * NST;
+    constexpr int NM = C::NM, LAG = C::LAG;
+    const uint32_t a_full = sbase + (uint32_t)C::OFF_BAR, a_empty = a_full + 8 * NST, a_mfull = a_empty + 8 * NST,
+                   a_mempty = a_mfull + 8 * NM;
     int *nfn_s = reinterpret_cast<int *>(smem + C::OFF_NFN);
     double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
     double *ys = xs + P, *zs = ys + P;
+    int *isx = reinterpret_cast<int *>(smem + C::OFF_IJK), *isy = isx + P, *isz = isy + P;
     double *red = reinterpret_cast<double *>(smem + C::OFF_RED);
     unsigned char *mbase = smem + C::OFF_META;
     double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
@@ -152,7 +160,10 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
             mbar_init(&bars[i], NPT);                 // + TMA bytes of the coefficient tile
             mbar_init(&bars[NST + i], NCW);
         }
-        for (int i = 0; i < NMETA; ++i) mbar_init(&bars[2 * NST + i], 1);
+        for (int i = 0; i < NM; ++i) {
+            mbar_init(&bars[2 * NST + i], 1);
+            mbar_init(&bars[2 * NST + NM + i], NPW);  // one arrival per producer warp that left the chunk
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -168,12 +179,12 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
         const int ptid = tid - NCW * 32, pwarp = warp - NCW;
         const uint32_t a_meta = smem_u32(mbase), a_cbuf = smem_u32(cbase);
         auto issue_meta = [&](uint32_t gc) {
-            const uint32_t bar = a_mfull + 8 * (gc % NMETA);
+            const uint32_t bar = a_mfull + 8 * (gc % NM);
             mbar_arrive_expect_tx_a(bar, meta_bytes);
-            bulk_g2s_a(a_meta + (gc % NMETA) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes, meta_bytes, bar);
+            bulk_g2s_a(a_meta + (gc % NM) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes, meta_bytes, bar);
         };
         if (ptid == 0)
-            for (uint32_t i = 0; i < NMETA && i < total; ++i) issue_meta(i);
+            for (uint32_t i = 0; i < NM && i < total; ++i) issue_meta(i);
         uint32_t g = 0;
         for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
             const int q0 = tile_id * P;
@@ -187,6 +198,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     const long long i = n / nyz, rem = n - i * nyz;
                     const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
                     xs[e] = p.gx[i]; ys[e] = p.gy[j]; zs[e] = p.gz[k];
+                    isx[e] = (int)i; isy[e] = j; isz[e] = k;
                 } else {
                     xs[e] = p.gx[n]; ys[e] = p.gy[n]; zs[e] = p.gz[n];
                 }
@@ -195,14 +207,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
             for (int mt = 0; mt < p.n_mtile; ++mt)
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
-                    mbar_wait_a(a_mfull + 8 * (g % NMETA), (g / NMETA) & 1);
+                    // The producer warps are NOT synchronised per chunk: a warp that is done with its items
+                    // of chunk g goes on to chunk g+1 (at most NST-1 chunks ahead of the slowest one, bounded
+                    // by the stage ring), so uneven item costs average out over several chunks.  The
+                    // chunk-table slot of chunk g-LAG is refilled once every warp has left that chunk.
+                    if (ptid == 0 && g >= LAG && g - LAG + NM < total) {
+                        const uint32_t h = g - LAG;
+                        mbar_wait_a(a_mempty + 8 * (h % NM), (h / NM) & 1);
+                        issue_meta(h + NM);
+                    }
+                    mbar_wait_a(a_mfull + 8 * (g % NM), (g / NM) & 1);
                     mbar_wait_a(a_empty + 8 * s, ((g / NST) & 1) ^ 1);   // consumers released the stage
                     if (ptid == 0) {
                         mbar_expect_tx_only_a(a_full + 8 * s, cbuf_bytes);
                         bulk_g2s_a(a_cbuf + s * cbuf_bytes, p.cblob + ((size_t)mt * p.nchunk + c) * C::CBUF_DOUBLES,
                                    cbuf_bytes, a_full + 8 * s);
                     }
-                    const unsigned char *mb = mbase + (size_t)(g % NMETA) * meta_bytes;
+                    const unsigned char *mb = mbase + (size_t)(g % NM) * meta_bytes;
                     const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
                     const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
                     const double2 *prims = reinterpret_cast<const double2 *>(mb + p.lay.off_prim);
@@ -213,11 +234,16 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     // chains); warps take items round-robin, rotated per chunk so that the same warp is not
                     // always the one with the extra item
                     constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
-                    const int nitems = hdr.nshell * PG;
-                    for (int item = (pwarp + g) % NPW; item < nitems; item += NPW) {
+                    // the host sorts the shells of a chunk by descending cost; items are dealt to the warps in
+                    // boustrophedon order (0..NPW-1, NPW-1..0, ...), rotated per chunk
+                    const int nitems = hdr.nshell * PG, wrot = (pwarp + g) % NPW;
+                    for (int r = 0; r * NPW < nitems; ++r) {
+                        const int item = r * NPW + ((r & 1) ? NPW - 1 - wrot : wrot);
+                        if (item >= nitems) continue;
                         const int sh = item / PG, pt = (item % PG) * (32 * NP) + lane;
+                        const AxTab tab{p.tabx, p.taby, p.tabz, p.nx, p.ny, p.nz, isx + pt, isy + pt, isz + pt};
                         gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
-                                                   p.one_code, p.exact_mixed);
+                                                   p.one_code, p.exact_mixed, tab);
                     }
                     // zero the rows that pad nfn up to the k-step of the MMA (coefficients there are 0,
                     // but stale shared memory could hold NaN/Inf bit patterns)
@@ -228,8 +254,8 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     }
                     if (ptid == 0) nfn_s[s] = kpad;
                     mbar_arrive_a(a_full + 8 * s);                       // release: tile + nfn visible
-                    named_bar(1, NPT);                                   // chunk table no longer read
-                    if (ptid == 0 && g + NMETA < total) issue_meta(g + NMETA);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(a_mempty + 8 * (g % NM));   // this warp no longer reads the chunk table
                 }
         }
     } else {
@@ -259,58 +285,83 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     for (int ib = 0; ib < BN; ++ib)
 #pragma unroll
                         for (int d = 0; d < D; ++d) acc[ia][ib][d][0] = acc[ia][ib][d][1] = 0.0;
-                for (int c = 0; c < p.nchunk; ++c, ++g) {
-                    const int s = g % NST;
-                    mbar_wait_a(a_full + 8 * s, (g / NST) & 1);          // AO tile + coefficient tile landed
-                    const int nk = nfn_s[s];                             // multiple of 4
-                    const double *ap = cbase + (size_t)s * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr;
-                    const double *bp = tbase + (size_t)s * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr;
-                    // Explicitly scheduled k-loop (volatile asm keeps the order): ncu showed every LDS that
-                    // refilled an A fragment right behind the last DMMA reading that register stalling on
-                    // the write-after-read hazard (~6 cycles per 4 DMMAs), plus the exposed LDS latency at
-                    // the head of each step.  Here the fragments of step k0+4 are fetched during step k0:
-                    // B into the other half of a double buffer at the start of the step, A[ia-1] only
-                    // after the DMMAs of block ia have been issued, so no load waits for a reader and no
-                    // DMMA waits for a load.
-                    const uint32_t a_ap = smem_u32(ap), a_bp = smem_u32(bp);
-                    double afr[AM], bfr[2][D][BN];
+                // ---- contraction over the chunks of this MO tile ------------------------------------------------
+                // One software pipeline over ALL k-steps of the pass: the fragments of the next step are fetched
+                // during the current one, across chunk boundaries too (the last step of chunk c prefetches the
+                // first fragments of chunk c+1 from the next stage of the ring), so the DMMA stream is only
+                // interrupted once per MO-tile pass.  ncu had shown ~8% of the consumer's time in the per-chunk
+                // prologue (barrier wait, pointer set-up, exposed LDS latency of the first 15 fragments).
+                // Register use is explicit: A fragments afr[AM], ONE set of B fragments bfr[D][BN]; a fragment
+                // register is refilled right after the last DMMA of the step that reads it.
+                double afr[AM], bfr[D][BN];
+                auto frag_addr = [&](uint32_t gg, uint32_t &aa, uint32_t &bb) {
+                    const int st = gg % NST;
+                    aa = smem_u32(cbase + (size_t)st * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr);
+                    bb = smem_u32(tbase + (size_t)st * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr);
+                };
+                // one k-step: DMMAs on the fragments in registers, refilled from (na, nb) for the next step.
+                // Order: B fragment outermost, MO blocks innermost.  B[d][ib] is refilled behind its AM DMMAs and
+                // needed again (D*BN-1)*AM DMMAs later; A[ia] is refilled during the last B pass and needed AM
+                // DMMAs later -- at 16 cycles per DMMA both distances (>= 96 cycles) cover the LDS latency under
+                // load (ncu: 9% of the consumer's samples were short-scoreboard stalls when the B fragments were
+                // refilled only 62 cycles ahead of their use).
+                auto step = [&](const uint32_t na, const uint32_t nb) {
 #pragma unroll
                     for (int d = 0; d < D; ++d)
 #pragma unroll
-                        for (int ib = 0; ib < BN; ++ib) bfr[0][d][ib] = lds64(a_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+                        for (int ib = 0; ib < BN; ++ib) {
 #pragma unroll
-                    for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(a_ap + (uint32_t)(ia * 8) * 8u);
-                    auto step = [&](const int k0, auto cur_tag) {
-                        constexpr int CUR = decltype(cur_tag)::value;
-                        // next step (clamped to the last one: a harmless reload at the end of the chunk)
-                        const int kn = (k0 + 4 < nk) ? k0 + 4 : k0;
-                        const uint32_t na = a_ap + (uint32_t)(kn * CS) * 8u, nb = a_bp + (uint32_t)(kn * PS) * 8u;
+                            for (int ia = 0; ia < AM; ++ia) {
+                                const bool owned = !(MB % WM != 0 && ia == AM - 1 && ia >= nblk);   // warp-uniform
+                                if (owned) dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr[d][ib]);
+                                if (d == D - 1 && ib == BN - 1) afr[ia] = lds64(na + (uint32_t)(ia * 8) * 8u);
+                            }
+                            bfr[d][ib] = lds64(nb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+                        }
+                };
+                uint32_t a_ap, a_bp;
+                frag_addr(g, a_ap, a_bp);
+                mbar_wait_a(a_full + 8 * (g % NST), (g / NST) & 1);      // AO tile + coefficient tile landed
+                int nk = nfn_s[g % NST];                                 // multiple of 4, >= 4
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib) bfr[d][ib] = lds64(a_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+#pragma unroll
+                for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(a_ap + (uint32_t)(ia * 8) * 8u);
+                for (int c = 0; c < p.nchunk; ++c, ++g) {
+                    const int s = g % NST;
+                    for (int k0 = 4; k0 < nk; k0 += 4)                   // steps 0 .. nk/4-2: next step in this chunk
+                        step(a_ap + (uint32_t)(k0 * CS) * 8u, a_bp + (uint32_t)(k0 * PS) * 8u);
+                    // last step of the chunk: refill from the next chunk of this pass (or, behind the last chunk,
+                    // harmlessly from this one)
+                    uint32_t n_ap = a_ap, n_bp = a_bp;
+                    int nk_next = nk;
+                    // With only two stages the consumer must hand its stage back BEFORE it waits for the next one
+                    // (otherwise the producers idle for a k-step per chunk: measured +5% on rho + laplacian), so
+                    // the pipeline is seamless only for NST >= 3.
+                    constexpr bool SEAMLESS = (NST >= 3);
+                    if (SEAMLESS && c + 1 < p.nchunk) {
+                        mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
+                        nk_next = nfn_s[(g + 1) % NST];
+                        frag_addr(g + 1, n_ap, n_bp);
+                    }
+                    step(n_ap, n_bp);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(a_empty + 8 * s);       // every read of this stage has returned
+                    if (!SEAMLESS && c + 1 < p.nchunk) {
+                        mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
+                        nk_next = nfn_s[(g + 1) % NST];
+                        frag_addr(g + 1, n_ap, n_bp);
 #pragma unroll
                         for (int d = 0; d < D; ++d)
 #pragma unroll
                             for (int ib = 0; ib < BN; ++ib)
-                                bfr[CUR ^ 1][d][ib] = lds64(nb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+                                bfr[d][ib] = lds64(n_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
 #pragma unroll
-                        for (int ia = 0; ia < AM; ++ia) {
-                            if (!(MB % WM != 0 && ia == AM - 1 && ia >= nblk)) {     // warp-uniform
-#pragma unroll
-                                for (int d = 0; d < D; ++d)
-#pragma unroll
-                                    for (int ib = 0; ib < BN; ++ib)
-                                        dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr[CUR][d][ib]);
-                            }
-                            if (ia >= 1) afr[ia - 1] = lds64(na + (uint32_t)((ia - 1) * 8) * 8u);
-                        }
-                        afr[AM - 1] = lds64(na + (uint32_t)((AM - 1) * 8) * 8u);
-                    };
-                    int k0 = 0;
-                    for (; k0 + 8 <= nk; k0 += 8) {
-                        step(k0, std::integral_constant<int, 0>{});
-                        step(k0 + 4, std::integral_constant<int, 1>{});
+                        for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(n_ap + (uint32_t)(ia * 8) * 8u);
                     }
-                    if (k0 < nk) step(k0, std::integral_constant<int, 0>{});
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(a_empty + 8 * s);
+                    a_ap = n_ap; a_bp = n_bp; nk = nk_next;
                 }
                 // ---- per-MO-tile epilogues: lane holds MO row tr of each block, points 2*tc + {0,1} -----
                 if (SINK == SINK_MO) {

@@ -245,6 +245,55 @@ class Engine:
             norm.ctypes.data if want_norm else None, flags))
         return rho, (delta if len(codes) else None), norm
 
+    # ---- detCI grid contractions ---------------------------------------------------------------------------
+    @staticmethod
+    def _ci_ncomp(mode, n_terms):
+        return 1 if mode == _lib.OKB_CI_RHO else (n_terms if mode == _lib.OKB_CI_PAIRS else 3)
+
+    def ci_contract(self, mode, terms, molist, molistdrv=None, n_mo=None, npts=None, ld=None, out=None, n_eval=None,
+                    flags=0):
+        """sum over MO pairs of given MO arrays (okb_ci_contract).  terms = (coef, ia, ib) flat arrays;
+        molist (n_mo, npts) / molistdrv (3, n_mo, npts) NumPy arrays, or device pointers (ints) with
+        OKB_FLAG_IN_DEVICE and explicit n_mo / npts / ld.  Only the first `n_eval` points (default: all)
+        are evaluated; the rest of a host output stays 0."""
+        coef, ia, ib = _lib.f64(terms[0]), _lib.i32(terms[1]), _lib.i32(terms[2])
+        in_dev = bool(flags & _lib.OKB_FLAG_IN_DEVICE)
+        out_dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        if not in_dev:
+            molist = _lib.f64(molist)
+            n_mo, npts = molist.shape
+            ld = npts
+            if molistdrv is not None:
+                molistdrv = _lib.f64(molistdrv)
+                if molistdrv.shape != (3, n_mo, npts):
+                    raise ValueError('molistdrv must have shape (3, NMO, N)')
+        ld = npts if ld is None else ld
+        n_eval = npts if n_eval is None else n_eval
+        ncomp = self._ci_ncomp(mode, len(coef))
+        if out is None:
+            out = self.host_array((ncomp, npts))
+            if n_eval < npts:
+                out[:, n_eval:] = 0.0
+        _lib.check(self.lib.okb_ci_contract(
+            self.ctx, mode, n_mo, n_eval, ld, molist if in_dev else molist.ctypes.data,
+            None if molistdrv is None else (molistdrv if in_dev else molistdrv.ctypes.data),
+            len(coef), _lib.dptr(coef), _lib.iptr(ia), _lib.iptr(ib), out if out_dev else out.ctypes.data,
+            npts, flags))
+        return out
+
+    def eval_ci(self, mode, terms, mo, grid, drv_codes=(1, 2, 3), p0=0, p1=None, out=None, flags=0):
+        """fused: MOs of `mo` evaluated on the device slab by slab and contracted there (okb_eval_ci)"""
+        coef, ia, ib = _lib.f64(terms[0]), _lib.i32(terms[1]), _lib.i32(terms[2])
+        p1 = grid.npts if p1 is None else p1
+        codes = _lib.i32(list(drv_codes))
+        out_dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        if out is None:
+            out = self.host_array((self._ci_ncomp(mode, len(coef)), p1 - p0))
+        _lib.check(self.lib.okb_eval_ci(self.ctx, mo.ptr, grid.ptr, p0, p1, mode, _lib.iptr(codes), len(coef),
+                                        _lib.dptr(coef), _lib.iptr(ia), _lib.iptr(ib),
+                                        out if out_dev else out.ctypes.data, flags))
+        return out
+
     def measure_fp64(self, kind=0, min_seconds=0.0):
         """dense FP64 TFLOP/s of this device: kind 0 DFMA, 1 DMMA m8n8k4, 2 mixed; burst when
         min_seconds <= 0, else sustained over back-to-back launches"""

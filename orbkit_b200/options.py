@@ -12,3 +12,5 @@ slice_length = 1e4   #: advisory: upper bound of points per device launch when >
 outputname = 'orbkit_b200'
 exact_mixed_derivatives = False  #: opt-in analytically correct xy/xz/yz AO derivatives
                                  #  (the reference drops cross terms, c_support.c:121-168)
+ci_merge_terms = False           #: detci.ci_core: merge duplicate orbital pairs before the launch (faster;
+                                 #  summation order then differs from the reference at the 1e-16 level)

@@ -1,0 +1,146 @@
+"""GPU parity of the detCI grid contractions (orbkit_b200.detci.ci_core, C ABI okb_ci_contract /
+okb_eval_ci) against
+   (1) the reference's own outputs for its test orbkit/test/detci/h3+.py (tests/golden/h3p_detci.npz)
+       and its committed golden refdata_h3+.npz,
+   (2) the pinned CPU oracle (oracle/oracle_ci.py) on seeded random term lists, bit for bit,
+   (3) properties at Config-5 scale (500 MOs, 1000 pairs): linearity in the coefficients, symmetry,
+       per-pair products summing to the contracted density.
+The contraction is bit-exact for identical MO arrays; MOs evaluated on the device carry the FP64
+tolerance of the grid path (|d| <= 1e-10*|ref| + 1e-14*max|ref|)."""
+import numpy
+import pytest
+
+from conftest import assert_close, load_golden
+from test_oracle_ci import lists_from_golden, random_lists
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ok():
+    import orbkit_b200
+    orbkit_b200.options.quiet = True
+    orbkit_b200.options.ci_merge_terms = False
+    return orbkit_b200
+
+
+@pytest.fixture(scope='module')
+def oci(oracle_mod):
+    import oracle_ci
+    return oracle_ci
+
+
+def test_h3p_reference_test_reproduced(ok, oci):
+    """the reference's detCI test, end to end on the device"""
+    from orbkit_b200.detci import ci_core
+    g = load_golden('h3p_detci')
+    qc = ok.QCinfo.from_arrays(g)
+    ok.grid.set_grid(g['x'], g['y'], g['z'], is_vector=False)
+    molist = ok.rho_compute(qc, calc_mo=True, slice_length=1e2, drv=[None, 'x', 'y', 'z', 'xx', 'yy', 'zz'])
+    mo, d1, d2 = molist[0], molist[1:4], molist[-3:]
+    for pair in range(int(g['n_pairs'])):
+        zero, sing = lists_from_golden(g, pair)
+        rho = ci_core.rho(zero, sing, mo, slice_length=1e2)
+        jab = ci_core.jab(zero, sing, mo, d1, slice_length=1e2)
+        nj = -numpy.sum(ci_core.jab(zero, sing, mo, d2, slice_length=1e2), axis=0)
+        anb = ci_core.a_nabla_b(zero, sing, mo, d1, slice_length=1e2)
+        assert rho.shape == (51, 51, 1) and jab.shape == (3, 51, 51, 1)
+        for got, key in ((rho, 'rho_01'), (jab, 'j_01'), (nj, 'nabla_j_01'), (anb, 'a_nabla_b_01')):
+            assert_close(got, g[key][pair], '%s pair %d' % (key, pair))
+            if 'published.' + key in g.files:            # the reference's own tolerance (test/tools.py:11-21)
+                assert numpy.allclose(got, g['published.' + key][pair], rtol=1e-3, atol=1e-5)
+        # the reference's slice driver never visits the point behind the last full slice
+        assert rho.reshape(-1)[-1] == 0.0 and (jab.reshape(3, -1)[:, -1] == 0.0).all()
+        # fused variants (MOs never leave the device) evaluate every point
+        full = ci_core.rho(zero, sing, mo, slice_length=mo[0].size)
+        assert_close(ci_core.rho_from_qc(qc, zero, sing), full, 'rho_from_qc')
+        assert_close(ci_core.jab_from_qc(qc, zero, sing), ci_core.jab(zero, sing, mo, d1, slice_length=2601), 'jab_from_qc')
+        assert_close(ci_core.jab_from_qc(qc, zero, sing, drv=['xx', 'yy', 'zz']),
+                     ci_core.jab(zero, sing, mo, d2, slice_length=2601), 'jab_from_qc d2')
+        assert_close(ci_core.a_nabla_b_from_qc(qc, zero, sing),
+                     ci_core.a_nabla_b(zero, sing, mo, d1, slice_length=2601), 'a_nabla_b_from_qc')
+
+
+def test_random_terms_bitwise_vs_oracle(ok, oci):
+    """same MO arrays in -> bit-identical results (reference expression order, no FMA contraction)"""
+    from orbkit_b200.detci import ci_core
+    rng = numpy.random.default_rng(21)
+    for n_mo, shape, n_det, n_sing in ((3, (1,), 0, 1), (7, (33,), 4, 19), (20, (5, 13, 4), 30, 400),
+                                       (64, (4099,), 100, 2500), (5, (130,), 3, 0)):
+        zero, sing = random_lists(rng, n_mo, n_det, n_sing)
+        mo = rng.normal(size=(n_mo,) + shape)
+        dmo = rng.normal(size=(3, n_mo) + shape)
+        n = mo[0].size
+        for sl in (1e4, 100, n):
+            if sl == 100 and n < 100:
+                continue
+            assert numpy.array_equal(ci_core.rho(zero, sing, mo, slice_length=sl), oci.rho(zero, sing, mo, sl))
+            assert numpy.array_equal(ci_core.jab(zero, sing, mo, dmo, slice_length=sl), oci.jab(zero, sing, mo, dmo, sl))
+            assert numpy.array_equal(ci_core.a_nabla_b(zero, sing, mo, dmo, slice_length=sl),
+                                     oci.a_nabla_b(zero, sing, mo, dmo, sl))
+        # the caller's arrays keep their shape (the reference reshapes them in place and restores, ci_core.py:112-135)
+        assert mo.shape == (n_mo,) + shape and dmo.shape == (3, n_mo) + shape
+    # empty grid, error conventions
+    assert ci_core.rho([[], []], [[], []], numpy.zeros((4, 0))).shape == (0,)
+    assert (ci_core.rho([[], []], [[], []], numpy.ones((4, 9))) == 0.0).all()
+    with pytest.raises(ValueError):
+        ci_core.rho([[], []], [[1.0], [[0, 4]]], numpy.ones((4, 9)))
+    with pytest.raises(ValueError):
+        ci_core.jab([[], []], [[1.0], [[0, 1]]], numpy.ones((4, 9)), numpy.ones((2, 4, 9)))
+
+
+def test_merged_terms_and_pair_products(ok, oci):
+    from orbkit_b200.detci import ci_core
+    rng = numpy.random.default_rng(22)
+    zero, sing = random_lists(rng, 12, 40, 900)
+    mo = rng.normal(size=(12, 777))
+    dmo = rng.normal(size=(3, 12, 777))
+    exact = ci_core.rho(zero, sing, mo)
+    exact_anb = ci_core.a_nabla_b(zero, sing, mo, dmo)
+    ok.options.ci_merge_terms = True
+    try:
+        assert_close(ci_core.rho(zero, sing, mo), exact, 'merged rho', rtol=1e-12, afloor=1e-13)
+        assert_close(ci_core.a_nabla_b(zero, sing, mo, dmo), exact_anb, 'merged a_nabla_b', rtol=1e-12, afloor=1e-13)
+        assert numpy.array_equal(ci_core.jab(zero, sing, mo, dmo), oci.jab(zero, sing, mo, dmo))   # never merged
+    finally:
+        ok.options.ci_merge_terms = False
+    pairs = numpy.array(sing[1][:50])
+    prod = ci_core.pair_products(pairs, mo)
+    assert prod.shape == (50, 777)
+    assert numpy.array_equal(prod, mo[pairs[:, 0]] * mo[pairs[:, 1]])
+
+
+def test_config5_scale_properties(ok):
+    """500 AOs / 500 MOs, 1000 random pairs on 32^3 points of the Config-5 generator: the fused device
+    path against (a) the two-step path through host MOs, (b) linearity, (c) sum of per-pair products"""
+    from orbkit_b200 import synth
+    from orbkit_b200.detci import ci_core
+    spec = synth.make_molecule(n_heavy=12, n_light=10, n_mo=500, seed=5, spherical=True)
+    qc = synth.to_qcinfo(spec)
+    n_mo = len(qc.mo_spec)
+    rng = numpy.random.default_rng(5)
+    pairs = rng.integers(0, n_mo, size=(1000, 2))
+    coef = rng.normal(size=1000)
+    zero = [[], []]
+    sing = [list(coef), [list(p) for p in pairs]]
+    ax = numpy.linspace(-9, 9, 32)
+    ok.grid.set_grid(ax, ax, ax, is_vector=False)
+    rho_dev = ci_core.rho_from_qc(qc, zero, sing)
+    mos = ok.rho_compute(qc, calc_mo=True, drv=[None, 'x', 'y', 'z'])
+    rho_host = ci_core.rho(zero, sing, mos[0], slice_length=mos[0][0].size)
+    assert_close(rho_dev, rho_host, 'fused vs two-step')
+    ref = numpy.einsum('k,kxyz,kxyz->xyz', coef, mos[0][pairs[:, 0]], mos[0][pairs[:, 1]])
+    assert_close(rho_dev, ref, 'fused vs einsum', rtol=1e-10, afloor=1e-13)
+    j_dev = ci_core.jab_from_qc(qc, zero, sing)
+    jref = -0.5 * (numpy.einsum('k,kxyz,dkxyz->dxyz', coef, mos[0][pairs[:, 0]], mos[1:4][:, pairs[:, 1]]) -
+                   numpy.einsum('k,kxyz,dkxyz->dxyz', coef, mos[0][pairs[:, 1]], mos[1:4][:, pairs[:, 0]]))
+    assert_close(j_dev, jref, 'jab fused vs einsum', rtol=1e-10, afloor=1e-13)
+    # linearity in the CI coefficients and antisymmetry of the flux density under a <-> b
+    sing2 = [list(2.5 * coef), sing[1]]
+    assert_close(ci_core.rho_from_qc(qc, zero, sing2), 2.5 * rho_dev, 'linearity', rtol=1e-13, afloor=1e-15)
+    swapped = [sing[0], [[b, a] for a, b in sing[1]]]
+    assert_close(ci_core.jab_from_qc(qc, zero, swapped), -j_dev, 'antisymmetry', rtol=1e-13, afloor=1e-15)
+    sub = mos[0][:, ::6, ::6, ::6]
+    prods = ci_core.pair_products(pairs, sub)
+    assert_close(numpy.tensordot(coef, prods, axes=1), ci_core.rho(zero, sing, sub, slice_length=sub[0].size),
+                 'sum of pair products', rtol=1e-12, afloor=1e-13)

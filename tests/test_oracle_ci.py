@@ -1,0 +1,107 @@
+"""CPU: the detCI oracle (oracle/oracle_ci.py) is pinned to the reference.
+
+  * port (okor_ci_* in libokoracle.so) == the reference's own cy_ci module (oracle/_ref) bit for bit on
+    random term lists and on the h3+ FCI fixture;
+  * both reproduce tests/golden/h3p_detci.npz, written by running the reference's test
+    orbkit/test/detci/h3+.py (tests/golden/make_golden_detci.py), and agree with the reference's
+    committed golden refdata_h3+.npz (`published.*`) to its own tolerance;
+  * host logic of orbkit_b200.detci.ci_core: flattening, merging.
+"""
+import numpy
+import pytest
+
+from conftest import load_golden
+
+
+def lists_from_golden(g, pair):
+    """rebuild the (zero, sing) Python lists of state pair `pair`"""
+    zc, zi, zn = g['p%d.zc' % pair], g['p%d.zi' % pair], g['p%d.zn' % pair]
+    zero = [[], []]
+    o = 0
+    for n in zn:
+        zero[0].append([float(c) for c in zc[o:o + n]])
+        zero[1].append([int(i) for i in zi[o:o + n]])
+        o += n
+    sing = [[float(c) for c in g['p%d.sc' % pair]],
+            [[int(a), int(b)] for a, b in zip(g['p%d.sa' % pair], g['p%d.sb' % pair])]]
+    return zero, sing
+
+
+def random_lists(rng, n_mo, n_det, n_sing):
+    zero = [[], []]
+    for _ in range(n_det):
+        k = int(rng.integers(1, 5))
+        zero[0].append([float(v) for v in rng.normal(size=k)])
+        zero[1].append([int(v) for v in rng.integers(0, n_mo, size=k)])
+    sing = [[float(v) for v in rng.normal(size=n_sing)],
+            [[int(a), int(b)] for a, b in rng.integers(0, n_mo, size=(n_sing, 2))]]
+    return zero, sing
+
+
+@pytest.fixture(scope='module')
+def oci(oracle_mod):
+    import oracle_ci
+    return oracle_ci
+
+
+def test_port_equals_reference_cy_ci_bitwise(oci):
+    if not oci.have_ref():
+        pytest.skip('oracle/_ref/cy_ci not built')
+    rng = numpy.random.default_rng(11)
+    for n_mo, npts, n_det, n_sing in ((3, 1, 0, 1), (7, 33, 4, 19), (20, 257, 30, 400)):
+        zero, sing = random_lists(rng, n_mo, n_det, n_sing)
+        mo = rng.normal(size=(n_mo, npts))
+        dmo = rng.normal(size=(3, n_mo, npts))
+        assert numpy.array_equal(oci.rho(zero, sing, mo, kind='port'), oci.rho(zero, sing, mo, kind='ref'))
+        assert numpy.array_equal(oci.jab(zero, sing, mo, dmo, kind='port'), oci.jab(zero, sing, mo, dmo, kind='ref'))
+        assert numpy.array_equal(oci.a_nabla_b(zero, sing, mo, dmo, kind='port'),
+                                 oci.a_nabla_b(zero, sing, mo, dmo, kind='ref'))
+
+
+def test_h3p_golden_reproduced(oci, oracle_mod):
+    """MOs of the H3+ FCI fixture from the (pinned) grid oracle -> CI contractions == what the reference
+    produced for its own test, bit for bit; and == the reference's committed golden to 1e-15."""
+    from orbkit_b200 import QCinfo
+    g = load_golden('h3p_detci')
+    qc = QCinfo.from_arrays(g)
+    mos = oracle_mod.rho_compute(qc, g['x'], g['y'], g['z'], is_vector=False, calc_mo=True,
+                                 drv=[None, 'x', 'y', 'z', 'xx', 'yy', 'zz'])
+    mo, d1, d2 = mos[0], mos[1:4], mos[4:7]
+    kinds = ['port'] + (['ref'] if oci.have_ref() else [])
+    for pair in range(int(g['n_pairs'])):
+        zero, sing = lists_from_golden(g, pair)
+        for kind in kinds:
+            # slice_length=1e2 as in the reference's test: 2601 points -> the last one is never visited (0.0)
+            assert numpy.array_equal(oci.rho(zero, sing, mo, 1e2, kind=kind), g['rho_01'][pair])
+            assert numpy.array_equal(oci.jab(zero, sing, mo, d1, 1e2, kind=kind), g['j_01'][pair])
+            assert numpy.array_equal(-oci.jab(zero, sing, mo, d2, 1e2, kind=kind).sum(axis=0), g['nabla_j_01'][pair])
+            assert numpy.array_equal(oci.a_nabla_b(zero, sing, mo, d1, 1e2, kind=kind), g['a_nabla_b_01'][pair])
+            assert g['rho_01'][pair].reshape(-1)[-1] == 0.0 and oci.rho(zero, sing, mo, kind=kind).reshape(-1)[-1] != 0.0
+    for key in ('rho_01', 'j_01', 'nabla_j_01'):
+        pub = g['published.' + key]
+        assert numpy.abs(g[key] - pub).max() <= 1e-15 * numpy.abs(pub).max()
+
+
+def test_flatten_and_merge_host_logic():
+    from orbkit_b200.detci import ci_core
+    zero = [[[1.0, 2.0], [0.5]], [[0, 1], [1]]]
+    sing = [[0.25, -0.75, 0.5], [[0, 2], [2, 0], [1, 1]]]
+    c, a, b = ci_core.flatten_terms(zero, sing)
+    assert c.tolist() == [1.0, 2.0, 0.5, 0.25, -0.75, 0.5]
+    assert a.tolist() == [0, 1, 1, 0, 2, 1] and b.tolist() == [0, 1, 1, 2, 0, 1]
+    c2, a2, b2 = ci_core.flatten_terms(zero, sing, with_zero=False)
+    assert c2.tolist() == [0.25, -0.75, 0.5] and a2.tolist() == [0, 2, 1]
+    mc, ma, mb = ci_core.merge_terms((c, a, b), 3, symmetric=True)
+    dense = numpy.zeros((3, 3))
+    for cc, aa, bb in zip(mc, ma, mb):
+        dense[aa, bb] += cc
+    want = numpy.zeros((3, 3))
+    for cc, aa, bb in zip(c, a, b):
+        want[min(aa, bb), max(aa, bb)] += cc
+    assert numpy.allclose(dense, want) and len(mc) == 3
+    mc, ma, mb = ci_core.merge_terms((c, a, b), 3, symmetric=False)
+    assert len(mc) == 4
+    with pytest.raises(ValueError):
+        ci_core.flatten_terms([[[1.0]], [[0, 1]]], sing)
+    with pytest.raises(ValueError):
+        ci_core.flatten_terms(zero, [[1.0], []])
