@@ -235,8 +235,9 @@ def run_b200(args):
         r = [numpy.zeros((len(gx), len(gy), len(gz)))]
     e2e_value = npts_total * e2e_steps / t_e2e
     d2h = (d1 - d0) / max(e2e_steps, 1)
-    if world > 1:                           # gathered result is read back by torch (.cpu()) on every rank
-        d2h += 8.0 * 4 * npts_total
+    h2d = (h1 - h0) / max(e2e_steps, 1)
+    if world > 1:                           # whole job: every rank copies its own shard into the shared host array
+        d2h, h2d = [float(v) for v in okdist.all_reduce_sum([d2h, h2d], local)]
     e2e_ok = bool(numpy.isfinite(r[0]).all() and r[0].shape == (len(gx), len(gy), len(gz)))
 
     if world > 1:
@@ -277,7 +278,7 @@ def run_b200(args):
                        'n_ao': N_AO, 'n_cart': 1140, 'n_mo': N_MO, 'derivative_sets': D_SETS,
                        'parallelism': 'points sharded over %d rank(s), no data-path collective' % world,
                        'l2': 'outputs 256 MB/step/GPU exceed the 126 MB L2; inputs are 1 MB of tables by design'},
-            'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': (h1 - h0) / max(e2e_steps, 1),
+            'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'api': 'orbkit_b200.rho_compute(qc, drv=["x","y","z"])',
                     'ok': e2e_ok},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,

@@ -139,6 +139,18 @@ int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long lo
                  const int *drv_codes, int n_drv, double *rho, double *delta_rho,
                  double *mo_norm, unsigned flags);
 
+/* The same three calls writing into rows of a LARGER array: ld_out = row stride of the output arrays in
+ * points (>= p1-p0; 0 means dense).  out / rho / delta_rho point at the first element of the point range
+ * inside its row.  This is how the ranks of a multi-GPU job write their point shards side by side into one
+ * shared host array (each GPU copies into its disjoint slice, no gather). */
+int okb_eval_ao_ld(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
+                   const int *drv_codes, int n_drv, double *out, long long ld_out, unsigned flags);
+int okb_eval_mo_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                   const int *drv_codes, int n_drv, double *out, long long ld_out, unsigned flags);
+int okb_eval_rho_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                    const int *drv_codes, int n_drv, double *rho, double *delta_rho, long long ld_out,
+                    double *mo_norm, unsigned flags);
+
 /* ---- (3) detCI grid contractions --------------------------------------------
  * Replace the per-slice loops cy_ci.get_rho / get_jab / get_a_nabla_b (orbkit/detci/cy_ci.pyx:70-97,
  * 156-186, 211-240) behind detci.ci_core.rho / jab / a_nabla_b (ci_core.py:85-267).  The Python lists

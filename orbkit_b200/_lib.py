@@ -75,6 +75,13 @@ SIGNATURES = {
     'okb_eval_rho': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_uint]),
+    'okb_eval_ao_ld': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                      ctypes.c_int, ctypes.c_void_p, ll, ctypes.c_uint]),
+    'okb_eval_mo_ld': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                      ctypes.c_int, ctypes.c_void_p, ll, ctypes.c_uint]),
+    'okb_eval_rho_ld': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ll, ctypes.c_void_p,
+                                       ctypes.c_uint]),
     'okb_ci_contract': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, c_double_p, c_int_p, c_int_p,
                                        ctypes.c_void_p, ll, ctypes.c_uint]),

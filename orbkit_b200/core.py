@@ -13,13 +13,14 @@ contraction per derivative code (slice_rho, core.py:179-308).  Here one fused ke
 evaluates every needed derivative set of the AOs tile by tile in shared memory, contracts them in
 registers and reduces to rho / delta_rho on chip; regular-grid coordinates are generated in-kernel;
 `numproc` and `slice_length` are accepted and ignored; when torch.distributed is initialised the
-point range is sharded over the ranks (one GPU each) and gathered at the end.
+point range is sharded over the ranks (one GPU each) and every rank's results stream into its range of
+one node-shared host array (dist.shared_host_array), which all ranks return.
 """
 import numpy
 
 from . import cy_core, cy_grid, grid, options
 from . import dist as okdist
-from ._lib import OKB_FLAG_EXACT_MIXED, OKB_FLAG_OUT_DEVICE
+from ._lib import OKB_FLAG_EXACT_MIXED
 from .display import display
 from .engine import get_engine, build_cart2sph_csr
 from .qcinfo import QCinfo
@@ -40,18 +41,6 @@ def _drv_list(drv):
         return list(drv)
     except TypeError:
         return [drv]
-
-
-def _to_host(t):
-    """device tensor -> NumPy through page-locked memory (torch's caching host allocator)"""
-    import torch
-    try:
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    except Exception:
-        return t.cpu().numpy()
-    host.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    return host.numpy()
 
 
 def _grid_handle(eng, x, y, z, is_vector):
@@ -154,40 +143,37 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
             delta = delta[[ucodes.index(c) for c in codes]]
         return rho, delta, norm
 
-    # ---- one rank per GPU: contiguous point shards, device outputs, NCCL gather -------------------
-    import torch
+    # ---- one rank per GPU: contiguous point shards written side by side into ONE node-shared host array ---
+    # (each rank's device -> host copies go straight into its own point range and overlap its compute; a
+    # barrier completes the result on every rank; no gather, no collective on the data path)
+    import torch.distributed as tdist
     rank, world = okdist.rank_world()
     p0, p1 = okdist.shard_range(npts, rank, world)
-    dev = torch.device('cuda', eng.device)
     n_loc = p1 - p0
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
-    fl = flags | OKB_FLAG_OUT_DEVICE
-    with torch.cuda.device(dev):
-        if calc_ao or calc_mo:
-            loc = torch.empty((len(codes), n_rows, max(n_loc, 1)), dtype=torch.float64, device=dev)[..., :n_loc]
-            loc = loc.contiguous()
-            if n_loc:
-                if calc_ao:
-                    eng.eval_ao(basis, g, codes, p0, p1, out=loc.data_ptr(), flags=fl)
-                else:
-                    eng.eval_mo(mo, g, codes, p0, p1, out=loc.data_ptr(), flags=fl)
-            eng.sync()
-            return _to_host(okdist.gather_points(loc, npts))
-        ucodes = [] if drv is None else sorted(set(codes))
-        loc = torch.zeros((1 + len(ucodes), max(n_loc, 1)), dtype=torch.float64, device=dev)
-        norm = None
+    if calc_ao or calc_mo:
+        full = okdist.shared_host_array((len(codes), n_rows, npts))
         if n_loc:
-            _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=loc[0].data_ptr(),
-                                      delta=loc[1:].data_ptr() if ucodes else None,
-                                      want_norm=want_norm, flags=fl)
-        eng.sync()
-        full = _to_host(okdist.gather_points(loc[:, :n_loc].contiguous(), npts))
-        if want_norm:
-            norm = okdist.all_reduce_sum(norm if norm is not None else numpy.zeros(mo.n_mo), eng.device)
-        delta = None
-        if drv is not None:
-            delta = full[1:][[ucodes.index(c) for c in codes]]
-        return full[0], delta, norm
+            dst = full.ctypes.data + 8 * p0
+            if calc_ao:
+                eng.eval_ao(basis, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
+            else:
+                eng.eval_mo(mo, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
+        tdist.barrier()
+        return full
+    ucodes = [] if drv is None else sorted(set(codes))
+    full = okdist.shared_host_array((1 + len(ucodes), npts))
+    norm = None
+    if n_loc:
+        _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=full.ctypes.data + 8 * p0,
+                                  delta=(full.ctypes.data + 8 * (npts + p0)) if ucodes else None,
+                                  want_norm=want_norm, flags=flags, ld=npts)
+    tdist.barrier()
+    if want_norm:
+        norm = okdist.all_reduce_sum(norm if norm is not None else numpy.zeros(mo.n_mo), eng.device)
+    delta = None
+    if drv is not None:
+        delta = full[1:] if ucodes == codes else full[1:][[ucodes.index(c) for c in codes]]
+    return full[0], delta, norm
 
 
 def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, numproc=1,

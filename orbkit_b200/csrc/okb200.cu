@@ -1033,6 +1033,7 @@ struct EvalReq {
     double *rho, *delta;
     double *mo_norm;
     unsigned flags;
+    long long ld_out = 0;   // row stride (points) of the caller's output arrays; 0 = dense (p1 - p0)
 };
 
 static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
@@ -1045,6 +1046,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     if (rq.n_codes < 0 || rq.n_codes > 64) return fail(OKB_ERR_ARG, "eval: bad number of derivative codes");
     if (rq.n_codes > 0 && !rq.codes) return fail(OKB_ERR_ARG, "eval: null derivative code list");
     const long long ntot = rq.p1 - rq.p0;
+    if (rq.ld_out != 0 && rq.ld_out < ntot) return fail(OKB_ERR_ARG, "eval: output row stride %lld < %lld points", rq.ld_out, ntot);
+    const long long ldo = rq.ld_out ? rq.ld_out : ntot;      // row stride of the caller's arrays
     if (ntot == 0) return OKB_OK;
     CU(cudaSetDevice(ctx->device));
 
@@ -1129,7 +1132,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
         double *dbase;          // device output base for this slab
         long long ld;
         if (dev_out) {
-            ld = ntot;
+            ld = ldo;
             dbase = nullptr;
         } else {
             ld = sn;
@@ -1193,11 +1196,11 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             if (rq.sink == SINK_RHO) {
                 if (rq.rho) CU(cudaMemcpyAsync(rq.rho + s0, dbase, wbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
                 if (rq.n_codes > 0)
-                    CU(cudaMemcpy2DAsync(rq.delta + s0, (size_t)ntot * sizeof(double), dbase + ld,
+                    CU(cudaMemcpy2DAsync(rq.delta + s0, (size_t)ldo * sizeof(double), dbase + ld,
                                          (size_t)ld * sizeof(double), wbytes, rq.n_codes,
                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
             } else {
-                CU(cudaMemcpy2DAsync(rq.out + s0, (size_t)ntot * sizeof(double), dbase, (size_t)ld * sizeof(double),
+                CU(cudaMemcpy2DAsync(rq.out + s0, (size_t)ldo * sizeof(double), dbase, (size_t)ld * sizeof(double),
                                      wbytes, n_out_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
             }
             CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
@@ -1216,31 +1219,44 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     return OKB_OK;
 }
 
-extern "C" int okb_eval_ao(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
-                           const int *drv_codes, int n_drv, double *out, unsigned flags) {
+extern "C" int okb_eval_ao_ld(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
+                              const int *drv_codes, int n_drv, double *out, long long ld_out, unsigned flags) {
     if (!out) return fail(OKB_ERR_ARG, "okb_eval_ao: null output");
     if (n_drv <= 0) return fail(OKB_ERR_ARG, "okb_eval_ao: need at least one derivative code");
-    EvalReq rq{SINK_AO, basis, nullptr, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags};
+    EvalReq rq{SINK_AO, basis, nullptr, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags, ld_out};
     return run_eval(ctx, rq);
 }
-
-extern "C" int okb_eval_mo(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+extern "C" int okb_eval_ao(okb_ctx *ctx, okb_basis *basis, okb_grid *grid, long long p0, long long p1,
                            const int *drv_codes, int n_drv, double *out, unsigned flags) {
+    return okb_eval_ao_ld(ctx, basis, grid, p0, p1, drv_codes, n_drv, out, 0, flags);
+}
+
+extern "C" int okb_eval_mo_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                              const int *drv_codes, int n_drv, double *out, long long ld_out, unsigned flags) {
     if (!mo) return fail(OKB_ERR_ARG, "okb_eval_mo: null MO handle");
     if (!out) return fail(OKB_ERR_ARG, "okb_eval_mo: null output");
     if (n_drv <= 0) return fail(OKB_ERR_ARG, "okb_eval_mo: need at least one derivative code");
-    EvalReq rq{SINK_MO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags};
+    EvalReq rq{SINK_MO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, out, nullptr, nullptr, nullptr, flags, ld_out};
     return run_eval(ctx, rq);
 }
+extern "C" int okb_eval_mo(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                           const int *drv_codes, int n_drv, double *out, unsigned flags) {
+    return okb_eval_mo_ld(ctx, mo, grid, p0, p1, drv_codes, n_drv, out, 0, flags);
+}
 
-extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
-                            const int *drv_codes, int n_drv, double *rho, double *delta_rho, double *mo_norm,
-                            unsigned flags) {
+extern "C" int okb_eval_rho_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                               const int *drv_codes, int n_drv, double *rho, double *delta_rho, long long ld_out,
+                               double *mo_norm, unsigned flags) {
     if (!mo) return fail(OKB_ERR_ARG, "okb_eval_rho: null MO handle");
     if (!rho) return fail(OKB_ERR_ARG, "okb_eval_rho: null rho output");
     if (n_drv > 0 && !delta_rho) return fail(OKB_ERR_ARG, "okb_eval_rho: null delta_rho output");
-    EvalReq rq{SINK_RHO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, nullptr, rho, delta_rho, mo_norm, flags};
+    EvalReq rq{SINK_RHO, mo->basis, mo, grid, p0, p1, drv_codes, n_drv, nullptr, rho, delta_rho, mo_norm, flags, ld_out};
     return run_eval(ctx, rq);
+}
+extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1,
+                            const int *drv_codes, int n_drv, double *rho, double *delta_rho, double *mo_norm,
+                            unsigned flags) {
+    return okb_eval_rho_ld(ctx, mo, grid, p0, p1, drv_codes, n_drv, rho, delta_rho, 0, mo_norm, flags);
 }
 
 // ---- detCI grid contractions ------------------------------------------------------------------------------------

@@ -299,38 +299,46 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     aa = smem_u32(cbase + (size_t)st * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr);
                     bb = smem_u32(tbase + (size_t)st * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr);
                 };
-                // one k-step: DMMAs on the fragments in registers, refilled from (na, nb) for the next step.
-                // Order: B fragment outermost, MO blocks innermost.  B[d][ib] is refilled behind its AM DMMAs and
-                // needed again (D*BN-1)*AM DMMAs later; A[ia] is refilled during the last B pass and needed AM
-                // DMMAs later -- at 16 cycles per DMMA both distances (>= 96 cycles) cover the LDS latency under
-                // load (ncu: 9% of the consumer's samples were short-scoreboard stalls when the B fragments were
-                // refilled only 62 cycles ahead of their use).
+                // One k-step = NB*AM DMMAs (NB = D*BN B fragments outermost, AM MO blocks innermost) on the fragments
+                // in registers; a fragment register is refilled behind the last DMMA of the step that reads it:
+                // B[j] behind pass j (needed again (NB-1)*AM DMMAs later), A[ia] during the last pass (needed again
+                // AM DMMAs later) -- both far above the LDS latency.
+                // Known residue (ncu, profiles/r01_ws_grad_refill.txt): a DMMA.8x8x4 reads its source registers
+                // only when it enters the pipe, so the LDS that overwrites one of them right behind it waits a few
+                // cycles, and with it the in-order warp: ~10% of the consumer's samples are short-scoreboard stalls
+                // on these 15 refills per step.  ptxas places a refill directly behind the last reader whatever the
+                // source order says (also when the value travels through a temporary and an opaque xor), so with ONE
+                // consumer warp per sub-partition this is the floor; two consumer warps per sub-partition hide it.
+                constexpr int NB = D * BN;
                 auto step = [&](const uint32_t na, const uint32_t nb) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+                        for (int ia = 0; ia < AM; ++ia) {
+                            const bool owned = !(MB % WM != 0 && ia == AM - 1 && ia >= nblk);   // warp-uniform
+                            if (owned)
+                                dmma_m8n8k4(acc[ia][j % BN][j / BN][0], acc[ia][j % BN][j / BN][1], afr[ia], bfr[j / BN][j % BN]);
+                            if (j == NB - 1) afr[ia] = lds64(na + (uint32_t)(ia * 8) * 8u);
+                        }
+                        bfr[j / BN][j % BN] = lds64(nb + (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u);
+                    }
+                };
+                auto load_all = [&](const uint32_t ca, const uint32_t cb) {     // fragments straight from shared memory
 #pragma unroll
                     for (int d = 0; d < D; ++d)
 #pragma unroll
-                        for (int ib = 0; ib < BN; ++ib) {
+                        for (int ib = 0; ib < BN; ++ib) bfr[d][ib] = lds64(cb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
 #pragma unroll
-                            for (int ia = 0; ia < AM; ++ia) {
-                                const bool owned = !(MB % WM != 0 && ia == AM - 1 && ia >= nblk);   // warp-uniform
-                                if (owned) dmma_m8n8k4(acc[ia][ib][d][0], acc[ia][ib][d][1], afr[ia], bfr[d][ib]);
-                                if (d == D - 1 && ib == BN - 1) afr[ia] = lds64(na + (uint32_t)(ia * 8) * 8u);
-                            }
-                            bfr[d][ib] = lds64(nb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
-                        }
+                    for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(ca + (uint32_t)(ia * 8) * 8u);
                 };
                 uint32_t a_ap, a_bp;
                 frag_addr(g, a_ap, a_bp);
                 mbar_wait_a(a_full + 8 * (g % NST), (g / NST) & 1);      // AO tile + coefficient tile landed
                 int nk = nfn_s[g % NST];                                 // multiple of 4, >= 4
-#pragma unroll
-                for (int d = 0; d < D; ++d)
-#pragma unroll
-                    for (int ib = 0; ib < BN; ++ib) bfr[d][ib] = lds64(a_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
-#pragma unroll
-                for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(a_ap + (uint32_t)(ia * 8) * 8u);
+                load_all(a_ap, a_bp);
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
+#pragma unroll 1
                     for (int k0 = 4; k0 < nk; k0 += 4)                   // steps 0 .. nk/4-2: next step in this chunk
                         step(a_ap + (uint32_t)(k0 * CS) * 8u, a_bp + (uint32_t)(k0 * PS) * 8u);
                     // last step of the chunk: refill from the next chunk of this pass (or, behind the last chunk,
@@ -353,13 +361,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
                         nk_next = nfn_s[(g + 1) % NST];
                         frag_addr(g + 1, n_ap, n_bp);
-#pragma unroll
-                        for (int d = 0; d < D; ++d)
-#pragma unroll
-                            for (int ib = 0; ib < BN; ++ib)
-                                bfr[d][ib] = lds64(n_bp + (uint32_t)(d * KC * PS + ib * 8) * 8u);
-#pragma unroll
-                        for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(n_ap + (uint32_t)(ia * 8) * 8u);
+                        load_all(n_ap, n_bp);
                     }
                     a_ap = n_ap; a_bp = n_bp; nk = nk_next;
                 }

@@ -3,11 +3,23 @@
 The reference parallelises by handing contiguous point ranges to forked workers
 (orbkit/core.py:437-447, 503-536; omp_functions.py:31-95).  Here each rank owns one contiguous
 point range; every grid point is independent given the (replicated) basis tables and MO
-coefficients, so there is NO data-path collective.  NVLink is used only for
-  * the final gather of the output shards (all_gather of equally padded shards), and
+coefficients, so there is NO data-path collective.
+
+Assembly of host results (the reference copies slice results into one preallocated array,
+core.py:527-536): the ranks of one node share ONE host array in POSIX shared memory
+(`shared_host_array`); every rank's kernel output streams device -> host straight into its own
+point range of that array (page-locked by cudaHostRegister, so the copies overlap the compute), and
+a barrier completes the result on every rank.  No NVLink or PCIe traffic beyond each shard's own
+bytes.  NVLink/NCCL is used only for
+  * `gather_points` when the caller wants the full result as a DEVICE tensor, and
   * the all-reduce of integrated quantities (MO norms, electron count).
 With the gloo backend the same code runs on CPU tensors (used by the world_size-2 tests).
 """
+import atexit
+import mmap
+import os
+import uuid
+
 import numpy
 
 ALIGN = 128   # shard boundaries fall on CTA tile boundaries
@@ -74,3 +86,72 @@ def all_reduce_sum(values, device=None):
         t = t.cuda(device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+# ---- one host array shared by the ranks of a node ------------------------------------------------------
+class _Segment:
+    """an mmap of a /dev/shm file that every rank of the job has opened (the file is unlinked once all
+    ranks hold it: the memory lives as long as a mapping does)"""
+
+    def __init__(self, nbytes, name, create):
+        path = os.path.join('/dev/shm', name)
+        fd = os.open(path, os.O_RDWR | (os.O_CREAT | os.O_EXCL if create else 0), 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, nbytes)
+            self.map = mmap.mmap(fd, nbytes)
+        finally:
+            os.close(fd)
+        self.nbytes = nbytes
+        self.path = path
+        self.registered = False
+
+    def register_cuda(self):
+        """page-lock the mapping for this process's CUDA context (async D2H into it then overlaps compute)"""
+        if self.registered:
+            return True
+        try:
+            import ctypes
+            import torch
+            addr = ctypes.addressof(ctypes.c_char.from_buffer(self.map))
+            err = torch.cuda.cudart().cudaHostRegister(addr, self.nbytes, 0)
+            self.registered = (int(err) == 0)
+        except Exception:
+            self.registered = False
+        return self.registered
+
+
+_segments = {}      # (nbytes, generation) -> _Segment
+_generation = {}    # nbytes -> how many arrays of this size were handed out
+
+
+def shared_host_array(shape, pin=True):
+    """float64 array of `shape` in node-shared memory, the SAME memory on every rank (collective call:
+    every rank must call it with the same shape).  Two segments per size are used in turn, so a result
+    stays valid until the second-next call with the same shape."""
+    import torch.distributed as dist
+    rank, world = rank_world()
+    nbytes = max(int(numpy.prod(shape)) * 8, 8)
+    gen = _generation.get(nbytes, 0)
+    _generation[nbytes] = gen + 1
+    key = (nbytes, gen & 1)
+    seg = _segments.get(key)
+    if seg is None:
+        name = ['okb200_%s' % uuid.uuid4().hex if rank == 0 else None]
+        if rank == 0:
+            seg = _Segment(nbytes, name[0], create=True)
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            seg = _Segment(nbytes, name[0], create=False)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(seg.path)
+        if pin:
+            seg.register_cuda()
+        _segments[key] = seg
+    return numpy.frombuffer(seg.map, dtype=numpy.float64, count=int(numpy.prod(shape))).reshape(shape)
+
+
+@atexit.register
+def _drop_segments():
+    _segments.clear()

@@ -204,44 +204,44 @@ class Engine:
             return numpy.empty(shape, dtype=numpy.float64)
 
     # ---- evaluation ---------------------------------------------------------------------------------------
-    def eval_ao(self, basis_entry, grid, codes, p0=0, p1=None, out=None, flags=0):
+    @staticmethod
+    def _ptr(a):
+        """address of a NumPy array, or the integer address itself (device pointers, slices of larger arrays)"""
+        return a if isinstance(a, int) else a.ctypes.data
+
+    def eval_ao(self, basis_entry, grid, codes, p0=0, p1=None, out=None, flags=0, ld=0):
+        """`ld`: row stride (points) of `out` when it addresses a range inside a larger array (0 = dense)"""
         handle_b, _, n_ao, _ = basis_entry
         p1 = grid.npts if p1 is None else p1
         codes = _lib.i32(codes)
-        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
         if out is None:
             out = self.host_array((len(codes), n_ao, p1 - p0))
-        ptr = out if dev else out.ctypes.data
-        _lib.check(self.lib.okb_eval_ao(self.ctx, handle_b.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes),
-                                        ptr, flags))
+        _lib.check(self.lib.okb_eval_ao_ld(self.ctx, handle_b.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes),
+                                           self._ptr(out), ld, flags))
         return out
 
-    def eval_mo(self, mo, grid, codes, p0=0, p1=None, out=None, flags=0):
+    def eval_mo(self, mo, grid, codes, p0=0, p1=None, out=None, flags=0, ld=0):
         p1 = grid.npts if p1 is None else p1
         codes = _lib.i32(codes)
-        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
         if out is None:
             out = self.host_array((len(codes), mo.n_mo, p1 - p0))
-        ptr = out if dev else out.ctypes.data
-        _lib.check(self.lib.okb_eval_mo(self.ctx, mo.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes), ptr,
-                                        flags))
+        _lib.check(self.lib.okb_eval_mo_ld(self.ctx, mo.ptr, grid.ptr, p0, p1, _lib.iptr(codes), len(codes),
+                                           self._ptr(out), ld, flags))
         return out
 
-    def eval_rho(self, mo, grid, codes, p0=0, p1=None, rho=None, delta=None, want_norm=False, flags=0):
+    def eval_rho(self, mo, grid, codes, p0=0, p1=None, rho=None, delta=None, want_norm=False, flags=0, ld=0):
         """returns (rho, delta_rho or None, mo_norm or None)"""
         p1 = grid.npts if p1 is None else p1
         codes = _lib.i32(codes)
-        dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
         n = p1 - p0
         if rho is None:
             rho = self.host_array((n,))
         if delta is None and len(codes):
             delta = self.host_array((len(codes), n))
         norm = numpy.zeros(mo.n_mo) if want_norm else None
-        _lib.check(self.lib.okb_eval_rho(
+        _lib.check(self.lib.okb_eval_rho_ld(
             self.ctx, mo.ptr, grid.ptr, p0, p1, _lib.iptr(codes) if len(codes) else None, len(codes),
-            rho if dev else rho.ctypes.data,
-            (delta if dev else delta.ctypes.data) if len(codes) else None,
+            self._ptr(rho), self._ptr(delta) if len(codes) else None, ld,
             norm.ctypes.data if want_norm else None, flags))
         return rho, (delta if len(codes) else None), norm
 

@@ -1,0 +1,73 @@
+"""GPU: the multi-rank driver (one process per rank, point shards written side by side into one
+node-shared host array) returns, on EVERY rank, exactly what a single process returns.
+Two ranks share cuda:0 here (process group on gloo, so no NCCL duplicate-GPU restriction); on a
+multi-GPU box the same code runs with one GPU per rank on nccl (bench.py --gpus N)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from conftest import REPO, golden_qc
+
+pytestmark = pytest.mark.gpu
+
+_WORKER = r'''
+import os, sys, numpy, torch
+import torch.distributed as dist
+sys.path.insert(0, %(repo)r)
+sys.path.insert(0, os.path.join(%(repo)r, 'tests'))
+rank = int(sys.argv[1])
+os.environ['LOCAL_RANK'] = '0'
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=rank, world_size=2)
+import orbkit_b200 as ok
+from conftest import golden_qc
+ok.options.quiet = True
+qc, a = golden_qc('synth_small_sph')
+ax, ay, az = numpy.linspace(-5, 5, 23), numpy.linspace(-4, 4, 17), numpy.linspace(-3, 3, 11)
+ok.grid.set_grid(ax, ay, az, is_vector=False)
+out = {}
+out['rho'], out['drho'] = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+r, d2, lap = ok.rho_compute(qc, laplacian=True)
+out['d2'], out['lap'] = d2, lap
+out['mo'] = ok.rho_compute(qc, calc_mo=True, drv=[None, 'z'])
+out['ao'] = ok.rho_compute(qc, calc_ao=True)
+ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)      # fewer points than one shard alignment
+out['vec_rho'] = ok.rho_compute(qc)
+out['again'] = ok.rho_compute(qc)                                # second segment generation
+numpy.savez(%(out)r + '_%%d.npz' %% rank, **{k: numpy.array(v) for k, v in out.items()})
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_two_ranks_equal_one_process(tmp_path):
+    import orbkit_b200 as ok
+    ok.options.quiet = True
+    qc, a = golden_qc('synth_small_sph')
+    ax, ay, az = numpy.linspace(-5, 5, 23), numpy.linspace(-4, 4, 17), numpy.linspace(-3, 3, 11)
+    ok.grid.set_grid(ax, ay, az, is_vector=False)
+    ref = {}
+    ref['rho'], ref['drho'] = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    _, ref['d2'], ref['lap'] = ok.rho_compute(qc, laplacian=True)
+    ref['mo'] = ok.rho_compute(qc, calc_mo=True, drv=[None, 'z'])
+    ref['ao'] = ok.rho_compute(qc, calc_ao=True)
+    ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
+    ref['vec_rho'] = ok.rho_compute(qc)
+    ref['again'] = ref['vec_rho']
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / 'dist_worker.py'
+    script.write_text(_WORKER % {'repo': REPO, 'port': port, 'out': str(tmp_path / 'res')})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    for r in range(2):
+        got = numpy.load(str(tmp_path / 'res') + '_%d.npz' % r)
+        for k, v in ref.items():
+            assert got[k].shape == numpy.asarray(v).shape, k
+            assert numpy.array_equal(got[k], v), 'rank %d: %s differs from the single-process result' % (r, k)

@@ -201,6 +201,7 @@ def test_shard_ranges_cover_and_balance():
 _GLOO_SCRIPT = r'''
 import os, sys, numpy, torch
 import torch.distributed as dist
+import os
 sys.path.insert(0, %(repo)r)
 from orbkit_b200 import dist as okdist
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=int(sys.argv[1]), world_size=2)
@@ -218,6 +219,18 @@ assert numpy.allclose(norm, [3.0, 4.0]), norm
 p0, p1 = okdist.shard_range(100, rank, world)
 local = torch.from_numpy(numpy.arange(100.0)[None, p0:p1].copy())
 assert numpy.array_equal(okdist.gather_points(local, 100).numpy()[0], numpy.arange(100.0))
+# node-shared host array: every rank writes its own point range, a barrier completes it on both
+for rep in range(3):                       # two segments are used in turn (a result survives one more call)
+    shared = okdist.shared_host_array((4, npts), pin=False)
+    p0, p1 = okdist.shard_range(npts, rank, world)
+    shared[:, p0:p1] = full[:, p0:p1] + rep
+    dist.barrier()
+    assert numpy.array_equal(shared, full + rep), 'shared host array'
+    if rep == 1:
+        assert numpy.array_equal(prev, full), 'previous generation still intact'
+    prev = shared
+    dist.barrier()
+assert not [f for f in os.listdir('/dev/shm') if f.startswith('okb200_')], 'segments are unlinked once attached'
 dist.barrier()
 dist.destroy_process_group()
 print('rank', rank, 'ok')
