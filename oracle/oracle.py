@@ -362,3 +362,40 @@ def rho_compute(qc, x, y, z, is_vector=False, calc_ao=False, calc_mo=False, drv=
     delta = np.concatenate([r[2] for r in results], axis=-1).reshape((len(drv),) + shape)
     ret = (rho, delta, delta.sum(axis=0)) if laplacian else (rho, delta)
     return ret + (mo_norm,) if return_norm else ret
+
+
+def gross_atomic_density(atom_indices, qc, x, y, z, is_vector=True, drv=None, kind='port'):
+    """orbkit/extras.py:306-385 for the atoms `atom_indices` (counting from ZERO, i.e. the `index` array
+    of extras.atom2index), operation by operation:
+        mo_info = sum_jj coeffs[ao_index[jj]] * ao[jj]            (plain += in AO order, :372-374)
+        rho_atom += occ_num * mo_list[ii_mo] * mo_info            (:375)
+    Returns (rho_atom, mo_atom) as lists per atom.
+
+    AO -> atom assignment: the reference enumerates `core.l_deg(l=type)` CARTESIAN functions per
+    shell (:365), which is only right for Cartesian bases; for spherical bases that enumeration runs
+    past / mislabels the AO rows (reference bug, unpinned by any test).  This restatement follows the
+    reference for Cartesian bases and assigns every spherical AO to the atom of its shell."""
+    ao_list = ao_creator(qc.geo_spec, qc.ao_spec, drv=drv, x=x, y=y, z=z, is_vector=is_vector, kind=kind)
+    mo_list = mo_creator(ao_list, qc.mo_spec, kind=kind)
+    N = mo_list.shape[1:]
+    cont_atom = np.asarray(qc.ao_spec.get_assign_cont_to_atoms(), dtype=int)
+    if qc.ao_spec.spherical:
+        ao_atom = cont_atom[np.asarray(qc.ao_spec.get_assign_lm_to_cont(), dtype=int)]
+    else:
+        ao_atom = np.repeat(cont_atom, np.asarray(qc.ao_spec.get_nlxlylz_per_cont(), dtype=int))
+    coeffs = _f64(qc.mo_spec.get_coeffs())
+    occ = _f64(qc.mo_spec.get_occ())
+    rho_atom, mo_atom = [], []
+    for a in atom_indices:
+        ao_index = [ll for ll in range(len(ao_atom)) if ao_atom[ll] == a]
+        rho = np.zeros(N)
+        mos = []
+        for ii_mo in range(coeffs.shape[0]):
+            mo_info = np.zeros(N)
+            for jj in ao_index:
+                mo_info += coeffs[ii_mo, jj] * ao_list[jj]
+            rho += occ[ii_mo] * mo_list[ii_mo] * mo_info
+            mos.append(mo_info)
+        rho_atom.append(rho)
+        mo_atom.append(mos)
+    return rho_atom, mo_atom

@@ -1341,7 +1341,8 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
         slab = std::max<long long>(1024, std::min(slab, npts));
     }
     const size_t tbytes = ci_terms_bytes(n_terms);
-    const size_t in_bytes = in_dev ? 0 : ((size_t)nsets * n_mo * slab * 8 + 255) / 256 * 256;
+    const long long lds = (slab + 1) & ~1LL;                 // even row stride of the staged MO rows (16-byte aligned)
+    const size_t in_bytes = in_dev ? 0 : ((size_t)nsets * n_mo * lds * 8 + 255) / 256 * 256;
     rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
     if (rc != OKB_OK) return rc;
     CiParams p{};
@@ -1356,15 +1357,15 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
             p.dmo = need_drv ? molistdrv + s0 : nullptr;
             p.ld = ld_in;
         } else {
-            CU(cudaMemcpy2DAsync(d_in, (size_t)sn * 8, molist + s0, (size_t)ld_in * 8, (size_t)sn * 8, n_mo,
+            CU(cudaMemcpy2DAsync(d_in, (size_t)lds * 8, molist + s0, (size_t)ld_in * 8, (size_t)sn * 8, n_mo,
                                  cudaMemcpyHostToDevice, ctx->stream));
             if (need_drv)
-                CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * sn, (size_t)sn * 8, molistdrv + s0, (size_t)ld_in * 8,
+                CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * lds, (size_t)lds * 8, molistdrv + s0, (size_t)ld_in * 8,
                                      (size_t)sn * 8, (size_t)3 * n_mo, cudaMemcpyHostToDevice, ctx->stream));
             ctx->h2d_bytes += (long long)nsets * n_mo * sn * 8;
             p.mo = d_in;
-            p.dmo = need_drv ? d_in + (size_t)n_mo * sn : nullptr;
-            p.ld = sn;
+            p.dmo = need_drv ? d_in + (size_t)n_mo * lds : nullptr;
+            p.ld = lds;
         }
         p.dstride = (long long)n_mo * p.ld;
         p.npts = sn;
@@ -1411,7 +1412,8 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
     long long slab = (long long)(((size_t)1 << 30) / per_pt) / 1024 * 1024;
     slab = std::max<long long>(1024, std::min(slab, npts));
     const size_t tbytes = ci_terms_bytes(n_terms);
-    const size_t in_bytes = ((size_t)nsets * n_mo * slab * 8 + 255) / 256 * 256;
+    const long long lds = (slab + 1) & ~1LL;                 // even row stride of the staged MO rows (16-byte aligned)
+    const size_t in_bytes = ((size_t)nsets * n_mo * lds * 8 + 255) / 256 * 256;
     rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
     if (rc != OKB_OK) return rc;
     CiParams p{};
@@ -1423,13 +1425,13 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
         const long long sn = std::min(slab, npts - s0);
         // MOs (+ derivative sets) of the slab, device resident: [nsets][n_mo][sn]
         EvalReq rq{SINK_MO, mo->basis, mo, grid, p0 + s0, p0 + s0 + sn, codes, nsets, d_in, nullptr, nullptr, nullptr,
-                   (flags & OKB_FLAG_EXACT_MIXED) | OKB_FLAG_OUT_DEVICE};
+                   (flags & OKB_FLAG_EXACT_MIXED) | OKB_FLAG_OUT_DEVICE, lds};
         rc = run_eval(ctx, rq);
         if (rc != OKB_OK) return rc;
         p.mo = d_in;
-        p.dmo = need_drv ? d_in + (size_t)n_mo * sn : nullptr;
-        p.ld = sn;
-        p.dstride = (long long)n_mo * sn;
+        p.dmo = need_drv ? d_in + (size_t)n_mo * lds : nullptr;
+        p.ld = lds;
+        p.dstride = (long long)n_mo * lds;
         p.npts = sn;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? npts : sn;

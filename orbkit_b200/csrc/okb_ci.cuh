@@ -92,4 +92,14 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     }
 }
 
+// Measured alternative (not kept): a tiled kernel that stages all n_mo row segments of a 24-32 point tile in shared
+// memory (bulk-async copies) so that HBM delivers every MO value exactly once.  Bit-identical results require the
+// sequential term order per point, i.e. parallelism only ACROSS points, and shared memory caps the points in flight
+// at ~48 per SM for 500 MOs: the kernel was latency bound and 2x (rho) to 4x (jab) SLOWER than this gather kernel
+// (7.6 / 63.8 ms against 3.8 / 16.4 ms for 1.5e6 points, 1000 pairs).  Splitting the term list over warps would fix
+// that at the price of a different summation order.  The gather kernel runs at 85% of the HBM bandwidth but moves
+// 3.5x the algorithmic bytes (ncu: 12.5 GB read for 3.5 GB of MO values; L1/L2 hit rates 1% / 8%): the MO rows are
+// re-fetched per term because n_mo KB per CTA times the resident CTAs exceeds the L2.  In the fused path
+// (okb_eval_ci) this kernel is < 8% of the time, the MO evaluation dominates.
+
 }  // namespace okb

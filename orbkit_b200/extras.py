@@ -1,5 +1,6 @@
 """User-facing wrappers over core.rho_compute with the reference's signatures
-(orbkit/extras.py: calc_mo :40-103, mo_set :105-205, calc_ao :208-260).
+(orbkit/extras.py: calc_mo :40-103, mo_set :105-205, calc_ao :208-260, atom2index :262-304,
+gross_atomic_density :306-385).
 
 File output (`otype`, orbkit/output/*) is outside the hot path: requesting it raises
 NotImplementedError; with otype=None (the library use) the return values are those of the reference.
@@ -66,3 +67,99 @@ def calc_ao(qc, drv=None, otype=None, ofid=None, numproc=None, slice_length=None
     _no_output(otype)
     return core.rho_compute(qc, calc_ao=True, drv=drv, slice_length=options.slice_length,
                             numproc=options.numproc)
+
+
+def atom2index(atom, geo_info=None):
+    """atom numbers (counting from one) -> (atom list, indices into geo_info counting from zero)
+    (extras.py:262-304)."""
+    if not isinstance(atom, (list, numpy.ndarray)):
+        atom = [atom]
+    if geo_info is not None:
+        col = numpy.array(geo_info)[:, 1]
+        index = []
+        for a in atom:
+            i = numpy.argwhere(col.astype(int) == a)
+            if len(i) != 1:
+                raise ValueError('No or multiple occurence of the atom number %d in geo_info!' % a)
+            index.append(int(i[0, 0]))
+        index = numpy.array(index, dtype=int)
+    else:
+        try:
+            index = numpy.array(atom, dtype=int)
+        except ValueError:
+            raise ValueError('Cannot convert atom to integer array!')
+    return atom, index
+
+
+def _ao_atoms(ao_spec):
+    """atom index (from zero) of every contracted AO, Cartesian or spherical"""
+    cont_atom = numpy.asarray(ao_spec.get_assign_cont_to_atoms(), dtype=int)
+    if ao_spec.spherical:
+        return cont_atom[numpy.asarray(ao_spec.get_assign_lm_to_cont(), dtype=int)]
+    return numpy.repeat(cont_atom, numpy.asarray(ao_spec.get_nlxlylz_per_cont(), dtype=int))
+
+
+def gross_atomic_density(atom, qc, bReturnmo=False, ao_list=None, mo_list=None, drv=None):
+    r"""Gross atomic density  rho^a = sum_i occ_i phi_i^a phi_i  with  phi_i^a = sum_{k on atom a} C_ik chi_k
+    for the selected atoms (extras.py:306-385).  Returns a list with one array of the grid's shape per
+    atom and, with `bReturnmo`, the gross atomic MOs mo_atom[a][i] as well.
+
+    Mechanism: phi_i^a is an MO with the coefficients of all other atoms zeroed, so [C ; C^a] is
+    evaluated as one set of 2 NMO orbitals by the fused AO->MO kernel and contracted on the device by the
+    pair kernel with the terms (occ_i, i, NMO+i) -- the reference's expression order, MO values never
+    cross PCIe.  Given `ao_list` / `mo_list` (host arrays) are honoured like in the reference; with `drv`
+    both factors are the derivative, as the reference computes them (extras.py:350-353).
+
+    Divergence: the reference counts AOs with the CARTESIAN degeneracy of every shell (extras.py:365), which
+    mis-assigns the AOs of spherical bases; here every AO belongs to the atom of its shell."""
+    from . import cy_core, grid
+    from ._lib import OKB_CI_RHO
+    from .detci import ci_core
+    from .engine import get_engine
+    from .tools import require, validate_drv
+    if isinstance(atom, str) and atom == 'all' or (not isinstance(atom, (list, numpy.ndarray, str)) and atom == -1):
+        atom = list(range(1, len(qc.geo_info) + 1))
+    atom, index = atom2index(atom, geo_info=qc.geo_info)
+    display('Computing the gross atomic density with respect to the atom(s) (internal numbering)')
+    display('\t%s\n' % (list(atom),))
+    coeffs = require(qc.mo_spec.get_coeffs(), dtype='f')
+    occ = require(qc.mo_spec.get_occ(), dtype='f')
+    n_mo, n_ao = coeffs.shape
+    ao_atom = _ao_atoms(qc.ao_spec)
+    if len(ao_atom) != n_ao:
+        raise ValueError('AO/atom assignment has %d entries for %d AOs' % (len(ao_atom), n_ao))
+    eng = get_engine()
+    terms = (occ, numpy.arange(n_mo, dtype=numpy.intc), numpy.arange(n_mo, 2 * n_mo, dtype=numpy.intc))
+    code = validate_drv(drv)
+    rho_atom, mo_atom = [], []
+    for a in index:
+        c_a = numpy.where(ao_atom[None, :] == a, coeffs, 0.0)
+        if ao_list is None and mo_list is None and code == 0 and not bReturnmo:
+            # fused: [C ; C^a] on the module grid, contracted on the device
+            x, y, z, is_vector, N = core._resolve_grid(None, None, None, None)
+            basis = eng.basis(require(qc.geo_spec, dtype='f'), qc.ao_spec)
+            if int(numpy.prod(N)) == 0:
+                rho_atom.append(numpy.zeros(N))
+                continue
+            stacked = eng.mos(basis, numpy.concatenate([coeffs, c_a]), numpy.concatenate([occ, occ]))
+            g = core._grid_handle(eng, x, y, z, is_vector)
+            rho_atom.append(eng.eval_ci(OKB_CI_RHO, terms, stacked, g).reshape(N))
+            continue
+        # components given by the caller, a derivative, or the gross atomic MOs requested: two steps
+        if ao_list is None:
+            ao = core.ao_creator(qc.geo_spec, qc.ao_spec, drv=drv)
+        else:
+            ao = require(ao_list, dtype='f')
+        shape = ao.shape[1:]
+        ao2 = ao.reshape((ao.shape[0], -1))
+        mo = cy_core.mocreator(ao2, coeffs) if mo_list is None else require(mo_list, dtype='f').reshape((n_mo, -1))
+        mo_a = cy_core.mocreator(ao2, c_a)
+        both = numpy.concatenate([mo, mo_a])
+        rho_atom.append(eng.ci_contract(OKB_CI_RHO, terms, both).reshape(shape))
+        if bReturnmo:
+            mo_atom.append([m.reshape(shape) for m in mo_a])
+    if bReturnmo:
+        display('Returning the gross atomic density and\n\tthe gross atomic molecular orbitals')
+        return rho_atom, mo_atom
+    display('Returning the gross atomic density')
+    return rho_atom

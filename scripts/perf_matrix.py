@@ -24,8 +24,8 @@ def timed(fn, reps=3):
     eng.sync()
     return e0.elapsed_time(e1) / reps
 
-def run(name, n_mo, spherical=True, N=200):
-    spec = synth.make_molecule(n_heavy=24, n_light=20, n_mo=n_mo, seed=0, spherical=spherical)
+def run(name, n_mo, spherical=True, N=200, heavy=24, light=20):
+    spec = synth.make_molecule(n_heavy=heavy, n_light=light, n_mo=n_mo, seed=0, spherical=spherical)
     qc = synth.to_qcinfo(spec)
     n_ao = qc.ao_spec.get_ao_num()
     ax = numpy.linspace(-12, 12, N)
@@ -55,11 +55,58 @@ def run(name, n_mo, spherical=True, N=200):
         print('%-14s %-9s pts %-9d %9.2f ms  %.3e pts/s  %-32s %s' % r)
     return rows
 
+def run_ci(name, n_heavy, n_light, n_pairs, N):
+    """Config 5: detCI-style batch -- n_pairs random MO pairs of an all-MO calculation.
+    (a) the pair contraction alone on device-resident MOs (HBM bound: 8*n_mo B/pt in, 8 B/pt out),
+    (b) the fused path okb_eval_ci (MOs evaluated slab by slab on the device, then contracted)."""
+    from orbkit_b200 import _lib
+    spec = synth.make_molecule(n_heavy=n_heavy, n_light=n_light, n_mo=n_heavy * 30 + n_light * 14, seed=5, spherical=True)
+    qc = synth.to_qcinfo(spec)
+    n_mo = len(qc.mo_spec)
+    n_ao = qc.ao_spec.get_ao_num()
+    rng = numpy.random.default_rng(5)
+    pairs = rng.integers(0, n_mo, size=(n_pairs, 2))
+    terms = (rng.normal(size=n_pairs), pairs[:, 0].astype(numpy.intc), pairs[:, 1].astype(numpy.intc))
+    ax = numpy.linspace(-10, 10, N)
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    g = eng.grid_regular(ax, ax, ax)
+    npts = N ** 3
+    rows = []
+    out = torch.zeros((3, npts), dtype=torch.float64, device=dev)
+    # (a) MOs (+ gradient) resident in HBM
+    nsub = min(npts, int(24e9 // (8 * 4 * n_mo)))
+    mobuf = torch.empty((4, n_mo, nsub), dtype=torch.float64, device=dev)
+    eng.eval_mo(mo, g, [0, 1, 2, 3], 0, nsub, out=mobuf.data_ptr(), flags=OKB_FLAG_OUT_DEVICE)
+    fl = OKB_FLAG_OUT_DEVICE | _lib.OKB_FLAG_IN_DEVICE
+    for label, mode, nset, ncomp in (('ci rho', _lib.OKB_CI_RHO, 1, 1), ('ci jab', _lib.OKB_CI_JAB, 4, 3)):
+        ms = timed(lambda: eng.ci_contract(mode, terms, mobuf[0].data_ptr(), mobuf[1:].data_ptr(), n_mo=n_mo, npts=nsub,
+                                           ld=nsub, out=out.data_ptr(), flags=fl))
+        gbs = 8.0 * (n_mo * nset + ncomp) * nsub / (ms * 1e-3) / 1e9
+        rows.append((name, label, nsub, ms, nsub / ms * 1e3, '%.0f GB/s alg (%d pairs)' % (gbs, n_pairs), eng.last_kernel()))
+    del mobuf
+    # (b) fused
+    for label, mode, D in (('rho_from_qc', _lib.OKB_CI_RHO, 1), ('jab_from_qc', _lib.OKB_CI_JAB, 4)):
+        ms = timed(lambda: eng.eval_ci(mode, terms, mo, g, out=out.data_ptr(), flags=OKB_FLAG_OUT_DEVICE), reps=2)
+        tf = 2.0 * n_mo * n_ao * D * npts / (ms * 1e-3) / 1e12
+        rows.append((name, label, npts, ms, npts / ms * 1e3, '%.2f TFLOP/s alg (MO part)' % tf, eng.last_kernel()))
+    for r in rows:
+        print('%-14s %-11s pts %-9d %9.2f ms  %.3e pts/s  %-32s %s' % r)
+    return rows
+
+
 if __name__ == '__main__':
     allrows = []
     allrows += run('c3 n_mo=82', 82)
     allrows += run('c3 n_mo=1000', 1000, N=100)
     allrows += run('c3 cart n_mo=82', 82, spherical=False, N=128)
+    if os.environ.get('PERF_BIG', '1') == '1':
+        allrows += run_ci('c5 500 MOs', 12, 10, 1000, 128)
+        # Config 2 shape (222 spherical AOs: 12 heavy x 14... here 6 C-like + 3 H-like = 222 AOs), 21 occupied MOs / all MOs, 150^3
+        allrows += run('c2 n_mo=21', 21, N=150, heavy=6, light=3)
+        allrows += run('c2 n_mo=222', 222, N=150, heavy=6, light=3)
+        # Config 4 shape: ~3000 AOs, 246 MOs, 256^3 (one GPU's share of the 8-GPU run is 1/8 of this)
+        allrows += run('c4 n_mo=246', 246, N=160, heavy=72, light=60)
     # end-to-end pieces of rho_compute on the bench workload
     spec = synth.make_molecule(n_heavy=24, n_light=20, n_mo=82, seed=0, spherical=True)
     qc = synth.to_qcinfo(spec)

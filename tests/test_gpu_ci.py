@@ -144,3 +144,36 @@ def test_config5_scale_properties(ok):
     prods = ci_core.pair_products(pairs, sub)
     assert_close(numpy.tensordot(coef, prods, axes=1), ci_core.rho(zero, sing, sub, slice_length=sub[0].size),
                  'sum of pair products', rtol=1e-12, afloor=1e-13)
+
+
+def test_gross_atomic_density(ok, oracle_mod):
+    """extras.gross_atomic_density (extras.py:306-385): fused device path, the two-step path with
+    caller-supplied components, derivatives and the gross atomic MOs against the oracle"""
+    from conftest import golden_qc
+    for name in ('h2o_molpro_cart', 'h2o_gaussian_sph'):
+        qc, a = golden_qc(name)
+        ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
+        ref_rho, ref_mo = oracle_mod.gross_atomic_density([0, 1, 2], qc, a['vx'], a['vy'], a['vz'], is_vector=True)
+        got = ok.extras.gross_atomic_density('all', qc)
+        assert len(got) == 3
+        for g, r in zip(got, ref_rho):
+            assert_close(g, r, name + ' gross atomic density')
+        # the atoms' densities add up to the density
+        assert_close(sum(got), ok.rho_compute(qc), name + ' sum over atoms', rtol=1e-10, afloor=1e-13)
+        # single atom by its number (counting from one), with the gross atomic MOs
+        rho2, mo2 = ok.extras.gross_atomic_density(2, qc, bReturnmo=True)
+        assert_close(rho2[0], ref_rho[1], name + ' atom 2')
+        assert len(mo2) == 1 and len(mo2[0]) == len(qc.mo_spec)
+        assert_close(numpy.array(mo2[0]), numpy.array(ref_mo[1]), name + ' gross atomic MOs')
+        # caller-supplied components, and a derivative
+        ao = ok.ao_creator(qc.geo_spec, qc.ao_spec)
+        mo = ok.mo_creator(ao, qc.mo_spec)
+        assert_close(ok.extras.gross_atomic_density([1, 3], qc, ao_list=ao, mo_list=mo)[1], ref_rho[2], name + ' given')
+        dref, _ = oracle_mod.gross_atomic_density([0], qc, a['vx'], a['vy'], a['vz'], is_vector=True, drv='x')
+        assert_close(ok.extras.gross_atomic_density(1, qc, drv='x')[0], dref[0], name + ' drv=x')
+    # regular grid shape
+    ax = numpy.linspace(-3, 3, 6)
+    ok.grid.set_grid(ax, ax, ax, is_vector=False)
+    assert ok.extras.gross_atomic_density(1, qc)[0].shape == (6, 6, 6)
+    with pytest.raises(ValueError):
+        ok.extras.gross_atomic_density(7, qc)
