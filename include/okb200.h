@@ -121,6 +121,15 @@ int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const double *y, int
                      const double *z, int nz, okb_grid **out);
 int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, const double *z,
                     long long npts, int coords_on_device, okb_grid **out);
+/* Product grids in spherical (kind 2: a0 = r, a1 = theta, a2 = phi; cy_grid.sph2cart, cy_grid.pyx:58-75) or
+ * cylindrical coordinates (kind 3: a0 = r, a1 = phi, a2 = zed; cy_grid.cyl2cart, cy_grid.pyx:79-97), first axis
+ * slowest.  The Cartesian coordinates are generated in the kernels (same expressions and multiplication order as
+ * the reference, sin/cos from the host libm): no coordinate upload.  affine (may be NULL) = 12 doubles, a row-major
+ * 3x3 matrix A and a translation t applied as A (x,y,z) + t (grid.grid_sym_op / grid_translate, grid.py:293-321). */
+#define OKB_GRID_SPHERICAL 2
+#define OKB_GRID_CYLINDRICAL 3
+int okb_grid_product(okb_ctx *ctx, int kind, const double *a0, int n0, const double *a1, int n1,
+                     const double *a2, int n2, const double *affine, okb_grid **out);
 int okb_grid_size(okb_grid *grid, long long *npts);
 int okb_grid_destroy(okb_grid *grid);
 

@@ -303,3 +303,33 @@ void okor_ci_a_nabla_b(double *out, long i0, long i1, long npts, long n_mo, cons
         }
     }
 }
+
+/* ---- non-Cartesian product grids (orbkit/cy_grid.pyx:58-97) ------------------------------
+ * xyz is [3][n0*n1*n2], first axis slowest; same expressions, same multiplication order. */
+void okor_sph2cart(double *xyz, const double *r, long nr, const double *theta, long nt,
+                   const double *phi, long np)
+{
+    long i, j, k, c = 0, n = nr * nt * np;
+    for (i = 0; i < nr; ++i)
+        for (j = 0; j < nt; ++j)
+            for (k = 0; k < np; ++k) {
+                xyz[c] = r[i] * sin(theta[j]) * cos(phi[k]);
+                xyz[n + c] = r[i] * sin(theta[j]) * sin(phi[k]);
+                xyz[2 * n + c] = r[i] * cos(theta[j]);
+                ++c;
+            }
+}
+
+void okor_cyl2cart(double *xyz, const double *r, long nr, const double *phi, long np,
+                   const double *zed, long nz)
+{
+    long i, j, k, c = 0, n = nr * np * nz;
+    for (i = 0; i < nr; ++i)
+        for (j = 0; j < np; ++j)
+            for (k = 0; k < nz; ++k) {
+                xyz[c] = r[i] * cos(phi[j]);
+                xyz[n + c] = r[i] * sin(phi[j]);
+                xyz[2 * n + c] = zed[k];
+                ++c;
+            }
+}

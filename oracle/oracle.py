@@ -399,3 +399,29 @@ def gross_atomic_density(atom_indices, qc, x, y, z, is_vector=True, drv=None, ki
         rho_atom.append(rho)
         mo_atom.append(mos)
     return rho_atom, mo_atom
+
+
+def sph2cart(r, theta, phi, kind='port'):
+    """cy_grid.sph2cart (orbkit/cy_grid.pyx:58-75): (3, Nr*Ntheta*Nphi) Cartesian coordinates."""
+    r, theta, phi = _f64(r), _f64(theta), _f64(phi)
+    if kind == 'ref':
+        return backend('ref').cy_grid.sph2cart(r, theta, phi)
+    out = np.zeros((3, len(r) * len(theta) * len(phi)))
+    lib = backend('port').L
+    lib.okor_sph2cart.restype = None
+    lib.okor_sph2cart(_dp(out), _dp(r), ctypes.c_long(len(r)), _dp(theta), ctypes.c_long(len(theta)), _dp(phi),
+                      ctypes.c_long(len(phi)))
+    return out
+
+
+def cyl2cart(r, phi, zed, kind='port'):
+    """cy_grid.cyl2cart (orbkit/cy_grid.pyx:79-97)."""
+    r, phi, zed = _f64(r), _f64(phi), _f64(zed)
+    if kind == 'ref':
+        return backend('ref').cy_grid.cyl2cart(r, phi, zed)
+    out = np.zeros((3, len(r) * len(phi) * len(zed)))
+    lib = backend('port').L
+    lib.okor_cyl2cart.restype = None
+    lib.okor_cyl2cart(_dp(out), _dp(r), ctypes.c_long(len(r)), _dp(phi), ctypes.c_long(len(phi)), _dp(zed),
+                      ctypes.c_long(len(zed)))
+    return out

@@ -66,6 +66,8 @@ SIGNATURES = {
                                         c_double_p, ctypes.c_int, c_void_pp]),
     'okb_grid_vector': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll,
                                        ctypes.c_int, c_void_pp]),
+    'okb_grid_product': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p,
+                                        ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_void_pp]),
     'okb_grid_size': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ll)]),
     'okb_grid_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'okb_eval_ao': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,

@@ -44,6 +44,8 @@ def _drv_list(drv):
 
 
 def _grid_handle(eng, x, y, z, is_vector):
+    if isinstance(x, grid.ProductGrid):          # spherical / cylindrical product grid generated on the device
+        return eng.grid_product(x.kind, x.axes[0], x.axes[1], x.axes[2], affine=x.affine)
     return eng.grid_vector(x, y, z) if is_vector else eng.grid_regular(x, y, z)
 
 
@@ -53,6 +55,9 @@ def _resolve_grid(x, y, z, is_vector, init_vector=False):
         display('\nSetting up the grid...')
         grid.grid_init(is_vector=init_vector)
         display(grid.get_grid())
+    pg = grid.product_grid()
+    if pg is not None and x is None and y is None and z is None and (is_vector is None or is_vector):
+        return pg, None, None, True, (pg.npts,)  # the coordinates exist only as a recipe (grid.sph2cart_vector, ...)
     x = grid.x if x is None else x
     y = grid.y if y is None else y
     z = grid.z if z is None else z
@@ -211,7 +216,7 @@ def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, num
         grid.grid_init()
         display(grid.get_grid())
     was_vector = grid.is_vector
-    x, y, z, _, N = _resolve_grid(grid.x, grid.y, grid.z, was_vector)
+    x, y, z, _, N = _resolve_grid(None, None, None, was_vector)
     mo_num = qc.ao_spec.get_ao_num() if calc_ao else len(qc.mo_spec)
     display('\nStarting the calculation of the %s...' % ('molecular orbitals' if calc_mo else 'density'))
     display('\nThere are %d contracted %s AOs' % (qc.ao_spec.get_ao_num(),

@@ -171,7 +171,9 @@ struct okb_mo {
 
 struct okb_grid {
     okb_ctx *ctx = nullptr;
-    int kind = 0;                            // 0 regular, 1 vector
+    int kind = 0;                            // 0 regular, 1 vector, 2 spherical product, 3 cylindrical product
+    bool has_aff = false;                    // product grids: affine map applied to the generated coordinates
+    double aff[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
     int nx = 0, ny = 0, nz = 0;
     long long npts = 0;
     double *gx = nullptr, *gy = nullptr, *gz = nullptr;
@@ -906,6 +908,50 @@ extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, c
     return OKB_OK;
 }
 
+// Product grids in non-Cartesian coordinates (cy_grid.sph2cart / cyl2cart, cy_grid.pyx:58-97): the coordinates are
+// generated in the kernels from the three axis vectors -- 0 input bytes per point instead of 24.  sin / cos of the
+// angular axes are taken here on the host (the same libm the reference's Cython code calls) so that the device
+// reproduces the reference's coordinates bit for bit.
+extern "C" int okb_grid_product(okb_ctx *ctx, int kind, const double *a0, int n0, const double *a1, int n1,
+                                const double *a2, int n2, const double *affine, okb_grid **out) {
+    if (!ctx || !out || !a0 || !a1 || !a2) return fail(OKB_ERR_ARG, "okb_grid_product: null argument");
+    *out = nullptr;
+    if (kind != 2 && kind != 3) return fail(OKB_ERR_ARG, "okb_grid_product: kind must be 2 (spherical) or 3 (cylindrical)");
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(OKB_ERR_ARG, "okb_grid_product: empty axis");
+    okb_grid *g = new okb_grid();
+    g->ctx = ctx;
+    g->kind = kind;
+    g->nx = n0; g->ny = n1; g->nz = n2;
+    g->npts = (long long)n0 * n1 * n2;
+    if (affine) {
+        g->has_aff = true;
+        memcpy(g->aff, affine, sizeof(double) * 12);
+    }
+    std::vector<double> t1((size_t)2 * n1), t2((size_t)2 * n2);
+    for (int j = 0; j < n1; ++j) {
+        t1[j] = kind == 2 ? sin(a1[j]) : cos(a1[j]);            // spherical: sin(theta), cos(theta)
+        t1[n1 + j] = kind == 2 ? cos(a1[j]) : sin(a1[j]);       // cylindrical: cos(phi), sin(phi)
+    }
+    for (int k = 0; k < n2; ++k) {
+        t2[k] = kind == 2 ? cos(a2[k]) : a2[k];                 // spherical: cos(phi), sin(phi); cylindrical: zed
+        t2[n2 + k] = kind == 2 ? sin(a2[k]) : 0.0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    double **dst[3] = {&g->gx, &g->gy, &g->gz};
+    const double *src[3] = {a0, t1.data(), t2.data()};
+    const size_t cnt[3] = {(size_t)n0, (size_t)2 * n1, (size_t)2 * n2};
+    for (int a = 0; a < 3; ++a) {
+        void *raw = nullptr;
+        int rcp = pool_get(ctx, sizeof(double) * cnt[a], &raw, &g->gbytes[a]);
+        if (rcp != OKB_OK) return rcp;
+        *dst[a] = reinterpret_cast<double *>(raw);
+        CU(cudaMemcpy(*dst[a], src[a], sizeof(double) * cnt[a], cudaMemcpyHostToDevice));
+        ctx->h2d_bytes += (long long)(sizeof(double) * cnt[a]);
+    }
+    *out = g;
+    return OKB_OK;
+}
+
 extern "C" int okb_grid_size(okb_grid *g, long long *npts) {
     if (!g || !npts) return fail(OKB_ERR_ARG, "null pointer");
     *npts = g->npts;
@@ -1146,6 +1192,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.grid_kind = g->kind;
             p.gx = g->gx; p.gy = g->gy; p.gz = g->gz;
             p.nx = g->nx; p.ny = g->ny; p.nz = g->nz;
+            p.has_aff = g->has_aff ? 1 : 0;
+            for (int q = 0; q < 12; ++q) p.aff[q] = g->aff[q];
             p.tabx = tabx; p.taby = taby; p.tabz = tabz;
             p.p0 = rq.p0 + s0;
             p.npts = (int)sn;

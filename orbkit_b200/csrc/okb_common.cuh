@@ -56,9 +56,13 @@ struct BlobLayout { int off_shell, off_prim, off_fn, off_row, off_term, off_aux,
 
 struct KParams {
     // grid
-    int grid_kind;                 // 0 regular (axes), 1 vector (coordinates)
-    const double *gx, *gy, *gz;
+    int grid_kind;                 // 0 regular (axes), 1 vector (coordinates), 2 spherical / 3 cylindrical product grid
+    const double *gx, *gy, *gz;    // kinds 0,1: axes / coordinates.  kinds 2,3: gx = r[nx]; gy = two tables [2][ny]; gz = [2][nz]
+                                   //   spherical   gy = sin(theta), cos(theta); gz = cos(phi), sin(phi)
+                                   //   cylindrical gy = cos(phi),   sin(phi);   gz = zed, (unused)
     int nx, ny, nz;
+    int has_aff;                   // product grids: (x,y,z) <- A (x,y,z) + t  (grid_sym_op / grid_translate)
+    double aff[12];                // A row-major, then t
     // regular grids: separable exponentials  c N exp(-a (x_i-X)^2), exp(-a (y_j-Y)^2), exp(-a (z_k-Z)^2)
     // per (primitive, axis point), [n_prim][n_axis] each; null -> evaluate exp(-a r^2) per point
     const double *tabx, *taby, *tabz;
@@ -90,6 +94,44 @@ struct AxTab {
     int nx, ny, nz;
     const int *ii, *jj, *kk;
 };
+
+// Coordinates (and, for regular grids, axis indices) of point number n of the grid.  The index runs first axis
+// slowest, last axis fastest (cy_grid.pyx:22-29, 67-75, 88-96).  Product grids reproduce the reference's expressions
+// r*sin(theta)*cos(phi), ... (cy_grid.pyx:70-72, 91-93) on host-computed sin/cos tables, multiplication order included.
+__device__ __forceinline__ void grid_point(const KParams &p, long long n, double &x, double &y, double &z, int &i, int &j,
+                                           int &k) {
+    if (p.grid_kind == 1) {
+        x = p.gx[n]; y = p.gy[n]; z = p.gz[n];
+        i = j = k = 0;
+        return;
+    }
+    const long long nyz = (long long)p.ny * p.nz;
+    const long long ii = n / nyz, rem = n - ii * nyz;
+    i = (int)ii;
+    j = (int)(rem / p.nz);
+    k = (int)(rem - (long long)j * p.nz);
+    if (p.grid_kind == 0) {
+        x = p.gx[i]; y = p.gy[j]; z = p.gz[k];
+        return;
+    }
+    const double r = p.gx[i];
+    if (p.grid_kind == 2) {              // x = r sin(theta) cos(phi), y = r sin(theta) sin(phi), z = r cos(theta)
+        const double rs = __dmul_rn(r, p.gy[j]);
+        x = __dmul_rn(rs, p.gz[k]);
+        y = __dmul_rn(rs, p.gz[p.nz + k]);
+        z = __dmul_rn(r, p.gy[p.ny + j]);
+    } else {                             // x = r cos(phi), y = r sin(phi), z = zed
+        x = __dmul_rn(r, p.gy[j]);
+        y = __dmul_rn(r, p.gy[p.ny + j]);
+        z = p.gz[k];
+    }
+    if (p.has_aff) {
+        const double X = x, Y = y, Z = z;
+        x = fma(p.aff[2], Z, fma(p.aff[1], Y, p.aff[0] * X)) + p.aff[9];
+        y = fma(p.aff[5], Z, fma(p.aff[4], Y, p.aff[3] * X)) + p.aff[10];
+        z = fma(p.aff[8], Z, fma(p.aff[7], Y, p.aff[6] * X)) + p.aff[11];
+    }
+}
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) -------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

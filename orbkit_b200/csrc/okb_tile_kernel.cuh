@@ -95,16 +95,7 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
         if (tid < P) {
             int q = q0 + tid;
             if (q >= p.npts) q = p.npts - 1;
-            const long long n = p.p0 + q;
-            if (p.grid_kind == 0) {
-                const long long nyz = (long long)p.ny * p.nz;
-                const long long i = n / nyz, rem = n - i * nyz;
-                const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
-                xs[tid] = p.gx[i]; ys[tid] = p.gy[j]; zs[tid] = p.gz[k];
-                isx[tid] = (int)i; isy[tid] = j; isz[tid] = k;
-            } else {
-                xs[tid] = p.gx[n]; ys[tid] = p.gy[n]; zs[tid] = p.gz[n];
-            }
+            grid_point(p, p.p0 + q, xs[tid], ys[tid], zs[tid], isx[tid], isy[tid], isz[tid]);
         }
         double osum[C::NOUT > 0 ? C::NOUT : 1][PT];
         if (SINK == SINK_RHO) {

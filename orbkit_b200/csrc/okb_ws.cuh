@@ -192,16 +192,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
             for (int e = ptid; e < P; e += NPT) {
                 int q = q0 + e;
                 if (q >= p.npts) q = p.npts - 1;
-                const long long n = p.p0 + q;
-                if (p.grid_kind == 0) {
-                    const long long nyz = (long long)p.ny * p.nz;
-                    const long long i = n / nyz, rem = n - i * nyz;
-                    const int j = (int)(rem / p.nz), k = (int)(rem - (long long)j * p.nz);
-                    xs[e] = p.gx[i]; ys[e] = p.gy[j]; zs[e] = p.gz[k];
-                    isx[e] = (int)i; isy[e] = j; isz[e] = k;
-                } else {
-                    xs[e] = p.gx[n]; ys[e] = p.gy[n]; zs[e] = p.gz[n];
-                }
+                grid_point(p, p.p0 + q, xs[e], ys[e], zs[e], isx[e], isy[e], isz[e]);
             }
             named_bar(1, NPT);
             for (int mt = 0; mt < p.n_mtile; ++mt)

@@ -176,6 +176,26 @@ class Engine:
         handle.npts = len(x) * len(y) * len(z)
         return self._put(self._grid, key, handle)
 
+    def grid_product(self, kind, a0, a1, a2, affine=None):
+        """spherical (kind 2: r, theta, phi) or cylindrical (kind 3: r, phi, zed) product grid whose Cartesian
+        coordinates are generated on the device; affine = (3x3 matrix, translation) or None"""
+        a0, a1, a2 = _lib.f64(a0), _lib.f64(a1), _lib.f64(a2)
+        aff = None
+        if affine is not None:
+            aff = _lib.f64(numpy.concatenate([numpy.asarray(affine[0], dtype=float).reshape(9),
+                                              numpy.asarray(affine[1], dtype=float).reshape(3)]))
+        key = b'p%d' % kind + _digest(a0, a1, a2, aff)
+        if key in self._grid:
+            self._grid.move_to_end(key)
+            return self._grid[key]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.okb_grid_product(self.ctx, kind, _lib.dptr(a0), len(a0), _lib.dptr(a1), len(a1),
+                                             _lib.dptr(a2), len(a2), _lib.dptr(aff) if aff is not None else None,
+                                             ctypes.byref(h)))
+        handle = _Handle(h, self.lib.okb_grid_destroy)
+        handle.npts = len(a0) * len(a1) * len(a2)
+        return self._put(self._grid, key, handle)
+
     def grid_vector(self, x, y, z, cache=True):
         x, y, z = _lib.f64(x), _lib.f64(y), _lib.f64(z)
         if not (len(x) == len(y) == len(z)):

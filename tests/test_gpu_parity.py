@@ -324,3 +324,48 @@ def test_benchmark_size_properties_200cube(ok, oracle_mod):
     # (2) two independent accumulation paths: sum_i occ_i * (sum_p phi_i^2)  ==  sum_p rho
     occ = qc.mo_spec.get_occ()
     assert abs((occ * norm_sum).sum() / rho.sum() - 1.0) < 1e-11
+
+
+def test_product_grids_generated_on_the_device(ok, oracle_mod):
+    """grid.sph2cart_vector / cyl2cart_vector (+ grid_sym_op / grid_translate): the kernels generate the Cartesian
+    coordinates from the three axis vectors.  Untransformed grids reproduce the reference's coordinates bit for
+    bit, so the results must be IDENTICAL to the vector-grid evaluation of those coordinates; transformed grids and
+    the oracle comparison use the stated tolerance."""
+    qc, _ = golden_qc('lih_psi4_sph_f')
+    rng = numpy.random.default_rng(12)
+    r = numpy.sort(rng.uniform(0.05, 4.0, 9))
+    th = numpy.linspace(0.0, numpy.pi, 7)
+    ph = numpy.linspace(0.0, 2 * numpy.pi, 11)
+    zed = numpy.linspace(-2.0, 2.5, 5)
+    for kind in ('sph', 'cyl'):
+        if kind == 'sph':
+            ok.grid.sph2cart_vector(r, th, ph)
+            xyz = oracle_mod.sph2cart(r, th, ph)
+        else:
+            ok.grid.cyl2cart_vector(r, ph, zed)
+            xyz = oracle_mod.cyl2cart(r, ph, zed)
+        assert ok.grid.product_grid() is not None
+        rho, drho = ok.rho_compute(qc, drv='xyz')
+        mo = ok.rho_compute(qc, calc_mo=True)
+        ao = ok.rho_compute(qc, calc_ao=True, drv=['zz'])
+        assert ok.grid.product_grid() is not None          # still a recipe: nobody asked for grid.x
+        assert rho.shape == (xyz.shape[1],) and mo.shape == (len(qc.mo_spec), xyz.shape[1])
+        ok.grid.set_grid(xyz[0], xyz[1], xyz[2], is_vector=True)
+        r2, d2 = ok.rho_compute(qc, drv='xyz')
+        assert numpy.array_equal(rho, r2) and numpy.array_equal(drho, d2)
+        assert numpy.array_equal(mo, ok.rho_compute(qc, calc_mo=True))
+        assert numpy.array_equal(ao, ok.rho_compute(qc, calc_ao=True, drv=['zz']))
+        rr, dr = oracle_mod.rho_compute(qc, xyz[0], xyz[1], xyz[2], is_vector=True, drv='xyz')
+        assert_close(rho, rr, kind + ' rho')
+        assert_close(drho, dr, kind + ' drho')
+    # symmetry operation + translation on the recipe == the reference's host transformation of the coordinates
+    ok.grid.sph2cart_vector(r, th, ph)
+    S = ok.grid.rot(0.7, 1)
+    ok.grid.grid_sym_op(S)
+    ok.grid.grid_translate(0.25, -0.5, 1.0)
+    rho = ok.rho_compute(qc)
+    assert ok.grid.product_grid() is not None
+    xyz = numpy.dot(S, oracle_mod.sph2cart(r, th, ph)) + numpy.array([[0.25], [-0.5], [1.0]])
+    assert_close(rho, oracle_mod.rho_compute(qc, xyz[0], xyz[1], xyz[2], is_vector=True), 'sym op', rtol=1e-9)
+    assert numpy.allclose(numpy.array([ok.grid.x, ok.grid.y, ok.grid.z]), xyz, rtol=0, atol=1e-14)
+    assert ok.grid.product_grid() is None

@@ -247,3 +247,36 @@ def test_world_size_2_gloo_gather_and_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_product_grid_state_is_lazy_and_materialises_like_the_reference():
+    """grid.sph2cart_vector / cyl2cart_vector / grid_sym_op / grid_translate keep a device recipe; grid.x/y/z
+    appear on first access with the reference's values (grid.py:293-321, 373-419)"""
+    from orbkit_b200 import grid, cy_grid
+    r, th, ph = numpy.linspace(0.1, 3, 4), numpy.linspace(0, numpy.pi, 5), numpy.linspace(0, 2 * numpy.pi, 6)
+    grid.sph2cart_vector(r, th, ph)
+    pg = grid.product_grid()
+    assert pg is not None and pg.kind == 2 and pg.npts == 120 and pg.affine is None
+    assert grid.is_initialized and grid.is_vector and not grid.is_regular
+    S = grid.rot(0.3, 2)
+    grid.grid_sym_op(S)
+    grid.grid_translate(0.5, -1.0, 2.0)
+    grid.grid_sym_op(grid.reflect(numpy.array([0, 1])))
+    assert grid.product_grid() is pg and pg.affine is not None
+    ref = numpy.dot(grid.reflect(numpy.array([0, 1])), numpy.dot(S, cy_grid.sph2cart(r, th, ph)) + numpy.array([[0.5], [-1.0], [2.0]]))
+    x = grid.x                                  # first access materialises and drops the recipe
+    assert grid.product_grid() is None
+    assert numpy.allclose(numpy.array([x, grid.y, grid.z]), ref, rtol=0, atol=1e-14)
+    assert grid.get_shape() == (120,)
+    # cylindrical, untouched: exactly the reference's expression values
+    grid.cyl2cart_vector(r, ph, [0.0, 1.0])
+    assert grid.product_grid().kind == 3
+    assert numpy.array_equal(numpy.array(grid.tolist()), cy_grid.cyl2cart(r, ph, [0.0, 1.0]))
+    assert grid.product_grid() is None
+    # set_grid / grid_init replace a pending recipe
+    grid.sph2cart_vector(r, th, ph)
+    grid.set_grid(numpy.arange(3.0), numpy.arange(2.0), numpy.arange(4.0), is_vector=False)
+    assert grid.product_grid() is None and len(grid.x) == 3 and not grid.is_vector
+    assert numpy.allclose(grid.inversion(), -numpy.eye(3)) and grid.rot(0.0, 1).shape == (3, 3)
+    with pytest.raises(ValueError):
+        grid.grid_sym_op(numpy.eye(2))
