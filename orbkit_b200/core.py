@@ -255,7 +255,7 @@ def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, num
         labels = qc.mo_spec.get_labels(format='print')
         for i in range(mo_num):
             display('\t%.6f\tMO %s' % (mo_norm[i] * grid.d3r, labels[i]))
-    if not was_vector:
+    if not was_vector and not options.quiet:     # (a reduction over the whole grid: skipped when nothing is printed)
         display('We have ' + str(numpy.sum(rho) * grid.d3r) + ' electrons.')
     rho = rho.reshape(N)
     if hdf5_file is not None:
@@ -329,7 +329,7 @@ def rho_compute_no_slice(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=F
 
     rho, delta_rho, _ = _compute(qc, x, y, z, is_vector, N, False, False, drv, False)
     rho = rho.reshape(N)
-    if not was_vector:
+    if not was_vector and not options.quiet:
         display('We have ' + str(numpy.sum(rho) * d3r) + ' electrons.')
     if drv is None:
         return (ao_list, mo_list, rho) if return_components else rho

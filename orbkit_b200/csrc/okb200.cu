@@ -975,7 +975,7 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 // ---- launch machinery ---------------------------------------------------------------------------------------
 // the kernel instantiations live in inst_*.cu (compiled in parallel); okb_variant.h declares their tables
 static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_val, &okb_variants_grad,
-                                               &okb_variants_lap, &okb_variants_all};
+                                               &okb_variants_lap, &okb_variants_all, &okb_variants_d2};
 
 static const Variant *pick_variant(int set, int sink, int n_mo) {
     const Variant *best = nullptr;
@@ -1106,7 +1106,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
 
     // Passes: normally one pass with the smallest covering set.  AO/MO requests whose code list has
     // duplicates or is a single code use one SET_ONE pass per requested slot.
-    struct Pass { int set; int one_code; int slot[10]; };
+    struct Pass { int set; int one_code; int slot[10]; int epi = 0; };
     std::vector<Pass> passes;
     bool dup = false;
     {
@@ -1121,7 +1121,22 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
         ps.set = set; ps.one_code = 0;
         for (int k = 0; k < 10; ++k) ps.slot[k] = -1;
         for (int i = 0; i < rq.n_codes; ++i) ps.slot[rq.codes[i]] = i;
-        passes.push_back(ps);
+        // rho + pure second derivatives only (laplacian=True): two passes of the 4-set kernels instead of one pass
+        // of the 7-set kernel -- 8/7 of the flops, but at the gradient kernel's efficiency (the 7-set kernel is
+        // starved of registers: 8 consumer + 4 producer warps; measured 438 -> 39x ms on the benchmark).
+        //   pass 1  SET_GRAD, epi 1: rho, and sum 2 occ (d_d phi)^2 into the slots of codes 4..6
+        //   pass 2  SET_D2,   epi 2: those slots += sum 2 occ phi d_dd phi
+        bool pure_second = (set == SET_LAP);
+        for (int i = 0; i < rq.n_codes; ++i) pure_second &= (rq.codes[i] >= 4 && rq.codes[i] <= 6);
+        static const bool one_pass = getenv("OKB_LAP_ONE_PASS") != nullptr;
+        if (pure_second && !one_pass) {
+            ps.set = SET_GRAD; ps.epi = 1;
+            passes.push_back(ps);
+            ps.set = SET_D2; ps.epi = 2;
+            passes.push_back(ps);
+        } else {
+            passes.push_back(ps);
+        }
     } else if (rq.n_codes == 1 || dup) {
         for (int i = 0; i < rq.n_codes; ++i) {
             Pass ps;
@@ -1200,7 +1215,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.ntiles = (int)((sn + v->P - 1) / v->P);
             // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); the generic sets
             // work on the all-Cartesian layout
-            const bool use_mix = !b->mix_is_cart && (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP);
+            const bool use_mix = !b->mix_is_cart &&
+                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2);
             const Layout &lo = use_mix ? b->mix : b->cart;
             p.meta = lo.meta_dev;
             p.lay = lo.lay;
@@ -1221,10 +1237,11 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             for (int k = 0; k < 10; ++k) p.slot[k] = ps.slot[k];
             p.one_code = ps.one_code;
             p.exact_mixed = (rq.flags & OKB_FLAG_EXACT_MIXED) ? 1 : 0;
+            p.epi = ps.epi;
             if (rq.sink == SINK_RHO) {
                 p.rho = dev_out ? rq.rho + s0 : dbase;
                 p.delta = dev_out ? (rq.delta ? rq.delta + s0 : nullptr) : dbase + ld;
-                p.mo_norm = norm_dev;
+                p.mo_norm = ps.epi == 2 ? nullptr : norm_dev;    // the second laplacian pass must not add the norms again
             } else {
                 p.out = dev_out ? rq.out + s0 : dbase;
             }

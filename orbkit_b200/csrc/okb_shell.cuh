@@ -212,8 +212,11 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
-    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP, "specialised sets");
-    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP);
+    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2, "specialised sets");
+    // N1 / N2: radial sums R1 / R2 needed; W1 / W2: first / pure second derivative rows written; O2: tile set of d2/dx2
+    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP || SET == SET_D2);
+    constexpr bool W1 = (SET == SET_GRAD || SET == SET_LAP), W2 = N2;
+    constexpr int O2 = (SET == SET_D2) ? 1 : 4;
     constexpr int D = set_ncodes(SET);
     double r[NP][3], rr[NP];
 #pragma unroll
@@ -236,13 +239,13 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
             g0[a][0] = 1.0;
 #pragma unroll
             for (int l = 1; l <= L + 1; ++l) g0[a][l] = g0[a][l - 1] * r[q][a];
-            if (N1) {
+            if (W1) {
 #pragma unroll
                 for (int l = 0; l <= L; ++l)
                     g1[a][l] = (l == 0) ? g0[a][1] * m2R1
                                         : fma(g0[a][l + 1], m2R1, g0[a][l - 1] * ((double)l * R0[q]));
             }
-            if (N2) {
+            if (W2) {
                 const double r2R2 = 4.0 * (r[q][a] * r[q][a]) * R2[q];
 #pragma unroll
                 for (int l = 0; l <= L; ++l) {
@@ -265,13 +268,15 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 if (N1) {
                     const double fxz = fz * g0[0][lx];
                     const double fxy = f * (g0[0][lx] * g0[1][ly]);
-                    o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
-                    o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
-                    o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
-                    if (N2) {
-                        o[((size_t)4 * KC + j) * STRIDE] = fyz * g2[0][lx];
-                        o[((size_t)5 * KC + j) * STRIDE] = fxz * g2[1][ly];
-                        o[((size_t)6 * KC + j) * STRIDE] = fxy * g2[2][lz];
+                    if (W1) {
+                        o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
+                        o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
+                        o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
+                    }
+                    if (W2) {
+                        o[((size_t)(O2 + 0) * KC + j) * STRIDE] = fyz * g2[0][lx];
+                        o[((size_t)(O2 + 1) * KC + j) * STRIDE] = fxz * g2[1][ly];
+                        o[((size_t)(O2 + 2) * KC + j) * STRIDE] = fxy * g2[2][lz];
                     }
                 }
             }
@@ -292,13 +297,15 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 if (N1) {
                     const double fxz = fz * g0[0][lx];
                     const double fxy = f * (g0[0][lx] * g0[1][ly]);
-                    v[j][1] = fyz * g1[0][lx];
-                    v[j][2] = fxz * g1[1][ly];
-                    v[j][3] = fxy * g1[2][lz];
-                    if (N2) {
-                        v[j][4] = fyz * g2[0][lx];
-                        v[j][5] = fxz * g2[1][ly];
-                        v[j][6] = fxy * g2[2][lz];
+                    if (W1) {
+                        v[j][1] = fyz * g1[0][lx];
+                        v[j][2] = fxz * g1[1][ly];
+                        v[j][3] = fxy * g1[2][lz];
+                    }
+                    if (W2) {
+                        v[j][O2 + 0] = fyz * g2[0][lx];
+                        v[j][O2 + 1] = fxz * g2[1][ly];
+                        v[j][O2 + 2] = fxy * g2[2][lz];
                     }
                 }
             }
@@ -329,8 +336,8 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp,
                                               int one_code, int exact, const AxTab &tab) {
-    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) {
-        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP) ? SET : SET_VAL;
+    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2) {
+        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2) ? SET : SET_VAL;
         if (sh.kind == 1) {                  // warp-uniform
             switch (sh.L) {
                 case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;

@@ -392,11 +392,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                                 const double phi = acc[ia][ib][0][e];
                                 if ((q0 + pt_w + ib * 8 + 2 * tc + e) < p.npts) nrm += phi * phi;
                                 osum[0][ib][e] += oc * (phi * phi);
-                                if (D >= 4) {
+                                if (SET == SET_D2) {
+                                    // second pass of rho + laplacian: sum_i 2 occ phi d2phi (the first pass added
+                                    // sum_i 2 occ (d phi)^2 and wrote rho)
+                                    osum[1][ib][e] += o2 * (acc[ia][ib][1][e] * phi);
+                                    osum[2][ib][e] += o2 * (acc[ia][ib][2][e] * phi);
+                                    osum[3][ib][e] += o2 * (acc[ia][ib][3][e] * phi);
+                                } else if (D >= 4) {
                                     const double gx = acc[ia][ib][1][e], gy = acc[ia][ib][2][e], gz = acc[ia][ib][3][e];
-                                    osum[1][ib][e] += o2 * (gx * phi);
-                                    osum[2][ib][e] += o2 * (gy * phi);
-                                    osum[3][ib][e] += o2 * (gz * phi);
+                                    if (SET == SET_GRAD && p.epi == 1) {         // first pass of rho + laplacian
+                                        osum[1][ib][e] += o2 * (gx * gx);
+                                        osum[2][ib][e] += o2 * (gy * gy);
+                                        osum[3][ib][e] += o2 * (gz * gz);
+                                    } else {
+                                        osum[1][ib][e] += o2 * (gx * phi);
+                                        osum[2][ib][e] += o2 * (gy * phi);
+                                        osum[3][ib][e] += o2 * (gz * phi);
+                                    }
                                     if (D >= 7) {
                                         osum[4][ib][e] += o2 * (acc[ia][ib][4][e] * phi + gx * gx);
                                         osum[5][ib][e] += o2 * (acc[ia][ib][5][e] * phi + gy * gy);
@@ -440,11 +452,15 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
 #pragma unroll
                     for (int w = 0; w < WM; ++w) sum += red[((size_t)w * C::NOUT + o) * P + pt];
                     if (q0 + pt < p.npts) {
+                        const bool two_pass = (SET == SET_D2) || (SET == SET_GRAD && p.epi == 1);
                         if (o == 0) {
-                            if (p.rho != nullptr) p.rho[q0 + pt] = sum;
+                            if (p.rho != nullptr && SET != SET_D2) p.rho[q0 + pt] = sum;
                         } else {
-                            const int sl = p.slot[o];
-                            if (sl >= 0) p.delta[(size_t)sl * p.ld + q0 + pt] = sum;
+                            const int sl = p.slot[two_pass ? o + 3 : o];     // two-pass laplacian: codes 4..6
+                            if (sl >= 0) {
+                                double *dst = p.delta + (size_t)sl * p.ld + q0 + pt;
+                                *dst = (SET == SET_D2) ? *dst + sum : sum;
+                            }
                         }
                     }
                 }

@@ -34,20 +34,17 @@ def build_cart2sph_csr(ao_spec):
     (contraction j0, (l,m)) the Cartesian rows of contraction j0 whose exponent triple matches each
     table term, with value coef*factor.  A table term without a matching Cartesian function raises
     (the reference would silently reuse the previous row index)."""
-    lxlylz = ao_spec.get_lxlylz()
-    assign = ao_spec.get_assign_lxlylz_to_cont()
-    rows_of = {}
-    for i, j in enumerate(assign):
-        rows_of.setdefault(int(j), []).append(i)
+    lxlylz = [tuple(t) for t in numpy.asarray(ao_spec.get_lxlylz()).tolist()]
+    assign = numpy.asarray(ao_spec.get_assign_lxlylz_to_cont()).tolist()
+    row_of = {}                      # (contraction, exponent triple) -> Cartesian row (the last match, like the reference)
+    for i, (j, e) in enumerate(zip(assign, lxlylz)):
+        row_of[(j, e)] = i
     ptr, col, val = [0], [], []
     for j0, lm in ao_spec.get_old_ao_spherical():
         exps, coefs, factor = get_cart2sph(int(lm[0]), int(lm[1]))
-        rows = rows_of[int(j0)]
+        j0 = int(j0)
         for e, c in zip(exps, coefs):
-            hit = None
-            for i in rows:
-                if tuple(int(v) for v in lxlylz[i]) == tuple(e):
-                    hit = i
+            hit = row_of.get((j0, tuple(e)))
             if hit is None:
                 raise ValueError('cartesian2spherical: contraction %d has no Cartesian function %s '
                                  'needed by (l,m)=%s' % (j0, e, tuple(lm)))
