@@ -169,11 +169,15 @@ int okb_eval_rho_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long
  *   OKB_CI_RHO        out[npts]          = sum_t coef mo[ia] mo[ib]
  *   OKB_CI_JAB        out[3][npts]       = sum_t -1/2 coef (mo[ia] dmo[d][ib] - mo[ib] dmo[d][ia])
  *   OKB_CI_A_NABLA_B  out[3][npts]       = sum_t coef mo[ia] dmo[d][ib]
- *   OKB_CI_PAIRS      out[n_terms][npts] = mo[ia] mo[ib]       (per-pair products; coef ignored) */
+ *   OKB_CI_PAIRS      out[n_terms][npts] = mo[ia] ket[ib]      (per-pair products, coef ignored; ket = molistdrv[n_mo][.]
+ *                     if given, else mo: the products of core.calc_mo_matrix, core.py:925-941)
+ *   OKB_CI_JAB_PAIRS  out[3][n_terms][npts] = -1/2 (mo[ia] dmo[d][ib] - mo[ib] dmo[d][ia]) per pair (extras.calc_jmo,
+ *                     extras.py:441-493, restricted to the requested pairs; coef ignored) */
 #define OKB_CI_RHO 0
 #define OKB_CI_JAB 1
 #define OKB_CI_A_NABLA_B 2
 #define OKB_CI_PAIRS 3
+#define OKB_CI_JAB_PAIRS 4
 #define OKB_FLAG_IN_DEVICE 4u    /* okb_ci_contract: molist / molistdrv are DEVICE pointers */
 /* Level 1: given MO arrays molist[n_mo][ld_in] and (JAB, A_NABLA_B) molistdrv[3][n_mo][ld_in]; the first
  * npts points of every row are contracted into the first npts entries of the rows of out[.][ld_out]
@@ -181,9 +185,10 @@ int okb_eval_rho_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long
 int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
                     const double *molist, const double *molistdrv, int n_terms, const double *coef,
                     const int *ia, const int *ib, double *out, long long ld_out, unsigned flags);
-/* Level 2 (fused): the MOs of `mo` (and, for JAB / A_NABLA_B, the three derivative sets drv_codes[3],
- * e.g. {1,2,3} or {4,5,6}) are evaluated slab by slab on the device over the points [p0, p1) of `grid`
- * and contracted there; MO values never cross PCIe.  out as above with npts = p1 - p0. */
+/* Level 2 (fused): the MOs of `mo` (and, for JAB / A_NABLA_B / JAB_PAIRS, the three derivative sets drv_codes[3],
+ * e.g. {1,2,3} or {4,5,6}; for PAIRS optionally ONE set drv_codes[0] for the second factor) are evaluated slab by
+ * slab on the device over the points [p0, p1) of `grid` and contracted there; MO values never cross PCIe.
+ * out as above with npts = p1 - p0. */
 int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long long p1, int mode,
                 const int *drv_codes, int n_terms, const double *coef, const int *ia,
                 const int *ib, double *out, unsigned flags);

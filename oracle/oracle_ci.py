@@ -126,3 +126,60 @@ def jab(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
 
 def a_nabla_b(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
     return _vec('get_a_nabla_b', 'okor_ci_a_nabla_b', zero, sing, molist, molistdrv, slice_length, kind)
+
+
+# ---- core.calc_mo_matrix / extras.calc_jmo ------------------------------------------------------------------
+def calc_mo_matrix(qc_a, x, y, z, is_vector=False, qc_b=None, drv=None, kind='port'):
+    """mo_matrix[d, n, m] = mo_bra[n] * d_drv[d] mo_ket[m] on the grid (core.py:841-941).
+
+    drv None -> ket = the MO values (one set); a string -> that one derivative; a list -> one set per entry
+    (core.py:881-890).  MOs come from the oracle's rho_compute(calc_mo=True) as in core.py:894-918.
+    NOTE: the reference's two-QCinfo branch raises TypeError for every input (`drv[ibra]` with a list index,
+    core.py:906); for qc_b the evident intent is restated here: bra = MO values of qc_a, ket = the requested sets
+    of qc_b.  That branch is therefore NOT pinned by any reference output."""
+    import oracle
+    if drv is None:
+        dl, iket = [None], [0]
+    elif not isinstance(drv, list):
+        dl, iket = [None, drv], [1]
+    else:
+        dl, iket = [None] + drv, list(range(1, len(drv) + 1))
+    if qc_b is None or qc_b is qc_a:
+        mo = oracle.rho_compute(qc_a, x, y, z, is_vector=is_vector, calc_mo=True, drv=dl, kind=kind)
+        mo_bra, mo_ket = mo[[0]], mo[iket]
+    else:
+        mo_bra = oracle.rho_compute(qc_a, x, y, z, is_vector=is_vector, calc_mo=True, drv=[None], kind=kind)
+        mo_ket = oracle.rho_compute(qc_b, x, y, z, is_vector=is_vector, calc_mo=True, drv=[dl[i] for i in iket],
+                                    kind=kind)
+    nmo_a, nmo_b = mo_bra.shape[1], mo_ket.shape[1]
+    out = np.zeros((mo_ket.shape[0], nmo_a) + mo_ket.shape[1:])
+    for n in range(nmo_a):                      # core.py:939-941
+        for m in range(nmo_b):
+            out[:, n, m] = mo_bra[:, n] * mo_ket[:, m]
+    return out
+
+
+def jmo_from_matrix(mo_matrix, indices):
+    """jmo[:, n] = -0.5 * (mo_matrix[:, i, j] - mo_matrix[:, j, i])   (extras.py:480-483)"""
+    jmo = np.zeros((mo_matrix.shape[0], len(indices)) + mo_matrix.shape[3:])
+    for n, (i, j) in enumerate(indices):
+        jmo[:, n] = - 0.5 * (mo_matrix[:, i, j] - mo_matrix[:, j, i])
+    return jmo
+
+
+def calc_jmo(qc, ij, x, y, z, is_vector=False, drv=['x', 'y', 'z'], kind='port', select=None):
+    """extras.calc_jmo (extras.py:441-493): the MOs named in `ij` are selected (numpy.unique), their
+    mo_matrix is formed and antisymmetrised per pair.  `select(qc, u)` returns the QCinfo restricted to the
+    MO indices u (defaults to qc.copy() + mo_spec[u], as the reference does)."""
+    ij = np.asarray(ij)
+    if ij.ndim == 1 and len(ij) == 2:
+        ij = ij.reshape((1, 2))
+    assert ij.ndim == 2 and ij.shape[1] == 2
+    u, indices = np.unique(ij, return_inverse=True)
+    indices = indices.reshape((-1, 2))
+    if select is None:
+        qs = qc.copy()
+        qs.mo_spec = qc.mo_spec[u]
+    else:
+        qs = select(qc, u)
+    return jmo_from_matrix(calc_mo_matrix(qs, x, y, z, is_vector=is_vector, drv=drv, kind=kind), indices)

@@ -339,25 +339,50 @@ def rho_compute_no_slice(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=F
             if return_components else (rho,) + delta)
 
 
-def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_hdf5=False, **kwargs):
-    """Products mo_bra[n] * d_drv mo_ket[m] on the grid (core.py:841-941); host-side outer product of
-    the device-computed MO arrays."""
+def _ket_sets(drv):
+    """the ket derivative sets of calc_mo_matrix (core.py:881-890): None -> the MO values, a string -> that one
+    derivative, a list -> one set per entry"""
     if drv is None:
-        dl, iket = [None], [0]
-    elif not isinstance(drv, list):
-        dl, iket = [None, drv], [1]
+        return [None]
+    return list(drv) if isinstance(drv, list) else [drv]
+
+
+def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_hdf5=False, **kwargs):
+    """mo_matrix[d, n, m] = mo_bra[n] * d_drv[d] mo_ket[m] on the module grid: ((NDRV, NMO_a, NMO_b) + N)
+    (core.py:841-941).
+
+    One QCinfo (the case extras.calc_jmo uses): per ket set the MOs and their derivative are evaluated slab by
+    slab on the device and the NMO^2 products are formed there (okb_eval_ci, OKB_CI_PAIRS); only the products
+    cross PCIe.  Two QCinfos: the reference's branch raises TypeError for every input (`drv[ibra]` with a list
+    index, core.py:906); its evident intent -- bra = MO values of qc_a, ket = the requested sets of qc_b -- is
+    implemented: both MO arrays are evaluated on the device and their products formed by okb_ci_contract."""
+    from ._lib import OKB_CI_PAIRS
+    if save_hdf5:
+        raise NotImplementedError('save_hdf5: file output is outside the grid-based compute path')
+    sets = _ket_sets(drv)
+    codes = [validate_drv(d) for d in sets]
+    x, y, z, is_vector, N = _resolve_grid(None, None, None, None, init_vector=False)
+    npts = int(numpy.prod(N))
+    eng = get_engine()
+    same = qc_b is None or qc_b is qc_a or qc_a == qc_b
+    nmo_a = len(qc_a.mo_spec)
+    nmo_b = nmo_a if same else len(qc_b.mo_spec)
+    if npts == 0 or nmo_a == 0 or nmo_b == 0:
+        return numpy.zeros((len(codes), nmo_a, nmo_b) + N)
+    ia = numpy.repeat(numpy.arange(nmo_a, dtype=numpy.intc), nmo_b)
+    ib = numpy.tile(numpy.arange(nmo_b, dtype=numpy.intc), nmo_a)
+    out = eng.host_array((len(codes), nmo_a * nmo_b, npts))
+    if same:
+        basis = eng.basis(require(qc_a.geo_spec, dtype='f'), qc_a.ao_spec)
+        mo = eng.mos(basis, qc_a.mo_spec.get_coeffs(), qc_a.mo_spec.get_occ())
+        g = _grid_handle(eng, x, y, z, is_vector)
+        terms = (numpy.zeros(len(ia)), ia, ib)
+        for d, code in enumerate(codes):
+            eng.eval_ci(OKB_CI_PAIRS, terms, mo, g, drv_codes=[code], out=out[d], flags=_flags())
     else:
-        dl, iket = [None] + drv, list(range(1, len(drv) + 1))
-    if qc_b is None or qc_a == qc_b:
-        mo = rho_compute(qc_a, calc_mo=True, drv=dl, numproc=numproc, slice_length=slice_length)
-        mo_bra, mo_ket = mo[[0]], mo[iket]
-    else:
-        mo_bra = rho_compute(qc_a, calc_mo=True, drv=[None], numproc=numproc, slice_length=slice_length)
-        mo_ket = rho_compute(qc_b, calc_mo=True, drv=[dl[i] for i in iket], numproc=numproc,
-                             slice_length=slice_length)
-    nmo_a, nmo_b = mo_bra.shape[1], mo_ket.shape[1]
-    out = numpy.zeros((mo_ket.shape[0], nmo_a) + mo_ket.shape[1:])
-    for n in range(nmo_a):
-        for m in range(nmo_b):
-            out[:, n, m] = mo_bra[:, n] * mo_ket[:, m]
-    return out
+        bra = _compute(qc_a, x, y, z, is_vector, N, False, True, None, False)[0]
+        ket = _compute(qc_b, x, y, z, is_vector, N, False, True, sets, False)
+        terms = (numpy.zeros(len(ia)), ia, (ib + nmo_a).astype(numpy.intc))
+        for d in range(len(codes)):
+            eng.ci_contract(OKB_CI_PAIRS, terms, numpy.concatenate([bra, ket[d]]), out=out[d])
+    return out.reshape((len(codes), nmo_a, nmo_b) + N)

@@ -1325,7 +1325,9 @@ extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long 
 }
 
 // ---- detCI grid contractions ------------------------------------------------------------------------------------
-static int ci_ncomp(int mode, int n_terms) { return mode == CI_RHO ? 1 : mode == CI_PAIRS ? n_terms : 3; }
+static int ci_ncomp(int mode, int n_terms, int nd) {
+    return mode == CI_RHO ? 1 : mode == CI_PAIRS ? n_terms : mode == CI_JPAIRS ? nd * n_terms : 3;
+}
 
 static int ci_reserve(okb_ctx *ctx, size_t bytes) {
     if (ctx->ci_bytes >= bytes) return OKB_OK;
@@ -1340,10 +1342,11 @@ static int ci_reserve(okb_ctx *ctx, size_t bytes) {
 static int ci_check(okb_ctx *ctx, int mode, int n_mo, int n_terms, const double *coef, const int *ia, const int *ib,
                     const double *out) {
     if (!ctx) return fail(OKB_ERR_ARG, "ci: null context");
-    if (mode < CI_RHO || mode > CI_PAIRS) return fail(OKB_ERR_ARG, "ci: unknown mode %d", mode);
+    if (mode < CI_RHO || mode > CI_JPAIRS) return fail(OKB_ERR_ARG, "ci: unknown mode %d", mode);
     if (n_mo <= 0) return fail(OKB_ERR_ARG, "ci: n_mo must be positive");
     if (n_terms < 0) return fail(OKB_ERR_ARG, "ci: negative term count");
-    if (n_terms > 0 && (!ia || !ib || (mode != CI_PAIRS && !coef))) return fail(OKB_ERR_ARG, "ci: null term array");
+    if (n_terms > 0 && (!ia || !ib || (mode != CI_PAIRS && mode != CI_JPAIRS && !coef)))
+        return fail(OKB_ERR_ARG, "ci: null term array");
     if (!out) return fail(OKB_ERR_ARG, "ci: null output");
     for (int t = 0; t < n_terms; ++t)
         if (ia[t] < 0 || ia[t] >= n_mo || ib[t] < 0 || ib[t] >= n_mo)
@@ -1376,12 +1379,14 @@ static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
         case CI_RHO: okb_ci_kernel<CI_RHO><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         case CI_JAB: okb_ci_kernel<CI_JAB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         case CI_ANB: okb_ci_kernel<CI_ANB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        case CI_JPAIRS: okb_ci_kernel<CI_JPAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         default: okb_ci_kernel<CI_PAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "ci kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
-    ctx->last_kernel = mode == CI_RHO ? "ci/rho" : mode == CI_JAB ? "ci/jab" : mode == CI_ANB ? "ci/a_nabla_b" : "ci/pairs";
+    ctx->last_kernel = mode == CI_RHO ? "ci/rho" : mode == CI_JAB ? "ci/jab" : mode == CI_ANB ? "ci/a_nabla_b"
+                       : mode == CI_JPAIRS ? "ci/jpairs" : "ci/pairs";
     return OKB_OK;
 }
 
@@ -1393,10 +1398,12 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
     if (npts < 0) return fail(OKB_ERR_ARG, "okb_ci_contract: negative point count");
     if (ld_in < npts || ld_out < npts) return fail(OKB_ERR_ARG, "okb_ci_contract: row stride smaller than the point count");
     if (npts == 0) return OKB_OK;
-    const bool need_drv = (mode == CI_JAB || mode == CI_ANB);
-    if (!molist || (need_drv && !molistdrv)) return fail(OKB_ERR_ARG, "okb_ci_contract: null MO array");
+    // derivative / second-factor sets that come with molistdrv: 3 for JAB, A_NABLA_B and JPAIRS, 1 (optional) for PAIRS
+    const int nd = (mode == CI_JAB || mode == CI_ANB || mode == CI_JPAIRS) ? 3 : (mode == CI_PAIRS && molistdrv) ? 1 : 0;
+    const bool need_drv = nd > 0;
+    if (!molist || (nd == 3 && !molistdrv)) return fail(OKB_ERR_ARG, "okb_ci_contract: null MO array");
     const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
-    const int nsets = need_drv ? 4 : 1, ncomp = ci_ncomp(mode, n_terms);
+    const int nsets = 1 + nd, ncomp = ci_ncomp(mode, n_terms, 3);
     CU(cudaSetDevice(ctx->device));
     // slab geometry: device-resident inputs and outputs need no staging at all
     const size_t per_pt = (in_dev ? 0 : (size_t)nsets * n_mo * 8) + (out_dev ? 0 : (size_t)ncomp * 8);
@@ -1426,7 +1433,7 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
                                  cudaMemcpyHostToDevice, ctx->stream));
             if (need_drv)
                 CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * lds, (size_t)lds * 8, molistdrv + s0, (size_t)ld_in * 8,
-                                     (size_t)sn * 8, (size_t)3 * n_mo, cudaMemcpyHostToDevice, ctx->stream));
+                                     (size_t)sn * 8, (size_t)nd * n_mo, cudaMemcpyHostToDevice, ctx->stream));
             ctx->h2d_bytes += (long long)nsets * n_mo * sn * 8;
             p.mo = d_in;
             p.dmo = need_drv ? d_in + (size_t)n_mo * lds : nullptr;
@@ -1434,6 +1441,7 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
         }
         p.dstride = (long long)n_mo * p.ld;
         p.npts = sn;
+        p.ncomp = 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? ld_out : sn;
         rc = ci_launch(ctx, mode, p);
@@ -1459,11 +1467,15 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
     if (p0 < 0 || p1 > grid->npts || p1 < p0) return fail(OKB_ERR_ARG, "okb_eval_ci: point range outside the grid");
     const long long npts = p1 - p0;
     if (npts == 0) return OKB_OK;
-    const bool need_drv = (mode == CI_JAB || mode == CI_ANB);
+    // JAB / A_NABLA_B / JPAIRS: three derivative sets drv_codes[0..2]; PAIRS: drv_codes (may be NULL) names ONE set for the
+    // second factor (NULL or code 0: the MO values themselves)
+    const int nd = (mode == CI_JAB || mode == CI_ANB || mode == CI_JPAIRS) ? 3
+                   : (mode == CI_PAIRS && drv_codes && drv_codes[0] != 0)  ? 1 : 0;
+    const bool need_drv = nd > 0;
     int codes[4] = {0, 1, 2, 3};
     if (need_drv) {
         if (!drv_codes) return fail(OKB_ERR_ARG, "okb_eval_ci: null derivative codes");
-        for (int d = 0; d < 3; ++d) {
+        for (int d = 0; d < nd; ++d) {
             if (drv_codes[d] < 1 || drv_codes[d] > 9) return fail(OKB_ERR_ARG, "okb_eval_ci: derivative code %d not in 1..9", drv_codes[d]);
             for (int e = 0; e < d; ++e)
                 if (drv_codes[e] == drv_codes[d]) return fail(OKB_ERR_ARG, "okb_eval_ci: duplicate derivative code");
@@ -1471,7 +1483,7 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
         }
     }
     const bool out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
-    const int n_mo = mo->n_mo, nsets = need_drv ? 4 : 1, ncomp = ci_ncomp(mode, n_terms);
+    const int n_mo = mo->n_mo, nsets = 1 + nd, ncomp = ci_ncomp(mode, n_terms, 3);
     CU(cudaSetDevice(ctx->device));
     const size_t per_pt = (size_t)nsets * n_mo * 8 + (out_dev ? 0 : (size_t)ncomp * 8);
     long long slab = (long long)(((size_t)1 << 30) / per_pt) / 1024 * 1024;
@@ -1498,6 +1510,7 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
         p.ld = lds;
         p.dstride = (long long)n_mo * lds;
         p.npts = sn;
+        p.ncomp = 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? npts : sn;
         rc = ci_launch(ctx, mode, p);

@@ -4,7 +4,10 @@
 //   CI_RHO    out[x]    = sum_t c_t mo[a_t][x] mo[b_t][x]
 //   CI_JAB    out[d][x] = sum_t -1/2 c_t (mo[a_t][x] dmo[d][b_t][x] - mo[b_t][x] dmo[d][a_t][x])
 //   CI_ANB    out[d][x] = sum_t c_t mo[a_t][x] dmo[d][b_t][x]
-//   CI_PAIRS  out[t][x] = mo[a_t][x] mo[b_t][x]                     (per-pair products, store bound)
+//   CI_PAIRS  out[t][x] = mo[a_t][x] ket[b_t][x]                    (per-pair products, store bound; ket = mo unless a
+//                                                                     second array is given: core.calc_mo_matrix, core.py:925-941)
+//   CI_JPAIRS out[d][t][x] = -1/2 (mo[a_t] dmo[d][b_t] - mo[b_t] dmo[d][a_t])   per pair, d < ncomp (extras.calc_jmo,
+//                                                                     extras.py:441-493, only the requested pairs)
 //
 // One thread owns one grid point and walks the term list in the caller's order with the reference's
 // expression order and NO fused multiply-add (__dmul_rn / __dadd_rn), so for the same MO arrays the
@@ -17,11 +20,11 @@
 
 namespace okb {
 
-enum { CI_RHO = 0, CI_JAB = 1, CI_ANB = 2, CI_PAIRS = 3 };
+enum { CI_RHO = 0, CI_JAB = 1, CI_ANB = 2, CI_PAIRS = 3, CI_JPAIRS = 4 };
 
 struct CiParams {
     const double *mo;          // [n_mo][ld]
-    const double *dmo;         // [3][n_mo][ld] (JAB, ANB) or null
+    const double *dmo;         // [3][n_mo][ld] (JAB, ANB), [ncomp][n_mo][ld] (JPAIRS), [n_mo][ld] second factor (PAIRS) or null
     long long ld;              // row stride of mo / dmo in points
     long long dstride;         // n_mo * ld: distance between the three derivative blocks
     long long npts;
@@ -30,6 +33,7 @@ struct CiParams {
     const int *ta, *tb;        // term orbital indices
     double *out;
     long long ldo;             // row stride of out in points
+    int ncomp;                 // JPAIRS: number of derivative components (1..3)
 };
 
 constexpr int CI_NT = 128;     // threads per CTA = points per CTA
@@ -43,7 +47,9 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     const bool live = x < p.npts;
     const long long xc = live ? x : p.npts - 1;              // clamp: every thread takes part in the staging
     const double *mo = p.mo + xc;
-    const double *d0 = (MODE == CI_JAB || MODE == CI_ANB) ? p.dmo + xc : nullptr;
+    const double *d0 = (MODE == CI_JAB || MODE == CI_ANB || MODE == CI_JPAIRS) ? p.dmo + xc
+                       : (MODE == CI_PAIRS && p.dmo != nullptr)                 ? p.dmo + xc
+                                                                                : mo;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     for (int t0 = 0; t0 < p.n_terms; t0 += CI_TB) {
         const int nb = min(CI_TB, p.n_terms - t0);
@@ -62,7 +68,17 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
                 // rho[x] += citmp*molist[sta,x]*molist[stb,x]        (cy_ci.pyx:88,95)
                 acc0 = __dadd_rn(acc0, __dmul_rn(__dmul_rn(c, __ldg(mo + ra)), __ldg(mo + rb)));
             } else if (MODE == CI_PAIRS) {
-                if (live) p.out[(long long)(t0 + e) * p.ldo + x] = __dmul_rn(__ldg(mo + ra), __ldg(mo + rb));
+                // mo_matrix[n,m] = mo_bra[n]*mo_ket[m]                                  (core.py:939-941)
+                if (live) p.out[(long long)(t0 + e) * p.ldo + x] = __dmul_rn(__ldg(mo + ra), __ldg(d0 + rb));
+            } else if (MODE == CI_JPAIRS) {
+                // jmo[:,n] = -0.5*(mo_matrix[:,i,j] - mo_matrix[:,j,i])                 (extras.py:482)
+                const double ma = __ldg(mo + ra), mb = __ldg(mo + rb);
+                for (int d = 0; d < p.ncomp; ++d) {
+                    const double db = __ldg(d0 + d * p.dstride + rb), da = __ldg(d0 + d * p.dstride + ra);
+                    if (live)
+                        p.out[((long long)d * p.n_terms + t0 + e) * p.ldo + x] =
+                            __dmul_rn(-0.5, __dadd_rn(__dmul_rn(ma, db), -__dmul_rn(mb, da)));
+                }
             } else {
                 const double ma = __ldg(mo + ra), mb = (MODE == CI_JAB) ? __ldg(mo + rb) : 0.0;
                 double v[3];
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
             }
         }
     }
-    if (!live || MODE == CI_PAIRS) return;
+    if (!live || MODE == CI_PAIRS || MODE == CI_JPAIRS) return;
     p.out[x] = acc0;
     if (MODE != CI_RHO) {
         p.out[p.ldo + x] = acc1;

@@ -265,7 +265,9 @@ class Engine:
     # ---- detCI grid contractions ---------------------------------------------------------------------------
     @staticmethod
     def _ci_ncomp(mode, n_terms):
-        return 1 if mode == _lib.OKB_CI_RHO else (n_terms if mode == _lib.OKB_CI_PAIRS else 3)
+        if mode == _lib.OKB_CI_RHO:
+            return 1
+        return n_terms if mode == _lib.OKB_CI_PAIRS else (3 * n_terms if mode == _lib.OKB_CI_JAB_PAIRS else 3)
 
     def ci_contract(self, mode, terms, molist, molistdrv=None, n_mo=None, npts=None, ld=None, out=None, n_eval=None,
                     flags=0):
@@ -282,8 +284,9 @@ class Engine:
             ld = npts
             if molistdrv is not None:
                 molistdrv = _lib.f64(molistdrv)
-                if molistdrv.shape != (3, n_mo, npts):
-                    raise ValueError('molistdrv must have shape (3, NMO, N)')
+                want = (n_mo, npts) if mode == _lib.OKB_CI_PAIRS else (3, n_mo, npts)
+                if molistdrv.shape != want:
+                    raise ValueError('molistdrv must have shape %s' % (want,))
         ld = npts if ld is None else ld
         n_eval = npts if n_eval is None else n_eval
         ncomp = self._ci_ncomp(mode, len(coef))

@@ -1,6 +1,6 @@
 """User-facing wrappers over core.rho_compute with the reference's signatures
 (orbkit/extras.py: calc_mo :40-103, mo_set :105-205, calc_ao :208-260, atom2index :262-304,
-gross_atomic_density :306-385).
+gross_atomic_density :306-385, calc_jmo :441-493).
 
 File output (`otype`, orbkit/output/*) is outside the hot path: requesting it raises
 NotImplementedError; with otype=None (the library use) the return values are those of the reference.
@@ -163,3 +163,50 @@ def gross_atomic_density(atom, qc, bReturnmo=False, ao_list=None, mo_list=None, 
         return rho_atom, mo_atom
     display('Returning the gross atomic density')
     return rho_atom
+
+
+def calc_jmo(qc, ij, drv=['x', 'y', 'z'], numproc=1, otype=None, ofid='', **kwargs):
+    """Transition electronic flux density between the molecular orbitals i and j for every pair in `ij`:
+    jmo[d, n] = -1/2 (mo_i d_d mo_j - mo_j d_d mo_i), shape ((len(drv), len(ij)) + N) (extras.py:441-493).
+
+    The reference forms the full NMO^2 product matrix of the selected orbitals (core.calc_mo_matrix) and then
+    picks the pairs; here the selected MOs and their derivative sets are evaluated slab by slab on the device and
+    only the requested pairs are formed there (okb_eval_ci, OKB_CI_JAB_PAIRS), with the reference's expression
+    order and no FMA contraction."""
+    from ._lib import OKB_CI_JAB_PAIRS, OKB_CI_PAIRS
+    from .engine import get_engine
+    from .tools import require, validate_drv
+    _no_output(otype)
+    ij = numpy.asarray(ij)
+    if ij.ndim == 1 and len(ij) == 2:
+        ij = ij.reshape((1, 2))
+    assert ij.ndim == 2
+    assert ij.shape[1] == 2
+    u, indices = numpy.unique(ij, return_inverse=True)
+    indices = indices.reshape((-1, 2))
+    qc_select = qc.copy()
+    qc_select.mo_spec = qc.mo_spec[u]
+    drv = list(drv) if isinstance(drv, (list, tuple)) else [drv]
+    codes = [validate_drv(d) for d in drv]
+    if any(c == 0 for c in codes):
+        raise ValueError('`drv` must name derivatives, e.g. ["x","y","z"]')
+    x, y, z, is_vector, N = core._resolve_grid(None, None, None, None)
+    npts, n = int(numpy.prod(N)), len(indices)
+    if npts == 0 or n == 0:
+        return numpy.zeros((len(codes), n) + N)
+    eng = get_engine()
+    basis = eng.basis(require(qc_select.geo_spec, dtype='f'), qc_select.ao_spec)
+    mo = eng.mos(basis, qc_select.mo_spec.get_coeffs(), qc_select.mo_spec.get_occ())
+    g = core._grid_handle(eng, x, y, z, is_vector)
+    ia = numpy.ascontiguousarray(indices[:, 0], dtype=numpy.intc)
+    ib = numpy.ascontiguousarray(indices[:, 1], dtype=numpy.intc)
+    if len(codes) == 3 and len(set(codes)) == 3:
+        out = eng.eval_ci(OKB_CI_JAB_PAIRS, (numpy.zeros(n), ia, ib), mo, g, drv_codes=codes, flags=core._flags())
+        return out.reshape((3, n) + N)
+    # any other number of components: the two products of every pair per component, combined on the host
+    jmo = numpy.zeros((len(codes), n, npts))
+    terms = (numpy.zeros(2 * n), numpy.concatenate([ia, ib]), numpy.concatenate([ib, ia]))
+    for d, code in enumerate(codes):
+        prod = eng.eval_ci(OKB_CI_PAIRS, terms, mo, g, drv_codes=[code], flags=core._flags())
+        jmo[d] = - 0.5 * (prod[:n] - prod[n:])
+    return jmo.reshape((len(codes), n) + N)

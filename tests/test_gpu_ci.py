@@ -177,3 +177,43 @@ def test_gross_atomic_density(ok, oracle_mod):
     assert ok.extras.gross_atomic_density(1, qc)[0].shape == (6, 6, 6)
     with pytest.raises(ValueError):
         ok.extras.gross_atomic_density(7, qc)
+
+
+def test_calc_mo_matrix_and_calc_jmo(ok, oci):
+    """core.calc_mo_matrix (core.py:841-941) and extras.calc_jmo (extras.py:441-493) on the device against the
+    reference's own outputs (tests/golden/h2o_mo_matrix.npz) and the pinned oracle"""
+    from conftest import golden_qc
+    qc, g = golden_qc('h2o_mo_matrix')
+    x, y, z = g['grid.x'], g['grid.y'], g['grid.z']
+    ok.grid.set_grid(x, y, z, is_vector=False)
+    eng = ok.engine.get_engine()
+    assert_close(ok.core.calc_mo_matrix(qc, drv=['x', 'y', 'z']), g['mm_xyz'], 'mo_matrix xyz')
+    assert eng.last_kernel() == 'ci/pairs'
+    assert_close(ok.core.calc_mo_matrix(qc), g['mm_none'], 'mo_matrix')
+    assert_close(ok.core.calc_mo_matrix(qc, drv='xx'), g['mm_xx'], 'mo_matrix xx')
+    assert_close(ok.extras.calc_jmo(qc, g['ij']), g['jmo'], 'jmo')
+    assert eng.last_kernel() == 'ci/jpairs'
+    assert_close(ok.extras.calc_jmo(qc, g['ij'], drv=['z', 'x']), g['jmo_zx'], 'jmo zx')
+    assert_close(ok.extras.calc_jmo(qc, [4, 1]), g['jmo_one'], 'jmo one pair')
+    # two QCinfos (the reference's branch raises TypeError, core.py:906): the restated intent, against the oracle
+    qa, qb = qc.copy(), qc.copy()
+    qa.mo_spec = qc.mo_spec[numpy.array([0, 1, 2])]
+    qb.mo_spec = qc.mo_spec[numpy.array([1, 2, 3, 4])]
+    got = ok.core.calc_mo_matrix(qa, qb, drv=['z', 'y'])
+    assert got.shape == (2, 3, 4, 5, 6, 7)
+    assert_close(got, oci.calc_mo_matrix(qa, x, y, z, qc_b=qb, drv=['z', 'y']), 'mo_matrix a,b')
+    # vector grid, ragged point count, more pairs than a term batch, a larger molecule
+    qc, a = golden_qc('synth_small_sph')
+    ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
+    rng = numpy.random.default_rng(5)
+    ij = rng.integers(0, len(qc.mo_spec), size=(300, 2))
+    got = ok.extras.calc_jmo(qc, ij)
+    ref = oci.calc_jmo(qc, ij, a['vx'], a['vy'], a['vz'], is_vector=True)
+    assert got.shape == (3, 300, len(a['vx']))
+    assert_close(got, ref, 'jmo synth')
+    # antisymmetry is exact: j(i, j) == -j(j, i)
+    assert numpy.array_equal(ok.extras.calc_jmo(qc, ij[:, ::-1]), -got)
+    with pytest.raises(ValueError):
+        ok.extras.calc_jmo(qc, ij, drv=[None, 'x', 'y'])
+    with pytest.raises(NotImplementedError):
+        ok.extras.calc_jmo(qc, ij, otype='h5')

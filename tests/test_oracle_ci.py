@@ -105,3 +105,19 @@ def test_flatten_and_merge_host_logic():
         ci_core.flatten_terms([[[1.0]], [[0, 1]]], sing)
     with pytest.raises(ValueError):
         ci_core.flatten_terms(zero, [[1.0], []])
+
+
+def test_mo_matrix_and_jmo_golden_reproduced(oci, oracle_mod):
+    """core.calc_mo_matrix / extras.calc_jmo restated in oracle_ci == the reference's own outputs
+    (tests/golden/h2o_mo_matrix.npz, written by running the reference: make_golden_jmo.py), bit for bit."""
+    from conftest import golden_qc
+    qc, g = golden_qc('h2o_mo_matrix')
+    x, y, z = g['grid.x'], g['grid.y'], g['grid.z']
+    for kind in ['port'] + (['ref'] if oracle_mod.have_ref() else []):
+        assert numpy.array_equal(oci.calc_mo_matrix(qc, x, y, z, drv=['x', 'y', 'z'], kind=kind), g['mm_xyz'])
+        assert numpy.array_equal(oci.calc_mo_matrix(qc, x, y, z, kind=kind), g['mm_none'])
+        assert numpy.array_equal(oci.calc_mo_matrix(qc, x, y, z, drv='xx', kind=kind), g['mm_xx'])
+        assert numpy.array_equal(oci.calc_jmo(qc, g['ij'], x, y, z, kind=kind), g['jmo'])
+        assert numpy.array_equal(oci.calc_jmo(qc, g['ij'], x, y, z, drv=['z', 'x'], kind=kind), g['jmo_zx'])
+        assert numpy.array_equal(oci.calc_jmo(qc, [4, 1], x, y, z, kind=kind), g['jmo_one'])
+    assert g['jmo'].shape == (3, 5, 5, 6, 7) and (g['jmo'][:, 3] == 0.0).all()     # the pair (3, 3) has no flux
