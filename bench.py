@@ -283,7 +283,7 @@ def run_b200(args):
                     'ok': e2e_ok},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
             'electrons': electrons}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -350,7 +350,7 @@ def run_reference(args):
                              'sample': sample, 'host_cores': cores},
             'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -364,6 +364,12 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     ap.add_argument('--no-peaks', action='store_true', help='skip the FP64 peak microbenchmarks (profiling runs)')
     args = ap.parse_args()
+    # stdout carries the ONE JSON line only: libraries that write to file descriptor 1 (NCCL's version banner at
+    # communicator creation) are sent to stderr; the JSON line goes to the original descriptor
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, 'w')
     if args.impl == 'reference':
         run_reference(args)
     else:
