@@ -193,6 +193,19 @@ int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long lon
                 const int *drv_codes, int n_terms, const double *coef, const int *ia,
                 const int *ib, double *out, unsigned flags);
 
+/* ---- output sink: Gaussian cube text (orbkit/output/cube.py:5-101, cube_creator) ------------------------------
+ * The data loop of cube_creator (cube.py:86-96) on the device: data[n_sets][nx][ny][nz] (C order, float64) becomes
+ * the text the reference writes -- per (x, y) row the nz * n_sets values ('%.5E' right-justified in 13 columns, the
+ * sets of one point next to each other), a newline behind every 6th value of the row and one at its end.  '%.5E' is
+ * correctly rounded (round-half-even on the exact binary value) like Python's float formatting, so the bytes are
+ * identical to the reference's.  The few header lines (cube.py:47-84) stay on the host.
+ * okb_cube_body_bytes: size of that text, nx * ny * (13 n + n/6 + 1) with n = nz * n_sets (-1 for bad extents).
+ * okb_format_cube: `data` host (default) or device (OKB_FLAG_IN_DEVICE) pointer; `text` host (default) or device
+ * (OKB_FLAG_OUT_DEVICE) buffer of `capacity` >= okb_cube_body_bytes(...) bytes; host buffers are staged in slabs. */
+long long okb_cube_body_bytes(int n_sets, long long nx, long long ny, long long nz);
+int okb_format_cube(okb_ctx *ctx, const double *data, int n_sets, long long nx, long long ny, long long nz,
+                    char *text, long long capacity, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,11 +10,12 @@ CUDA kernels behind the C ABI of include/okb200.h; there is no CPU fallback.
 from . import options, grid, tools, cy_grid
 from .qcinfo import QCinfo
 from .orbitals import AOClass, MOClass
-from . import cy_core, core, extras, detci
+from . import cy_core, core, extras, detci, output
 from .core import ao_creator, mo_creator, rho_compute, rho_compute_no_slice
 from .extras import calc_ao, calc_mo, mo_set
+from .output import main_output
 
 __version__ = '0.1.0'
-__all__ = ['options', 'grid', 'tools', 'cy_grid', 'cy_core', 'core', 'extras', 'detci', 'QCinfo', 'AOClass',
+__all__ = ['options', 'grid', 'tools', 'cy_grid', 'cy_core', 'core', 'extras', 'detci', 'output', 'main_output', 'QCinfo', 'AOClass',
            'MOClass', 'ao_creator', 'mo_creator', 'rho_compute', 'rho_compute_no_slice', 'calc_ao',
            'calc_mo', 'mo_set']

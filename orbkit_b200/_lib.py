@@ -90,6 +90,9 @@ SIGNATURES = {
     'okb_eval_ci': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, ctypes.c_int,
                                    c_int_p, ctypes.c_int, c_double_p, c_int_p, c_int_p, ctypes.c_void_p,
                                    ctypes.c_uint]),
+    'okb_cube_body_bytes': (ll, [ctypes.c_int, ll, ll, ll]),
+    'okb_format_cube': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ll, ll, ll, ctypes.c_void_p, ll,
+                                       ctypes.c_uint]),
 }
 
 _lock = threading.Lock()

@@ -30,6 +30,7 @@
 #include "okb_ws.cuh"      // pad_stride
 #include "okb_misc.cuh"
 #include "okb_ci.cuh"
+#include "okb_text.cuh"
 
 using namespace okb;
 
@@ -210,6 +211,7 @@ extern "C" int okb_ctx_create(int device, okb_ctx **out) {
         CU(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     }
+    CU(cudaMemcpyToSymbol(g_pow10, OKB_POW10_TABLE, sizeof(OKB_POW10_TABLE)));   // '%.5E' formatter (okb_text.cuh)
     *out = c;
     return OKB_OK;
 }
@@ -1519,6 +1521,76 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
             CU(cudaMemcpy2DAsync(out + s0, (size_t)npts * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,
                                  cudaMemcpyDeviceToHost, ctx->stream));
             ctx->d2h_bytes += (long long)ncomp * sn * 8;
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (!out_dev) CU(cudaStreamSynchronize(ctx->stream));
+    return OKB_OK;
+}
+
+// ---- cube text (output sink) ------------------------------------------------------------------------------------
+extern "C" long long okb_cube_body_bytes(int n_sets, long long nx, long long ny, long long nz) {
+    if (n_sets <= 0 || nx < 0 || ny < 0 || nz < 0) return -1;
+    return nx * ny * cube_row_bytes(nz * n_sets);
+}
+
+extern "C" int okb_format_cube(okb_ctx *ctx, const double *data, int n_sets, long long nx, long long ny, long long nz,
+                               char *text, long long capacity, unsigned flags) {
+    if (!ctx) return fail(OKB_ERR_ARG, "okb_format_cube: null context");
+    if (n_sets <= 0 || nx < 0 || ny < 0 || nz < 0) return fail(OKB_ERR_ARG, "okb_format_cube: bad extents");
+    if (nz * n_sets > (1ll << 31) - 1 || nz > (1ll << 31) - 1) return fail(OKB_ERR_ARG, "okb_format_cube: row too long");
+    const long long nrows = nx * ny, n = nz * n_sets, rb = cube_row_bytes(n), total = nrows * rb;
+    if (capacity < total) return fail(OKB_ERR_ARG, "okb_format_cube: text buffer of %lld bytes, %lld needed", capacity, total);
+    if (nrows == 0) return OKB_OK;
+    if (!data || !text) return fail(OKB_ERR_ARG, "okb_format_cube: null buffer");
+    const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
+    CU(cudaSetDevice(ctx->device));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(okb_cube_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CUBE_SMEM));
+        attr_set = true;
+    }
+    // rows per slab: staged input + staged text of at most ~256 MB
+    const size_t per_row = (in_dev ? 0 : (size_t)n * 8) + (out_dev ? 0 : (size_t)rb);
+    long long slab = per_row ? std::max<long long>(1, (long long)(((size_t)256 << 20) / per_row)) : nrows;
+    slab = std::min(slab, nrows);
+    // a slab's text must start 16-byte aligned only for speed; any offset is handled by the kernel
+    const size_t in_bytes = in_dev ? 0 : (((size_t)slab * n * 8 + 255) / 256) * 256;
+    const size_t out_bytes = out_dev ? 0 : (size_t)slab * rb + 16;
+    if (in_bytes + out_bytes) {
+        int rc = ci_reserve(ctx, in_bytes + out_bytes);
+        if (rc != OKB_OK) return rc;
+    }
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
+    for (long long r0 = 0; r0 < nrows; r0 += slab) {
+        const long long rn = std::min(slab, nrows - r0);
+        CubeParams p{};
+        if (in_dev) {
+            p.data = data + r0 * nz;
+            p.set_stride = nrows * nz;
+        } else {
+            double *d_in = reinterpret_cast<double *>(base);
+            CU(cudaMemcpy2DAsync(d_in, (size_t)rn * nz * 8, data + r0 * nz, (size_t)nrows * nz * 8, (size_t)rn * nz * 8,
+                                 n_sets, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += (long long)n_sets * rn * nz * 8;
+            p.data = d_in;
+            p.set_stride = rn * nz;
+        }
+        p.nrows = rn;
+        p.nz = (int)nz;
+        p.n_sets = n_sets;
+        p.row0 = r0;
+        p.text = out_dev ? text + r0 * rb : reinterpret_cast<char *>(base + in_bytes);
+        p.total_values = rn * n;
+        const long long nblk = (p.total_values + CUBE_VPB - 1) / CUBE_VPB;
+        okb_cube_kernel<<<(unsigned)nblk, CUBE_NT, CUBE_SMEM, ctx->stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "cube kernel launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ctx->last_kernel = "cube/format";
+        if (!out_dev) {
+            CU(cudaMemcpyAsync(text + r0 * rb, p.text, (size_t)rn * rb, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += rn * rb;
             CU(cudaStreamSynchronize(ctx->stream));
         }
     }

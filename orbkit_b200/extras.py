@@ -2,48 +2,61 @@
 (orbkit/extras.py: calc_mo :40-103, mo_set :105-205, calc_ao :208-260, atom2index :262-304,
 gross_atomic_density :306-385, calc_jmo :441-493).
 
-File output (`otype`, orbkit/output/*) is outside the hot path: requesting it raises
-NotImplementedError; with otype=None (the library use) the return values are those of the reference.
+File output: `otype` "cb" / "cube" (Gaussian cube files, formatted on the device: orbkit_b200.output) with the
+reference's file naming; the other output types of orbkit/output/* are outside the hot path and raise
+NotImplementedError.  With otype=None (the library use) the return values are those of the reference.
 """
+import os
+
 import numpy
 
 from . import core, options
 from .display import display
 
 
-def _no_output(otype):
-    if otype is not None:
-        raise NotImplementedError('orbkit_b200 implements the grid-based compute path only; write the '
-                                  'returned arrays with the reference\'s output module (otype=%r)' % (otype,))
+def _write(data, qc, ofid, otype, **kwargs):
+    """main_output as the reference's extras functions call it (skipped with options.no_output)"""
+    if otype is None or options.no_output:
+        return []
+    from .output import main_output
+    return main_output(data, qc, outputname=ofid, otype=otype, **kwargs)
 
 
 def calc_mo(qc, fid_mo_list, drv=None, otype=None, ofid=None, numproc=None, slice_length=None):
     """Selected molecular orbitals (or derivatives) on the grid: ((NMO,)+N) or ((NDRV,NMO)+N)."""
-    _no_output(otype)
     mo_spec = qc.mo_spec[fid_mo_list] if not isinstance(fid_mo_list, str) or fid_mo_list != 'all_mo' \
         else qc.mo_spec.select('all_mo')
     qc_select = qc.copy()
     qc_select.mo_spec = mo_spec
-    return core.rho_compute(qc_select, calc_mo=True, drv=drv,
-                            slice_length=options.slice_length if slice_length is None else slice_length,
-                            numproc=options.numproc if numproc is None else numproc)
+    mo_list = core.rho_compute(qc_select, calc_mo=True, drv=drv,
+                               slice_length=options.slice_length if slice_length is None else slice_length,
+                               numproc=options.numproc if numproc is None else numproc)
+    if otype is None:
+        return mo_list
+    if ofid is None:                                          # extras.py:87-93
+        outputname, group = options.outputname.split('@') if '@' in options.outputname else (options.outputname, '')
+        outputname, autootype = os.path.splitext(outputname)
+        ofid = '%s_MO%s@%s' % (outputname, autootype, group)
+    _write(mo_list, qc_select, ofid, otype, datalabels=qc_select.mo_spec.get_labels(),
+           dataindices=qc_select.mo_spec.get_indices(), drv=drv)
+    return mo_list
 
 
 def mo_set(qc, fid_mo_list, drv=None, laplacian=None, otype=None, ofid=None, return_all=True,
            numproc=None, slice_length=None):
     """Density (and derivatives) of selected MO sets; rows: one rho per set, then the derivative
     rows of every set (extras.py:105-205)."""
-    _no_output(otype)
     sets = fid_mo_list
     if isinstance(sets, str) or (len(sets) and not isinstance(sets[0], (list, tuple, numpy.ndarray))):
         sets = [sets]
     laplacian = bool(laplacian)
-    datasets, delta = [], []
+    datasets, delta, labels, delta_labels = [], [], [], []
     for sel in sets:
         qc_select = qc.copy()
         qc_select.mo_spec = qc.mo_spec.select(sel) if not isinstance(sel, str) or sel != 'all_mo' \
             else qc.mo_spec.select('all_mo')
-        display('\nStarting with the molecular orbital list \n\tmo_set:%s' % (sel,))
+        label = 'mo_set:' + (sel if isinstance(sel, str) else ','.join(str(i) for i in sel))
+        display('\nStarting with the molecular orbital list \n\t%s' % label)
         data = core.rho_compute(qc_select, drv=drv, laplacian=laplacian,
                                 slice_length=options.slice_length if slice_length is None else slice_length,
                                 numproc=options.numproc if numproc is None else numproc)
@@ -53,20 +66,29 @@ def mo_set(qc, fid_mo_list, drv=None, laplacian=None, otype=None, ofid=None, ret
             rho, delta_rho, lap = data
             delta.extend(delta_rho)
             delta.append(lap)
+            delta_labels.extend(['d^2/d%s^2 %s' % (i, label) for i in 'xyz'])
+            delta_labels.append('laplacian_of_' + label)
         else:
             rho, delta_rho = data
             delta.extend(delta_rho)
+            delta_labels.extend(['d/d%s %s' % (i, label) for i in drv])
         datasets.append(rho)
+        labels.append(label)
     datasets = numpy.array(datasets)
     delta = numpy.array(delta) if delta else numpy.zeros((0,) + datasets.shape[1:])
-    return numpy.append(datasets, delta, axis=0)
+    data = numpy.append(datasets, delta, axis=0)
+    delta_labels.append('mo_set')
+    _write(data, qc, options.outputname if ofid is None else ofid, otype, datalabels=labels + delta_labels, drv=None)
+    return data
 
 
 def calc_ao(qc, drv=None, otype=None, ofid=None, numproc=None, slice_length=None):
     """All atomic orbitals (or derivatives) on the grid: ((NAO,)+N) or ((NDRV,NAO)+N)."""
-    _no_output(otype)
-    return core.rho_compute(qc, calc_ao=True, drv=drv, slice_length=options.slice_length,
-                            numproc=options.numproc)
+    ao_list = core.rho_compute(qc, calc_ao=True, drv=drv, slice_length=options.slice_length,
+                               numproc=options.numproc)
+    _write(ao_list, qc, '%s_AO' % options.outputname if ofid is None else ofid, otype,
+           datalabels=qc.ao_spec.get_labels(), drv=drv)
+    return ao_list
 
 
 def atom2index(atom, geo_info=None):
@@ -176,7 +198,6 @@ def calc_jmo(qc, ij, drv=['x', 'y', 'z'], numproc=1, otype=None, ofid='', **kwar
     from ._lib import OKB_CI_JAB_PAIRS, OKB_CI_PAIRS
     from .engine import get_engine
     from .tools import require, validate_drv
-    _no_output(otype)
     ij = numpy.asarray(ij)
     if ij.ndim == 1 and len(ij) == 2:
         ij = ij.reshape((1, 2))
@@ -192,6 +213,12 @@ def calc_jmo(qc, ij, drv=['x', 'y', 'z'], numproc=1, otype=None, ofid='', **kwar
         raise ValueError('`drv` must name derivatives, e.g. ["x","y","z"]')
     x, y, z, is_vector, N = core._resolve_grid(None, None, None, None)
     npts, n = int(numpy.prod(N)), len(indices)
+    labels = qc_select.mo_spec.get_labels(format='short')
+    datalabels = ['j( %s , %s )' % (labels[i], labels[j]) for i, j in indices]
+
+    def finish(jmo):
+        _write(jmo, qc, ofid, otype, datalabels=datalabels, drv=drv)
+        return jmo
     if npts == 0 or n == 0:
         return numpy.zeros((len(codes), n) + N)
     eng = get_engine()
@@ -202,11 +229,11 @@ def calc_jmo(qc, ij, drv=['x', 'y', 'z'], numproc=1, otype=None, ofid='', **kwar
     ib = numpy.ascontiguousarray(indices[:, 1], dtype=numpy.intc)
     if len(codes) == 3 and len(set(codes)) == 3:
         out = eng.eval_ci(OKB_CI_JAB_PAIRS, (numpy.zeros(n), ia, ib), mo, g, drv_codes=codes, flags=core._flags())
-        return out.reshape((3, n) + N)
+        return finish(out.reshape((3, n) + N))
     # any other number of components: the two products of every pair per component, combined on the host
     jmo = numpy.zeros((len(codes), n, npts))
     terms = (numpy.zeros(2 * n), numpy.concatenate([ia, ib]), numpy.concatenate([ib, ia]))
     for d, code in enumerate(codes):
         prod = eng.eval_ci(OKB_CI_PAIRS, terms, mo, g, drv_codes=[code], flags=core._flags())
         jmo[d] = - 0.5 * (prod[:n] - prod[n:])
-    return jmo.reshape((len(codes), n) + N)
+    return finish(jmo.reshape((len(codes), n) + N))

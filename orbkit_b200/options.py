@@ -9,7 +9,8 @@ quiet = False        #: suppress terminal output (display.py:27-42)
 no_log = True        #: no .oklog file (the CLI/logging layer is out of scope)
 numproc = 1          #: advisory
 slice_length = 1e4   #: advisory: upper bound of points per device launch when > 0
-outputname = 'orbkit_b200'
+outputname = 'orbkit_b200'  #: base name of output files (extras.calc_mo / calc_ao / mo_set with otype='cb')
+no_output = False           #: skip file output even if an otype is given (options.py:512)
 exact_mixed_derivatives = False  #: opt-in analytically correct xy/xz/yz AO derivatives
                                  #  (the reference drops cross terms, c_support.c:121-168)
 ci_merge_terms = False           #: detci.ci_core: merge duplicate orbital pairs before the launch (faster;
