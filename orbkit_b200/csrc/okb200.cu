@@ -976,17 +976,25 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 
 // ---- launch machinery ---------------------------------------------------------------------------------------
 // the kernel instantiations live in inst_*.cu (compiled in parallel); okb_variant.h declares their tables
-static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_val, &okb_variants_grad,
+// (SINK_AO: the first matching entry is the default, i.e. the tile kernel; the warp-specialised "aows/" kernels measured
+// the same throughput -- the AO generators, not the stores, bound calc_ao -- and stay selectable for A/B runs)
+static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_aows, &okb_variants_val, &okb_variants_grad,
                                                &okb_variants_lap, &okb_variants_all, &okb_variants_d2};
 
-static const Variant *pick_variant(int set, int sink, int n_mo) {
+// ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
+static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false) {
     const Variant *best = nullptr;
     long long best_cost = 0;
     for (const VariantTable *tab : g_tables)
       for (int iv = 0; iv < tab->n; ++iv) {
         const Variant &v = tab->v[iv];
         if (v.set != set || v.sink != sink) continue;
-        if (sink == SINK_AO) return &v;
+        if (sink == SINK_AO) {
+            static const char *force_ao = getenv("OKB_AO_VARIANT");      // A/B measurements only
+            if (force_ao && force_ao[0] && set == SET_VAL && !strstr(v.name, force_ao)) continue;
+            if (!ao_bulk_ok && strncmp(v.name, "aows/", 5) == 0) continue;
+            return &v;
+        }
         // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
@@ -1183,7 +1191,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
 
     const double *tabx = nullptr, *taby = nullptr, *tabz = nullptr;
     // (not for SINK_AO: its store-bound kernel has too few warps to hide the table loads -- measured 1.6x slower)
-    if (rq.sink != SINK_AO) {
+    static const bool ao_tables = getenv("OKB_AO_TABLES") != nullptr;      // A/B measurements only
+    if (rq.sink != SINK_AO || ao_tables) {
         rc = ensure_axis_tables(ctx, b, g, &tabx, &taby, &tabz);
         if (rc != OKB_OK) return rc;
     }
@@ -1203,7 +1212,12 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             if (slab_idx >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
         }
         for (const Pass &ps : passes) {
-            const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo);
+            bool ao_bulk_ok = false;
+            if (rq.sink == SINK_AO) {
+                const double *obase = dev_out ? rq.out + s0 : dbase;
+                ao_bulk_ok = (reinterpret_cast<uintptr_t>(obase) % 16 == 0) && (ld % 2 == 0);
+            }
+            const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo, ao_bulk_ok);
             if (!v) return fail(OKB_ERR_UNSUPPORTED, "no kernel variant for set %d sink %d", ps.set, rq.sink);
             KParams p{};
             p.grid_kind = g->kind;
@@ -1249,8 +1263,9 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             }
             const size_t smem = v->smem(lo.lay.stride);
             if (smem > 227 * 1024) return fail(OKB_ERR_UNSUPPORTED, "variant %s needs %zu bytes of shared memory", v->name, smem);
-            // SINK_AO CTAs are small (8 warps, < 100 KB): two per SM overlap generation and stores
-            const int grid = std::min(p.ntiles, ctx->sm_count * (rq.sink == SINK_AO ? 2 : 1));
+            // SINK_AO CTAs are small: several per SM overlap generation and stores (the launcher asks the occupancy
+            // calculator how many)
+            const int grid = rq.sink == SINK_AO ? -ctx->sm_count : std::min(p.ntiles, ctx->sm_count);
             cudaError_t e = v->launch(p, grid, smem, ctx->stream);
             if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", v->name, cudaGetErrorString(e));
             ctx->launches++;

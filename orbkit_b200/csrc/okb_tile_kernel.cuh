@@ -34,8 +34,10 @@ struct Cfg {
 };
 
 // ---- the kernel -------------------------------------------------------------------------------------
-template <int SET, int MW, int PT, int NW, int SINK>
-__global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
+// NPT: points per thread and shell in the generation phase (0 = automatic: 2 where PT is even and the set is small);
+// MINB: CTAs per SM the register allocation must allow (__launch_bounds__)
+template <int SET, int MW, int PT, int NW, int SINK, int NPT = 0, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB) okb_grid_kernel(const KParams p) {
     using C = Cfg<SET, MW, PT, NW, SINK>;
     constexpr int D = C::D, P = C::P, MC = C::MC;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(NW * 32, 1) okb_grid_kernel(const KParams p) {
         const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
         double *tile = tbase + (size_t)(gc & 1) * C::TILE_DOUBLES;
         // a thread evaluates NP points (32 apart) of one shell at a time: independent dependency chains
-        constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
+        constexpr int NP = NPT > 0 ? NPT : (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
         const int nitems = hdr.nshell * PG;
         for (int item = warp; item < nitems; item += NW) {
             const int s = item / PG, pt = (item % PG) * (32 * NP) + lane;

@@ -1,0 +1,44 @@
+"""Golden fixture for the fchk reader, written by RUNNING THE REFERENCE's reader (orbkit/read/gaussian_fchk.py).
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden_read.py
+
+Writes tests/golden/read_fchk.npz: per case `<c>.<flat QCinfo arrays>` (make_golden.qc_arrays) of
+    cart      h2o_rhf_cart.fchk, all_mo=True          (6D 10F basis)
+    uhf_beta  h2o_uhf_sph.fchk, all_mo=True, spin='beta'
+    uhf_occ   h2o_uhf_sph.fchk, all_mo=False
+The input files are copied unchanged to tests/golden/inputs/ (program outputs of Gaussian, test data of the reference).
+The spherical restricted / unrestricted cases are pinned by h2o_gaussian_sph*.npz / h2o_gaussian_uhf.npz (make_golden.py).
+"""
+import os
+import sys
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg     # noqa: E402
+
+
+def main():
+    scratch = mg.build_reference()
+    sys.path.insert(0, scratch)
+    mg.shim()
+    from orbkit import options, read
+    options.quiet = True
+    options.no_log = True
+    gdir = os.path.join(scratch, 'orbkit', 'test', 'outputs_for_testing', 'gaussian')
+    out = {}
+    for name, fn, kw in [('cart', 'h2o_rhf_cart.fchk', dict(all_mo=True)),
+                         ('uhf_beta', 'h2o_uhf_sph.fchk', dict(all_mo=True, spin='beta')),
+                         ('uhf_occ', 'h2o_uhf_sph.fchk', dict(all_mo=False))]:
+        qc = read.main_read(os.path.join(gdir, fn), **kw)
+        for k, v in mg.qc_arrays(qc).items():
+            out[name + '.' + k] = v
+        out[name + '.etot'] = numpy.array(qc.etot)
+        print(name, len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
+    numpy.savez_compressed(os.path.join(HERE, 'read_fchk.npz'), **out)
+
+
+if __name__ == '__main__':
+    main()

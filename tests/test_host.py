@@ -280,3 +280,56 @@ def test_product_grid_state_is_lazy_and_materialises_like_the_reference():
     assert numpy.allclose(grid.inversion(), -numpy.eye(3)) and grid.rot(0.0, 1).shape == (3, 3)
     with pytest.raises(ValueError):
         grid.grid_sym_op(numpy.eye(2))
+
+
+# ---- readers (orbkit_b200.read) ------------------------------------------------------------------------------------
+def _flat_qc(qc):
+    ao, mo = qc.ao_spec.todict(), qc.mo_spec.todict()
+    out = {'geo_spec': numpy.asarray(qc.geo_spec), 'geo_info': numpy.asarray(qc.geo_info, dtype=str)}
+    for k in ['normalized', 'spherical', '_assign_cont_to_atoms', '_nprim_per_cont', '_prim_coeffs',
+              '_assign_prim_to_cont', '_lxlylz', '_assign_lxlylz_to_cont', '_nlxlylz_per_cont']:
+        out['ao.' + k] = numpy.asarray(ao[k])
+    out['ao._cont_types'] = numpy.asarray(ao['_cont_types'], dtype=str)
+    if ao['spherical']:
+        out['ao._lm'] = numpy.asarray(ao['_lm'], dtype=numpy.intc)
+        out['ao._assign_lm_to_cont'] = numpy.asarray(ao['_assign_lm_to_cont'])
+    for k in ('coeffs', 'occ', 'eig'):
+        out['mo.' + k] = numpy.asarray(mo[k], dtype=float)
+    out['mo.sym'] = numpy.asarray(mo['sym'], dtype=str)
+    out['mo.spin'] = numpy.asarray(mo['spin'], dtype=str)
+    return out
+
+
+def test_fchk_reader_equals_reference_reader():
+    """read_gaussian_fchk == the reference's reader on the reference's own Gaussian test outputs: every flat QCinfo array
+    identical (goldens written by running the reference: make_golden.py, make_golden_read.py)"""
+    import io
+    import os
+    from conftest import GOLDEN, load_golden
+    from orbkit_b200 import read, options
+    options.quiet = True
+    inputs = os.path.join(GOLDEN, 'inputs')
+    extra = load_golden('read_fchk')
+    cases = [(load_golden('h2o_gaussian_sph'), '', 'h2o_rhf_sph.fchk', dict(all_mo=True)),
+             (load_golden('h2o_gaussian_sph_occ'), '', 'h2o_rhf_sph.fchk', dict(all_mo=False)),
+             (load_golden('h2o_gaussian_uhf'), '', 'h2o_uhf_sph.fchk', dict(all_mo=True)),
+             (extra, 'cart.', 'h2o_rhf_cart.fchk', dict(all_mo=True)),
+             (extra, 'uhf_beta.', 'h2o_uhf_sph.fchk', dict(all_mo=True, spin='beta')),
+             (extra, 'uhf_occ.', 'h2o_uhf_sph.fchk', dict(all_mo=False))]
+    for g, prefix, fn, kw in cases:
+        qc = read.main_read(os.path.join(inputs, fn), **kw)
+        for k, v in _flat_qc(qc).items():
+            ref = g[prefix + k]
+            assert v.shape == ref.shape and (v == ref).all(), (fn, kw, k)
+        if prefix:
+            assert qc.etot == float(g[prefix + 'etot'])
+    # file objects (text and binary), explicit itype, error conventions
+    with open(os.path.join(inputs, 'h2o_rhf_sph.fchk'), 'rb') as f:
+        qb = read.main_read(io.BytesIO(f.read()), itype='fchk', all_mo=True)
+    assert qb == read.read_gaussian_fchk(os.path.join(inputs, 'h2o_rhf_sph.fchk'), all_mo=True)
+    with pytest.raises(IOError):
+        read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), spin='alpha')        # restricted file
+    with pytest.raises(IOError):
+        read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
+    with pytest.raises(NotImplementedError):
+        read.main_read('something.molden')
