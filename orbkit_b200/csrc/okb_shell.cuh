@@ -11,8 +11,9 @@
 // and 3..9 multiplications per function.  Shells with any other ordering (wfn f order, explicit
 // lxlylz) and the SET_ALL / SET_ONE requests keep the generic path.
 //
-// exp(-t) is evaluated by exp_neg(): k = round(-t*4/ln2), Cody-Waite reduction to |r| <= ln2/8,
-// degree-9 Taylor polynomial (truncation 6.5e-18), 2^(k/4) by selects + exponent add.  Relative error
+// exp(-t) is evaluated by exp_neg(): k = round(-t*64/ln2), Cody-Waite reduction to |r| <= ln2/128,
+// degree-5 Taylor polynomial, 2^((k mod 64)/64) from a 64-entry table + exponent add (10 FP64 instructions instead of the
+// 15 of the earlier degree-9 / 2^(k/4)-by-selects form, kept under OKB_EXP_POLY9 for A/B builds).  Relative error
 // ~3e-16; results below the normal range (t > 708, values < 3.3e-308) are flushed to 0.
 #pragma once
 #include <type_traits>
@@ -21,6 +22,48 @@
 
 namespace okb {
 
+// 2^(j/64), j = 0..63, correctly rounded
+static __device__ const double OKB_EXP2_64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
+#ifndef OKB_EXP_POLY9
+__device__ __forceinline__ double exp_neg(double t) {
+    // e^{-t}, 0 <= t < 708:  k = round(-t 64/ln2), r = -t - k ln2/64 (Cody-Waite, |r| <= ln2/128), degree-5 Taylor
+    // polynomial (truncation r^6/720 < 3.6e-17), times 2^((k & 63)/64) from a 512-byte table (L1 resident), exponent add
+    const double x = -t;
+    const double MAGIC = 6755399441055744.0;                 // 2^52 + 2^51: round-to-nearest-integer
+    double kd = fma(x, 92.33248261689366, MAGIC);            // 64/ln2
+    const int ki = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -0x1.62e42fee00000p-7, x);            // ln2/64, leading 32 bits (k < 2^17: the product is exact)
+    r = fma(kd, -0x1.a39ef35793c76p-39, r);                  // ln2/64, rest
+    double p = 8.3333333333333332e-03;                       // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= __ldg(&OKB_EXP2_64[ki & 63]);
+    const int m = ki >> 6;                                   // arithmetic shift: floor(k/64)
+    return __hiloint2double(__double2hiint(p) + (m << 20), __double2loint(p));
+}
+#else
 __device__ __forceinline__ double exp_neg(double t) {
     // e^{-t}, 0 <= t < 708
     const double x = -t;
@@ -47,6 +90,7 @@ __device__ __forceinline__ double exp_neg(double t) {
     const int m = ki >> 2;                                   // arithmetic shift: floor(k/4)
     return __hiloint2double(__double2hiint(p) + (m << 20), __double2loint(p));
 }
+#endif
 
 // Molden order of the Cartesian exponents, packed lx | ly<<4 | lz<<8 (tools.py:118-135)
 __host__ __device__ constexpr int std_lxyz(int L, int j) {
