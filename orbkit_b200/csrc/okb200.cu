@@ -79,6 +79,8 @@ struct okb_ctx {
     size_t norm_cap = 0;
     void *ci_buf = nullptr;                  // detCI: term arrays + MO slab + output slab
     size_t ci_bytes = 0;
+    double *phi_buf = nullptr;               // rho + laplacian: MO values between the two passes
+    size_t phi_bytes = 0;
     // Recycled device buffers of destroyed handles (chunk tables, coefficient tiles, axes, axis tables).
     // cudaFree sporadically takes 5-600 ms next to large page-locked host buffers (measured:
     // scripts/e2e_probe.py, e2e_probe2.py), so handle churn must not free.
@@ -228,6 +230,7 @@ extern "C" int okb_ctx_destroy(okb_ctx *c) {
     }
     if (c->norm_dev) cudaFree(c->norm_dev);
     if (c->ci_buf) cudaFree(c->ci_buf);
+    if (c->phi_buf) cudaFree(c->phi_buf);
     for (auto &e : c->pool) cudaFree(e.first);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
@@ -979,7 +982,7 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 // (SINK_AO: the first matching entry is the default, i.e. the tile kernel; the warp-specialised "aows/" kernels measured
 // the same throughput -- the AO generators, not the stores, bound calc_ao -- and stay selectable for A/B runs)
 static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_aows, &okb_variants_val, &okb_variants_grad,
-                                               &okb_variants_lap, &okb_variants_all, &okb_variants_d2};
+                                               &okb_variants_lap, &okb_variants_all, &okb_variants_d2, &okb_variants_d2p};
 
 // ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
 static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false) {
@@ -1118,6 +1121,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     // duplicates or is a single code use one SET_ONE pass per requested slot.
     struct Pass { int set; int one_code; int slot[10]; int epi = 0; };
     std::vector<Pass> passes;
+    bool phi_cache = false;                  // two-pass rho + laplacian with the MO values kept in ctx->phi_buf
     bool dup = false;
     {
         int seen[10] = {0};
@@ -1139,7 +1143,17 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
         bool pure_second = (set == SET_LAP);
         for (int i = 0; i < rq.n_codes; ++i) pure_second &= (rq.codes[i] >= 4 && rq.codes[i] <= 6);
         static const bool one_pass = getenv("OKB_LAP_ONE_PASS") != nullptr;
-        if (pure_second && !one_pass) {
+        static const bool no_cache = getenv("OKB_LAP_NO_PHI_CACHE") != nullptr;     // A/B measurements only
+        if (pure_second && !one_pass && !no_cache) {
+            // the first pass leaves the MO values in HBM (8 n_mo bytes per point written once, read once: ~1 % of the
+            // pass), so the second pass contracts the three second-derivative sets only: 4 + 3 = 7 sets, the algorithmic
+            // count, instead of 4 + 4
+            ps.set = SET_GRAD; ps.epi = 3;
+            passes.push_back(ps);
+            ps.set = SET_D2P; ps.epi = 2;
+            passes.push_back(ps);
+            phi_cache = true;
+        } else if (pure_second && !one_pass) {
             ps.set = SET_GRAD; ps.epi = 1;
             passes.push_back(ps);
             ps.set = SET_D2; ps.epi = 2;
@@ -1211,6 +1225,26 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             dbase = reinterpret_cast<double *>(ctx->slab[buf]);
             if (slab_idx >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
         }
+        // Sub-ranges of the slab: only the two-pass laplacian with cached MO values cuts it further, so that the scratch
+        // of MO values (8 n_mo bytes per point) stays bounded; every other request runs the slab in one piece.
+        long long sub_pts = sn, ldp = 0;
+        if (phi_cache) {
+            const char *force_pts = getenv("OKB_PHI_CACHE_PTS");                     // tests: force several sub-ranges
+            const long long budget_pts = force_pts ? atoll(force_pts) : (long long)(((size_t)8 << 30) / (8 * (size_t)rq.mo->n_mo));
+            sub_pts = std::min(sn, std::max<long long>(budget_pts / 1024 * 1024, 1024));
+            ldp = (sub_pts + 1) & ~1LL;
+            const size_t need = (size_t)rq.mo->n_mo * (size_t)ldp * sizeof(double);
+            if (ctx->phi_bytes < need) {
+                CU(cudaStreamSynchronize(ctx->stream));
+                if (ctx->phi_buf) CU(cudaFree(ctx->phi_buf));
+                ctx->phi_buf = nullptr;
+                ctx->phi_bytes = 0;
+                CU(cudaMalloc(&ctx->phi_buf, need));
+                ctx->phi_bytes = need;
+            }
+        }
+        for (long long u0 = 0; u0 < sn; u0 += sub_pts) {
+        const long long un = std::min(sub_pts, sn - u0);
         for (const Pass &ps : passes) {
             bool ao_bulk_ok = false;
             if (rq.sink == SINK_AO) {
@@ -1226,13 +1260,14 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.has_aff = g->has_aff ? 1 : 0;
             for (int q = 0; q < 12; ++q) p.aff[q] = g->aff[q];
             p.tabx = tabx; p.taby = taby; p.tabz = tabz;
-            p.p0 = rq.p0 + s0;
-            p.npts = (int)sn;
-            p.ntiles = (int)((sn + v->P - 1) / v->P);
+            p.p0 = rq.p0 + s0 + u0;
+            p.npts = (int)un;
+            p.ntiles = (int)((un + v->P - 1) / v->P);
             // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); the generic sets
             // work on the all-Cartesian layout
             const bool use_mix = !b->mix_is_cart &&
-                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2);
+                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
+                                  ps.set == SET_D2P);
             const Layout &lo = use_mix ? b->mix : b->cart;
             p.meta = lo.meta_dev;
             p.lay = lo.lay;
@@ -1255,11 +1290,13 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.exact_mixed = (rq.flags & OKB_FLAG_EXACT_MIXED) ? 1 : 0;
             p.epi = ps.epi;
             if (rq.sink == SINK_RHO) {
-                p.rho = dev_out ? rq.rho + s0 : dbase;
-                p.delta = dev_out ? (rq.delta ? rq.delta + s0 : nullptr) : dbase + ld;
+                p.rho = dev_out ? (rq.rho ? rq.rho + s0 + u0 : nullptr) : dbase + u0;
+                p.delta = dev_out ? (rq.delta ? rq.delta + s0 + u0 : nullptr) : dbase + ld + u0;
                 p.mo_norm = ps.epi == 2 ? nullptr : norm_dev;    // the second laplacian pass must not add the norms again
+                p.phi = ctx->phi_buf;
+                p.ldp = ldp;
             } else {
-                p.out = dev_out ? rq.out + s0 : dbase;
+                p.out = (dev_out ? rq.out + s0 : dbase) + u0;
             }
             const size_t smem = v->smem(lo.lay.stride);
             if (smem > 227 * 1024) return fail(OKB_ERR_UNSUPPORTED, "variant %s needs %zu bytes of shared memory", v->name, smem);
@@ -1271,6 +1308,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             ctx->launches++;
             ctx->last_kernel = v->name;
         }
+        }   // sub-ranges
         if (!dev_out) {
             CU(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));

@@ -32,11 +32,14 @@ namespace okb {
 constexpr int KC = 32;            // max Cartesian functions per chunk
 constexpr int NMETA = 3;          // chunk-table buffers in flight
 enum { SET_VAL = 0, SET_GRAD = 1, SET_LAP = 2, SET_ALL = 3, SET_ONE = 4,
-       SET_D2 = 5 };   // SET_D2: value + the three pure second derivatives (codes 0,4,5,6): second pass of rho + laplacian
+       SET_D2 = 5,     // SET_D2: value + the three pure second derivatives (codes 0,4,5,6): second pass of rho + laplacian
+       SET_D2P = 6 };  // SET_D2P: the three pure second derivatives only (codes 4,5,6): second pass when the first one
+                       // left the MO values in HBM (KParams::phi)
 enum { SINK_AO = 0, SINK_MO = 1, SINK_RHO = 2 };
 
 __host__ __device__ constexpr int set_ncodes(int set) {
-    return set == SET_VAL ? 1 : (set == SET_GRAD || set == SET_D2) ? 4 : set == SET_LAP ? 7 : set == SET_ALL ? 10 : 1;
+    return set == SET_VAL ? 1 : (set == SET_GRAD || set == SET_D2) ? 4 : set == SET_D2P ? 3 : set == SET_LAP ? 7
+           : set == SET_ALL ? 10 : 1;
 }
 
 // ---- chunk tables (one fixed-stride blob per chunk, 16-byte aligned sections) ---------------
@@ -87,7 +90,10 @@ struct KParams {
     int slot[10];                  // code -> output slot, -1 = not requested
     int one_code, exact_mixed;
     int epi;                       // SINK_RHO epilogue: 0 standard; 1 (SET_GRAD) rho and sum 2 occ (d phi)^2 into the slots of
-                                   // codes 4..6; 2 (SET_D2) ADD sum 2 occ phi d2 phi to those slots (two-pass rho + laplacian)
+                                   // codes 4..6; 2 (SET_D2 / SET_D2P) ADD sum 2 occ phi d2 phi to those slots (two-pass rho +
+                                   // laplacian); 3 = 1 + the MO values are left in `phi` for a SET_D2P second pass
+    double *phi;                   // [n_mtile*MC][ldp] MO values of the launch's points (epi 3 writes, SET_D2P reads)
+    long long ldp;
 };
 
 // Axis tables of a regular grid as the AO generators see them; ii/jj/kk point at the axis indices of the
@@ -223,7 +229,7 @@ __device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__
                                           const FnMeta *__restrict__ fns, double x, double y, double z,
                                           double *__restrict__ tp, int one_code, int exact) {
     constexpr bool N1 = (SET != SET_VAL);
-    constexpr bool N2 = (SET == SET_LAP || SET == SET_ALL || SET == SET_ONE || SET == SET_D2);
+    constexpr bool N2 = (SET == SET_LAP || SET == SET_ALL || SET == SET_ONE || SET == SET_D2 || SET == SET_D2P);
     constexpr int LEVEL = N2 ? 2 : (N1 ? 1 : 0);
     const double X = x - sh.cx, Y = y - sh.cy, Z = z - sh.cz;
     const double rr = X * X + Y * Y + Z * Z;
@@ -268,6 +274,12 @@ __device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__
             continue;
         }
         const double yz = ay.q0 * az.q0, xz = ax.q0 * az.q0, xy = ax.q0 * ay.q0;
+        if (SET == SET_D2P) {
+            o[0] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
+            o[(size_t)1 * KC * P] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
+            o[(size_t)2 * KC * P] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
+            continue;
+        }
         o[0] = f * (R0 * ax.q0 * yz);
         if (SET == SET_D2) {
             o[(size_t)1 * KC * P] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));

@@ -256,11 +256,12 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
-    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2, "specialised sets");
-    // N1 / N2: radial sums R1 / R2 needed; W1 / W2: first / pure second derivative rows written; O2: tile set of d2/dx2
-    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP || SET == SET_D2);
-    constexpr bool W1 = (SET == SET_GRAD || SET == SET_LAP), W2 = N2;
-    constexpr int O2 = (SET == SET_D2) ? 1 : 4;
+    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P, "specialised sets");
+    // N1 / N2: radial sums R1 / R2 needed; W0 / W1 / W2: value / first / pure second derivative rows written; O2: tile set
+    // of d2/dx2
+    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP || SET == SET_D2 || SET == SET_D2P);
+    constexpr bool W0 = (SET != SET_D2P), W1 = (SET == SET_GRAD || SET == SET_LAP), W2 = N2;
+    constexpr int O2 = (SET == SET_D2) ? 1 : (SET == SET_D2P) ? 0 : 4;
     constexpr int D = set_ncodes(SET);
     double r[NP][3], rr[NP];
 #pragma unroll
@@ -308,7 +309,7 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 const double f = ff[j].f;
                 const double fz = f * g0[2][lz];
                 const double fyz = fz * g0[1][ly];
-                o[(size_t)j * STRIDE] = fyz * (R0[q] * g0[0][lx]);
+                if (W0) o[(size_t)j * STRIDE] = fyz * (R0[q] * g0[0][lx]);
                 if (N1) {
                     const double fxz = fz * g0[0][lx];
                     const double fxy = f * (g0[0][lx] * g0[1][ly]);
@@ -337,7 +338,7 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 const double f = ax[j];
                 const double fz = f * g0[2][lz];
                 const double fyz = fz * g0[1][ly];
-                v[j][0] = fyz * (R0[q] * g0[0][lx]);
+                if (W0) v[j][0] = fyz * (R0[q] * g0[0][lx]);
                 if (N1) {
                     const double fxz = fz * g0[0][lx];
                     const double fxy = f * (g0[0][lx] * g0[1][ly]);
@@ -380,8 +381,8 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp,
                                               int one_code, int exact, const AxTab &tab) {
-    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2) {
-        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2) ? SET : SET_VAL;
+    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) {
+        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) ? SET : SET_VAL;
         if (sh.kind == 1) {                  // warp-uniform
             switch (sh.L) {
                 case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;

@@ -15,8 +15,8 @@ struct Variant {
 };
 struct VariantTable { const Variant *v; int n; };
 
-// defined in inst_ao_ws.cu, inst_tile.cu, inst_ws_val.cu, inst_ws_grad.cu, inst_ws_lap.cu, inst_ws_all.cu, inst_ws_d2.cu
+// defined in inst_ao_ws.cu, inst_tile.cu, inst_ws_val.cu, inst_ws_grad.cu, inst_ws_lap.cu, inst_ws_all.cu, inst_ws_d2.cu, inst_ws_d2p.cu
 extern const VariantTable okb_variants_tile, okb_variants_val, okb_variants_grad, okb_variants_lap, okb_variants_all,
-    okb_variants_d2, okb_variants_aows;
+    okb_variants_d2, okb_variants_d2p, okb_variants_aows;
 
 }  // namespace okb

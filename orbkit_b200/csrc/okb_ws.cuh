@@ -389,8 +389,21 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         for (int ib = 0; ib < BN; ++ib)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
+                                if (SET == SET_D2P) {
+                                    // second pass of rho + laplacian on the MO values the first pass left in HBM:
+                                    // sum_i 2 occ phi d2phi
+                                    const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
+                                    const double phi = (q < p.npts && mo < p.n_mo) ? __ldg(p.phi + (size_t)mo * p.ldp + q) : 0.0;
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) osum[d][ib][e] += o2 * (acc[ia][ib][d][e] * phi);
+                                    continue;
+                                }
                                 const double phi = acc[ia][ib][0][e];
                                 if ((q0 + pt_w + ib * 8 + 2 * tc + e) < p.npts) nrm += phi * phi;
+                                if (SET == SET_GRAD && p.epi == 3) {
+                                    const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
+                                    if (q < p.npts && mo < p.n_mo) p.phi[(size_t)mo * p.ldp + q] = phi;
+                                }
                                 osum[0][ib][e] += oc * (phi * phi);
                                 if (SET == SET_D2) {
                                     // second pass of rho + laplacian: sum_i 2 occ phi d2phi (the first pass added
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                                     osum[3][ib][e] += o2 * (acc[ia][ib][3][e] * phi);
                                 } else if (D >= 4) {
                                     const double gx = acc[ia][ib][1][e], gy = acc[ia][ib][2][e], gz = acc[ia][ib][3][e];
-                                    if (SET == SET_GRAD && p.epi == 1) {         // first pass of rho + laplacian
+                                    if (SET == SET_GRAD && p.epi != 0) {         // first pass of rho + laplacian
                                         osum[1][ib][e] += o2 * (gx * gx);
                                         osum[2][ib][e] += o2 * (gy * gy);
                                         osum[3][ib][e] += o2 * (gz * gz);
@@ -452,8 +465,11 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
 #pragma unroll
                     for (int w = 0; w < WM; ++w) sum += red[((size_t)w * C::NOUT + o) * P + pt];
                     if (q0 + pt < p.npts) {
-                        const bool two_pass = (SET == SET_D2) || (SET == SET_GRAD && p.epi == 1);
-                        if (o == 0) {
+                        const bool two_pass = (SET == SET_D2) || (SET == SET_GRAD && p.epi != 0);
+                        if (SET == SET_D2P) {                                // all three sums go to the slots of codes 4..6
+                            const int sl = p.slot[o + 4];
+                            if (sl >= 0) p.delta[(size_t)sl * p.ld + q0 + pt] += sum;
+                        } else if (o == 0) {
                             if (p.rho != nullptr && SET != SET_D2) p.rho[q0 + pt] = sum;
                         } else {
                             const int sl = p.slot[two_pass ? o + 3 : o];     // two-pass laplacian: codes 4..6

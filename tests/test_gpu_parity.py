@@ -369,3 +369,32 @@ def test_product_grids_generated_on_the_device(ok, oracle_mod):
     assert_close(rho, oracle_mod.rho_compute(qc, xyz[0], xyz[1], xyz[2], is_vector=True), 'sym op', rtol=1e-9)
     assert numpy.allclose(numpy.array([ok.grid.x, ok.grid.y, ok.grid.z]), xyz, rtol=0, atol=1e-14)
     assert ok.grid.product_grid() is None
+
+
+def test_laplacian_phi_cache_subranges(ok, oracle_mod, monkeypatch):
+    """rho + laplacian runs as SET_GRAD (MO values left in HBM) + SET_D2P (three second-derivative sets): the same
+    results with the scratch cut into several sub-ranges, with ragged point counts, and as the uncached two-pass form"""
+    from orbkit_b200 import synth
+    spec = synth.make_molecule(n_heavy=3, n_light=3, n_mo=101, seed=4, spherical=True)
+    qc = synth.to_qcinfo(spec)
+    rng = numpy.random.default_rng(8)
+    x, y, z = rng.uniform(-8, 8, size=(3, 5003))
+    set_vector(ok, x, y, z)
+    rr, dr, lr = oracle_mod.rho_compute(qc, x, y, z, is_vector=True, laplacian=True)
+    r, d, l = ok.rho_compute(qc, laplacian=True)
+    assert ok.engine.get_engine().last_kernel().startswith('ws-dmma/SET_D2P/')
+    assert_close(r, rr, 'rho')
+    assert_close(d, dr, 'd2rho')
+    assert_close(l, lr, 'laplacian', afloor=3e-14)
+    monkeypatch.setenv('OKB_PHI_CACHE_PTS', '2048')          # 3 sub-ranges: 2048 + 2048 + 907
+    r2, d2, l2 = ok.rho_compute(qc, laplacian=True)
+    monkeypatch.delenv('OKB_PHI_CACHE_PTS')
+    assert numpy.array_equal(r, r2) and numpy.array_equal(d, d2) and numpy.array_equal(l, l2)
+    # the MO norms of the first pass are not disturbed by the second one
+    eng = ok.engine.get_engine()
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    g = eng.grid_vector(x, y, z)
+    _, _, nrm = eng.eval_rho(mo, g, [4, 5, 6], want_norm=True)
+    mo_ref = oracle_mod.rho_compute(qc, x, y, z, is_vector=True, calc_mo=True)
+    assert_close(nrm, (mo_ref ** 2).sum(axis=1), 'mo_norm', rtol=1e-12)
