@@ -1,8 +1,8 @@
 """Readers -> QCinfo for the grid path (orbkit/read/high_level.py:33-79).
 
 Only the formats BASELINE configs[0] names are built: Gaussian formatted checkpoint files
-(read_gaussian_fchk, orbkit/read/gaussian_fchk.py:11-324).  The other nine readers of the reference stay with the
-reference; `main_read` raises NotImplementedError for them.
+(read_gaussian_fchk, orbkit/read/gaussian_fchk.py:11-324) and Molden files (read_molden, orbkit/read/molden.py:47-402).
+The other readers of the reference stay with the reference; `main_read` raises NotImplementedError for them.
 
 Mechanism: an fchk file is a sequence of named sections (`<name, 40 columns> <type I/R/C> [N=] <value or count>` followed,
 for arrays, by the values).  The file is cut into sections once, the arrays are converted by NumPy, and the QCinfo is
@@ -16,7 +16,7 @@ import numpy
 from .display import display
 from .orbitals import MOClass
 from .qcinfo import QCinfo
-from .tools import orbit, lquant
+from .tools import orbit, lquant, exp as cart_exponents
 
 SYMBOLS = ('H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y Zr '
            'Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta W Re Os Ir '
@@ -152,8 +152,251 @@ def read_gaussian_fchk(fname, all_mo=False, spin=None, **kwargs):
     return qc
 
 
-readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk}
-_OTHER = ('molden', 'aomix', 'gamess', 'gaussian.log', 'gaussian_log', 'wfn', 'wfx', 'cclib', 'native')
+# ---- Molden ---------------------------------------------------------------------------------------------------------
+_FLOAT = r'([-+]?\d+\.?\d*[ed]?[+-]?\d+|NaN)'
+_RE_MOLDEN = re.compile(r'\[\s*molden\s+format\s*\]', re.I)
+_RE_ATOMS = re.compile(r'\[atoms\]\s*\(?(angs|au)\)?', re.I)
+_RE_ATOM = re.compile(r'\s*([a-z]+)\s+(\d+)\s+(\d+)\s+' + r'\s+'.join((_FLOAT,) * 3), re.I)
+_RE_BASIS = re.compile(r'\s*(\d+)\s+(\d+)$', re.I)
+_RE_CONTRACTION = re.compile(r'\s*([a-z]+)\s+(\d+)\s+(\d+(\.\d+)?)\s*($)', re.I)
+_RE_PRIMITIVE = re.compile(r'\s*' + r'\s+'.join((_FLOAT,) * 2), re.I)
+_SPH_FLAGS, _CART_FLAGS = ['5d', '7f', '9g'], ['6d', '10f', '15g']
+_RE_FLAGLINE = re.compile(r'\[((' + '|'.join(_SPH_FLAGS + _CART_FLAGS) + r')+)\]', re.I)
+_RE_FLAG = re.compile(r'(\d+[dfg])', re.I)
+_RE_SYM = re.compile(r'\s*sym\s*=\s*(\S+)', re.I)
+_RE_ENERGY = re.compile(r'\s*ene(?:rgy)?\s*=\s*' + _FLOAT, re.I)
+_RE_SPIN = re.compile(r'\s*spin\s*=\s*(alpha|beta)', re.I)
+_RE_OCC = re.compile(r'\s*occup\s*=\s*' + _FLOAT, re.I)
+_RE_COEFF = re.compile(r'\s*(\d+)\s+' + _FLOAT, re.I)
+# Angstrom -> Bohr exactly as orbkit/units.py:5-28 derives it (CODATA 2014 constants)
+_H, _E, _ME, _E0 = 6.626070040 * 1e-34, 1.6021766208 * 1e-19, 9.10938356 * 1e-31, 8.854187817 * 1e-12
+_HBAR = _H / (2 * numpy.pi)
+AA_TO_A0 = 1e-10 / (4 * numpy.pi * _E0 * _HBAR ** 2 / (_ME * _E ** 2))
+
+
+def _dfact(n):
+    r = 1.0
+    while n > 1:
+        r *= n
+        n -= 2
+    return r
+
+
+def cartesian_self_overlap(ao_spec):
+    """<chi|chi> of every contracted Cartesian function: the diagonal the reference takes from
+    analytical_integrals.get_ao_overlap (molden.py:378-381), here in closed form -- all primitives of a contraction share
+    their centre, so  S = sum_pq c_p c_q N_p N_q  prod_axis (2l-1)!! / (2(a_p+a_q))^l  (pi/(a_p+a_q))^(3/2)  with the
+    primitive norm N = ao_norm of c_support.c:177-188."""
+    out = []
+    for rec in ao_spec:
+        c = numpy.asarray(rec['coeffs'], dtype=float).reshape((-1, 2))
+        a, w = c[:, 0], c[:, 1]
+        s = a[:, None] + a[None, :]
+        lxlylz = rec['lxlylz'] if 'lxlylz' in rec else cart_exponents[lquant[rec['type']]]
+        for lx, ly, lz in lxlylz:
+            L = lx + ly + lz
+            if rec['pnum'] < 0:
+                n = numpy.ones_like(a)
+            else:
+                n = (2.0 / numpy.pi) ** 0.75 * 2.0 ** L * a ** ((2.0 * L + 3.0) / 4.0) / numpy.sqrt(
+                    _dfact(2 * lx - 1) * _dfact(2 * ly - 1) * _dfact(2 * lz - 1))
+            ang = _dfact(2 * lx - 1) * _dfact(2 * ly - 1) * _dfact(2 * lz - 1) / (2.0 * s) ** L
+            out.append(float(((w * n)[:, None] * (w * n)[None, :] * ang * (numpy.pi / s) ** 1.5).sum()))
+    return numpy.array(out)
+
+
+def read_molden(fname, all_mo=False, spin=None, i_md=-1, interactive=False, **kwargs):
+    """QCinfo of a Molden file (molden.py:47-402): [Atoms], [GTO], the [5D]/[7F]/[9G] flags, [MO]; `i_md` selects the
+    [Molden Format] section of files that hold several (never asked for interactively here)."""
+    if isinstance(fname, str):
+        with open(fname, 'r') as f:
+            text = f.read()
+        name = fname
+    else:
+        text = fname.read()
+        name = getattr(fname, 'name', '<stream>')
+        if isinstance(text, bytes):
+            text = text.decode()
+    entries = [m.start() for m in _RE_MOLDEN.finditer(text)]
+    if not entries:
+        raise IOError('The input file {:s} is no valid molden file!\n\nIt does not contain the keyword: '
+                      '[Molden Format]\n'.format(name))
+    if len(entries) > 1:
+        i_md = list(range(len(entries)))[i_md]
+        display('\tFound {:d} [Molden Format] keywords; selecting the element with index {:d}.'.format(len(entries), i_md))
+        text = text[entries[i_md]:(entries + [None])[i_md + 1]]
+    lines = text.splitlines()
+    qc = QCinfo()
+    qc.geo_info, qc.geo_spec = [], []
+    sph_flags, cart_flags, angular = [], [], []
+    by_orca, angstrom = False, False
+    at_num, ao_type, row = 0, '', 0
+    iline = 0
+    for iline, line in enumerate(lines):
+        low = line.lower()
+        if 'orca' in low:
+            by_orca = True
+            continue
+        if '_ENERGY=' in line:
+            try:
+                qc.etot = float(line.split()[1])
+            except IndexError:
+                pass
+            continue
+        m = _RE_ATOMS.match(line)
+        if m:
+            angstrom = m.group(1).lower() == 'angs'
+            continue
+        m = _RE_ATOM.match(line)
+        if m:
+            qc.geo_info.append(list(m.groups()[:3]))
+            qc.geo_spec.append([float(f) for f in m.groups()[3:]])
+            continue
+        if '[sto]' in low:
+            raise IOError('orbkit does not work for STOs!\nEXIT\n')
+        m = _RE_BASIS.match(line)
+        if m:
+            at_num = int(m.group(1)) - 1
+            continue
+        m = _RE_FLAGLINE.match(low)
+        if m:
+            for flag in _RE_FLAG.findall(m.group(1)):
+                (sph_flags if flag in _SPH_FLAGS else cart_flags).append(flag)
+        m = _RE_CONTRACTION.match(line)
+        if m:
+            row, ao_type, pnum = 0, m.group(1).lower(), int(m.group(2))
+            for l in ao_type:                       # "sp" shells become two contractions
+                qc.ao_spec.append({'atom': at_num, 'type': l, 'pnum': -pnum if by_orca else pnum,
+                                   'coeffs': numpy.zeros((pnum, 2))})
+                if l not in angular:
+                    angular.append(l)
+            continue
+        m = _RE_PRIMITIVE.match(line)
+        if m:
+            vals = numpy.array(low.replace('d', 'e').split(), dtype=numpy.float64)
+            for i in range(len(ao_type)):
+                qc.ao_spec[-len(ao_type) + i]['coeffs'][row, :] = [vals[0], vals[1 + i]]
+            row += 1
+            continue
+        if '[mo]' in low:
+            break
+    # Cartesian or spherical functions?
+    max_l = max(lquant[l] for l in angular)
+    cartesian = True
+    if max_l >= 2:
+        used = orbit[2:max_l + 1]
+        sph = [f for f in sph_flags if f[-1] in used]
+        cart = [f for f in cart_flags if f[-1] in used]
+        if sph and cart:
+            raise IOError('The input file {} contains mixed spherical and Cartesian function ({}).'.format(
+                name, ', '.join(sph + cart)))
+        cartesian = not bool(sph)
+    n_basis = sum(((lquant[ao['type']] + 1) * (lquant[ao['type']] + 2) // 2) if cartesian else (2 * lquant[ao['type']] + 1)
+                  for ao in qc.ao_spec)
+    # [MO]
+    mos = []
+    pending = {'sym': None, 'energy': None, 'occ_num': None, 'spin': None}
+    new_mo, has_alpha, has_beta, restricted = False, False, False, False
+    counters = {}
+    for line in lines[iline:]:
+        m = _RE_COEFF.match(line)
+        if m:
+            if new_mo:
+                sym = pending['sym']
+                digits = re.search(r'\d+', sym) if sym else None
+                if digits:
+                    a = digits.group()
+                    if sym == a:
+                        sym = '{:s}.1'.format(a)
+                    elif not sym.startswith(a):
+                        counters[a] = counters.get(a, 0) + 1
+                        sym = '{:d}.{:s}'.format(counters[a], sym)
+                sym = sym or '%d.1' % (len(mos) + 1)
+                mos.append({'coeffs': numpy.zeros(n_basis), 'sym': sym, 'energy': pending['energy'],
+                            'occ_num': pending['occ_num'], 'spin': pending['spin'] or 'alpha'})
+                pending = {'sym': None, 'energy': None, 'occ_num': None, 'spin': None}
+                new_mo = False
+            value = float(m.group(2))
+            if numpy.isnan(value):
+                display('Warning: coefficient {:d} of MO {:s} is NaN! Using zero instead'.format(int(m.group(1)) - 1,
+                                                                                               mos[-1]['sym']))
+            else:
+                mos[-1]['coeffs'][int(m.group(1)) - 1] = value
+            continue
+        new_mo = True
+        m = _RE_SYM.match(line)
+        if m:
+            pending['sym'] = m.group(1)
+            continue
+        m = _RE_ENERGY.match(line)
+        if m:
+            pending['energy'] = m.group(1)
+            continue
+        m = _RE_SPIN.match(line)
+        if m:
+            pending['spin'] = m.group(1).lower()
+            has_alpha |= pending['spin'] == 'alpha'
+            has_beta |= pending['spin'] == 'beta'
+            continue
+        m = _RE_OCC.match(line)
+        if m:
+            pending['occ_num'] = float(m.group(1))
+            restricted |= pending['occ_num'] > 1.0001
+            continue
+    if spin is not None:
+        if restricted:
+            raise IOError('The keyword `spin` is only supported for unrestricted calculations.')
+        if spin not in ('alpha', 'beta'):
+            raise IOError('`spin=%s` is not a valid option' % spin)
+        if not has_alpha and not has_beta:
+            raise IOError('Molecular orbitals in `molden` file do not contain `Spin=` keyword')
+        if (spin == 'alpha' and not has_alpha) or (spin == 'beta' and not has_beta):
+            raise IOError('You requested `%s` orbitals, but None of them are present.' % spin)
+        display('Reading only molecular orbitals of spin %s.' % spin)
+    if sph_flags:
+        qc.ao_spec.set_lm_dict(p=[1, 0])
+    if not all_mo:
+        mos = [mo for mo in mos if mo['occ_num'] >= 0.0000001]
+    if spin is not None:
+        mos = [mo for mo in mos if mo['spin'] == spin]
+    for mo in mos:
+        if restricted:
+            del mo['spin']
+        else:
+            mo['sym'] += '_%s' % mo['spin'][0]
+    syms = [mo['sym'] for mo in mos]
+    if syms[1:] == syms[:-1]:                      # ORCA gives every orbital the same name
+        tail = syms[0].split('.')[-1]
+        for i, mo in enumerate(mos):
+            mo['sym'] = '%d.%s' % (i + 1, tail)
+    # geometry: symbol, index, charge; Angstrom -> Bohr
+    qc.geo_info = numpy.array([[get_atom_symbol(a[0]), a[1], str(float(a[2]))] for a in qc.geo_info])
+    qc.geo_spec = numpy.array(qc.geo_spec, dtype=float)
+    if angstrom:
+        qc.geo_spec *= AA_TO_A0
+    # normalisation of the contracted functions (molden.py:375-398)
+    norm = cartesian_self_overlap(qc.ao_spec)
+    if numpy.abs(norm - 1.0).max() > 1e-5:
+        display('The atomic orbitals are not normalized correctly, renormalizing...\n')
+        if not by_orca:
+            j = 0
+            for ao in qc.ao_spec:
+                ao['coeffs'][:, 1] /= numpy.sqrt(norm[j])
+                l = lquant[ao['type']]
+                j += (l + 1) * (l + 2) // 2
+        else:
+            qc.ao_spec[0]['N'] = 1 / numpy.sqrt(norm[:, numpy.newaxis])
+        if cart_flags:
+            raise NotImplementedError('renormalisation of Cartesian d/f/g shells with omitted CCA factors '
+                                      '(cy_overlap.ommited_cca_norm) is not built; use the reference reader')
+    qc.mo_spec = MOClass(mos)
+    qc.mo_spec.update()
+    qc.ao_spec.update()
+    return qc
+
+
+readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden}
+_OTHER = ('aomix', 'gamess', 'gaussian.log', 'gaussian_log', 'wfn', 'wfx', 'cclib', 'native')
 
 
 def find_itype(fname):
@@ -171,6 +414,8 @@ def find_itype(fname):
             head = f.read(4096)
         if 'Number of atoms' in head and re.search(r'^.{40} {3}[IR] ', head, re.M):
             return 'fchk'
+        if _RE_MOLDEN.search(head):
+            return 'molden'
     raise NotImplementedError('cannot determine the type of %r; pass itype=' % (name,))
 
 
@@ -180,7 +425,7 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
         itype = find_itype(fname)
     if itype not in readers:
         if itype in _OTHER:
-            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk files; use the reference\'s reader for %r and pass '
+            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk and Molden files; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
     if check_norm:

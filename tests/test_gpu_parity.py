@@ -291,6 +291,40 @@ def test_config1_h2o_80cube_full_parity(ok, oracle_mod):
     assert abs(rho.sum() * d3r - 10.0) < 0.15                       # 10 electrons; the O 1s cusp is under-resolved at 0.15 bohr
 
 
+def test_config1_end_to_end_fchk_to_cube(ok, oracle_mod, tmp_path):
+    """BASELINE configs[0] from the file to the file: main_read(h2o_rhf_sph.fchk) -> grid_init 80^3 on [-6,6]^3 ->
+    rho_compute -> main_output(otype='cb'); the cube file equals the reference's text of the oracle's density wherever
+    the two densities round to the same six digits (everywhere but at a handful of exact rounding boundaries)"""
+    import os
+    import oracle_out
+    from conftest import GOLDEN
+    qc = ok.main_read(os.path.join(GOLDEN, 'inputs', 'h2o_rhf_sph.fchk'), all_mo=False)
+    ok.grid.min_, ok.grid.max_, ok.grid.N_ = [-6.0] * 3, [6.0] * 3, [80] * 3
+    ok.grid.delta_ = [0, 0, 0]
+    ok.grid.is_initialized = False
+    ok.grid.grid_init()
+    rho = ok.rho_compute(qc)
+    fn = ok.main_output(rho, qc, outputname=str(tmp_path / 'h2o_rho'), otype='cb', datalabels='rho')[0]
+    ax = numpy.linspace(-6.0, 6.0, 80)
+    kind = 'ref' if oracle_mod.have_ref() else 'port'
+    r_ref = oracle_mod.rho_compute(qc, ax, ax, ax, is_vector=False, numproc=4, slice_length=20000, kind=kind)
+    assert_close(rho, r_ref, 'C1 rho from the fchk file')
+    got = open(fn, 'rb').read()
+    # the file is exactly the reference's text of the density that was computed here ...
+    head = ok.output.cube_header(1, qc.geo_info, qc.geo_spec, comments='rho').encode()
+    assert got[:len(head)] == head
+    sample = rho[::9, ::7]                                     # rows (x, y) of the file: 13*80 + 13 + 1 bytes each
+    rb = 13 * 80 + 80 // 6 + 1
+    for ix, x in enumerate(range(0, 80, 9)):
+        for iy, y in enumerate(range(0, 80, 7)):
+            off = len(head) + (x * 80 + y) * rb
+            assert got[off:off + rb] == oracle_out.cube_body(sample[ix:ix + 1, iy:iy + 1]), (x, y)
+    # ... and its numbers are the oracle's density to the six printed digits
+    vals = numpy.array(got[len(head):].split(), dtype=float).reshape(80, 80, 80)
+    assert numpy.abs(vals - r_ref).max() <= 5.001e-6 * numpy.abs(r_ref).max()
+    assert numpy.all(numpy.abs(vals - r_ref) <= 5.001e-6 * numpy.maximum(numpy.abs(r_ref), 1e-300) + 1e-99)
+
+
 def test_benchmark_size_properties_200cube(ok, oracle_mod):
     """The benchmark workload itself (1000 AOs, 82 MOs, 200^3 points): parity on a random sub-sample
     against the reference objects, and size-independent properties of the full result."""

@@ -332,4 +332,34 @@ def test_fchk_reader_equals_reference_reader():
     with pytest.raises(IOError):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
     with pytest.raises(NotImplementedError):
-        read.main_read('something.molden')
+        read.main_read('something.wfn')
+
+
+def test_molden_reader_equals_reference_reader():
+    """read_molden == the reference's reader on its Molpro and Psi4 test outputs.  Molpro files: every flat QCinfo array
+    identical.  The Psi4 file triggers the renormalisation of the contractions (molden.py:375-398), whose self-overlaps
+    are taken from a closed form here instead of the reference's recursion: primitive coefficients agree to 1 ulp."""
+    import os
+    from conftest import GOLDEN, load_golden
+    from orbkit_b200 import read, options
+    options.quiet = True
+    inputs = os.path.join(GOLDEN, 'inputs')
+    for fix, fn, exact in [('h2o_molpro_cart', 'h2o_rhf_sph.molden', True), ('nh3_molpro', 'nh3.mold', True),
+                           ('lih_psi4_sph_f', 'lih_cis_aug-cc-pVTZ.out.default.molden', False)]:
+        g = load_golden(fix)
+        qc = read.main_read(os.path.join(inputs, fn), all_mo=True)
+        for k, v in _flat_qc(qc).items():
+            ref = g[k]
+            assert v.shape == ref.shape, (fn, k)
+            if exact or v.dtype.kind != 'f':
+                assert (v == ref).all(), (fn, k)
+            else:
+                assert numpy.allclose(v, ref, rtol=1e-14, atol=0.0), (fn, k)
+    occ = read.main_read(os.path.join(inputs, 'h2o_rhf_sph.molden'))
+    assert len(occ.mo_spec) == 5 and (occ.mo_spec.get_occ() == 2.0).all()
+    norms = read.cartesian_self_overlap(occ.ao_spec)
+    assert numpy.abs(norms - 1.0).max() < 1e-5            # Molpro writes normalised contractions
+    with pytest.raises(IOError):
+        read.main_read(os.path.join(inputs, 'h2o_rhf_sph.molden'), spin='alpha')
+    with pytest.raises(IOError):
+        read.read_molden(os.path.join(inputs, 'h2o_rhf_sph.fchk'))
