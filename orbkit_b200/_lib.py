@@ -14,7 +14,7 @@ import threading
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libokb200.so')
+LIB_PATH = os.environ.get('OKB_LIB_PATH') or os.path.join(_HERE, 'libokb200.so')   # override: A/B builds only
 SRC = os.path.join(_HERE, 'csrc', 'okb200.cu')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -117,6 +117,7 @@ def build(force=False, verbose=False, jobs=None):
     os.makedirs(objdir, exist_ok=True)
     hdr_time = max(os.path.getmtime(h) for h in headers)
     nvcc = os.environ.get('NVCC', 'nvcc')
+    extra = os.environ.get('OKB_NVCC_EXTRA', '').split()        # A/B builds, e.g. -DOKB_REFILL_DEP
 
     def obj_of(u):
         return os.path.join(objdir, os.path.basename(u)[:-3] + '.o')
@@ -128,7 +129,7 @@ def build(force=False, verbose=False, jobs=None):
     todo = [u for u in units if stale(u)]
 
     def compile_one(u):
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', obj_of(u), u]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ['-c', '-o', obj_of(u), u]
         if verbose:
             print(' '.join(cmd))
         subprocess.check_call(cmd)

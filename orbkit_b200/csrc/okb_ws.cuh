@@ -300,6 +300,10 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 // on these 15 refills per step.  ptxas places a refill directly behind the last reader whatever the
                 // source order says (also when the value travels through a temporary and an opaque xor), so with ONE
                 // consumer warp per sub-partition this is the floor; two consumer warps per sub-partition hide it.
+                // Two timing experiments of round 1 (profiles/README.md): making each refill data dependent on the accumulator
+                // of its last reader (so that ptxas schedules it by the DMMA result latency) makes ptxas cluster all refills at
+                // the end of the step: 206.6 ms instead of 192.3; dropping the 11 A refills altogether (wrong results): 182.2 ms,
+                // i.e. all A refills together cost 5 %, the 15 refills about 8 % -- an upper bound for any refill scheme.
                 constexpr int NB = D * BN;
                 auto step = [&](const uint32_t na, const uint32_t nb) {
 #pragma unroll
