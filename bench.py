@@ -209,6 +209,36 @@ def run_b200(args):
     if world > 1:
         electrons = float(okdist.all_reduce_sum([electrons], local)[0])
 
+    # ---- the other request types of the path on the same molecule and shard, device resident (reported, not the
+    # headline): rho only, rho + laplacian (BASELINE configs[2]), all-AO store (the HBM-bound request) -----------------
+    also = None
+    if not args.no_also:
+        def timed(fn, reps=2):
+            fn()
+            eng.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(reps):
+                    fn()
+                e1.record(stream)
+            eng.sync()
+            return e0.elapsed_time(e1) / reps
+        ms_rho = timed(lambda: eng.eval_rho(mo, g, [], p0, p1, rho=out[0].data_ptr(), flags=OKB_FLAG_OUT_DEVICE))
+        ms_lap = timed(lambda: eng.eval_rho(mo, g, [4, 5, 6], p0, p1, rho=out[0].data_ptr(), delta=out[1:].data_ptr(),
+                                            flags=OKB_FLAG_OUT_DEVICE))
+        n_sub = min(n_loc, 1000000) // 1024 * 1024
+        aobuf = torch.empty((1, N_AO, n_sub), dtype=torch.float64, device=dev)
+        ms_ao = timed(lambda: eng.eval_ao(basis, g, [0], p0, p0 + n_sub, out=aobuf.data_ptr(), flags=OKB_FLAG_OUT_DEVICE))
+        ao_kernel = eng.last_kernel()
+        del aobuf
+        also = {'rho_ms': round(ms_rho, 3), 'rho_tflops_alg': round(2.0 * N_MO * N_AO * n_loc / ms_rho / 1e9, 2),
+                'rho_laplacian_ms': round(ms_lap, 3),
+                'rho_laplacian_tflops_alg': round(2.0 * N_MO * N_AO * 7 * n_loc / ms_lap / 1e9, 2),
+                'calc_ao_ms_per_1e6_points': round(ms_ao * 1e6 / n_sub, 3),
+                'calc_ao_gbs_stored': round(8.0 * N_AO * n_sub / ms_ao / 1e6, 1), 'calc_ao_kernel': ao_kernel,
+                'note': 'per GPU, device resident, same molecule; algorithmic flops 2*n_mo*n_ao*D per point (D = 1, 7)'}
+
     # ---- end to end through the public API: QCinfo + grid in, NumPy out, every step ------------------
     ok.grid.set_grid(gx, gy, gz, is_vector=False)
     e2e_steps = max(1, min(args.steps, 5))
@@ -282,7 +312,7 @@ def run_b200(args):
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'api': 'orbkit_b200.rho_compute(qc, drv=["x","y","z"])',
                     'ok': e2e_ok},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-            'electrons': electrons}
+            'electrons': electrons, 'also': also}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -363,6 +393,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     ap.add_argument('--no-peaks', action='store_true', help='skip the FP64 peak microbenchmarks (profiling runs)')
+    ap.add_argument('--no-also', action='store_true', help='skip the secondary request types (profiling runs)')
     args = ap.parse_args()
     # stdout carries the ONE JSON line only: libraries that write to file descriptor 1 (NCCL's version banner at
     # communicator creation) are sent to stderr; the JSON line goes to the original descriptor

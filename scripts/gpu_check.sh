@@ -10,10 +10,10 @@ echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-peaks > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-peaks --no-also > gpurun_out/bench_under_ncu.log 2>&1
 tail -n 12 gpurun_out/launches.csv
 echo "== ncu full capture of the fused kernel"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:okb_ws_kernel -s 3 -c 1 -f -o gpurun_out/prof_fused \
-    python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-peaks > gpurun_out/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-peaks --no-also > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out/
 fi
