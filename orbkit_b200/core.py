@@ -156,7 +156,7 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
     p0, p1 = okdist.shard_range(npts, rank, world)
     n_loc = p1 - p0
     if calc_ao or calc_mo:
-        full = okdist.shared_host_array((len(codes), n_rows, npts))
+        full = okdist.shared_host_array((len(codes), n_rows, npts), own=(p0, p1))
         if n_loc:
             dst = full.ctypes.data + 8 * p0
             if calc_ao:
@@ -166,7 +166,7 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
         tdist.barrier()
         return full
     ucodes = [] if drv is None else sorted(set(codes))
-    full = okdist.shared_host_array((1 + len(ucodes), npts))
+    full = okdist.shared_host_array((1 + len(ucodes), npts), own=(p0, p1))
     norm = None
     if n_loc:
         _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=full.ctypes.data + 8 * p0,

@@ -1313,15 +1313,21 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             CU(cudaEventRecord(ctx->ev_compute[buf], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute[buf], 0));
             const size_t wbytes = (size_t)sn * sizeof(double);
-            if (rq.sink == SINK_RHO) {
-                if (rq.rho) CU(cudaMemcpyAsync(rq.rho + s0, dbase, wbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                if (rq.n_codes > 0)
-                    CU(cudaMemcpy2DAsync(rq.delta + s0, (size_t)ldo * sizeof(double), dbase + ld,
-                                         (size_t)ld * sizeof(double), wbytes, rq.n_codes,
-                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
-            } else {
-                CU(cudaMemcpy2DAsync(rq.out + s0, (size_t)ldo * sizeof(double), dbase, (size_t)ld * sizeof(double),
-                                     wbytes, n_out_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            // Few rows: one copy per row, so that a caller may page-lock just the row segments it receives (a pitched
+            // copy is rejected when its bounding range mixes page-locked and pageable memory: dist.shared_host_array
+            // locks only the rank's own point range of every row).  Many rows: one pitched copy.
+            double *hrow0 = rq.sink == SINK_RHO ? rq.delta : rq.out;
+            const double *drow0 = rq.sink == SINK_RHO ? dbase + ld : dbase;
+            const size_t nrow2d = rq.sink == SINK_RHO ? (size_t)rq.n_codes : n_out_rows;
+            if (rq.sink == SINK_RHO && rq.rho)
+                CU(cudaMemcpyAsync(rq.rho + s0, dbase, wbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (nrow2d > 0 && nrow2d <= 64) {
+                for (size_t r = 0; r < nrow2d; ++r)
+                    CU(cudaMemcpyAsync(hrow0 + r * (size_t)ldo + s0, drow0 + r * (size_t)ld, wbytes, cudaMemcpyDeviceToHost,
+                                       ctx->copy_stream));
+            } else if (nrow2d > 0) {
+                CU(cudaMemcpy2DAsync(hrow0 + s0, (size_t)ldo * sizeof(double), drow0, (size_t)ld * sizeof(double), wbytes,
+                                     nrow2d, cudaMemcpyDeviceToHost, ctx->copy_stream));
             }
             CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
             ctx->d2h_bytes += (long long)(wbytes * n_out_rows);
