@@ -811,8 +811,11 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
                 for (int i = 0; i < MC; ++i) {
                     const int mo = mt * MC + i;
                     if (mo >= m->n_mo) continue;
-                    dst[(size_t)kk * CS + i] = kr.is_sph ? m->csph[(size_t)mo * b->n_ao + kr.index]
-                                                         : m->ccart[(size_t)mo * b->n_cart + kr.index];
+                    // MO blocks of 8 are stored in pairs, row by row: (block 2q, row r) and (block 2q+1, row r) are
+                    // neighbours, so that a consumer lane fetches its A fragments of two blocks with one 16-byte load
+                    const int blk = i >> 3, r = i & 7, pos = (blk >> 1) * 16 + 2 * r + (blk & 1);
+                    dst[(size_t)kk * CS + pos] = kr.is_sph ? m->csph[(size_t)mo * b->n_ao + kr.index]
+                                                           : m->ccart[(size_t)mo * b->n_cart + kr.index];
                 }
             }
         }
@@ -1604,11 +1607,7 @@ extern "C" int okb_format_cube(okb_ctx *ctx, const double *data, int n_sets, lon
     if (!data || !text) return fail(OKB_ERR_ARG, "okb_format_cube: null buffer");
     const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
     CU(cudaSetDevice(ctx->device));
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(okb_cube_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CUBE_SMEM));
-        attr_set = true;
-    }
+    static_assert(CUBE_SMEM <= 48 * 1024, "the cube kernel fits the default dynamic shared memory limit");
     // rows per slab: staged input + staged text of at most ~256 MB
     const size_t per_row = (in_dev ? 0 : (size_t)n * 8) + (out_dev ? 0 : (size_t)rb);
     long long slab = per_row ? std::max<long long>(1, (long long)(((size_t)256 << 20) / per_row)) : nrows;

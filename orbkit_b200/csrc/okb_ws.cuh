@@ -85,6 +85,8 @@ struct WsCfg {
     }
     static_assert(2 * NST + 2 * NM <= 32, "barrier area");
     static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
+    // MO blocks are fetched in pairs (one 16-byte load) when every warp row starts on an even block
+    static constexpr bool PAIRED = (WM == 1 || AM % 2 == 0);
     static_assert(P % 32 == 0, "whole warps of points for the producers");
     static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
 };
@@ -127,6 +129,9 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double &v0, double &v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
 }
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -287,7 +292,12 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 double afr[AM], bfr[D][BN];
                 auto frag_addr = [&](uint32_t gg, uint32_t &aa, uint32_t &bb) {
                     const int st = gg % NST;
-                    aa = smem_u32(cbase + (size_t)st * C::CBUF_DOUBLES + (size_t)tc * CS + mo_w + tr);
+                    // coefficient rows hold the MO blocks in pairs (okb200.cu: mo_blob): block b, row r at
+                    // (b/2)*16 + 2r + (b&1); this lane's row of the warp's first pair:
+                    // (mo_w = 8 * first block of the warp row; an odd first block -- WM > 1 with odd AM -- starts in
+                    // the second slot of its pair)
+                    const int fb = mo_w >> 3;
+                    aa = smem_u32(cbase + (size_t)st * C::CBUF_DOUBLES + (size_t)tc * CS + (fb >> 1) * 16 + (fb & 1) + 2 * tr);
                     bb = smem_u32(tbase + (size_t)st * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr);
                 };
                 // One k-step = NB*AM DMMAs (NB = D*BN B fragments outermost, AM MO blocks innermost) on the fragments
@@ -305,6 +315,11 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 // the end of the step: 206.6 ms instead of 192.3; dropping the 11 A refills altogether (wrong results): 182.2 ms,
                 // i.e. all A refills together cost 5 %, the 15 refills about 8 % -- an upper bound for any refill scheme.
                 constexpr int NB = D * BN;
+                // unpaired fallback: byte offset of the warp's block ia relative to the slot of its first block
+                auto aoff = [&](int ia) -> uint32_t {
+                    const int fb = mo_w >> 3, b = fb + ia;
+                    return (uint32_t)(((b >> 1) * 16 + (b & 1)) - ((fb >> 1) * 16 + (fb & 1))) * 8u;
+                };
                 auto step = [&](const uint32_t na, const uint32_t nb) {
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
@@ -313,7 +328,14 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                             const bool owned = !(MB % WM != 0 && ia == AM - 1 && ia >= nblk);   // warp-uniform
                             if (owned)
                                 dmma_m8n8k4(acc[ia][j % BN][j / BN][0], acc[ia][j % BN][j / BN][1], afr[ia], bfr[j / BN][j % BN]);
-                            if (j == NB - 1) afr[ia] = lds64(na + (uint32_t)(ia * 8) * 8u);
+                            if (j == NB - 1) {               // A fragments of the next step: one 16-byte load per block pair
+                                if (C::PAIRED) {
+                                    if (ia & 1) lds128(na + (uint32_t)((ia >> 1) * 16) * 8u, afr[ia - 1], afr[ia]);
+                                    else if (ia == AM - 1) afr[ia] = lds64(na + (uint32_t)((ia >> 1) * 16) * 8u);
+                                } else {
+                                    afr[ia] = lds64(na + aoff(ia));
+                                }
+                            }
                         }
                         bfr[j / BN][j % BN] = lds64(nb + (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u);
                     }
@@ -323,8 +345,14 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     for (int d = 0; d < D; ++d)
 #pragma unroll
                         for (int ib = 0; ib < BN; ++ib) bfr[d][ib] = lds64(cb + (uint32_t)(d * KC * PS + ib * 8) * 8u);
+                    if (C::PAIRED) {
 #pragma unroll
-                    for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(ca + (uint32_t)(ia * 8) * 8u);
+                        for (int ia = 0; ia + 1 < AM; ia += 2) lds128(ca + (uint32_t)((ia >> 1) * 16) * 8u, afr[ia], afr[ia + 1]);
+                        if (AM & 1) afr[AM - 1] = lds64(ca + (uint32_t)((AM >> 1) * 16) * 8u);
+                    } else {
+#pragma unroll
+                        for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(ca + aoff(ia));
+                    }
                 };
                 uint32_t a_ap, a_bp;
                 frag_addr(g, a_ap, a_bp);
