@@ -16,7 +16,8 @@
 //   consumers  NCW = WM x WN warps (registers raised by setmaxnreg): warp (wm, wn) owns the MO blocks
 //              [wm*AM, min((wm+1)*AM, MB)) x point blocks [wn*BN, (wn+1)*BN) (blocks of 8), an
 //              (8 AM) x (8 BN) x D register tile of 2*AM*BN*D doubles per thread.  Per k-step of 4:
-//              AM + D*BN conflict-free LDS.64 feed AM*BN*D DMMAs.  Warps wm = 0..WM-1 of one wn share
+//              ceil(AM/2) LDS.128 (MO blocks are stored in pairs, see mo_blob in okb200.cu) + D*BN LDS.64, all
+//              conflict free, feed AM*BN*D DMMAs.  Warps wm = 0..WM-1 of one wn share
 //              an SM sub-partition (warp % 4 == wn for WN == 4), so while one waits on a barrier or a
 //              fragment load the other keeps the pipe busy.
 //   hand-over  mbarriers: full[s] (one arrival per producer thread + the TMA bytes of the coefficient
@@ -26,7 +27,8 @@
 //                                       B[k][n] = ao[d][k0 + T%4][pt0 + T/4] (col-major 4x8)
 //                                       C[m][n] : m = T/4, n = 2*(T%4) + {0,1}
 // Shared-memory rows are padded to a stride = 4 (mod 16) doubles so that both fragment loads touch
-// 32 distinct 8-byte words per half-warp (2 wavefronts per LDS.64, the minimum).
+// 32 distinct 8-byte words per half-warp (2 wavefronts per LDS.64, the minimum; the 16-byte A loads touch every
+// 16-byte slot of a 128-byte line exactly twice per half-warp).
 #pragma once
 #include <type_traits>
 
