@@ -7,7 +7,7 @@ namespace okb {
 
 static const Variant table[] = {
     OKB_WS(SET_D2P, 11, 1, 1, 4, 8, 3, SINK_RHO), OKB_WS(SET_D2P, 12, 1, 1, 4, 8, 3, SINK_RHO),
-    OKB_WS(SET_D2P, 3, 1, 1, 4, 8, 3, SINK_RHO),
+    OKB_WS(SET_D2P, 3, 1, 1, 4, 12, 3, SINK_RHO), OKB_WS(SET_D2P, 3, 1, 1, 4, 8, 3, SINK_RHO),
 };
 OKB_TABLE(okb_variants_d2p, table);
 

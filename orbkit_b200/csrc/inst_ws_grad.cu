@@ -11,6 +11,8 @@ static const Variant table[] = {
     // value + gradient (D=4): 4 consumer + 8 producer warps, P = 32
     OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 11, 1, 1, 4, 8, 3, SINK_RHO),
     OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 12, 1, 1, 4, 8, 3, SINK_RHO),
+    // narrow MO tiles are bound by the AO generation: 12 producer warps (listed first: wins the tie of the cost model)
+    OKB_WS(SET_GRAD, 3, 1, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 12, 3, SINK_RHO),
     OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_RHO),
     // (two consumer warps per sub-partition -- WM=2 with 4 or 8 producer warps -- measured 265 / 238 ms against
     // 192 ms on the benchmark: DMMA wins the FP64 pipe arbitration and the producers starve)
