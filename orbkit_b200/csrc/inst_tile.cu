@@ -11,7 +11,7 @@ static const Variant table[] = {
     // AO sinks (no contraction): P = 128 points for values, fewer for the derivative sets
     // (the first entry of a set is the default; OKB_AO_VARIANT=<substring of the name> picks another one for A/B runs)
     OKB_VARIANT_AO(SET_VAL, 4, 8, 2, 2), OKB_VARIANT_AO(SET_VAL, 2, 8, 2, 3),
-    OKB_VARIANT(SET_ONE, 1, 4, 8, SINK_AO),
+    OKB_VARIANT_AO(SET_ONE, 4, 8, 2, 2),
     OKB_VARIANT(SET_GRAD, 1, 2, 8, SINK_AO), OKB_VARIANT(SET_LAP, 1, 1, 8, SINK_AO),
     OKB_VARIANT(SET_ALL, 1, 1, 8, SINK_AO),
 };

@@ -1270,7 +1270,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             // work on the all-Cartesian layout
             const bool use_mix = !b->mix_is_cart &&
                                  (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
-                                  ps.set == SET_D2P);
+                                  ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));
             const Layout &lo = use_mix ? b->mix : b->cart;
             p.meta = lo.meta_dev;
             p.lay = lo.lay;

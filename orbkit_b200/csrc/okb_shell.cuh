@@ -251,16 +251,21 @@ __device__ __forceinline__ void radial_sums_tab(const ShellMeta &sh, const doubl
 }
 
 // One standard shell for NP points of the same thread (points pt, pt+32, ...: tile columns tp[32*q]).
-template <int SET, int L, int STRIDE, bool SPH, int NP>
+// ONLY (SET_ONE requests): 1..6 = write just that derivative code (d/dx, d/dy, d/dz, d2/dx2, d2/dy2, d2/dz2) as the single
+// set of the tile; 0 = the sets of SET.
+template <int SET, int L, int STRIDE, bool SPH, int NP, int ONLY = 0>
 __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
-    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P, "specialised sets");
+    static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P ||
+                      (SET == SET_ONE && ONLY >= 1 && ONLY <= 6), "specialised sets");
+    static_assert(ONLY == 0 || SET == SET_ONE, "ONLY selects the code of a SET_ONE request");
     // N1 / N2: radial sums R1 / R2 needed; W0 / W1 / W2: value / first / pure second derivative rows written; O2: tile set
     // of d2/dx2
-    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP || SET == SET_D2 || SET == SET_D2P);
-    constexpr bool W0 = (SET != SET_D2P), W1 = (SET == SET_GRAD || SET == SET_LAP), W2 = N2;
+    constexpr bool N1 = (SET != SET_VAL), N2 = (SET == SET_LAP || SET == SET_D2 || SET == SET_D2P || ONLY >= 4);
+    constexpr bool W0 = (SET != SET_D2P && ONLY == 0), W1 = (SET == SET_GRAD || SET == SET_LAP);
+    constexpr bool W2 = (SET == SET_LAP || SET == SET_D2 || SET == SET_D2P);
     constexpr int O2 = (SET == SET_D2) ? 1 : (SET == SET_D2P) ? 0 : 4;
     constexpr int D = set_ncodes(SET);
     double r[NP][3], rr[NP];
@@ -284,13 +289,13 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
             g0[a][0] = 1.0;
 #pragma unroll
             for (int l = 1; l <= L + 1; ++l) g0[a][l] = g0[a][l - 1] * r[q][a];
-            if (W1) {
+            if (W1 || ONLY == a + 1) {
 #pragma unroll
                 for (int l = 0; l <= L; ++l)
                     g1[a][l] = (l == 0) ? g0[a][1] * m2R1
                                         : fma(g0[a][l + 1], m2R1, g0[a][l - 1] * ((double)l * R0[q]));
             }
-            if (W2) {
+            if (W2 || ONLY == a + 4) {
                 const double r2R2 = 4.0 * (r[q][a] * r[q][a]) * R2[q];
 #pragma unroll
                 for (int l = 0; l <= L; ++l) {
@@ -323,6 +328,12 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                         o[((size_t)(O2 + 1) * KC + j) * STRIDE] = fxz * g2[1][ly];
                         o[((size_t)(O2 + 2) * KC + j) * STRIDE] = fxy * g2[2][lz];
                     }
+                    if (ONLY == 1) o[(size_t)j * STRIDE] = fyz * g1[0][lx];
+                    if (ONLY == 2) o[(size_t)j * STRIDE] = fxz * g1[1][ly];
+                    if (ONLY == 3) o[(size_t)j * STRIDE] = fxy * g1[2][lz];
+                    if (ONLY == 4) o[(size_t)j * STRIDE] = fyz * g2[0][lx];
+                    if (ONLY == 5) o[(size_t)j * STRIDE] = fxz * g2[1][ly];
+                    if (ONLY == 6) o[(size_t)j * STRIDE] = fxy * g2[2][lz];
                 }
             }
         } else {
@@ -352,6 +363,12 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                         v[j][O2 + 1] = fxz * g2[1][ly];
                         v[j][O2 + 2] = fxy * g2[2][lz];
                     }
+                    if (ONLY == 1) v[j][0] = fyz * g1[0][lx];
+                    if (ONLY == 2) v[j][0] = fxz * g1[1][ly];
+                    if (ONLY == 3) v[j][0] = fxy * g1[2][lz];
+                    if (ONLY == 4) v[j][0] = fyz * g2[0][lx];
+                    if (ONLY == 5) v[j][0] = fxz * g2[1][ly];
+                    if (ONLY == 6) v[j][0] = fxy * g2[2][lz];
                 }
             }
             static_for<0, 2 * L + 1>([&](auto rc) {
@@ -373,6 +390,32 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
     }
 }
 
+// standard shells of L <= 4 (kind 1: Cartesian rows, kind 2: spherical rows): the straight-line code; returns false for
+// every other shell
+template <int S, int STRIDE, int NP, int ONLY>
+__device__ __forceinline__ bool gen_shell_try_std(const ShellMeta &sh, const double2 *__restrict__ prims,
+                                                  const FnMeta *__restrict__ fns, const double *__restrict__ aux,
+                                                  const double *__restrict__ xs, const double *__restrict__ ys,
+                                                  const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
+    if (sh.kind == 1) {                  // warp-uniform
+        switch (sh.L) {
+            case 0: gen_shell_std<S, 0, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 1: gen_shell_std<S, 1, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 2: gen_shell_std<S, 2, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 3: gen_shell_std<S, 3, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 4: gen_shell_std<S, 4, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            default: return false;
+        }
+    } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
+        switch (sh.L) {
+            case 2: gen_shell_std<S, 2, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 3: gen_shell_std<S, 3, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            default: gen_shell_std<S, 4, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+        }
+    }
+    return false;
+}
+
 // dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one.
 // xs/ys/zs point at the coordinates of the thread's first point; its NP points are 32 apart.
 template <int SET, int STRIDE, int NP>
@@ -381,24 +424,24 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp,
                                               int one_code, int exact, const AxTab &tab) {
-    if (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) {
-        constexpr int S = (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) ? SET : SET_VAL;
-        if (sh.kind == 1) {                  // warp-uniform
-            switch (sh.L) {
-                case 0: gen_shell_std<S, 0, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                case 1: gen_shell_std<S, 1, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                case 2: gen_shell_std<S, 2, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                case 3: gen_shell_std<S, 3, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                case 4: gen_shell_std<S, 4, STRIDE, false, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                default: break;
-            }
-        } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
-            switch (sh.L) {
-                case 2: gen_shell_std<S, 2, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                case 3: gen_shell_std<S, 3, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-                default: gen_shell_std<S, 4, STRIDE, true, NP>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return;
-            }
+    if constexpr (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) {
+        if (gen_shell_try_std<SET, STRIDE, NP, 0>(sh, prims, fns, aux, xs, ys, zs, tp, tab)) return;
+    }
+    if constexpr (SET == SET_ONE) {
+        // single first or pure second derivatives (ao_creator / mo_creator with drv = x .. zz, cy_core.aocreator with
+        // drv = 1..6): the straight-line code of that one code; the mixed derivatives 7..9 keep the generic path
+        // (they reproduce the reference's incomplete formulas, c_support.c:121-168)
+        bool done = false;
+        switch (one_code) {              // warp-uniform
+            case 1: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 1>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            case 2: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 2>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            case 3: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 3>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            case 4: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 4>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            case 5: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 5>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            case 6: done = gen_shell_try_std<SET_ONE, STRIDE, NP, 6>(sh, prims, fns, aux, xs, ys, zs, tp, tab); break;
+            default: break;
         }
+        if (done) return;
     }
 #pragma unroll 1
     for (int q = 0; q < NP; ++q)
