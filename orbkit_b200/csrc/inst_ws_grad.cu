@@ -16,6 +16,8 @@ static const Variant table[] = {
     OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 3, 1, 1, 4, 8, 3, SINK_RHO),
     // (two consumer warps per sub-partition -- WM=2 with 4 or 8 producer warps -- measured 265 / 238 ms against
     // 192 ms on the benchmark: DMMA wins the FP64 pipe arbitration and the producers starve)
+    // 80-wide tile: less padding for MO counts such as 222 (3 x 80 instead of 3 x 88) or 160
+    OKB_WS(SET_GRAD, 10, 1, 1, 4, 8, 3, SINK_MO), OKB_WS(SET_GRAD, 10, 1, 1, 4, 8, 3, SINK_RHO),
 };
 OKB_TABLE(okb_variants_grad, table);
 

@@ -13,6 +13,8 @@ static const Variant table[] = {
     OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 12, 4, 1, 4, 12, 3, SINK_RHO),
     OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 3, 4, 1, 4, 12, 3, SINK_RHO),
     OKB_WS(SET_ONE, 12, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_ONE, 3, 4, 1, 4, 12, 3, SINK_MO),
+    // 80-wide tile: less padding for MO counts such as 222 (3 x 80 instead of 3 x 88) or 160
+    OKB_WS(SET_VAL, 10, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 10, 4, 1, 4, 12, 3, SINK_RHO),
 };
 OKB_TABLE(okb_variants_val, table);
 
