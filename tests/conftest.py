@@ -51,3 +51,12 @@ def oracle_mod():
         subprocess.check_call(['make', '-C', d, 'CC=gcc'])
     import oracle
     return oracle
+
+
+def reader_input(name, directory):
+    """one of the program outputs of tests/golden/reader_inputs.npz written to `directory`; returns its path"""
+    data = load_golden('reader_inputs')['file.' + name]
+    path = os.path.join(str(directory), name)
+    with open(path, 'wb') as f:
+        f.write(data.tobytes())
+    return path

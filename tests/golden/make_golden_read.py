@@ -7,7 +7,9 @@ Writes tests/golden/read_fchk.npz: per case `<c>.<flat QCinfo arrays>` (make_gol
     cart      h2o_rhf_cart.fchk, all_mo=True          (6D 10F basis)
     uhf_beta  h2o_uhf_sph.fchk, all_mo=True, spin='beta'
     uhf_occ   h2o_uhf_sph.fchk, all_mo=False
-The input files are copied unchanged to tests/golden/inputs/ (program outputs of Gaussian, test data of the reference).
+and tests/golden/reader_inputs.npz: the bytes of the quantum-chemistry program outputs the readers are tested on
+(`file.<name>`; Gaussian fchk, Molpro / Psi4 Molden files from the reference's test data orbkit/test/outputs_for_testing) --
+the tests write them to a scratch directory and read them with orbkit_b200.read.
 The spherical restricted / unrestricted cases are pinned by h2o_gaussian_sph*.npz / h2o_gaussian_uhf.npz (make_golden.py).
 """
 import os
@@ -38,6 +40,14 @@ def main():
         out[name + '.etot'] = numpy.array(qc.etot)
         print(name, len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
     numpy.savez_compressed(os.path.join(HERE, 'read_fchk.npz'), **out)
+    odir = os.path.join(scratch, 'orbkit', 'test', 'outputs_for_testing')
+    files = {}
+    for rel in ['gaussian/h2o_rhf_sph.fchk', 'gaussian/h2o_uhf_sph.fchk', 'gaussian/h2o_rhf_cart.fchk',
+                'molpro/h2o_rhf_sph.molden', 'molpro/nh3.mold', 'psi4/lih_cis_aug-cc-pVTZ.out.default.molden']:
+        with open(os.path.join(odir, rel), 'rb') as f:
+            files['file.' + os.path.basename(rel)] = numpy.frombuffer(f.read(), dtype=numpy.uint8)
+    numpy.savez_compressed(os.path.join(HERE, 'reader_inputs.npz'), **files)
+    print('reader_inputs.npz:', sorted(files))
 
 
 if __name__ == '__main__':

@@ -297,8 +297,8 @@ def test_config1_end_to_end_fchk_to_cube(ok, oracle_mod, tmp_path):
     the two densities round to the same six digits (everywhere but at a handful of exact rounding boundaries)"""
     import os
     import oracle_out
-    from conftest import GOLDEN
-    qc = ok.main_read(os.path.join(GOLDEN, 'inputs', 'h2o_rhf_sph.fchk'), all_mo=False)
+    from conftest import reader_input
+    qc = ok.main_read(reader_input('h2o_rhf_sph.fchk', tmp_path), all_mo=False)
     ok.grid.min_, ok.grid.max_, ok.grid.N_ = [-6.0] * 3, [6.0] * 3, [80] * 3
     ok.grid.delta_ = [0, 0, 0]
     ok.grid.is_initialized = False

@@ -300,15 +300,17 @@ def _flat_qc(qc):
     return out
 
 
-def test_fchk_reader_equals_reference_reader():
+def test_fchk_reader_equals_reference_reader(tmp_path):
     """read_gaussian_fchk == the reference's reader on the reference's own Gaussian test outputs: every flat QCinfo array
     identical (goldens written by running the reference: make_golden.py, make_golden_read.py)"""
     import io
     import os
-    from conftest import GOLDEN, load_golden
+    from conftest import load_golden, reader_input
     from orbkit_b200 import read, options
     options.quiet = True
-    inputs = os.path.join(GOLDEN, 'inputs')
+    inputs = str(tmp_path)
+    for name in ('h2o_rhf_sph.fchk', 'h2o_uhf_sph.fchk', 'h2o_rhf_cart.fchk'):
+        reader_input(name, inputs)
     extra = load_golden('read_fchk')
     cases = [(load_golden('h2o_gaussian_sph'), '', 'h2o_rhf_sph.fchk', dict(all_mo=True)),
              (load_golden('h2o_gaussian_sph_occ'), '', 'h2o_rhf_sph.fchk', dict(all_mo=False)),
@@ -335,15 +337,17 @@ def test_fchk_reader_equals_reference_reader():
         read.main_read('something.wfn')
 
 
-def test_molden_reader_equals_reference_reader():
+def test_molden_reader_equals_reference_reader(tmp_path):
     """read_molden == the reference's reader on its Molpro and Psi4 test outputs.  Molpro files: every flat QCinfo array
     identical.  The Psi4 file triggers the renormalisation of the contractions (molden.py:375-398), whose self-overlaps
     are taken from a closed form here instead of the reference's recursion: primitive coefficients agree to 1 ulp."""
     import os
-    from conftest import GOLDEN, load_golden
+    from conftest import load_golden, reader_input
     from orbkit_b200 import read, options
     options.quiet = True
-    inputs = os.path.join(GOLDEN, 'inputs')
+    inputs = str(tmp_path)
+    for name in ('h2o_rhf_sph.molden', 'nh3.mold', 'lih_cis_aug-cc-pVTZ.out.default.molden', 'h2o_rhf_sph.fchk'):
+        reader_input(name, inputs)
     for fix, fn, exact in [('h2o_molpro_cart', 'h2o_rhf_sph.molden', True), ('nh3_molpro', 'nh3.mold', True),
                            ('lih_psi4_sph_f', 'lih_cis_aug-cc-pVTZ.out.default.molden', False)]:
         g = load_golden(fix)
