@@ -982,9 +982,10 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 
 // ---- launch machinery ---------------------------------------------------------------------------------------
 // the kernel instantiations live in inst_*.cu (compiled in parallel); okb_variant.h declares their tables
-// (SINK_AO: the first matching entry is the default, i.e. the tile kernel; the warp-specialised "aows/" kernels measured
-// the same throughput -- the AO generators, not the stores, bound calc_ao -- and stay selectable for A/B runs)
-static const VariantTable *const g_tables[] = {&okb_variants_tile, &okb_variants_aows, &okb_variants_val, &okb_variants_grad,
+// (SINK_AO: the first matching entry is the default: the warp-specialised "aows/" kernels for the derivative sets -- twice
+// the throughput of the tile kernel there -- and the tile kernel for plain values, where both measure the same because the
+// AO generators, not the stores, bound calc_ao)
+static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants_tile, &okb_variants_val, &okb_variants_grad,
                                                &okb_variants_lap, &okb_variants_all, &okb_variants_d2, &okb_variants_d2p};
 
 // ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
@@ -997,8 +998,14 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         if (v.set != set || v.sink != sink) continue;
         if (sink == SINK_AO) {
             static const char *force_ao = getenv("OKB_AO_VARIANT");      // A/B measurements only
-            if (force_ao && force_ao[0] && set == SET_VAL && !strstr(v.name, force_ao)) continue;
-            if (!ao_bulk_ok && strncmp(v.name, "aows/", 5) == 0) continue;
+            if (force_ao && force_ao[0]) {
+                // a forced name that carries a set ("...SET_GRAD...") only applies to requests of that set
+                static const char *const set_names[] = {"SET_VAL", "SET_GRAD", "SET_LAP", "SET_ALL", "SET_ONE", "SET_D2", "SET_D2P"};
+                const bool applies = !strstr(force_ao, "SET_") || strstr(force_ao, set_names[set]);
+                if (applies && !strstr(v.name, force_ao)) continue;
+            }
+            const bool is_aows = strncmp(v.name, "aows/", 5) == 0;
+            if (is_aows && (!ao_bulk_ok || (set == SET_VAL && !(force_ao && force_ao[0])))) continue;
             return &v;
         }
         // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
@@ -1254,7 +1261,16 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                 const double *obase = dev_out ? rq.out + s0 : dbase;
                 ao_bulk_ok = (reinterpret_cast<uintptr_t>(obase) % 16 == 0) && (ld % 2 == 0);
             }
+            // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP/D2/D2P and the single codes
+            // 1..6 of ONE); the generic sets work on the all-Cartesian layout
+            const bool use_mix = !b->mix_is_cart &&
+                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
+                                  ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));
+            const Layout &lo = use_mix ? b->mix : b->cart;
             const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo, ao_bulk_ok);
+            // (a basis with very large chunk tables may not leave the stage ring of an "aows/" kernel enough shared memory)
+            if (v && rq.sink == SINK_AO && ao_bulk_ok && v->smem(lo.lay.stride) > 227 * 1024)
+                v = pick_variant(ps.set, rq.sink, 1, false);
             if (!v) return fail(OKB_ERR_UNSUPPORTED, "no kernel variant for set %d sink %d", ps.set, rq.sink);
             KParams p{};
             p.grid_kind = g->kind;
@@ -1266,12 +1282,6 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.p0 = rq.p0 + s0 + u0;
             p.npts = (int)un;
             p.ntiles = (int)((un + v->P - 1) / v->P);
-            // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP); the generic sets
-            // work on the all-Cartesian layout
-            const bool use_mix = !b->mix_is_cart &&
-                                 (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
-                                  ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));
-            const Layout &lo = use_mix ? b->mix : b->cart;
             p.meta = lo.meta_dev;
             p.lay = lo.lay;
             p.nchunk = (int)lo.chunks.size();
