@@ -76,6 +76,8 @@ def cube_body(data):
         import torch
         if data.dtype != torch.float64 or not data.is_contiguous():
             raise ValueError('device data must be a C-contiguous float64 tensor')
+        if data.device.index != eng.device:
+            raise ValueError('device data lives on cuda:%s, the engine on cuda:%d' % (data.device.index, eng.device))
         torch.cuda.current_stream(data.device).synchronize()    # the formatter runs on the context's own stream
         ptr, flags = data.data_ptr(), _lib.OKB_FLAG_IN_DEVICE
     else:
