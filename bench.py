@@ -161,7 +161,7 @@ def run_b200(args):
 
     # ---- resident inputs: tables, coefficients, axes on the device; outputs stay in HBM -------------
     basis = eng.basis(qc.geo_spec, qc.ao_spec)
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc.mo_spec)
     g = eng.grid_regular(gx, gy, gz)
     p0, p1 = okdist.shard_range(npts_total, rank, world)
     n_loc = p1 - p0
@@ -241,34 +241,165 @@ def run_b200(args):
 
     # ---- end to end through the public API: QCinfo + grid in, NumPy out, every step ------------------
     ok.grid.set_grid(gx, gy, gz, is_vector=False)
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = args.steps
 
     def e2e_step():
         eng.clear_caches()                  # tables / coefficients / axes are uploaded again
         return ok.rho_compute(qc, drv=DRV)
 
+    def time_e2e(fn, steps, sync_ranks=True):
+        """wall time per step of `fn` (max over ranks when `sync_ranks`), 3 untimed calls first"""
+        r = None
+        for _ in range(3):
+            r = fn()
+        if sync_ranks:
+            barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if sync_ranks:
+            barrier(world)
+            dt = max_over_ranks(dt, world, dev)
+        return dt / steps, r
+
     if args.no_e2e:
         e2e_steps = 0
-    for _ in range(3 if e2e_steps else 0):   # page-locked result buffers come from a caching allocator
-        r = e2e_step()
-    barrier(world)
     h0, d0 = eng.traffic()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier(world)
+    r = [numpy.zeros((len(gx), len(gy), len(gz)))]
+    t_e2e = float('nan')
+    if e2e_steps:
+        for _ in range(3):                  # page-locked result buffers come from a caching allocator
+            r = e2e_step()
+        barrier(world)
+        h0, d0 = eng.traffic()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        barrier(world)
     h1, d1 = eng.traffic()
     t_e2e = max_over_ranks(t_e2e, world, dev)
-    if not e2e_steps:
-        r = [numpy.zeros((len(gx), len(gy), len(gz)))]
-    e2e_value = npts_total * e2e_steps / t_e2e
+    e2e_value = npts_total * e2e_steps / t_e2e if e2e_steps else None
     d2h = (d1 - d0) / max(e2e_steps, 1)
     h2d = (h1 - h0) / max(e2e_steps, 1)
     if world > 1:                           # whole job: every rank copies its own shard into the shared host array
         d2h, h2d = [float(v) for v in okdist.all_reduce_sum([d2h, h2d], local)]
     e2e_ok = bool(numpy.isfinite(r[0]).all() and r[0].shape == (len(gx), len(gy), len(gz)))
+    del r
+
+    # ---- STRONG scaling in the same run (north_star: "sharding grid points across the 8 GPUs"): a FIXED grid over the
+    # N ranks, device-timed and through rho_compute, against the same grid on one GPU (rank 0 alone) -----------------
+    strong = None
+    if not args.no_strong:
+        strong = {'efficiency_def': 't_1 / (N * t_N); t_1 measured on rank 0 alone in this run'}
+        cases = [('c3_200cube', spec, qc, numpy.linspace(-BOX, BOX, GRID_N), ALG_FLOPS_PER_POINT, args.steps)]
+        if not args.no_c4:
+            spec4 = synth.make_molecule(n_heavy=72, n_light=60, n_mo=246, seed=0, spherical=True)
+            cases.append(('c4_256cube', spec4, synth.to_qcinfo(spec4), numpy.linspace(-BOX, BOX, 256),
+                          2.0 * 246 * 3000 * 4, 2))
+        for name, sp_, qc_, ax_, flops_pt, ksteps in cases:
+            n_all = len(ax_) ** 3
+            b_ = eng.basis(qc_.geo_spec, qc_.ao_spec)
+            m_ = eng.mos_of(b_, qc_.mo_spec)
+            g_ = eng.grid_regular(ax_, ax_, ax_)
+            q0, q1 = okdist.shard_range(n_all, rank, world)
+            buf = torch.zeros((4, n_all if rank == 0 else max(q1 - q0, 1)), dtype=torch.float64, device=dev)
+
+            def dev_ms(a, b_end, reps):
+                ld = buf.shape[1]
+                f = lambda: eng.eval_rho(m_, g_, codes, a, b_end, rho=buf[0].data_ptr(), delta=buf[1:].data_ptr(),
+                                         flags=OKB_FLAG_OUT_DEVICE, ld=ld)
+                f()
+                eng.sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    for _ in range(reps):
+                        f()
+                    e1.record(stream)
+                eng.sync()
+                return e0.elapsed_time(e1) / reps
+            barrier(world)
+            t_n = max_over_ranks(dev_ms(q0, q1, ksteps) if q1 > q0 else 0.0, world, dev)
+            t_1 = t_n
+            if world > 1:
+                t_1 = dev_ms(0, n_all, max(1, min(ksteps, 3))) if rank == 0 else 0.0
+                t_1 = max_over_ranks(t_1, world, dev)
+            del buf
+            ok.grid.set_grid(ax_, ax_, ax_, is_vector=False)
+            fn = lambda: ok.rho_compute(qc_, drv=DRV)
+            e_n, res = time_e2e(fn, ksteps)
+            e_n *= 1e3
+            e_ok = bool(res[0].shape == (len(ax_),) * 3 and numpy.isfinite(res[1]).all())
+            del res
+            e_1 = e_n
+            if world > 1:
+                e_1 = 0.0
+                if rank == 0:
+                    with okdist.local_only():
+                        e_1, res = time_e2e(fn, max(1, min(ksteps, 5)), sync_ranks=False)
+                    e_1 *= 1e3
+                    del res
+                e_1 = max_over_ranks(e_1, world, dev)
+            strong[name] = {'points': n_all, 'steps': ksteps,
+                            'device_ms_1gpu': round(t_1, 3), 'device_ms': round(t_n, 3),
+                            'device_efficiency': round(t_1 / (world * t_n), 4),
+                            'device_points_per_s': n_all / (t_n * 1e-3),
+                            'device_tflops_alg': round(flops_pt * n_all / (t_n * 1e-3) / 1e12, 2),
+                            'e2e_ms_1gpu': round(e_1, 3), 'e2e_ms': round(e_n, 3),
+                            'e2e_efficiency': round(e_1 / (world * e_n), 4),
+                            'e2e_points_per_s': n_all / (e_n * 1e-3), 'e2e_ok': e_ok}
+        ok.grid.set_grid(gx, gy, gz, is_vector=False)
+
+    # ---- device-side gather of the shards over NVLink (dist.gather_points on NCCL): the alternative assembly for
+    # callers that want the full result as a device tensor (SURVEY 8e) ---------------------------------------------
+    gather = None
+    if world > 1:
+        shard = torch.zeros((4, n_loc), dtype=torch.float64, device=dev)
+        full = okdist.gather_points(shard, npts_total)
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            full = okdist.gather_points(shard, npts_total)
+        e1.record()
+        torch.cuda.synchronize()
+        g_ms = max_over_ranks(e0.elapsed_time(e1) / 5, world, dev)
+        recv = 32.0 * (npts_total - n_loc)
+        gather = {'api': 'orbkit_b200.dist.gather_points (NCCL all-gather + unpadding copy)', 'ms': round(g_ms, 3),
+                  'bytes_received_per_rank': recv, 'gbs_per_rank': round(recv / (g_ms * 1e-3) / 1e9, 1),
+                  'nvlink_peak_gbs_per_direction': 900.0}
+        del full, shard
+
+    # ---- small-call latency (the reference's cubature example calls rho_compute thousands of times on small vector
+    # grids with new points each time, examples/basic_examples/orbkit_interface_to_cubature.py:76-102) ---------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        with okdist.local_only():
+            rng = numpy.random.default_rng(1)
+            pts = rng.uniform(-BOX, BOX, size=(64, 3, 1000))
+
+            def call(i):
+                ok.grid.x, ok.grid.y, ok.grid.z = pts[i % 64]
+                ok.grid.is_initialized, ok.grid.is_vector = True, True
+                return ok.rho_compute(qc, drv=None, numproc=1)
+            ok.grid.set_grid(pts[0][0], pts[0][1], pts[0][2], is_vector=True)
+            for i in range(10):
+                call(i)
+            t0 = time.perf_counter()
+            ncall = 200
+            for i in range(ncall):
+                out1 = call(i)
+            us = (time.perf_counter() - t0) / ncall * 1e6
+            latency = {'api': 'orbkit_b200.rho_compute(qc) on a NEW 1000-point vector grid per call, handles cached',
+                       'us_per_call': round(us, 1), 'points_per_call': 1000, 'calls': ncall,
+                       'ok': bool(out1.shape == (1000,) and numpy.isfinite(out1).all())}
+        ok.grid.set_grid(gx, gy, gz, is_vector=False)
+    barrier(world)
 
     if world > 1:
         import torch.distributed as dist
@@ -311,6 +442,7 @@ def run_b200(args):
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'api': 'orbkit_b200.rho_compute(qc, drv=["x","y","z"])',
                     'ok': e2e_ok},
+            'strong': strong, 'gather': gather, 'latency': latency,
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
             'electrons': electrons, 'also': also}
     print(json.dumps(line), flush=True)
@@ -340,13 +472,29 @@ def cpu_baseline(spec, args, steps=1):
     import cpu_bench
     cores = os.cpu_count() or 1
     workers = min(cores, 64)
-    npts = workers * 16000 if args.cpu_points <= 0 else args.cpu_points
+    npts = workers * 20000 if args.cpu_points <= 0 else args.cpu_points
     x, y, z = cpu_sample(1, npts)
     res = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=2000, repeats=steps)
+    # the reference's default slice_length (core.py:314: 1e4) as well: two slices per worker
+    res4 = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=10000, repeats=steps)
+    # one small call (1000 new points, density only) on one core: what the cubature example pays per call
+    import oracle
+    from orbkit_b200 import synth
+    qc = synth.to_qcinfo(spec)
+    rng = numpy.random.default_rng(1)
+    px, py, pz = rng.uniform(-BOX, BOX, size=(3, 1000))
+    kind = cpu_bench.default_kind()
+    oracle.rho_compute(qc, px, py, pz, is_vector=True, kind=kind)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        oracle.rho_compute(qc, px, py, pz, is_vector=True, kind=kind)
+    small_us = (time.perf_counter() - t0) / 2 * 1e6
     return {'value': res['points_per_s'], 'unit': 'points/s', 'cores': res['cores'], 'kind': res['kind'],
             'sample': '%d contiguous points from the middle x-plane of the 200^3 grid, %d worker processes, '
                       'slices of 2000 points (reference Pool driver, core.py:503-536); %.1f s'
-                      % (res['npts'], res['cores'], res['seconds']), 'host_cores': cores}
+                      % (res['npts'], res['cores'], res['seconds']), 'host_cores': cores,
+            'value_slice_1e4': res4['points_per_s'], 'seconds_slice_1e4': round(res4['seconds'], 2),
+            'us_per_1000_point_call_1core': round(small_us, 1)}
 
 
 def run_reference(args):
@@ -359,9 +507,10 @@ def run_reference(args):
     import cpu_bench
     cores = os.cpu_count() or 1
     workers = min(cores, 64)
-    npts = workers * 16000 if args.cpu_points <= 0 else args.cpu_points
+    npts = workers * 20000 if args.cpu_points <= 0 else args.cpu_points
     x, y, z = cpu_sample(1, npts)
     kind = cpu_bench.default_kind()
+    res4 = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=10000, kind=kind)   # reported beside
     times = []
     for s in range(args.warmup + args.steps):
         res = cpu_bench.time_cpu(spec, x, y, z, DRV, nproc=workers, slice_length=2000, kind=kind)
@@ -377,7 +526,7 @@ def run_reference(args):
             'data': 'synthetic (seeded random molecule and MO coefficients)',
             'config': {'workload': WORKLOAD, 'sample': sample},
             'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': res['cores'], 'kind': res['kind'],
-                             'sample': sample, 'host_cores': cores},
+                             'sample': sample, 'host_cores': cores, 'value_slice_1e4': res4['points_per_s']},
             'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -389,11 +538,14 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--cpu-points', type=int, default=0, help='size of the CPU sample (0: 16000 per worker, about 10-15 s)')
+    ap.add_argument('--cpu-points', type=int, default=0, help='size of the CPU sample (0: 20000 per worker, about 12 s per slice length)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     ap.add_argument('--no-peaks', action='store_true', help='skip the FP64 peak microbenchmarks (profiling runs)')
     ap.add_argument('--no-also', action='store_true', help='skip the secondary request types (profiling runs)')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling block')
+    ap.add_argument('--no-c4', action='store_true', help='strong-scaling block without the 3000-AO / 256^3 case')
+    ap.add_argument('--no-latency', action='store_true', help='skip the small-call latency block')
     args = ap.parse_args()
     # stdout carries the ONE JSON line only: libraries that write to file descriptor 1 (NCCL's version banner at
     # communicator creation) are sent to stderr; the JSON line goes to the original descriptor

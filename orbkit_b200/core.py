@@ -127,7 +127,7 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
     npts = int(numpy.prod(N))
     codes = [0] if drv is None else [validate_drv(d) for d in drv]
     if not calc_ao:
-        mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+        mo = eng.mos_of(basis, qc.mo_spec)
     n_rows = basis[2] if calc_ao else (mo.n_mo if calc_mo else 1)
     if npts == 0:
         if calc_mo or calc_ao:
@@ -155,24 +155,39 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
     rank, world = okdist.rank_world()
     p0, p1 = okdist.shard_range(npts, rank, world)
     n_loc = p1 - p0
+    shared = okdist.single_node()         # else: every rank evaluates into a local array and the shards are all-gathered
     if calc_ao or calc_mo:
-        full = okdist.shared_host_array((len(codes), n_rows, npts), own=(p0, p1))
+        if shared:
+            full = okdist.shared_host_array((len(codes), n_rows, npts), own=(p0, p1))
+            if n_loc:
+                dst = full.ctypes.data + 8 * p0
+                if calc_ao:
+                    eng.eval_ao(basis, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
+                else:
+                    eng.eval_mo(mo, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
+            tdist.barrier()
+            return full
+        loc = numpy.zeros((len(codes), n_rows, 0))
         if n_loc:
-            dst = full.ctypes.data + 8 * p0
-            if calc_ao:
-                eng.eval_ao(basis, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
-            else:
-                eng.eval_mo(mo, g, codes, p0, p1, out=dst, flags=flags, ld=npts)
-        tdist.barrier()
-        return full
+            loc = eng.eval_ao(basis, g, codes, p0, p1, flags=flags) if calc_ao else eng.eval_mo(mo, g, codes, p0, p1, flags=flags)
+        return okdist.gather_rows(loc, npts, p0, p1).reshape((len(codes), n_rows, npts))
     ucodes = [] if drv is None else sorted(set(codes))
-    full = okdist.shared_host_array((1 + len(ucodes), npts), own=(p0, p1))
     norm = None
-    if n_loc:
-        _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=full.ctypes.data + 8 * p0,
-                                  delta=(full.ctypes.data + 8 * (npts + p0)) if ucodes else None,
-                                  want_norm=want_norm, flags=flags, ld=npts)
-    tdist.barrier()
+    if shared:
+        full = okdist.shared_host_array((1 + len(ucodes), npts), own=(p0, p1))
+        if n_loc:
+            _, _, norm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=full.ctypes.data + 8 * p0,
+                                      delta=(full.ctypes.data + 8 * (npts + p0)) if ucodes else None,
+                                      want_norm=want_norm, flags=flags, ld=npts)
+        tdist.barrier()
+    else:
+        loc = numpy.zeros((1 + len(ucodes), n_loc))
+        if n_loc:
+            r_loc, d_loc, norm = eng.eval_rho(mo, g, ucodes, p0, p1, want_norm=want_norm, flags=flags)
+            loc[0] = r_loc
+            if ucodes:
+                loc[1:] = d_loc
+        full = okdist.gather_rows(loc, npts, p0, p1)
     if want_norm:
         norm = okdist.all_reduce_sum(norm if norm is not None else numpy.zeros(mo.n_mo), eng.device)
     delta = None
@@ -374,7 +389,7 @@ def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_
     out = eng.host_array((len(codes), nmo_a * nmo_b, npts))
     if same:
         basis = eng.basis(require(qc_a.geo_spec, dtype='f'), qc_a.ao_spec)
-        mo = eng.mos(basis, qc_a.mo_spec.get_coeffs(), qc_a.mo_spec.get_occ())
+        mo = eng.mos_of(basis, qc_a.mo_spec)
         g = _grid_handle(eng, x, y, z, is_vector)
         terms = (numpy.zeros(len(ia)), ia, ib)
         for d, code in enumerate(codes):

@@ -854,12 +854,20 @@ extern "C" int okb_mo_destroy(okb_mo *m) {
 }
 
 // ---- grids -----------------------------------------------------------------------------------------------
+extern "C" int okb_grid_destroy(okb_grid *g);
+// destroys a half-built grid on every early return of its constructor (CU() / pool_get failures)
+struct GridGuard {
+    okb_grid *g;
+    ~GridGuard() { if (g) okb_grid_destroy(g); }
+    okb_grid *release() { okb_grid *r = g; g = nullptr; return r; }
+};
 extern "C" int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const double *y, int ny,
                                 const double *z, int nz, okb_grid **out) {
     if (!ctx || !out || !x || !y || !z) return fail(OKB_ERR_ARG, "okb_grid_regular: null argument");
     *out = nullptr;
     if (nx <= 0 || ny <= 0 || nz <= 0) return fail(OKB_ERR_ARG, "okb_grid_regular: empty axis");
     okb_grid *g = new okb_grid();
+    GridGuard guard{g};
     g->ctx = ctx;
     g->kind = 0;
     g->nx = nx; g->ny = ny; g->nz = nz;
@@ -879,7 +887,7 @@ extern "C" int okb_grid_regular(okb_ctx *ctx, const double *x, int nx, const dou
     CU(cudaMemcpy(g->gy, y, sizeof(double) * ny, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g->gz, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
     ctx->h2d_bytes += (long long)sizeof(double) * (nx + ny + nz);
-    *out = g;
+    *out = guard.release();
     return OKB_OK;
 }
 
@@ -889,6 +897,7 @@ extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, c
     *out = nullptr;
     if (npts <= 0) return fail(OKB_ERR_ARG, "okb_grid_vector: empty grid");
     okb_grid *g = new okb_grid();
+    GridGuard guard{g};
     g->ctx = ctx;
     g->kind = 1;
     g->npts = npts;
@@ -912,7 +921,7 @@ extern "C" int okb_grid_vector(okb_ctx *ctx, const double *x, const double *y, c
         CU(cudaStreamSynchronize(ctx->stream));
         ctx->h2d_bytes += 3ll * (long long)sizeof(double) * npts;
     }
-    *out = g;
+    *out = guard.release();
     return OKB_OK;
 }
 
@@ -927,6 +936,7 @@ extern "C" int okb_grid_product(okb_ctx *ctx, int kind, const double *a0, int n0
     if (kind != 2 && kind != 3) return fail(OKB_ERR_ARG, "okb_grid_product: kind must be 2 (spherical) or 3 (cylindrical)");
     if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(OKB_ERR_ARG, "okb_grid_product: empty axis");
     okb_grid *g = new okb_grid();
+    GridGuard guard{g};
     g->ctx = ctx;
     g->kind = kind;
     g->nx = n0; g->ny = n1; g->nz = n2;
@@ -956,7 +966,7 @@ extern "C" int okb_grid_product(okb_ctx *ctx, int kind, const double *a0, int n0
         CU(cudaMemcpy(*dst[a], src[a], sizeof(double) * cnt[a], cudaMemcpyHostToDevice));
         ctx->h2d_bytes += (long long)(sizeof(double) * cnt[a]);
     }
-    *out = g;
+    *out = guard.release();
     return OKB_OK;
 }
 

@@ -139,7 +139,7 @@ def _from_qc(mode, qc, zero, sing, drv, x, y, z, is_vector):
     x, y, z, is_vector, N = _resolve_grid(x, y, z, is_vector)
     eng = get_engine()
     basis = eng.basis(require(qc.geo_spec, dtype='f'), qc.ao_spec)
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc.mo_spec)
     ncomp = 1 if mode == OKB_CI_RHO else 3
     lead = () if ncomp == 1 else (3,)
     if int(numpy.prod(N)) == 0:

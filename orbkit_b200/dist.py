@@ -25,7 +25,25 @@ import numpy
 ALIGN = 128   # shard boundaries fall on CTA tile boundaries
 
 
+_local_only = False
+
+
+class local_only:
+    """context manager: inside it this process works alone (is_distributed() is False) although a process group
+    exists -- bench.py times the one-GPU run of a strong-scaling pair on rank 0 with it"""
+
+    def __enter__(self):
+        global _local_only
+        self.prev, _local_only = _local_only, True
+
+    def __exit__(self, *exc):
+        global _local_only
+        _local_only = self.prev
+
+
 def is_distributed():
+    if _local_only:
+        return False
     try:
         import torch.distributed as dist
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -89,8 +107,43 @@ def all_reduce_sum(values, device=None):
 
 
 # ---- one host array shared by the ranks of a node ------------------------------------------------------
+def single_node():
+    """True when every rank of the job runs on this host (the shared-memory assembly needs that); decided once by
+    an all-gather of (hostname, boot id)"""
+    global _single_node
+    if _single_node is None:
+        import socket
+        import torch.distributed as dist
+        if os.environ.get('OKB_DIST_FORCE_GATHER'):
+            _single_node = False
+            return _single_node
+        try:
+            boot = open('/proc/sys/kernel/random/boot_id').read().strip()
+        except OSError:
+            boot = ''
+        mine = (socket.gethostname(), boot)
+        everyone = [None] * dist.get_world_size()
+        dist.all_gather_object(everyone, mine)
+        _single_node = all(e == everyone[0] for e in everyone)
+    return _single_node
+
+
+_single_node = None
+
+
+def all_reduce_min(values, device=None):
+    """element-wise minimum of a small integer vector over all ranks (agreement on which cached segments are free)"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.int64)
+    if dist.get_backend() == 'nccl':
+        t = t.cuda(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return [int(v) for v in t.cpu().tolist()]
+
+
 class _Segment:
-    """an mmap of a /dev/shm file that every rank of the job has opened (the file is unlinked once all
+    """an mmap of a /dev/shm file that every rank of the node has opened (the file is unlinked once all
     ranks hold it: the memory lives as long as a mapping does)"""
 
     def __init__(self, nbytes, name, create):
@@ -104,13 +157,19 @@ class _Segment:
             os.close(fd)
         self.nbytes = nbytes
         self.path = path
-        self.registered = False
+        self.locked = []            # page-locked (address, nbytes) ranges of this process
+        self.key = None
+        self.user = None            # weak reference to the array handed out last
+
+    def busy(self):
+        """does the caller still hold the array (or a view of it) that was handed out last?"""
+        return self.user is not None and self.user() is not None
 
     def register_cuda(self, ranges=None):
         """page-lock the mapping for this process's CUDA context (async D2H into it then overlaps compute).
         `ranges`: byte ranges [(offset, nbytes), ...] this rank writes -- only those pages are locked (page-locking
         is the expensive part of a new segment: every rank locking all of a 0.5 GB array took 1.7 s at 8 ranks)."""
-        if self.registered:
+        if self.locked:
             return True
         try:
             import ctypes
@@ -119,35 +178,69 @@ class _Segment:
             rt = torch.cuda.cudart()
             if not ranges:
                 ranges = [(0, self.nbytes)]
-            page, ok, last_end = mmap.PAGESIZE, True, 0
+            page, last_end = mmap.PAGESIZE, 0
             for off, n in sorted(ranges):
                 a = max(off // page * page, last_end)                # page aligned, never twice the same page
                 b = min(-(-(off + n) // page) * page, -(-self.nbytes // page) * page)
                 if b > a:
-                    ok = ok and int(rt.cudaHostRegister(base + a, b - a, 0)) == 0
+                    if int(rt.cudaHostRegister(base + a, b - a, 0)) != 0:
+                        self.release_cuda()
+                        return False
+                    self.locked.append((base + a, b - a))
                     last_end = b
-            self.registered = ok
         except Exception:
-            self.registered = False
-        return self.registered
+            self.release_cuda()
+        return bool(self.locked)
+
+    def release_cuda(self):
+        if not self.locked:
+            return
+        try:
+            import torch
+            rt = torch.cuda.cudart()
+            for addr, _ in self.locked:
+                rt.cudaHostUnregister(addr)
+        except Exception:
+            pass
+        self.locked = []
 
 
-_segments = {}      # (nbytes, generation) -> _Segment
-_generation = {}    # nbytes -> how many arrays of this size were handed out
+# Cached segments in creation order -- the SAME list on every rank, because segments are created, reused and evicted
+# collectively on state all ranks agreed on (the all-reduced free flags below).
+_segments = []
+CACHE_BYTES = 8 << 30       # free segments beyond this total are unmapped, oldest first
+
+
+def _drop(seg):
+    seg.release_cuda()
+    seg.user = None            # the mapping itself goes away with its last view
 
 
 def shared_host_array(shape, pin=True, own=None):
-    """float64 array of `shape` in node-shared memory, the SAME memory on every rank (collective call:
-    every rank must call it with the same shape).  Two segments per size are used in turn, so a result
-    stays valid until the second-next call with the same shape.  `own = (p0, p1)`: this rank writes the
-    entries [p0, p1) of the last axis of every row; with at most 64 rows only those pages are page-locked."""
+    """float64 array of `shape` in node-shared memory, the SAME memory on every rank (collective call: every rank
+    must call it with the same shape).  `own = (p0, p1)`: this rank writes the entries [p0, p1) of the last axis of
+    every row; with at most 64 rows only those pages are page-locked.
+
+    Life time: the array (and every view of it) stays valid for as long as ANY rank holds a reference to it -- a
+    cached segment is handed out again only when every rank reported it free (one all-reduce of a few integers per
+    call, which is also the barrier that orders the previous readers before the next writers).  Segments are keyed by
+    (shape, own range), so the page-locked ranges always match the rows a rank writes; free segments beyond
+    CACHE_BYTES are unmapped."""
+    import weakref
     import torch.distributed as dist
     rank, world = rank_world()
-    nbytes = max(int(numpy.prod(shape)) * 8, 8)
-    gen = _generation.get(nbytes, 0)
-    _generation[nbytes] = gen + 1
-    key = (nbytes, gen & 1)
-    seg = _segments.get(key)
+    shape = tuple(int(v) for v in shape)
+    count = int(numpy.prod(shape))
+    nbytes = max(count * 8, 8)
+    key = (shape, None if own is None else (int(own[0]), int(own[1])), bool(pin))
+    # agreement: a segment is free only if no rank still holds its array.  (`key` differs between ranks only in the
+    # own range, which is a function of the rank: equal shapes <=> equal positions in the list.)
+    free = all_reduce_min([0 if s.busy() else 1 for s in _segments] + [1]) if _segments else [1]
+    seg = None
+    for s, f in zip(_segments, free):
+        if f and s.key == key:
+            seg = s
+            break
     if seg is None:
         name = ['okb200_%s' % uuid.uuid4().hex if rank == 0 else None]
         if rank == 0:
@@ -158,6 +251,7 @@ def shared_host_array(shape, pin=True, own=None):
         dist.barrier()
         if rank == 0:
             os.unlink(seg.path)
+        seg.key = key
         if pin:
             ranges = None
             rows = int(numpy.prod(shape[:-1])) if len(shape) > 1 else 1
@@ -166,10 +260,35 @@ def shared_host_array(shape, pin=True, own=None):
                 ranges = [((r * n_last + own[0]) * 8, (own[1] - own[0]) * 8) for r in range(rows) if own[1] > own[0]]
                 ranges = ranges or [(0, 8)]
             seg.register_cuda(ranges)
-        _segments[key] = seg
-    return numpy.frombuffer(seg.map, dtype=numpy.float64, count=int(numpy.prod(shape))).reshape(shape)
+        # evict agreed-free segments, oldest first, while the cache is over its budget (same decision on every rank)
+        total = nbytes + sum(s.nbytes for s in _segments)
+        keep = []
+        for s, f in zip(_segments, free):
+            if f and total > CACHE_BYTES:
+                total -= s.nbytes
+                _drop(s)
+            else:
+                keep.append(s)
+        _segments[:] = keep + [seg]
+    root = numpy.frombuffer(seg.map, dtype=numpy.float64, count=count)
+    seg.user = weakref.ref(root)     # every view (the reshaped array, its rows, slices of those) keeps `root` alive as its .base
+    return root.reshape(shape)
+
+
+def gather_rows(local, npts, p0, p1):
+    """Multi-node fallback of the shared-memory assembly: every rank contributes the columns [p0, p1) of a
+    (rows, npts) host result; all ranks return the full array (all-gather over the process group)."""
+    import torch
+    import torch.distributed as dist
+    local = numpy.ascontiguousarray(local, dtype=numpy.float64).reshape((-1, p1 - p0))
+    t = torch.from_numpy(local)
+    if dist.get_backend() == 'nccl':
+        t = t.cuda()
+    return gather_points(t, npts).cpu().numpy()
 
 
 @atexit.register
 def _drop_segments():
+    for s in _segments:
+        _drop(s)
     _segments.clear()

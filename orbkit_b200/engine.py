@@ -55,6 +55,24 @@ def build_cart2sph_csr(ao_spec):
             numpy.asarray(val, dtype=numpy.float64))
 
 
+def _stamped_key(obj, slot, compute):
+    """`compute()` (a digest of the object's flat arrays), cached on the object for as long as the arrays it was taken
+    from are the ones the getters hand out: AOClass / MOClass rebuild them in update() and stamp every rebuild
+    (orbitals.py `_stamp`) -- the reference's own caching rule (`_up_to_date`, orbitals.py:336-409, 760-832).
+    Objects without a stamp (e.g. the reference's classes) are hashed on every call."""
+    if getattr(obj, '_up_to_date', False) and getattr(obj, '_stamp', None) is not None:
+        hit = obj.__dict__.get(slot)
+        if hit is not None and hit[0] == obj._stamp:
+            return hit[1]
+    key = compute()
+    if getattr(obj, '_up_to_date', False) and getattr(obj, '_stamp', None) is not None:
+        try:
+            obj.__dict__[slot] = (obj._stamp, key)
+        except Exception:
+            pass
+    return key
+
+
 class _Handle:
     def __init__(self, ptr, destroy):
         self.ptr, self._destroy = ptr, destroy
@@ -74,6 +92,8 @@ class _Handle:
 class Engine:
     """Owns the okb_ctx of one CUDA device and small LRU caches of device handles."""
     CACHE = 8
+    VECTOR_CACHE_POINTS = 1 << 18     # larger vector grids are uploaded per call: hashing 24 B/point to find a cached
+                                      # copy costs as much as the upload, and cached copies would pile up in HBM
 
     def __init__(self, device=None):
         self.lib = _lib.load()
@@ -101,13 +121,12 @@ class Engine:
             cache.popitem(last=False)     # the C handle is destroyed when its last Python ref dies
         return handle
 
-    def basis(self, geo_spec, ao_spec):
-        """Device basis tables for (geo_spec, ao_spec); returns (handle, n_cart, n_ao)."""
+    @staticmethod
+    def _ao_arrays(ao_spec):
         lxlylz = _lib.i32(ao_spec.get_lxlylz())
         assign = _lib.i32(ao_spec.get_nlxlylz_per_cont())
         coeffs = _lib.f64(ao_spec.get_prim_coeffs())
         pnum = _lib.i32(ao_spec.get_nprim_per_cont())
-        geo = _lib.f64(geo_spec)
         atoms = _lib.i32(ao_spec.get_assign_cont_to_atoms())
         normalized = int(ao_spec.get_normalized())
         renorm = getattr(ao_spec, 'get_renorm', lambda: None)()
@@ -117,14 +136,25 @@ class Engine:
             renorm = _lib.f64(numpy.asarray(renorm, dtype=float).reshape(-1))
             if renorm.shape[0] != lxlylz.shape[0]:
                 raise ValueError("ao_spec[0]['N'] must hold one factor per Cartesian function")
-        spherical = bool(ao_spec.spherical)
         lm = None
-        if spherical:
+        if bool(ao_spec.spherical):
             lm = numpy.array([[j, l, m] for j, (l, m) in ao_spec.get_old_ao_spherical()], dtype=numpy.intc)
-        key = _digest(lxlylz, assign, coeffs, pnum, geo, atoms, numpy.array([normalized]), renorm, lm)
+        return lxlylz, assign, coeffs, pnum, atoms, normalized, renorm, lm
+
+    def basis(self, geo_spec, ao_spec):
+        """Device basis tables for (geo_spec, ao_spec); returns (handle, n_cart, n_ao, key)."""
+        geo = _lib.f64(geo_spec)
+        arrays = []
+
+        def ao_digest():
+            arrays.append(self._ao_arrays(ao_spec))
+            lxlylz, assign, coeffs, pnum, atoms, normalized, renorm, lm = arrays[0]
+            return _digest(lxlylz, assign, coeffs, pnum, atoms, numpy.array([normalized]), renorm, lm)
+        key = _stamped_key(ao_spec, '_okb_ao_key', ao_digest) + _digest(geo)
         if key in self._basis:
             self._basis.move_to_end(key)
             return self._basis[key]
+        lxlylz, assign, coeffs, pnum, atoms, normalized, renorm, lm = arrays[0] if arrays else self._ao_arrays(ao_spec)
         if geo.ndim != 2 or geo.shape[1] != 3:
             raise ValueError('geo_spec must have shape (n_atoms, 3)')
         h = ctypes.c_void_p()
@@ -134,13 +164,28 @@ class Engine:
             normalized, _lib.dptr(renorm) if renorm is not None else None, ctypes.byref(h)))
         handle = _Handle(h, self.lib.okb_basis_destroy)
         n_cart = n_ao = lxlylz.shape[0]
-        if spherical:
+        if bool(ao_spec.spherical):
             ptr, col, val = build_cart2sph_csr(ao_spec)
             n_ao = len(ptr) - 1
             _lib.check(self.lib.okb_basis_set_cart2sph(h, n_ao, _lib.iptr(ptr), _lib.iptr(col), _lib.dptr(val)))
         return self._put(self._basis, key, (handle, n_cart, n_ao, key))
 
-    def mos(self, basis_entry, coeffs, occ):
+    def mos_of(self, basis_entry, mo_spec):
+        """MO coefficient handle of an MOClass-like object (get_coeffs / get_occ); a stamped object (see
+        _stamped_key) is not copied or hashed again while its flat arrays are unchanged"""
+        got = []
+
+        def mo_digest():
+            got.append((_lib.f64(mo_spec.get_coeffs()), _lib.f64(mo_spec.get_occ())))
+            return _digest(*got[0])
+        key = basis_entry[3] + _stamped_key(mo_spec, '_okb_mo_key', mo_digest)
+        if key in self._mo:
+            self._mo.move_to_end(key)
+            return self._mo[key]
+        coeffs, occ = got[0] if got else (_lib.f64(mo_spec.get_coeffs()), _lib.f64(mo_spec.get_occ()))
+        return self.mos(basis_entry, coeffs, occ, key=key)
+
+    def mos(self, basis_entry, coeffs, occ, key=None):
         handle_b, _, n_ao, bkey = basis_entry
         coeffs = _lib.f64(coeffs)
         occ = _lib.f64(occ)
@@ -148,7 +193,8 @@ class Engine:
             raise ValueError('MO coefficients have shape %s but the basis has %d AOs' % (coeffs.shape, n_ao))
         if occ.shape != (coeffs.shape[0],):
             raise ValueError('occupation numbers and MO coefficients differ in length')
-        key = bkey + _digest(coeffs, occ)
+        if key is None:
+            key = bkey + _digest(coeffs, occ)
         if key in self._mo:
             self._mo.move_to_end(key)
             return self._mo[key]
@@ -197,6 +243,7 @@ class Engine:
         x, y, z = _lib.f64(x), _lib.f64(y), _lib.f64(z)
         if not (len(x) == len(y) == len(z)):
             raise ValueError('Dimensions of x-, y-, and z- coordinate differ!')
+        cache = cache and len(x) <= self.VECTOR_CACHE_POINTS
         key = b'v' + _digest(x, y, z) if cache else None
         if cache and key in self._grid:
             self._grid.move_to_end(key)

@@ -223,7 +223,7 @@ def calc_jmo(qc, ij, drv=['x', 'y', 'z'], numproc=1, otype=None, ofid='', **kwar
         return numpy.zeros((len(codes), n) + N)
     eng = get_engine()
     basis = eng.basis(require(qc_select.geo_spec, dtype='f'), qc_select.ao_spec)
-    mo = eng.mos(basis, qc_select.mo_spec.get_coeffs(), qc_select.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc_select.mo_spec)
     g = core._grid_handle(eng, x, y, z, is_vector)
     ia = numpy.ascontiguousarray(indices[:, 0], dtype=numpy.intc)
     ib = numpy.ascontiguousarray(indices[:, 1], dtype=numpy.intc)

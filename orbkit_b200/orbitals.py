@@ -22,6 +22,9 @@ import numpy
 from .tools import exp, lquant, require
 
 
+import itertools as _itertools
+_STAMPS = _itertools.count(1)
+
 class AOClass(UserList):
     def __init__(self, data=None, seq=(), restart=None):
         if isinstance(data, list):
@@ -178,6 +181,7 @@ class AOClass(UserList):
         self._renorm = (numpy.asarray(self.data[0]['N'], dtype=float)
                         if 'N' in self.data[0] else None)
         self._up_to_date = True
+        self._stamp = next(_STAMPS)       # identifies this state of the flat arrays (engine handle caches)
 
     def is_normlized(self, force=False):
         if force or not self._up_to_date:
@@ -353,6 +357,7 @@ class MOClass(UserList):
         self.beta_index = [i for i, s in enumerate(spin) if s.startswith('b')]
         self.spinpolarized = len(self.beta_index) != 0
         self._up_to_date = True
+        self._stamp = next(_STAMPS)       # identifies this state of the flat arrays (engine handle caches)
 
     def _get(self, name):
         if not self._up_to_date:

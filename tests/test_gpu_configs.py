@@ -122,7 +122,7 @@ def test_config4_3000ao_slab_of_256cube(ok, oracle_mod):
     assert p1 - p0 == npts // 8
     eng = get_engine()
     basis = eng.basis(qc.geo_spec, qc.ao_spec)
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc.mo_spec)
     g = eng.grid_regular(ax, ax, ax)
     rho, drho, norm = eng.eval_rho(mo, g, [1, 2, 3], p0, p1, want_norm=True)
     assert rho.shape == (p1 - p0,) and drho.shape == (3, p1 - p0) and numpy.isfinite(drho).all() and (rho >= 0).all()

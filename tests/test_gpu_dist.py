@@ -37,6 +37,15 @@ out['ao'] = ok.rho_compute(qc, calc_ao=True)
 ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)      # fewer points than one shard alignment
 out['vec_rho'] = ok.rho_compute(qc)
 out['again'] = ok.rho_compute(qc)                                # second segment generation
+# ADVICE r01: results of consecutive same-shape calls that are all KEPT must not alias (extras.mo_set keeps the
+# densities of every MO set in a list and converts after the loop)
+sets = []
+for lo in range(0, 8, 2):
+    q = qc.copy()
+    q.mo_spec = qc.mo_spec[lo:lo + 2]
+    sets.append(ok.rho_compute(q))
+for i, r in enumerate(sets):
+    out['set%%d' %% i] = r
 numpy.savez(%(out)r + '_%%d.npz' %% rank, **{k: numpy.array(v) for k, v in out.items()})
 dist.barrier()
 dist.destroy_process_group()
@@ -58,6 +67,11 @@ def test_two_ranks_equal_one_process(tmp_path):
     ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
     ref['vec_rho'] = ok.rho_compute(qc)
     ref['again'] = ref['vec_rho']
+    for i, lo in enumerate(range(0, 8, 2)):
+        q = qc.copy()
+        q.mo_spec = qc.mo_spec[lo:lo + 2]
+        ref['set%d' % i] = ok.rho_compute(q)
+    assert not numpy.array_equal(ref['set0'], ref['set2'])
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / 'dist_worker.py'
     script.write_text(_WORKER % {'repo': REPO, 'port': port, 'out': str(tmp_path / 'res')})

@@ -219,17 +219,48 @@ assert numpy.allclose(norm, [3.0, 4.0]), norm
 p0, p1 = okdist.shard_range(100, rank, world)
 local = torch.from_numpy(numpy.arange(100.0)[None, p0:p1].copy())
 assert numpy.array_equal(okdist.gather_points(local, 100).numpy()[0], numpy.arange(100.0))
-# node-shared host array: every rank writes its own point range, a barrier completes it on both
-for rep in range(3):                       # two segments are used in turn (a result survives one more call)
-    shared = okdist.shared_host_array((4, npts), pin=False)
+# node-shared host array: every rank writes its own point range, a barrier completes it on both.
+# Life time (ADVICE r01): a result stays valid for as long as ANY rank holds it -- five same-shape calls whose results
+# are all kept (rank 1 keeps only views of them) never alias; a segment is reused once every rank dropped its array.
+assert okdist.single_node()
+kept = []
+for rep in range(5):
     p0, p1 = okdist.shard_range(npts, rank, world)
+    shared = okdist.shared_host_array((4, npts), pin=False, own=(p0, p1))
     shared[:, p0:p1] = full[:, p0:p1] + rep
     dist.barrier()
     assert numpy.array_equal(shared, full + rep), 'shared host array'
-    if rep == 1:
-        assert numpy.array_equal(prev, full), 'previous generation still intact'
-    prev = shared
-    dist.barrier()
+    kept.append(shared if rank == 0 else shared[1:, 5:])
+    del shared
+for rep, arr in enumerate(kept):
+    assert numpy.array_equal(arr, (full + rep) if rank == 0 else (full + rep)[1:, 5:]), 'result %%d was overwritten' %% rep
+assert len(okdist._segments) == 5
+dist.barrier()
+# rank 0 drops everything, rank 1 still holds result 3: only segments free on BOTH ranks are handed out again
+if rank == 0:
+    kept = []
+else:
+    kept = [kept[3]]
+again = okdist.shared_host_array((4, npts), pin=False, own=okdist.shard_range(npts, rank, world))
+assert len(okdist._segments) == 5, 'a free segment is reused'
+again[:] = -1.0
+dist.barrier()
+if rank == 1:
+    assert numpy.array_equal(kept[0], (full + 3)[1:, 5:]), 'a held result was handed out again'
+del again
+# another shape gets its own segment; the budget evicts free segments (same decision on both ranks)
+okdist.CACHE_BYTES = 4 * npts * 8 * 2
+other = okdist.shared_host_array((2, npts), pin=False)
+other[:] = rank
+dist.barrier()
+assert len(okdist._segments) <= 3, len(okdist._segments)
+if rank == 1:
+    assert numpy.array_equal(kept[0], (full + 3)[1:, 5:])
+del other, kept
+# multi-node fallback: the shards are all-gathered instead
+p0, p1 = okdist.shard_range(npts, rank, world)
+assert numpy.array_equal(okdist.gather_rows(full[:, p0:p1], npts, p0, p1), full)
+dist.barrier()
 assert not [f for f in os.listdir('/dev/shm') if f.startswith('okb200_')], 'segments are unlinked once attached'
 dist.barrier()
 dist.destroy_process_group()
