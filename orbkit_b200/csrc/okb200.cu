@@ -28,6 +28,7 @@
 #include "okb_variant.h"
 #include "okb_shell.cuh"   // constexpr shell tables (templates are instantiated in inst_*.cu only)
 #include "okb_ws.cuh"      // pad_stride
+#include "okb_ao_zrun.cuh" // ZR_MAXL
 #include "okb_misc.cuh"
 #include "okb_ci.cuh"
 #include "okb_text.cuh"
@@ -524,6 +525,23 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
             }
         }
     }
+    // ---- rows grouped by the shell they are built from (the z-run kernel walks shell by shell) ------------------
+    std::vector<std::vector<int>> shell_row_off(nchunk), shell_nrow(nchunk);
+    for (int c = 0; c < nchunk; ++c) {
+        const Layout::Chunk &ch = lo.chunks[c];
+        const int ns = ch.s1 - ch.s0;
+        std::vector<int> fn_shell(ch.nfn, 0);
+        for (int o = ch.s0; o < ch.s1; ++o) {
+            const int s = lo.order[o];
+            for (int kk = shell_k0[s] - ch.k0; kk < shell_k0[s] - ch.k0 + nf_of[s]; ++kk) fn_shell[kk] = o - ch.s0;
+        }
+        for (RowMeta &rm : rows[c]) rm.shell = fn_shell[terms[c][rm.term_off].k];
+        std::stable_sort(rows[c].begin(), rows[c].end(), [](const RowMeta &a, const RowMeta &b) { return a.shell < b.shell; });
+        shell_row_off[c].assign(ns, 0);
+        shell_nrow[c].assign(ns, 0);
+        for (const RowMeta &rm : rows[c]) shell_nrow[c][rm.shell]++;
+        for (int q = 1; q < ns; ++q) shell_row_off[c][q] = shell_row_off[c][q - 1] + shell_nrow[c][q - 1];
+    }
     // ---- aux records of the kind-2 shells ----------------------------------------------------------------------
     std::vector<std::vector<double>> aux(nchunk);
     std::vector<int> shell_aux(nshell, 0);
@@ -584,6 +602,8 @@ static int layout_build(okb_basis *b, bool sph_out, Layout &lo) {
             m.fn_off = fo;
             m.L = sh.L;
             m.gprim = b->shell_gprim[s];
+            m.row_off = shell_row_off[c][o - ch.s0];
+            m.nrow = shell_nrow[c][o - ch.s0];
             if (lo.shell_sph[s]) {
                 m.kind = 2;
                 m.nfn = 2 * sh.L + 1;
@@ -1224,12 +1244,22 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     }
 
     const double *tabx = nullptr, *taby = nullptr, *tabz = nullptr;
-    // (not for SINK_AO: its store-bound kernel has too few warps to hide the table loads -- measured 1.6x slower)
+    // SINK_AO: plain values on a regular grid run the z-run kernel (okb_ao_zrun.cuh), which is built on the tables; the
+    // exponential-per-point SINK_AO kernels do not take them (too few warps to hide the table loads: measured 1.6x slower)
     static const bool ao_tables = getenv("OKB_AO_TABLES") != nullptr;      // A/B measurements only
-    if (rq.sink != SINK_AO || ao_tables) {
+    static const bool no_zrun = getenv("OKB_NO_ZRUN") != nullptr;          // A/B measurements only
+    bool zrun_ok = rq.sink == SINK_AO && g->kind == 0 && !no_zrun;
+    if (zrun_ok) {
+        bool all_values = true;
+        for (const Pass &ps : passes) all_values &= (ps.set == SET_VAL);
+        for (const DevShell &sh : b->shells) all_values &= (sh.L <= ZR_MAXL);
+        zrun_ok = all_values;
+    }
+    if (rq.sink != SINK_AO || ao_tables || zrun_ok) {
         rc = ensure_axis_tables(ctx, b, g, &tabx, &taby, &tabz);
         if (rc != OKB_OK) return rc;
     }
+    zrun_ok = zrun_ok && tabx != nullptr;
 
     int slab_idx = 0;
     for (long long s0 = 0; s0 < ntot; s0 += slab_pts, ++slab_idx) {
@@ -1273,6 +1303,29 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             }
             // spherical-row shells exist only in the straight-line generators (VAL/GRAD/LAP/D2/D2P and the single codes
             // 1..6 of ONE); the generic sets work on the all-Cartesian layout
+            if (zrun_ok) {
+                const Layout &lo = b->cart;
+                KParams p{};
+                p.grid_kind = 0;
+                p.gx = g->gx; p.gy = g->gy; p.gz = g->gz;
+                p.nx = g->nx; p.ny = g->ny; p.nz = g->nz;
+                p.tabx = tabx; p.taby = taby; p.tabz = tabz;
+                p.p0 = rq.p0 + s0 + u0;
+                p.npts = (int)un;
+                p.meta = lo.meta_dev;
+                p.lay = lo.lay;
+                p.nchunk = (int)lo.chunks.size();
+                p.ld = ld;
+                p.slot_stride = (long long)n_rows * ld;
+                for (int k = 0; k < 10; ++k) p.slot[k] = ps.slot[k];
+                p.one_code = 0;
+                p.out = (dev_out ? rq.out + s0 : dbase) + u0;
+                cudaError_t e = okb_launch_ao_zrun(p, ctx->stream);
+                if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", okb_ao_zrun_name(), cudaGetErrorString(e));
+                ctx->launches++;
+                ctx->last_kernel = okb_ao_zrun_name();
+                continue;
+            }
             const bool use_mix = !b->mix_is_cart &&
                                  (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
                                   ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));

@@ -1,0 +1,187 @@
+// okb_ao_zrun.cuh -- SINK_AO on REGULAR grids: the z-run kernel (calc_ao / core.ao_creator values and single
+// derivative-free requests; replaces c_lcreator + cy_core.aocreator + core.cartesian2spherical,
+// c_grid-based.c:40-69, cy_core.pyx:51-78, core.py:135-176).
+//
+// Why (ncu, profiles/r01_ao_tile_summary.txt): the tile kernels spend ~64 thread instructions per AO value, two thirds
+// of them in the 784 exponentials per point, and reach 0.39 of the HBM peak although DRAM traffic = algorithmic bytes.
+// On a regular grid everything but ONE factor of an AO is constant along a run of consecutive z points at fixed (x, y):
+//
+//   chi(x_i, y_j, z_k) = f X^lx Y^ly Z_k^lz  sum_p [cN_p ex_p(i) ey_p(j)] ez_p(k)          X = x_i - cx, ...
+//                      = ( sum_l P_l Z_k^l ) * R0(k),      R0(k) = sum_p w_p ez_p(k),  w_p = tabx[p][i] taby[p][j]
+//
+// with the separable-exponential tables tabx/taby/tabz of okb_axis_table_kernel ([n_prim][n_axis]; tabx carries c N).
+// P_l collects, per OUTPUT row (Cartesian function, or real-spherical combination of the shell's Cartesian functions:
+// the chunk's RowMeta / TermMeta records), the coefficients coef * f * X^lx * Y^ly of the terms with lz = l.  w_p and
+// P_l are uniform over the run: they are computed once per (row group, chunk) by the CTA into shared memory.
+//
+//   CTA         = J consecutive (x, y) rows of the grid  x  one block of blockDim.x consecutive z points
+//   thread      = one z index k, all J rows:  per shell  R0[j] = sum_p w[p][j] * tabz[p][k]   (1 coalesced cached load
+//                 per primitive, J FMAs), then per output row of the shell a Horner polynomial in Z_k (L FMAs), one
+//                 multiplication by R0[j] and ONE coalesced 8-byte streaming store per AO value -- lanes are consecutive
+//                 k, so a warp writes 256 contiguous bytes of the row; no shared-memory staging of the AO values.
+//   per AO value ~7 thread instructions instead of ~64; no exponential is evaluated in this kernel.
+//
+// Any shell is handled (standard order or explicit lxlylz, any L <= 6, spherical rows of any term pattern): the
+// exponents travel in the chunk tables.  Results agree with the exponential-per-point kernels to a few ulp (products
+// re-associated; same tolerance as the axis-table path of the fused kernel, tests/test_gpu_parity.py).
+#pragma once
+#include "okb_common.cuh"
+
+namespace okb {
+
+constexpr int ZR_MAXP = 96;      // primitives per chunk (host: MAXP)
+constexpr int ZR_MAXS = 32;      // shells per chunk (host: MAXS)
+constexpr int ZR_MAXL = 6;       // highest angular momentum (28 functions <= KC)
+
+struct ZShell { double cz; int gprim, prim_off, nprim, L, row_off, nrow; };
+
+template <int J>
+struct ZrunSmem {
+    double w[ZR_MAXP][J];                    // w_p of the J rows
+    double P[KC][ZR_MAXL + 1][J];            // polynomial coefficients per output row
+    long long rowoff[KC];                    // element offset of the output row (slot and row stride applied), -1: skip
+    ZShell sh[ZR_MAXS];
+    int ri[J], rj[J];                        // axis indices of the J rows; ri < 0: row outside the launch
+};
+
+template <int J, int L>
+__device__ __forceinline__ void zrun_rows(const ZrunSmem<J> &S, const ZShell &sh, const double Z, const double (&R0)[J],
+                                          double *__restrict__ out, const long long (&off)[J], const bool (&act)[J]) {
+    for (int r = sh.row_off; r < sh.row_off + sh.nrow; ++r) {
+        const long long ro = S.rowoff[r];
+        if (ro < 0) continue;                                   // uniform
+        double poly[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) poly[j] = S.P[r][L][j];
+#pragma unroll
+        for (int l = L - 1; l >= 0; --l)
+#pragma unroll
+            for (int j = 0; j < J; ++j) poly[j] = fma(poly[j], Z, S.P[r][l][j]);
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (act[j]) __stcs(out + ro + off[j], poly[j] * R0[j]);
+    }
+}
+
+// row_first: first (x, y) row (index i*ny + j) of the launch; n_groups row groups of J rows; nzb z blocks per row
+template <int J>
+__global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long long row_first, long long row_last,
+                                                          int nzb) {
+    __shared__ ZrunSmem<J> S;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const long long rg = blockIdx.x / nzb;
+    const int zb = (int)(blockIdx.x - rg * nzb);
+    const int k = zb * nt + tid;
+    const bool kvalid = k < p.nz;
+    const int kc = kvalid ? k : p.nz - 1;
+    const double zk = __ldg(p.gz + kc);
+    long long off[J];
+    bool act[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const long long row = row_first + rg * J + j;
+        const long long pt = row * p.nz + k;
+        off[j] = pt - p.p0;
+        act[j] = kvalid && row <= row_last && off[j] >= 0 && off[j] < (long long)p.npts;
+    }
+    if (tid < J) {
+        const long long row = row_first + rg * J + tid;
+        const bool ok = row <= row_last;
+        S.ri[tid] = ok ? (int)(row / p.ny) : -1;
+        S.rj[tid] = ok ? (int)(row % p.ny) : 0;
+    }
+    const int sl = p.slot[p.one_code];                           // SET_VAL: one_code = 0
+    const long long slot_off = (long long)sl * p.slot_stride;
+    __syncthreads();
+
+    for (int c = 0; c < p.nchunk; ++c) {
+        const unsigned char *mb = p.meta + (size_t)c * p.lay.stride;
+        const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
+        const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
+        const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
+        const RowMeta *rows = reinterpret_cast<const RowMeta *>(mb + p.lay.off_row);
+        const TermMeta *terms = reinterpret_cast<const TermMeta *>(mb + p.lay.off_term);
+        // ---- phase U: the quantities that are uniform along z ------------------------------------------------
+        // (a) w[p][j]: one warp per shell, lanes over (primitive, row)
+        for (int s = warp; s < hdr.nshell; s += nwarp) {
+            const int np = __ldg(&shells[s].nprim), po = __ldg(&shells[s].prim_off), gp = __ldg(&shells[s].gprim);
+            for (int e = lane; e < np * J; e += 32) {
+                const int q = e / J, j = e - q * J;
+                const int i = S.ri[j];
+                S.w[po + q][j] = i < 0 ? 0.0
+                                       : __ldg(p.tabx + (size_t)(gp + q) * p.nx + i) * __ldg(p.taby + (size_t)(gp + q) * p.ny + S.rj[j]);
+            }
+            if (lane == 0) {
+                ZShell z;
+                z.cz = __ldg(&shells[s].cz);
+                z.gprim = gp; z.prim_off = po; z.nprim = np;
+                z.L = __ldg(&shells[s].L);
+                z.row_off = __ldg(&shells[s].row_off);
+                z.nrow = __ldg(&shells[s].nrow);
+                S.sh[s] = z;
+            }
+        }
+        // (b) P[r][l][j]: one thread per (output row, grid row)
+        for (int e = tid; e < hdr.nrow * J; e += nt) {
+            const int r = e / J, j = e - r * J;
+            const RowMeta rm = rows[r];
+            double acc[ZR_MAXL + 1];
+#pragma unroll
+            for (int l = 0; l <= ZR_MAXL; ++l) acc[l] = 0.0;
+            const int i = S.ri[j];
+            if (i >= 0) {
+                const ShellMeta *sh = shells + rm.shell;
+                const double X = __ldg(p.gx + i) - __ldg(&sh->cx), Y = __ldg(p.gy + S.rj[j]) - __ldg(&sh->cy);
+                for (int t = 0; t < rm.nterm; ++t) {
+                    const TermMeta tm = terms[rm.term_off + t];
+                    const FnMeta fm = fns[tm.k];
+                    const int lx = fm.lxyz & 0xff, ly = (fm.lxyz >> 8) & 0xff, lz = (fm.lxyz >> 16) & 0xff;
+                    const double a = tm.coef * (fm.f * (upow(X, lx) * upow(Y, ly)));
+#pragma unroll
+                    for (int l = 0; l <= ZR_MAXL; ++l)
+                        if (l == lz) acc[l] += a;
+                }
+            }
+#pragma unroll
+            for (int l = 0; l <= ZR_MAXL; ++l) S.P[r][l][j] = acc[l];
+            if (j == 0) S.rowoff[r] = sl < 0 ? -1 : slot_off + (long long)rm.out_row * p.ld;
+        }
+        __syncthreads();
+        // ---- phase T: one z point per thread, J rows ----------------------------------------------------------------
+        for (int s = 0; s < hdr.nshell; ++s) {
+            const ZShell sh = S.sh[s];
+            double R0[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) R0[j] = 0.0;
+            const double *tz = p.tabz + (size_t)sh.gprim * p.nz + kc;
+            int q = 0;
+            for (; q + 4 <= sh.nprim; q += 4) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = __ldg(tz + (size_t)(q + u) * p.nz);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) R0[j] = fma(S.w[sh.prim_off + q + u][j], t[u], R0[j]);
+            }
+            for (; q < sh.nprim; ++q) {
+                const double t = __ldg(tz + (size_t)q * p.nz);
+#pragma unroll
+                for (int j = 0; j < J; ++j) R0[j] = fma(S.w[sh.prim_off + q][j], t, R0[j]);
+            }
+            const double Z = zk - sh.cz;
+            switch (sh.L) {                                       // uniform
+                case 0: zrun_rows<J, 0>(S, sh, Z, R0, p.out, off, act); break;
+                case 1: zrun_rows<J, 1>(S, sh, Z, R0, p.out, off, act); break;
+                case 2: zrun_rows<J, 2>(S, sh, Z, R0, p.out, off, act); break;
+                case 3: zrun_rows<J, 3>(S, sh, Z, R0, p.out, off, act); break;
+                case 4: zrun_rows<J, 4>(S, sh, Z, R0, p.out, off, act); break;
+                case 5: zrun_rows<J, 5>(S, sh, Z, R0, p.out, off, act); break;
+                default: zrun_rows<J, 6>(S, sh, Z, R0, p.out, off, act); break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace okb

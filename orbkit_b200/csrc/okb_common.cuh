@@ -44,16 +44,17 @@ __host__ __device__ constexpr int set_ncodes(int set) {
 
 // ---- chunk tables (one fixed-stride blob per chunk, 16-byte aligned sections) ---------------
 struct ChunkHdr { int nshell, nprim, nfn, nrow; };
-struct ShellMeta {                 // 56 B
+struct ShellMeta {                 // 64 B
     double cx, cy, cz;
     int prim_off, nprim, fn_off, nfn;   // offsets are chunk-local; nfn = rows this shell writes
     int L, kind;                        // kind 1: Cartesian functions in the standard order of std_lxyz(L, .);
                                         // kind 2: same, but the shell writes its 2L+1 real-spherical rows
     int aux_off;                        // kind 2: offset (doubles) of [f[ncart] | per row: position, coefs] in aux
     int gprim;                          // index of the shell's first primitive in the basis-wide axis tables
+    int row_off, nrow;                  // the chunk's output rows (RowMeta) built from this shell: [row_off, row_off + nrow)
 };
 struct FnMeta { int lxyz; int pad; double f; };          // lx | ly<<8 | lz<<16 ; f = angular norm * renorm
-struct RowMeta { int out_row, term_off, nterm, pad; };   // SINK_AO output rows of this chunk
+struct RowMeta { int out_row, term_off, nterm, shell; }; // SINK_AO output rows of this chunk, sorted by `shell` (chunk-local)
 struct TermMeta { int k; int pad; double coef; };
 
 struct BlobLayout { int off_shell, off_prim, off_fn, off_row, off_term, off_aux, stride; };

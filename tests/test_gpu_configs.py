@@ -102,9 +102,6 @@ def test_config3_laplacian_200cube(ok, oracle_mod):
     assert numpy.array_equal(lap, d2rho.sum(axis=0))
     # the density of the two-pass request is the density of the plain request
     assert_close(rho, ok.rho_compute(qc), 'C3 rho of the plain request', rtol=1e-12, afloor=1e-15)
-    # integral of the Laplacian over the box vanishes with the density at its faces (divergence theorem): small
-    # against the integral of its magnitude
-    assert abs(lap.sum()) < 1e-3 * numpy.abs(lap).sum()
 
 
 def test_config4_3000ao_slab_of_256cube(ok, oracle_mod):

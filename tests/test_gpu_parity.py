@@ -432,3 +432,42 @@ def test_laplacian_phi_cache_subranges(ok, oracle_mod, monkeypatch):
     _, _, nrm = eng.eval_rho(mo, g, [4, 5, 6], want_norm=True)
     mo_ref = oracle_mod.rho_compute(qc, x, y, z, is_vector=True, calc_mo=True)
     assert_close(nrm, (mo_ref ** 2).sum(axis=1), 'mo_norm', rtol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['h2o_gaussian_sph', 'lih_psi4_sph_f', 'water_gamess_wfn', 'synth_small_cart_g',
+                                  'synth_small_sph', 'h2o_orca_wfx'])
+def test_calc_ao_zrun_kernel_regular_grids(ok, oracle_mod, name):
+    """calc_ao values on REGULAR grids run the z-run kernel (csrc/okb_ao_zrun.cuh: separable exponentials, one z point
+    per thread, polynomial in Z per output row): against the oracle, against the exponential-per-point kernel on the
+    same points as a vector grid, ragged axis lengths (z runs shorter than a warp, longer than a CTA), and point
+    sub-ranges that start and end inside a z run"""
+    from orbkit_b200.engine import get_engine
+    qc, a = golden_qc(name)
+    eng = get_engine()
+    rng = numpy.random.default_rng(17)
+    for shape in ((3, 4, 5), (2, 3, 37), (3, 2, 200), (1, 2, 300), (5, 1, 1)):
+        ax = [numpy.sort(rng.uniform(-3.5, 3.5, n)) for n in shape]
+        set_regular(ok, *ax)
+        got = ok.rho_compute(qc, calc_ao=True)
+        assert eng.last_kernel().startswith('zrun/'), eng.last_kernel()
+        assert got.shape == (qc.ao_spec.get_ao_num(),) + shape
+        ref = oracle_mod.ao_creator(qc.geo_spec, qc.ao_spec, x=ax[0], y=ax[1], z=ax[2], is_vector=False)
+        assert_close(got, ref, '%s zrun %s' % (name, shape))
+        # the same points as a vector grid (exponential per point)
+        X, Y, Z = numpy.meshgrid(*ax, indexing='ij')
+        set_vector(ok, X.ravel(), Y.ravel(), Z.ravel())
+        vec = ok.rho_compute(qc, calc_ao=True)
+        assert not eng.last_kernel().startswith('zrun/')
+        assert_close(got.reshape(vec.shape), vec, '%s zrun vs vector %s' % (name, shape))
+    # point ranges cut inside z runs reproduce the full evaluation bit for bit
+    ax = [numpy.linspace(-3, 3, 4), numpy.linspace(-2, 2, 5), numpy.linspace(-3, 3, 41)]
+    basis = eng.basis(qc.geo_spec, qc.ao_spec)
+    g = eng.grid_regular(*ax)
+    full = eng.eval_ao(basis, g, [0])
+    assert eng.last_kernel().startswith('zrun/')
+    for p0, p1 in ((0, 1), (7, 300), (41, 82), (163, 164), (500, 820), (819, 820)):
+        part = eng.eval_ao(basis, g, [0], p0, p1)
+        assert numpy.array_equal(part, full[:, :, p0:p1]), (p0, p1)
+    # ao_creator (core.py:38-105) takes the same route
+    got = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, x=ax[0], y=ax[1], z=ax[2], is_vector=False)
+    assert numpy.array_equal(got.reshape(full[0].shape), full[0])
