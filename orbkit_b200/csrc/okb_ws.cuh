@@ -89,6 +89,20 @@ struct WsCfg {
     static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
     // MO blocks are fetched in pairs (one 16-byte load) when every warp row starts on an even block
     static constexpr bool PAIRED = (WM == 1 || AM % 2 == 0);
+    // ROT: the consumer walks TWO k-steps (8 rows) per loop iteration with the A fragments in a small ring of register
+    // buffers and the B fragments double buffered, so that no fragment load overwrites a register a neighbouring DMMA
+    // still reads (see the consumer loop).  NPAIR block pairs per k-step, NP2 pair slots per double step, NBUF ring
+    // buffers (a divisor of NP2), prefetch distance PD = NBUF - 2 slots.
+    static constexpr int NPAIR = (AM + 1) / 2;
+    static constexpr int NP2 = 2 * NPAIR;
+    static constexpr int NBUF = (NP2 % 3 == 0) ? 3 : (NP2 % 4 == 0) ? 4 : (NP2 % 5 == 0) ? 5 : NP2;
+    static constexpr int PD = NBUF - 2;
+#ifdef OKB_NO_ROT
+    static constexpr bool ROT = false;
+#else
+    static constexpr bool ROT = (WM == 1 && NST >= 3 && D <= 4 && NPAIR >= 2 && NBUF <= 5);
+#endif
+    static constexpr int KSTEP = ROT ? 8 : 4;                  // rows the tile is padded to
     static_assert(P % 32 == 0, "whole warps of points for the producers");
     static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
 };
@@ -243,9 +257,9 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
                                                    p.one_code, p.exact_mixed, tab);
                     }
-                    // zero the rows that pad nfn up to the k-step of the MMA (coefficients there are 0,
+                    // zero the rows that pad nfn up to the k-step of the consumer loop (coefficients there are 0,
                     // but stale shared memory could hold NaN/Inf bit patterns)
-                    const int kpad = (hdr.nfn + 3) & ~3;
+                    const int kpad = (hdr.nfn + C::KSTEP - 1) & ~(C::KSTEP - 1);
                     for (int e = ptid; e < (kpad - hdr.nfn) * D * P; e += NPT) {
                         const int pt = e % P, r = e / P, d = r % D, k = hdr.nfn + r / D;
                         tile[((size_t)d * KC + k) * PS + pt] = 0.0;
@@ -359,7 +373,76 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 uint32_t a_ap, a_bp;
                 frag_addr(g, a_ap, a_bp);
                 mbar_wait_a(a_full + 8 * (g % NST), (g / NST) & 1);      // AO tile + coefficient tile landed
-                int nk = nfn_s[g % NST];                                 // multiple of 4, >= 4
+                int nk = nfn_s[g % NST];                                 // multiple of KSTEP, >= KSTEP
+                if constexpr (C::ROT) {
+                    // ---- rotating-register double step ----------------------------------------------------------------
+                    // ncu (profiles/r01_ws_grad_v3_regions.txt, source page): in the one-set scheme above every fragment
+                    // load overwrites a register that the DMMA right in front of it reads; the DMMA collects its operands
+                    // over several cycles, the load waits for that (short scoreboard) and with it the in-order warp:
+                    // ~7 cycles per load, 10 loads per 704-cycle k-step.  Here a load never targets a register with a
+                    // reader less than one pair slot (4-8 DMMAs) behind it, wherever ptxas moves it:
+                    //   A  pair slot q of the double step reads ring buffer q % NBUF and the load for slot q + PD goes to
+                    //      buffer (q + PD) % NBUF, last read in slot q - 2;
+                    //   B  the k-step of half h reads set h and loads set h ^ 1 (fragment j in slot j of the half).
+                    // Order inside a slot: B fragment outer, the two MO blocks of the pair inner -- every accumulator
+                    // sees the k-steps in the same order as before, so the results are bit-identical.
+                    constexpr int NPAIR = C::NPAIR, NP2 = C::NP2, NBUF = C::NBUF, PD = C::PD;
+                    double abuf[NBUF][2], bset[2][NB];
+                    constexpr uint32_t A_HALF = (uint32_t)(4 * CS) * 8u, B_HALF = (uint32_t)(4 * PS) * 8u;
+                    auto b_off = [](int j) -> uint32_t { return (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u; };
+                    auto dstep = [&](const uint32_t ca, const uint32_t cb, const uint32_t na, const uint32_t nb) {
+                        static_for<0, NP2>([&](auto qc) {
+                            constexpr int q = decltype(qc)::value;
+                            constexpr int h = q / NPAIR, pq = q % NPAIR;
+                            constexpr int t = q + PD, tt = t % NP2, th = tt / NPAIR, tp = tt % NPAIR;
+                            const uint32_t abase = (t >= NP2 ? na : ca) + (uint32_t)th * A_HALF + (uint32_t)tp * 128u;
+                            if constexpr (2 * tp + 1 < AM) lds128(abase, abuf[tt % NBUF][0], abuf[tt % NBUF][1]);
+                            else abuf[tt % NBUF][0] = lds64(abase);
+                            const uint32_t bbase = (h == 0) ? cb + B_HALF : nb;
+#pragma unroll
+                            for (int j = 0; j < NB; ++j)
+                                if (j % NPAIR == pq) bset[h ^ 1][j] = lds64(bbase + b_off(j));
+#pragma unroll
+                            for (int j = 0; j < NB; ++j)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e)
+                                    if (2 * pq + e < AM)
+                                        dmma_m8n8k4(acc[2 * pq + e][j % BN][j / BN][0], acc[2 * pq + e][j % BN][j / BN][1],
+                                                    abuf[q % NBUF][e], bset[h][j]);
+                        });
+                    };
+                    auto load_first = [&](const uint32_t ca, const uint32_t cb) {
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) bset[0][j] = lds64(cb + b_off(j));
+                        static_for<0, PD>([&](auto tc_) {
+                            constexpr int t = decltype(tc_)::value, th = t / NPAIR, tp = t % NPAIR;
+                            const uint32_t abase = ca + (uint32_t)th * A_HALF + (uint32_t)tp * 128u;
+                            if constexpr (2 * tp + 1 < AM) lds128(abase, abuf[t % NBUF][0], abuf[t % NBUF][1]);
+                            else abuf[t % NBUF][0] = lds64(abase);
+                        });
+                    };
+                    load_first(a_ap, a_bp);
+                    for (int c = 0; c < p.nchunk; ++c, ++g) {
+                        const int s = g % NST;
+#pragma unroll 1
+                        for (int k0 = 8; k0 < nk; k0 += 8) {
+                            dstep(a_ap, a_bp, a_ap + 2 * A_HALF, a_bp + 2 * B_HALF);
+                            a_ap += 2 * A_HALF;
+                            a_bp += 2 * B_HALF;
+                        }
+                        uint32_t n_ap = a_ap, n_bp = a_bp;               // behind the last chunk: harmless reloads
+                        int nk_next = nk;
+                        if (c + 1 < p.nchunk) {
+                            mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
+                            nk_next = nfn_s[(g + 1) % NST];
+                            frag_addr(g + 1, n_ap, n_bp);
+                        }
+                        dstep(a_ap, a_bp, n_ap, n_bp);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(a_empty + 8 * s);   // every read of this stage has returned
+                        a_ap = n_ap; a_bp = n_bp; nk = nk_next;
+                    }
+                } else {
                 load_all(a_ap, a_bp);
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
@@ -390,6 +473,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     }
                     a_ap = n_ap; a_bp = n_bp; nk = nk_next;
                 }
+                }   // !ROT
                 // ---- per-MO-tile epilogues: lane holds MO row tr of each block, points 2*tc + {0,1} -----
                 if (SINK == SINK_MO) {
 #pragma unroll
