@@ -36,6 +36,9 @@
 
 namespace okb {
 
+#ifndef OKB_CSLACK
+#define OKB_CSLACK 56
+#endif
 __host__ __device__ constexpr int pad_stride(int n) { return n + ((4 - (n % 16)) + 16) % 16; }
 
 // MB: MO blocks of 8 per CTA tile; WM x WN consumer warps; BN point blocks per warp; NPW producer warps
@@ -60,7 +63,7 @@ struct WsCfg {
     // registers of a consumer thread beyond its accumulators: A/B fragments, addresses, loop state.  One consumer
     // warpgroup with a full tile gets 56 (ptxas otherwise recycles a B-fragment register as address register and
     // refills it right in front of its use); big tiles on two warpgroups leave the producers > 100 registers.
-    static constexpr int CREG_SLACK = (NCW == 8 && ACC_REGS > 160) ? 32 : (NCW == 4 && ACC_REGS >= 160) ? 56 : 40;
+    static constexpr int CREG_SLACK = (NCW == 8 && ACC_REGS > 160) ? 32 : (NCW == 4 && ACC_REGS >= 160) ? OKB_CSLACK : 40;
     static constexpr int CREG_WANT = ((ACC_REGS + CREG_SLACK + 7) / 8 * 8 > 248) ? 248 : (ACC_REGS + CREG_SLACK + 7) / 8 * 8;
     static constexpr int PREG_MAX = ((NT * LAUNCH_REGS - NCW * 32 * CREG_WANT) / (NPW * 32)) / 8 * 8;
     static constexpr int PREG_CAP = LAUNCH_REGS < 152 ? LAUNCH_REGS : 152;   // setmaxnreg.dec may only lower
@@ -95,12 +98,12 @@ struct WsCfg {
     // buffers (a divisor of NP2), prefetch distance PD = NBUF - 2 slots.
     static constexpr int NPAIR = (AM + 1) / 2;
     static constexpr int NP2 = 2 * NPAIR;
-    static constexpr int NBUF = (NP2 % 3 == 0) ? 3 : (NP2 % 4 == 0) ? 4 : (NP2 % 5 == 0) ? 5 : NP2;
-    static constexpr int PD = NBUF - 2;
+    static constexpr int NBUF = (NP2 % 3 == 0) ? 3 : 2;         // ring buffers (a divisor of NP2)
+    static constexpr int PD = 1;                                // the pair of slot q + 1 is fetched during slot q
 #ifdef OKB_NO_ROT
     static constexpr bool ROT = false;
 #else
-    static constexpr bool ROT = (WM == 1 && NST >= 3 && D <= 4 && NPAIR >= 2 && NBUF <= 5);
+    static constexpr bool ROT = (WM == 1 && NST >= 3 && D <= 4 && NPAIR >= 2);
 #endif
     static constexpr int KSTEP = ROT ? 8 : 4;                  // rows the tile is padded to
     static_assert(P % 32 == 0, "whole warps of points for the producers");
@@ -379,29 +382,44 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     // ncu (profiles/r01_ws_grad_v3_regions.txt, source page): in the one-set scheme above every fragment
                     // load overwrites a register that the DMMA right in front of it reads; the DMMA collects its operands
                     // over several cycles, the load waits for that (short scoreboard) and with it the in-order warp:
-                    // ~7 cycles per load, 10 loads per 704-cycle k-step.  Here a load never targets a register with a
-                    // reader less than one pair slot (4-8 DMMAs) behind it, wherever ptxas moves it:
-                    //   A  pair slot q of the double step reads ring buffer q % NBUF and the load for slot q + PD goes to
-                    //      buffer (q + PD) % NBUF, last read in slot q - 2;
-                    //   B  the k-step of half h reads set h and loads set h ^ 1 (fragment j in slot j of the half).
-                    // Order inside a slot: B fragment outer, the two MO blocks of the pair inner -- every accumulator
-                    // sees the k-steps in the same order as before, so the results are bit-identical.
+                    // ~7 cycles per load, 10 loads per 704-cycle k-step.  ptxas moves loads and DMMAs freely (only register
+                    // dependencies hold them), merges fragment registers as it likes and puts a load right behind the
+                    // last reader of whatever register it picked, so source order and register naming alone achieve
+                    // nothing.  What does hold is a data dependency, so:
+                    //   * the A fragments of a k-step are no longer all resident: the k-step walks the MO block PAIRS
+                    //     (slot = one pair x all B fragments, 4-8 DMMAs) and the pair of slot q + 1 is fetched during
+                    //     slot q into a small ring of register buffers; the B fragments are double buffered (the k-step
+                    //     of half h reads set h and fetches set h ^ 1);
+                    //   * every fetch address depends on the RESULT of a DMMA of the current slot (`+ lo32(acc) * zero`,
+                    //     one IMAD; zero is a kernel argument that is always 0): the load cannot issue before that DMMA
+                    //     has completed, by which time every register that is free was last read at least a DMMA latency
+                    //     ago, and it is still early enough for its first use one slot later.
+                    // Order per accumulator is unchanged (k-steps in sequence), so the results are bit-identical.
                     constexpr int NPAIR = C::NPAIR, NP2 = C::NP2, NBUF = C::NBUF, PD = C::PD;
                     double abuf[NBUF][2], bset[2][NB];
                     constexpr uint32_t A_HALF = (uint32_t)(4 * CS) * 8u, B_HALF = (uint32_t)(4 * PS) * 8u;
                     auto b_off = [](int j) -> uint32_t { return (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u; };
+                    const int zero = p.zero;
+                    auto tie = [&](const uint32_t addr, const double anchor) -> uint32_t {
+                        return addr + (uint32_t)(__double2loint(anchor) * zero);
+                    };
+                    constexpr int BSLOT = NPAIR >= 2 ? NPAIR - 2 : 0;          // the slot whose DMMAs anchor the B fetches
                     auto dstep = [&](const uint32_t ca, const uint32_t cb, const uint32_t na, const uint32_t nb) {
                         static_for<0, NP2>([&](auto qc) {
                             constexpr int q = decltype(qc)::value;
                             constexpr int h = q / NPAIR, pq = q % NPAIR;
+                            // the B fragments of the next k-step first: issued while set h is still needed by every
+                            // DMMA of this half, so the two sets cannot share registers
+                            if constexpr (pq == 0) {
+                                const uint32_t bbase = (h == 0) ? cb + B_HALF : nb;
+#pragma unroll
+                                for (int j = 0; j < NB; ++j) bset[h ^ 1][j] = lds64(bbase + b_off(j));
+                            }
+                            // the pair of slot q + 1
                             constexpr int t = q + PD, tt = t % NP2, th = tt / NPAIR, tp = tt % NPAIR;
                             const uint32_t abase = (t >= NP2 ? na : ca) + (uint32_t)th * A_HALF + (uint32_t)tp * 128u;
                             if constexpr (2 * tp + 1 < AM) lds128(abase, abuf[tt % NBUF][0], abuf[tt % NBUF][1]);
                             else abuf[tt % NBUF][0] = lds64(abase);
-                            const uint32_t bbase = (h == 0) ? cb + B_HALF : nb;
-#pragma unroll
-                            for (int j = 0; j < NB; ++j)
-                                if (j % NPAIR == pq) bset[h ^ 1][j] = lds64(bbase + b_off(j));
 #pragma unroll
                             for (int j = 0; j < NB; ++j)
 #pragma unroll

@@ -16,7 +16,7 @@ for i in range(8):
     t = [time.perf_counter()]
     eng.clear_caches(); t.append(time.perf_counter())
     basis = eng.basis(qc.geo_spec, qc.ao_spec); t.append(time.perf_counter())
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ()); t.append(time.perf_counter())
+    mo = eng.mos_of(basis, qc.mo_spec); t.append(time.perf_counter())
     g = eng.grid_regular(ax, ax, ax); t.append(time.perf_counter())
     rho = eng.host_array((8000000,)); d = eng.host_array((3, 8000000)); t.append(time.perf_counter())
     eng.eval_rho(mo, g, [1, 2, 3], rho=rho, delta=d); t.append(time.perf_counter())

@@ -14,7 +14,7 @@ dev = torch.device('cuda', 0)
 qc = synth.to_qcinfo(synth.make_molecule(n_heavy=24, n_light=20, n_mo=82, seed=0, spherical=True))
 ax = numpy.linspace(-12, 12, 200)
 basis = eng.basis(qc.geo_spec, qc.ao_spec)
-mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+mo = eng.mos_of(basis, qc.mo_spec)
 g = eng.grid_regular(ax, ax, ax)
 out = torch.zeros((4, 8000000), dtype=torch.float64, device=dev)
 for _ in range(4):

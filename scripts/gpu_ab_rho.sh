@@ -13,7 +13,7 @@ eng = get_engine(); dev = torch.device('cuda', eng.device)
 stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
 qc = synth.to_qcinfo(synth.make_molecule(n_heavy=24, n_light=20, n_mo=82, seed=0, spherical=True))
 ax = numpy.linspace(-12, 12, 200)
-basis = eng.basis(qc.geo_spec, qc.ao_spec); mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ()); g = eng.grid_regular(ax, ax, ax)
+basis = eng.basis(qc.geo_spec, qc.ao_spec); mo = eng.mos_of(basis, qc.mo_spec); g = eng.grid_regular(ax, ax, ax)
 codes = [int(c) for c in "$codes".split()] if "$codes".strip() else []
 out = torch.zeros((8, 8000000), dtype=torch.float64, device=dev)
 f = lambda: eng.eval_rho(mo, g, codes, rho=out[0].data_ptr(), delta=out[1:].data_ptr() if codes else None, flags=OKB_FLAG_OUT_DEVICE)

@@ -30,7 +30,7 @@ def run(name, n_mo, spherical=True, N=200, heavy=24, light=20):
     n_ao = qc.ao_spec.get_ao_num()
     ax = numpy.linspace(-12, 12, N)
     basis = eng.basis(qc.geo_spec, qc.ao_spec)
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc.mo_spec)
     g = eng.grid_regular(ax, ax, ax)
     npts = N ** 3
     out = torch.zeros((8, npts), dtype=torch.float64, device=dev)
@@ -69,7 +69,7 @@ def run_ci(name, n_heavy, n_light, n_pairs, N):
     terms = (rng.normal(size=n_pairs), pairs[:, 0].astype(numpy.intc), pairs[:, 1].astype(numpy.intc))
     ax = numpy.linspace(-10, 10, N)
     basis = eng.basis(qc.geo_spec, qc.ao_spec)
-    mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+    mo = eng.mos_of(basis, qc.mo_spec)
     g = eng.grid_regular(ax, ax, ax)
     npts = N ** 3
     rows = []
@@ -115,7 +115,7 @@ if __name__ == '__main__':
     for i in range(5):
         eng.clear_caches()
         t0 = time.perf_counter(); basis = eng.basis(qc.geo_spec, qc.ao_spec); t1 = time.perf_counter()
-        mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ()); t2 = time.perf_counter()
+        mo = eng.mos_of(basis, qc.mo_spec); t2 = time.perf_counter()
         g = eng.grid_regular(ax, ax, ax); t3 = time.perf_counter()
         rho = eng.host_array((8000000,)); d = eng.host_array((3, 8000000)); t4 = time.perf_counter()
         eng.eval_rho(mo, g, [1, 2, 3], rho=rho, delta=d); t5 = time.perf_counter()

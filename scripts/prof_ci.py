@@ -15,7 +15,7 @@ pairs = rng.integers(0, 500, size=(1000, 2))
 terms = (rng.normal(size=1000), pairs[:, 0].astype(numpy.intc), pairs[:, 1].astype(numpy.intc))
 ax = numpy.linspace(-10, 10, 96)
 basis = eng.basis(qc.geo_spec, qc.ao_spec)
-mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+mo = eng.mos_of(basis, qc.mo_spec)
 g = eng.grid_regular(ax, ax, ax)
 n = 96 ** 3
 buf = torch.empty((4, 500, n), dtype=torch.float64, device=dev)
