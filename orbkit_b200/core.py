@@ -196,6 +196,73 @@ def _compute(qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm):
     return full[0], delta, norm
 
 
+def _compute_to_store(path, qc, x, y, z, is_vector, N, calc_ao, calc_mo, drv, want_norm, members=()):
+    """`_compute` with the results streamed into the file `path` (save_hdf5=, core.py:478-501): point slabs come
+    off the device into two page-locked buffers and a writer thread puts them at their place in the file while the
+    next slab is evaluated (orbkit_b200/store.py) -- the result never exists as one host array.  Returns
+    (arrays, mo_norm): `arrays` maps the dataset names 'rho', 'delta_rho', 'mo_list' / 'ao_list' to read-only arrays
+    of the final shapes (memory maps of the finished file)."""
+    from . import store as okstore
+    eng = get_engine()
+    geo_spec = require(qc.geo_spec, dtype='f')
+    basis = eng.basis(geo_spec, qc.ao_spec)
+    npts = int(numpy.prod(N))
+    codes = [0] if drv is None else [validate_drv(d) for d in drv]
+    mo = None if calc_ao else eng.mos_of(basis, qc.mo_spec)
+    n_rows = basis[2] if calc_ao else (mo.n_mo if calc_mo else 1)
+    rank, world = okdist.rank_world()
+    barrier = None
+    if world > 1:
+        import torch.distributed as tdist
+        barrier = tdist.barrier
+    st = okstore.ResultStore(path, rank, world, barrier)
+    for name, value in members:
+        st.put(name, value)
+    ucodes = [] if drv is None else sorted(set(codes))
+    if calc_ao or calc_mo:
+        lead = (n_rows,) if drv is None else (len(codes), n_rows)
+        sets = [(('ao_list' if calc_ao else 'mo_list'), st.create('ao_list' if calc_ao else 'mo_list', lead + N, npts))]
+        rows_total = len(codes) * n_rows
+    else:
+        sets = [('rho', st.create('rho', N, npts))]
+        if drv is not None:
+            sets.append(('delta_rho', st.create('delta_rho', (len(codes),) + N, npts)))
+        rows_total = 1 + len(ucodes)
+    norm = numpy.zeros(mo.n_mo) if (want_norm and mo is not None and not calc_mo) else None
+    p_lo, p_hi = okdist.shard_range(npts, rank, world) if world > 1 else (0, npts)
+    if npts:
+        g = _grid_handle(eng, x, y, z, is_vector)
+        flags = _flags()
+        slab = max(1024, okstore.SLAB_BYTES // (8 * rows_total) // 1024 * 1024)
+        bufs = [eng.host_array((rows_total * slab,)) for _ in range(2)]
+        busy = [[], []]
+        for i, p0 in enumerate(range(p_lo, p_hi, slab)):
+            p1 = min(p0 + slab, p_hi)
+            for f in busy[i % 2]:                    # the buffer's previous slab has reached the file
+                f.result()
+            view = bufs[i % 2][:rows_total * (p1 - p0)].reshape((rows_total, p1 - p0))
+            if calc_ao:
+                eng.eval_ao(basis, g, codes, p0, p1, out=view, flags=flags)
+                busy[i % 2] = [st.write_async(sets[0][1], p0, p1, view)]
+            elif calc_mo:
+                eng.eval_mo(mo, g, codes, p0, p1, out=view, flags=flags)
+                busy[i % 2] = [st.write_async(sets[0][1], p0, p1, view)]
+            else:
+                _, _, nrm = eng.eval_rho(mo, g, ucodes, p0, p1, rho=view[0], delta=view[1:] if ucodes else None,
+                                         want_norm=norm is not None, flags=flags)
+                if norm is not None:
+                    norm += nrm
+                busy[i % 2] = [st.write_async(sets[0][1], p0, p1, view[0])]
+                if drv is not None:
+                    order = [1 + ucodes.index(c) for c in codes]
+                    block = view[order] if order != list(range(1, 1 + len(codes))) else view[1:]
+                    busy[i % 2].append(st.write_async(sets[1][1], p0, p1, block))
+    st.close()
+    if norm is not None and world > 1:
+        norm = okdist.all_reduce_sum(norm, eng.device)
+    return st.arrays(), norm
+
+
 def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, numproc=1,
                 slice_length=1e4, vector=None, save_hdf5=False, **kwargs):
     r"""Density, molecular orbitals, atomic orbitals or derivatives thereof on `orbkit_b200.grid`.
@@ -239,16 +306,20 @@ def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, num
             ('' if calc_ao else ' and %d MOs to be calculated.' % mo_num))
 
     show_norm = (not was_vector) and drv is None and not options.quiet
-    res = _compute(qc, x, y, z, was_vector, N, calc_ao, calc_mo, drv, want_norm=show_norm and not calc_mo)
-
-    hdf5_file = None
     if save_hdf5:
-        import h5py
-        hdf5_file = h5py.File(str(save_hdf5), 'w')
-        for k, v in (('x', grid.x), ('y', grid.y), ('z', grid.z)):
-            hdf5_file['grid/' + k] = v
-        hdf5_file['grid/is_vector'] = False
-        hdf5_file['grid/is_regular'] = was_vector
+        # the reference's datasets (core.py:478-501) streamed slab by slab into the file; the returned arrays are
+        # read-only maps of the file instead of a full host copy (`numpy.array(x)` materialises one)
+        members = (('grid/x', grid.x), ('grid/y', grid.y), ('grid/z', grid.z), ('grid/is_vector', False),
+                   ('grid/is_regular', was_vector))
+        arrays, mo_norm = _compute_to_store(save_hdf5, qc, x, y, z, was_vector, N, calc_ao, calc_mo, drv,
+                                            show_norm and not calc_mo, members)
+        if calc_mo:
+            res = arrays['ao_list' if calc_ao else 'mo_list']
+            res = res.reshape((1, mo_num, -1)) if drv is None else res.reshape((len(drv), mo_num, -1))
+        else:
+            res = (arrays['rho'].reshape(-1), arrays['delta_rho'].reshape((len(drv), -1)) if is_drv else None, mo_norm)
+    else:
+        res = _compute(qc, x, y, z, was_vector, N, calc_ao, calc_mo, drv, want_norm=show_norm and not calc_mo)
 
     if calc_mo:
         mo_list = res[0] if drv is None else res
@@ -258,11 +329,7 @@ def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, num
             for i in range(mo_num):
                 display('\t%.6f\t%s %s' % (numpy.sum(numpy.square(mo_list[i])) * grid.d3r,
                                              'AO' if calc_ao else 'MO', labels[i]))
-        mo_list = mo_list.reshape(((mo_num,) if drv is None else (len(drv), mo_num,)) + N)
-        if hdf5_file is not None:
-            hdf5_file['ao_list' if calc_ao else 'mo_list'] = mo_list
-            hdf5_file.close()
-        return mo_list
+        return mo_list.reshape(((mo_num,) if drv is None else (len(drv), mo_num,)) + N)
 
     rho, delta_rho, mo_norm = res
     if show_norm:
@@ -273,16 +340,9 @@ def rho_compute(qc, calc_ao=False, calc_mo=False, drv=None, laplacian=False, num
     if not was_vector and not options.quiet:     # (a reduction over the whole grid: skipped when nothing is printed)
         display('We have ' + str(numpy.sum(rho) * grid.d3r) + ' electrons.')
     rho = rho.reshape(N)
-    if hdf5_file is not None:
-        hdf5_file['rho'] = rho
     if not is_drv:
-        if hdf5_file is not None:
-            hdf5_file.close()
         return rho
     delta_rho = delta_rho.reshape((len(drv),) + N)
-    if hdf5_file is not None:
-        hdf5_file['delta_rho'] = delta_rho
-        hdf5_file.close()
     if laplacian:
         return rho, delta_rho, delta_rho.sum(axis=0)
     return rho, delta_rho
@@ -372,8 +432,6 @@ def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_
     index, core.py:906); its evident intent -- bra = MO values of qc_a, ket = the requested sets of qc_b -- is
     implemented: both MO arrays are evaluated on the device and their products formed by okb_ci_contract."""
     from ._lib import OKB_CI_PAIRS
-    if save_hdf5:
-        raise NotImplementedError('save_hdf5: file output is outside the grid-based compute path')
     sets = _ket_sets(drv)
     codes = [validate_drv(d) for d in sets]
     x, y, z, is_vector, N = _resolve_grid(None, None, None, None, init_vector=False)
@@ -400,4 +458,13 @@ def calc_mo_matrix(qc_a, qc_b=None, drv=None, numproc=1, slice_length=1e4, save_
         terms = (numpy.zeros(len(ia)), ia, (ib + nmo_a).astype(numpy.intc))
         for d in range(len(codes)):
             eng.ci_contract(OKB_CI_PAIRS, terms, numpy.concatenate([bra, ket[d]]), out=out[d])
-    return out.reshape((len(codes), nmo_a, nmo_b) + N)
+    out = out.reshape((len(codes), nmo_a, nmo_b) + N)
+    if save_hdf5:
+        # the reference's file (core.py:919-938): the grid and the dataset 'mo_matrix'
+        from . import store as okstore
+        members = dict(x=grid.x, y=grid.y, z=grid.z, is_vector=bool(grid.is_vector))
+        if okstore.wants_hdf5(save_hdf5) and okstore.have_h5py():
+            okstore.hdf5_write(save_hdf5, mode='w', mo_matrix=out, grid=members)
+        else:
+            okstore.npz_write(save_hdf5, mode='w', compress=False, mo_matrix=out, grid=members)
+    return out

@@ -1320,7 +1320,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                 for (int k = 0; k < 10; ++k) p.slot[k] = ps.slot[k];
                 p.one_code = 0;
                 p.out = (dev_out ? rq.out + s0 : dbase) + u0;
-                cudaError_t e = okb_launch_ao_zrun(p, ctx->stream);
+                cudaError_t e = okb_launch_ao_zrun(p, ctx->sm_count, ctx->stream);
                 if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", okb_ao_zrun_name(), cudaGetErrorString(e));
                 ctx->launches++;
                 ctx->last_kernel = okb_ao_zrun_name();

@@ -14,7 +14,7 @@
 // the chunk's RowMeta / TermMeta records), the coefficients coef * f * X^lx * Y^ly of the terms with lz = l.  w_p and
 // P_l are uniform over the run: they are computed once per (row group, chunk) by the CTA into shared memory.
 //
-//   CTA         = J consecutive (x, y) rows of the grid  x  one block of blockDim.x consecutive z points
+//   CTA         = RG groups of J consecutive (x, y) rows of the grid  x  one block of blockDim.x consecutive z points
 //   thread      = one z index k, all J rows:  per shell  R0[j] = sum_p w[p][j] * tabz[p][k]   (1 coalesced cached load
 //                 per primitive, J FMAs), then per output row of the shell a Horner polynomial in Z_k (L FMAs), one
 //                 multiplication by R0[j] and ONE coalesced 8-byte streaming store per AO value -- lanes are consecutive
@@ -41,12 +41,12 @@ struct ZrunSmem {
     double P[KC][ZR_MAXL + 1][J];            // polynomial coefficients per output row
     long long rowoff[KC];                    // element offset of the output row (slot and row stride applied), -1: skip
     ZShell sh[ZR_MAXS];
-    int ri[J], rj[J];                        // axis indices of the J rows; ri < 0: row outside the launch
+    int nshell;
 };
 
 template <int J, int L>
 __device__ __forceinline__ void zrun_rows(const ZrunSmem<J> &S, const ZShell &sh, const double Z, const double (&R0)[J],
-                                          double *__restrict__ out, const long long (&off)[J], const bool (&act)[J]) {
+                                          double *__restrict__ out, const long long off0, const int nz, const unsigned act) {
     for (int r = sh.row_off; r < sh.row_off + sh.nrow; ++r) {
         const long long ro = S.rowoff[r];
         if (ro < 0) continue;                                   // uniform
@@ -57,59 +57,59 @@ __device__ __forceinline__ void zrun_rows(const ZrunSmem<J> &S, const ZShell &sh
         for (int l = L - 1; l >= 0; --l)
 #pragma unroll
             for (int j = 0; j < J; ++j) poly[j] = fma(poly[j], Z, S.P[r][l][j]);
+        double *o = out + ro + off0;
 #pragma unroll
         for (int j = 0; j < J; ++j)
-            if (act[j]) __stcs(out + ro + off[j], poly[j] * R0[j]);
+            if (act & (1u << j)) __stcs(o + (long long)j * nz, poly[j] * R0[j]);
     }
 }
 
-// row_first: first (x, y) row (index i*ny + j) of the launch; n_groups row groups of J rows; nzb z blocks per row
+// Grid: blockIdx.x = (block of RG row groups) * nzb + z block.  A CTA walks  chunk (outer) x its RG row groups (inner):
+// the tabz slices of a chunk's primitives (~25 x blockDim.x doubles) are then re-read RG times in a row and stay in L1,
+// instead of streaming the whole table (1.25 MB for the benchmark molecule) from L2 once per row group.  The uniform
+// quantities of iteration i + 1 are prepared (phase U) into the other half of a two-deep shared-memory ring before
+// iteration i is evaluated (phase T): one CTA barrier per iteration.
 template <int J>
 __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long long row_first, long long row_last,
-                                                          int nzb) {
-    __shared__ ZrunSmem<J> S;
+                                                          int nzb, int RG) {
+    __shared__ ZrunSmem<J> S2[2];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    const long long rg = blockIdx.x / nzb;
-    const int zb = (int)(blockIdx.x - rg * nzb);
+    const long long rgb = blockIdx.x / nzb;                      // block of RG row groups
+    const int zb = (int)(blockIdx.x - rgb * nzb);
     const int k = zb * nt + tid;
     const bool kvalid = k < p.nz;
     const int kc = kvalid ? k : p.nz - 1;
     const double zk = __ldg(p.gz + kc);
-    long long off[J];
-    bool act[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const long long row = row_first + rg * J + j;
-        const long long pt = row * p.nz + k;
-        off[j] = pt - p.p0;
-        act[j] = kvalid && row <= row_last && off[j] >= 0 && off[j] < (long long)p.npts;
-    }
-    if (tid < J) {
-        const long long row = row_first + rg * J + tid;
-        const bool ok = row <= row_last;
-        S.ri[tid] = ok ? (int)(row / p.ny) : -1;
-        S.rj[tid] = ok ? (int)(row % p.ny) : 0;
-    }
     const int sl = p.slot[p.one_code];                           // SET_VAL: one_code = 0
     const long long slot_off = (long long)sl * p.slot_stride;
-    __syncthreads();
+    const long long ngroups = (row_last - row_first + J) / J;
+    long long g0 = rgb * RG;
+    const int nrg = (int)((ngroups - g0) < RG ? (ngroups - g0) : RG);
+    const int niter = p.nchunk * nrg;
 
-    for (int c = 0; c < p.nchunk; ++c) {
+    // phase U of iteration `it` (chunk it / nrg, row group g0 + it % nrg) into S2[it & 1]
+    auto phase_u = [&](int it) {
+        ZrunSmem<J> &S = S2[it & 1];
+        const int c = it / nrg;
+        const long long row0 = row_first + (g0 + (it - c * nrg)) * J;
         const unsigned char *mb = p.meta + (size_t)c * p.lay.stride;
         const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(mb);
         const ShellMeta *shells = reinterpret_cast<const ShellMeta *>(mb + p.lay.off_shell);
         const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
         const RowMeta *rows = reinterpret_cast<const RowMeta *>(mb + p.lay.off_row);
         const TermMeta *terms = reinterpret_cast<const TermMeta *>(mb + p.lay.off_term);
-        // ---- phase U: the quantities that are uniform along z ------------------------------------------------
         // (a) w[p][j]: one warp per shell, lanes over (primitive, row)
         for (int s = warp; s < hdr.nshell; s += nwarp) {
             const int np = __ldg(&shells[s].nprim), po = __ldg(&shells[s].prim_off), gp = __ldg(&shells[s].gprim);
             for (int e = lane; e < np * J; e += 32) {
                 const int q = e / J, j = e - q * J;
-                const int i = S.ri[j];
-                S.w[po + q][j] = i < 0 ? 0.0
-                                       : __ldg(p.tabx + (size_t)(gp + q) * p.nx + i) * __ldg(p.taby + (size_t)(gp + q) * p.ny + S.rj[j]);
+                const long long row = row0 + j;
+                double w = 0.0;
+                if (row <= row_last) {
+                    const int i = (int)(row / p.ny), jj = (int)(row - (long long)i * p.ny);
+                    w = __ldg(p.tabx + (size_t)(gp + q) * p.nx + i) * __ldg(p.taby + (size_t)(gp + q) * p.ny + jj);
+                }
+                S.w[po + q][j] = w;
             }
             if (lane == 0) {
                 ZShell z;
@@ -128,10 +128,11 @@ __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long 
             double acc[ZR_MAXL + 1];
 #pragma unroll
             for (int l = 0; l <= ZR_MAXL; ++l) acc[l] = 0.0;
-            const int i = S.ri[j];
-            if (i >= 0) {
+            const long long row = row0 + j;
+            if (row <= row_last) {
+                const int i = (int)(row / p.ny), jj = (int)(row - (long long)i * p.ny);
                 const ShellMeta *sh = shells + rm.shell;
-                const double X = __ldg(p.gx + i) - __ldg(&sh->cx), Y = __ldg(p.gy + S.rj[j]) - __ldg(&sh->cy);
+                const double X = __ldg(p.gx + i) - __ldg(&sh->cx), Y = __ldg(p.gy + jj) - __ldg(&sh->cy);
                 for (int t = 0; t < rm.nterm; ++t) {
                     const TermMeta tm = terms[rm.term_off + t];
                     const FnMeta fm = fns[tm.k];
@@ -146,9 +147,26 @@ __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long 
             for (int l = 0; l <= ZR_MAXL; ++l) S.P[r][l][j] = acc[l];
             if (j == 0) S.rowoff[r] = sl < 0 ? -1 : slot_off + (long long)rm.out_row * p.ld;
         }
-        __syncthreads();
-        // ---- phase T: one z point per thread, J rows ----------------------------------------------------------------
-        for (int s = 0; s < hdr.nshell; ++s) {
+        if (tid == 0) S.nshell = hdr.nshell;
+    };
+
+    if (niter > 0) phase_u(0);
+    __syncthreads();
+    for (int it = 0; it < niter; ++it) {
+        if (it + 1 < niter) phase_u(it + 1);
+        // ---- phase T: one z point per thread, J rows --------------------------------------------------------------------
+        const ZrunSmem<J> &S = S2[it & 1];
+        const int c = it / nrg;
+        const long long row0 = row_first + (g0 + (it - c * nrg)) * J;
+        const long long off0 = row0 * p.nz + k - p.p0;
+        unsigned act = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const long long o = off0 + (long long)j * p.nz;
+            if (kvalid && row0 + j <= row_last && o >= 0 && o < (long long)p.npts) act |= 1u << j;
+        }
+        const int nshell = S.nshell;
+        for (int s = 0; s < nshell; ++s) {
             const ZShell sh = S.sh[s];
             double R0[J];
 #pragma unroll
@@ -171,13 +189,13 @@ __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long 
             }
             const double Z = zk - sh.cz;
             switch (sh.L) {                                       // uniform
-                case 0: zrun_rows<J, 0>(S, sh, Z, R0, p.out, off, act); break;
-                case 1: zrun_rows<J, 1>(S, sh, Z, R0, p.out, off, act); break;
-                case 2: zrun_rows<J, 2>(S, sh, Z, R0, p.out, off, act); break;
-                case 3: zrun_rows<J, 3>(S, sh, Z, R0, p.out, off, act); break;
-                case 4: zrun_rows<J, 4>(S, sh, Z, R0, p.out, off, act); break;
-                case 5: zrun_rows<J, 5>(S, sh, Z, R0, p.out, off, act); break;
-                default: zrun_rows<J, 6>(S, sh, Z, R0, p.out, off, act); break;
+                case 0: zrun_rows<J, 0>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                case 1: zrun_rows<J, 1>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                case 2: zrun_rows<J, 2>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                case 3: zrun_rows<J, 3>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                case 4: zrun_rows<J, 4>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                case 5: zrun_rows<J, 5>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
+                default: zrun_rows<J, 6>(S, sh, Z, R0, p.out, off0, p.nz, act); break;
             }
         }
         __syncthreads();

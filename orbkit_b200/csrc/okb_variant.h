@@ -20,7 +20,7 @@ extern const VariantTable okb_variants_tile, okb_variants_val, okb_variants_grad
     okb_variants_d2, okb_variants_d2p, okb_variants_aows;
 
 // z-run SINK_AO kernel for regular grids (inst_ao_zrun.cu)
-cudaError_t okb_launch_ao_zrun(const KParams &p, cudaStream_t st);
+cudaError_t okb_launch_ao_zrun(const KParams &p, int sm_count, cudaStream_t st);
 const char *okb_ao_zrun_name();
 
 }  // namespace okb

@@ -117,6 +117,38 @@ def cube_creator(data, filename, geo_info, geo_spec, comments='', labels=None, *
     return filename
 
 
+H5_SYNONYMS = ('h5', 'hdf5')
+NPZ_SYNONYMS = ('npz', 'numpy')
+
+
+def _to_host(data):
+    return data.detach().cpu().numpy() if _is_device_tensor(data) else numpy.asarray(data)
+
+
+def hdf5_creator(data, filename, qcinfo=None, gname='', ftype='hdf5', mode='w', attrs={}, **kwargs):
+    """HDF5 or .npz container with the reference's groups (orbkit/output/hdf5.py:10-54): `data`, `grid/{x,y,z,
+    is_vector,is_regular}`, optional attributes and `qcinfo/...` (QCinfo.todict() with date and time).
+    ftype 'hdf5'/'h5' needs h5py (ImportError otherwise); 'numpy'/'npz' writes a zip of .npy members."""
+    import time
+    from . import store
+    if ftype.lower() in H5_SYNONYMS:
+        write = store.hdf5_write
+    elif ftype.lower() in NPZ_SYNONYMS:
+        write = store.npz_write
+    else:
+        raise NotImplementedError('File format {0} not implemented for writing.'.format(ftype.lower()))
+    fn = write(filename, mode=mode, gname=gname, data=numpy.asarray(data), **kwargs)
+    write(fn, mode='a', gname=os.path.join(gname, 'grid'), x=grid.x, y=grid.y, z=grid.z,
+          is_vector=bool(grid.is_vector), is_regular=bool(grid.is_regular))
+    if attrs:
+        write(fn, mode='a', gname=gname + '_attrs', **attrs)
+    if qcinfo is not None:
+        d = dict(qcinfo.todict())
+        d['date'], d['time'] = time.strftime('%Y-%m-%d'), time.strftime('%H:%M:%S')
+        write(fn, mode='a', gname=os.path.join(gname, 'qcinfo'), **d)
+    return fn
+
+
 def main_output(data, qc=None, outputname='data', otype='auto', gname='', drv=None, omit=[], datalabels='',
                 dataindices=None, mode='w', **kwargs):
     """Writes `data` as cube file(s) with the reference's naming scheme (high_level.py:59-342, cube branch):
@@ -135,21 +167,33 @@ def main_output(data, qc=None, outputname='data', otype='auto', gname='', drv=No
             if ext != '' or len(otype) == 1:
                 otype[i] = ext[1:]
     otype = [i for i in otype if i not in omit]
-    other = [i for i in otype if i not in CUBE_SYNONYMS]
+    other = [i for i in otype if i not in CUBE_SYNONYMS + H5_SYNONYMS + NPZ_SYNONYMS]
     if other:
-        raise NotImplementedError('orbkit_b200 writes cube files (otype "cb"/"cube") only; %r belong to the reference\'s '
-                                  'output module' % (other,))
+        raise NotImplementedError('orbkit_b200 writes cube files ("cb"/"cube"), HDF5 ("h5") and "npz" containers; %r '
+                                  'belong to the reference\'s output module' % (other,))
     if not otype:
         return []
+    written = []
+    base = outputname if isinstance(outputname, str) else outputname[-1]
+    for t in otype:                     # containers take the data as it is, on any grid (high_level.py:298-311)
+        if t in H5_SYNONYMS:
+            display('\nSaving to Hierarchical Data Format file (HDF5)...\n\t' + base + '.' + t)
+            written.append(hdf5_creator(_to_host(data), base + '.' + t, qcinfo=qc, gname=gname, ftype='hdf5', mode=mode))
+        elif t in NPZ_SYNONYMS:
+            display('\nSaving to a compressed .npz archive...\n\t' + base + '.npz')
+            written.append(hdf5_creator(_to_host(data), base, qcinfo=qc, gname=gname, ftype='numpy', mode=mode))
+    otype = [i for i in otype if i in CUBE_SYNONYMS]
+    if not otype:
+        return written
     ext = otype[0]
     if grid.is_vector and not grid.is_regular:
         display('For a non-regular vector grid (`if grid.is_vector and not grid.is_regular`)')
         display('only HDF5 is available as output format...')
         display('Skipping all other formats...')
-        return []
+        return written
     if qc is None:
         display('\nFor cube file output `qc` is a required keyword parameter in `main_output`.')
-        return []
+        return written
     dev = _is_device_tensor(data)
     if not dev:
         data = numpy.asarray(data)
@@ -159,7 +203,7 @@ def main_output(data, qc=None, outputname='data', otype='auto', gname='', drv=No
         drv = [drv]
     if data.ndim < dims:
         display('data.ndim < ndim of grid')
-        return []
+        return written
     elif data.ndim == dims:
         data = data[None, None]
     elif data.ndim == dims + 1:
@@ -169,7 +213,7 @@ def main_output(data, qc=None, outputname='data', otype='auto', gname='', drv=No
             drv = list(range(data.shape[0]))
     else:
         display('data.ndim > (ndim of grid) +2')
-        return []
+        return written
     if is_regular_vector:
         # a regular grid stored as a vector: the point index is x-major, z fastest (cy_grid.pyx:22-29)
         display('\nConverting the regular 1d vector grid to a 3d regular grid.')
@@ -186,7 +230,6 @@ def main_output(data, qc=None, outputname='data', otype='auto', gname='', drv=No
         fid, label_id, it = '%(f)s_%(d)s.', '%(d)s %(f)s', [(i, i) for i in range(data.shape[0])]
     else:
         fid, label_id, it = '%(f)s.', '%(f)s', [(0, None)]
-    written = []
     for idrv, jdrv in it:
         for idata in range(data.shape[1]):
             if isstr:

@@ -398,3 +398,69 @@ def test_molden_reader_equals_reference_reader(tmp_path):
         read.main_read(os.path.join(inputs, 'h2o_rhf_sph.molden'), spin='alpha')
     with pytest.raises(IOError):
         read.read_molden(os.path.join(inputs, 'h2o_rhf_sph.fchk'))
+
+
+# ---- streaming result store (orbkit_b200.store) ---------------------------------------------------------------------
+def test_result_store_streams_slabs_into_an_npz(tmp_path):
+    """save_hdf5 sink (core.py:478-501): column slabs written out of order land at their place; the finished file is
+    a plain .npz (numpy.load reads it) with the reference's dataset names, and arrays() maps it without a host copy"""
+    from orbkit_b200 import store
+    rng = numpy.random.default_rng(3)
+    N = (7, 5, 11)
+    npts = int(numpy.prod(N))
+    mo = rng.normal(size=(2, 3, npts))
+    rho = rng.normal(size=npts)
+    st = store.ResultStore(str(tmp_path / 'out'))            # no .h5 / .npz suffix -> out.npz
+    st.put('grid/x', numpy.arange(7.0))
+    st.put('grid/is_vector', False)
+    d_mo = st.create('mo_list', (2, 3) + N, npts)
+    d_rho = st.create('rho', N, npts)
+    bounds = [0, 40, 41, 200, npts]
+    for a, b in reversed(list(zip(bounds[:-1], bounds[1:]))):
+        st.write_async(d_mo, a, b, numpy.ascontiguousarray(mo[:, :, a:b]))
+        st.write_async(d_rho, a, b, rho[a:b].copy())
+    st.close()
+    assert st.path.endswith('out.npz') and not os.path.exists(st.path + '.parts')
+    with numpy.load(st.path) as f:
+        assert sorted(f.files) == ['grid/is_vector', 'grid/x', 'mo_list', 'rho']
+        assert numpy.array_equal(f['mo_list'], mo.reshape((2, 3) + N)) and numpy.array_equal(f['rho'], rho.reshape(N))
+        assert numpy.array_equal(f['grid/x'], numpy.arange(7.0)) and not f['grid/is_vector']
+    arr = st.arrays()
+    assert isinstance(arr['mo_list'], numpy.memmap) and arr['mo_list'].shape == (2, 3) + N
+    assert numpy.array_equal(arr['mo_list'], mo.reshape((2, 3) + N)) and numpy.array_equal(arr['rho'], rho.reshape(N))
+    # containers of main_output: groups become member prefixes, None is skipped, dictionaries nest
+    fn = store.npz_write(str(tmp_path / 'c'), gname='g', data=mo, skip=None, grid={'x': numpy.arange(3.0), 'is_vector': True})
+    with numpy.load(fn) as f:
+        assert sorted(f.files) == ['g/data', 'g/grid/is_vector', 'g/grid/x'] and numpy.array_equal(f['g/data'], mo)
+    assert store._lead_dims((3, 5, 4, 4, 4), 64) == (3, 5) and store._lead_dims((64,), 64) == ()
+    if not store.have_h5py():
+        with pytest.raises(ImportError):
+            store.hdf5_write(str(tmp_path / 'x.h5'), data=mo)
+
+
+def test_main_output_npz_container(tmp_path):
+    """main_output(otype='npz') (output/high_level.py:306-311, output/hdf5.py:10-54): data, grid and qcinfo groups"""
+    import orbkit_b200 as ok
+    from conftest import golden_qc
+    ok.options.quiet = True
+    qc, a = golden_qc('h2o_gaussian_sph')
+    ok.grid.set_grid(numpy.arange(3.0), numpy.arange(4.0), numpy.arange(5.0), is_vector=False)
+    data = numpy.random.default_rng(0).normal(size=(2, 3, 4, 5))
+    out = ok.main_output(data, qc, outputname=str(tmp_path / 'res'), otype='npz', gname='run1')
+    assert out == [str(tmp_path / 'res') + '.npz']
+    with numpy.load(out[0]) as f:
+        assert numpy.array_equal(f['run1/data'], data)
+        assert numpy.array_equal(f['run1/grid/y'], numpy.arange(4.0)) and not f['run1/grid/is_vector']
+        assert numpy.allclose(f['run1/qcinfo/geo_spec'], qc.geo_spec)
+        assert numpy.array_equal(f['run1/qcinfo/mo_spec/coeffs'], qc.mo_spec.get_coeffs())
+        assert numpy.array_equal(f['run1/qcinfo/ao_spec/_lxlylz'], qc.ao_spec.get_lxlylz())
+        assert 'run1/qcinfo/date' in f.files
+    # 'auto' takes the type from the file name; cube and npz together
+    both = ok.main_output(data[0, 0], qc, outputname=str(tmp_path / 'b'), otype=['npz'])
+    assert both == [str(tmp_path / 'b') + '.npz']
+    from orbkit_b200 import store
+    if not store.have_h5py():
+        with pytest.raises(ImportError):
+            ok.main_output(data, qc, outputname=str(tmp_path / 'h'), otype='h5')
+    with pytest.raises(NotImplementedError):
+        ok.main_output(data, qc, outputname=str(tmp_path / 'h'), otype='am')
