@@ -69,7 +69,7 @@ __device__ __forceinline__ void zrun_rows(const ZrunSmem<J> &S, const ZShell &sh
 // instead of streaming the whole table (1.25 MB for the benchmark molecule) from L2 once per row group.  The uniform
 // quantities of iteration i + 1 are prepared (phase U) into the other half of a two-deep shared-memory ring before
 // iteration i is evaluated (phase T): one CTA barrier per iteration.
-template <int J>
+template <int J, int PF>
 __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long long row_first, long long row_last,
                                                           int nzb, int RG) {
     __shared__ ZrunSmem<J> S2[2];
@@ -166,6 +166,16 @@ __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long 
             if (kvalid && row0 + j <= row_last && o >= 0 && o < (long long)p.npts) act |= 1u << j;
         }
         const int nshell = S.nshell;
+        // the tabz values of the first PF primitives of shell s + 1 are fetched before the rows of shell s are written:
+        // most shells have one to three primitives, and a load issued right in front of its use costs a full L2 round trip
+        double tn[PF > 0 ? PF : 1];
+        if (PF > 0 && nshell > 0) {
+            const ZShell s0 = S.sh[0];
+            const double *tz0 = p.tabz + (size_t)s0.gprim * p.nz + kc;
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (u < s0.nprim) tn[u] = __ldg(tz0 + (size_t)u * p.nz);
+        }
         for (int s = 0; s < nshell; ++s) {
             const ZShell sh = S.sh[s];
             double R0[J];
@@ -173,6 +183,25 @@ __global__ void __launch_bounds__(256) okb_ao_zrun_kernel(const KParams p, long 
             for (int j = 0; j < J; ++j) R0[j] = 0.0;
             const double *tz = p.tabz + (size_t)sh.gprim * p.nz + kc;
             int q = 0;
+            if (PF > 0) {
+                double t[PF > 0 ? PF : 1];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) t[u] = tn[u];
+                if (s + 1 < nshell) {
+                    const ZShell sn = S.sh[s + 1];
+                    const double *tzn = p.tabz + (size_t)sn.gprim * p.nz + kc;
+#pragma unroll
+                    for (int u = 0; u < PF; ++u)
+                        if (u < sn.nprim) tn[u] = __ldg(tzn + (size_t)u * p.nz);
+                }
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (u < sh.nprim) {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) R0[j] = fma(S.w[sh.prim_off + u][j], t[u], R0[j]);
+                    }
+                q = sh.nprim < PF ? sh.nprim : PF;
+            }
             for (; q + 4 <= sh.nprim; q += 4) {
                 double t[4];
 #pragma unroll

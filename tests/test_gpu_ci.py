@@ -216,4 +216,4 @@ def test_calc_mo_matrix_and_calc_jmo(ok, oci):
     with pytest.raises(ValueError):
         ok.extras.calc_jmo(qc, ij, drv=[None, 'x', 'y'])
     with pytest.raises(NotImplementedError):
-        ok.extras.calc_jmo(qc, ij, otype='h5')
+        ok.extras.calc_jmo(qc, ij, otype='am')

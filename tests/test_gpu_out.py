@@ -136,4 +136,4 @@ def test_calc_mo_writes_cube_files(ok, tmp_path):
     ok.options.no_output = False
     assert not os.path.exists(str(tmp_path / 'none_0.cb'))
     with pytest.raises(NotImplementedError):
-        ok.main_output(rho, qc, outputname=base, otype='h5')
+        ok.main_output(rho, qc, outputname=base, otype='am')
