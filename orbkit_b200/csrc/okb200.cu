@@ -169,8 +169,12 @@ struct okb_mo {
     std::vector<double> ccart;               // [n_mo][n_cart] in Cartesian rows (C' = C T)
     std::vector<double> csph;                // [n_mo][n_ao] as given (spherical bases only)
     std::vector<double> occ;
-    struct Blob { double *c = nullptr; double *occ = nullptr; int n_mtile = 0; size_t c_bytes = 0, occ_bytes = 0; };
-    std::map<int, Blob> blobs;               // keyed by 2*MC + (mix layout ? 1 : 0)
+    struct Blob {
+        double *c = nullptr, *occ = nullptr, *crem = nullptr;
+        int n_mtile = 0;
+        size_t c_bytes = 0, occ_bytes = 0, crem_bytes = 0;
+    };
+    std::map<int, Blob> blobs;               // keyed by 2*(16*MC + rem) + (mix layout ? 1 : 0)
 };
 
 struct okb_grid {
@@ -811,8 +815,11 @@ extern "C" int okb_mo_create(okb_ctx *ctx, okb_basis *b, int n_mo, const double 
     return OKB_OK;
 }
 
-static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blob **out) {
-    const int key = 2 * MC + (is_mix ? 1 : 0);
+// MC: orbitals of an MO tile contracted by the consumer warps (DMMA blocks), rem: remainder orbitals of the tile contracted
+// by the producer warps (okb_ws.cuh); the tile holds MCT = MC + rem orbitals
+static int mo_blob(okb_mo *m, int MC, int rem, const Layout &lo, bool is_mix, okb_mo::Blob **out) {
+    const int MCT = MC + rem;
+    const int key = 2 * (MC * 16 + rem) + (is_mix ? 1 : 0);
     auto it = m->blobs.find(key);
     if (it != m->blobs.end()) {
         *out = &it->second;
@@ -820,16 +827,24 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
     }
     okb_basis *b = m->basis;
     const int nchunk = (int)lo.chunks.size();
-    const int n_mtile = (m->n_mo + MC - 1) / MC;
+    const int n_mtile = (m->n_mo + MCT - 1) / MCT;
     const int CS = pad_stride(MC);           // row stride = 4 (mod 16) doubles: conflict-free MMA fragment loads
     std::vector<double> blob((size_t)n_mtile * nchunk * KC * CS, 0.0);
+    std::vector<double> crem((size_t)n_mtile * nchunk * KC * std::max(rem, 1), 0.0);
     for (int mt = 0; mt < n_mtile; ++mt)
         for (int c = 0; c < nchunk; ++c) {
             double *dst = blob.data() + ((size_t)mt * nchunk + c) * KC * CS;
+            double *rdst = crem.data() + ((size_t)mt * nchunk + c) * KC * rem;
             for (int kk = 0; kk < lo.chunks[c].nfn; ++kk) {
                 const KRow &kr = lo.krow[lo.chunks[c].k0 + kk];
+                for (int r = 0; r < rem; ++r) {          // [row][rem]: one 16-byte load per row for rem = 2
+                    const int mo = mt * MCT + MC + r;
+                    if (mo >= m->n_mo) continue;
+                    rdst[(size_t)kk * rem + r] = kr.is_sph ? m->csph[(size_t)mo * b->n_ao + kr.index]
+                                                           : m->ccart[(size_t)mo * b->n_cart + kr.index];
+                }
                 for (int i = 0; i < MC; ++i) {
-                    const int mo = mt * MC + i;
+                    const int mo = mt * MCT + i;
                     if (mo >= m->n_mo) continue;
                     // MO blocks of 8 are stored in pairs, row by row: (block 2q, row r) and (block 2q+1, row r) are
                     // neighbours, so that a consumer lane fetches its A fragments of two blocks with one 16-byte load
@@ -839,7 +854,7 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
                 }
             }
         }
-    std::vector<double> occ((size_t)n_mtile * MC, 0.0);
+    std::vector<double> occ((size_t)n_mtile * MCT, 0.0);
     std::copy(m->occ.begin(), m->occ.end(), occ.begin());
     okb_mo::Blob bl;
     bl.n_mtile = n_mtile;
@@ -852,6 +867,13 @@ static int mo_blob(okb_mo *m, int MC, const Layout &lo, bool is_mix, okb_mo::Blo
         rcp = pool_get(m->ctx, occ.size() * sizeof(double), &raw, &bl.occ_bytes);
         if (rcp != OKB_OK) return rcp;
         bl.occ = reinterpret_cast<double *>(raw);
+        if (rem > 0) {
+            rcp = pool_get(m->ctx, crem.size() * sizeof(double), &raw, &bl.crem_bytes);
+            if (rcp != OKB_OK) return rcp;
+            bl.crem = reinterpret_cast<double *>(raw);
+            CU(cudaMemcpy(bl.crem, crem.data(), crem.size() * sizeof(double), cudaMemcpyHostToDevice));
+            m->ctx->h2d_bytes += (long long)(crem.size() * sizeof(double));
+        }
     }
     CU(cudaMemcpy(bl.c, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(bl.occ, occ.data(), occ.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -868,6 +890,7 @@ extern "C" int okb_mo_destroy(okb_mo *m) {
     for (auto &kv : m->blobs) {
         pool_put(m->ctx, kv.second.c, kv.second.c_bytes);
         pool_put(m->ctx, kv.second.occ, kv.second.occ_bytes);
+        if (kv.second.crem) pool_put(m->ctx, kv.second.crem, kv.second.crem_bytes);
     }
     delete m;
     return OKB_OK;
@@ -1016,10 +1039,12 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 // the throughput of the tile kernel there -- and the tile kernel for plain values, where both measure the same because the
 // AO generators, not the stores, bound calc_ao)
 static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants_tile, &okb_variants_val, &okb_variants_grad,
-                                               &okb_variants_lap, &okb_variants_all, &okb_variants_d2, &okb_variants_d2p};
+                                               &okb_variants_lap, &okb_variants_all, &okb_variants_d2, &okb_variants_d2p,
+                                               &okb_variants_rem};
 
 // ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
-static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false) {
+// meta_stride > 0: skip the MO-tile variants whose shared memory does not fit with chunk tables of that size
+static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false, int meta_stride = 0) {
     const Variant *best = nullptr;
     long long best_cost = 0;
     for (const VariantTable *tab : g_tables)
@@ -1041,12 +1066,15 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         // OKB_VARIANT=<substring of a variant name> forces a configuration (A/B measurements only)
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
+        if (meta_stride > 0 && v.smem(meta_stride) > 227 * 1024) continue;
         // Every MO tile regenerates the AO tiles, and the producers run beside the consumers: a pass over one
         // MO tile costs max(contraction ~ MC, generation).  Measured on the 1000-AO molecule the two balance at
         // MC ~ 45-60 for every set (profiles/r01_perf_matrix.txt), so narrow tiles are charged as 48 wide.
         // Prefer the wider tile on ties (fewer AO regenerations).
+        // Remainder orbitals (v.rem of the v.MC, contracted by the producer warps) are charged 3 DMMA columns each:
+        // 82 MOs go to the 80 + 2 tile (86) instead of the 88-wide one, 83..88 MOs stay on the latter.
         const long long n_tiles = (n_mo + v.MC - 1) / v.MC;
-        const long long cost = n_tiles * std::max(v.MC, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
+        const long long cost = n_tiles * std::max(v.MC + 2 * v.rem, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;
@@ -1330,7 +1358,8 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                                  (ps.set == SET_VAL || ps.set == SET_GRAD || ps.set == SET_LAP || ps.set == SET_D2 ||
                                   ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));
             const Layout &lo = use_mix ? b->mix : b->cart;
-            const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo, ao_bulk_ok);
+            const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo, ao_bulk_ok,
+                                            rq.sink == SINK_AO ? 0 : lo.lay.stride);
             // (a basis with very large chunk tables may not leave the stage ring of an "aows/" kernel enough shared memory)
             if (v && rq.sink == SINK_AO && ao_bulk_ok && v->smem(lo.lay.stride) > 227 * 1024)
                 v = pick_variant(ps.set, rq.sink, 1, false);
@@ -1352,9 +1381,10 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
             p.n_mo = 0;
             if (rq.sink != SINK_AO) {
                 okb_mo::Blob *bl = nullptr;
-                rc = mo_blob(rq.mo, v->MC, lo, use_mix, &bl);
+                rc = mo_blob(rq.mo, v->MC - v->rem, v->rem, lo, use_mix, &bl);
                 if (rc != OKB_OK) return rc;
                 p.cblob = bl->c;
+                p.crem = bl->crem;
                 p.occ = bl->occ;
                 p.n_mtile = bl->n_mtile;
                 p.n_mo = rq.mo->n_mo;

@@ -95,7 +95,8 @@ struct KParams {
                                    // laplacian); 3 = 1 + the MO values are left in `phi` for a SET_D2P second pass
     double *phi;                   // [n_mtile*MC][ldp] MO values of the launch's points (epi 3 writes, SET_D2P reads)
     long long ldp;
-    int zero;                      // always 0, but only the host knows: okb_ws.cuh ties fragment loads to DMMA results with it
+    const double *crem;            // [n_mtile][nchunk][KC][REM] coefficients of the remainder orbitals of each MO tile
+                                   // (okb_ws.cuh, REM > 0: contracted by the producer warps), else null
 };
 
 // Axis tables of a regular grid as the AO generators see them; ii/jj/kk point at the axis indices of the

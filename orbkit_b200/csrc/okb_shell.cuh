@@ -250,14 +250,23 @@ __device__ __forceinline__ void radial_sums_tab(const ShellMeta &sh, const doubl
     if (i < sh.nprim) radial_group_tab<1, NP, N1, N2>(pp, tab, i, ox, oy, oz, R0, R1, R2);
 }
 
+// Hook of the generators for the remainder orbitals of okb_ws.cuh (REM > 0): ra.row(k, q, v) is called once per tile row k
+// (chunk-local) and point q of the thread with the D values the generator has just written; NoRem compiles to nothing.
+struct NoRem {
+    static constexpr bool on = false;
+    template <int D>
+    __device__ __forceinline__ void row(int, int, const double (&)[D]) const {}
+};
+
 // One standard shell for NP points of the same thread (points pt, pt+32, ...: tile columns tp[32*q]).
 // ONLY (SET_ONE requests): 1..6 = write just that derivative code (d/dx, d/dy, d/dz, d2/dx2, d2/dy2, d2/dz2) as the single
 // set of the tile; 0 = the sets of SET.
-template <int SET, int L, int STRIDE, bool SPH, int NP, int ONLY = 0>
+template <int SET, int L, int STRIDE, bool SPH, int NP, int ONLY = 0, class RA = NoRem>
 __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
-                                              const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
+                                              const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab,
+                                              const RA &ra = RA()) {
     static_assert(SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P ||
                       (SET == SET_ONE && ONLY >= 1 && ONLY <= 6), "specialised sets");
     static_assert(ONLY == 0 || SET == SET_ONE, "ONLY selects the code of a SET_ONE request");
@@ -314,27 +323,31 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 const double f = ff[j].f;
                 const double fz = f * g0[2][lz];
                 const double fyz = fz * g0[1][ly];
-                if (W0) o[(size_t)j * STRIDE] = fyz * (R0[q] * g0[0][lx]);
+                double w[D];                               // the row's values, tile set by tile set
+                if (W0) w[0] = fyz * (R0[q] * g0[0][lx]);
                 if (N1) {
                     const double fxz = fz * g0[0][lx];
                     const double fxy = f * (g0[0][lx] * g0[1][ly]);
                     if (W1) {
-                        o[((size_t)1 * KC + j) * STRIDE] = fyz * g1[0][lx];
-                        o[((size_t)2 * KC + j) * STRIDE] = fxz * g1[1][ly];
-                        o[((size_t)3 * KC + j) * STRIDE] = fxy * g1[2][lz];
+                        w[1] = fyz * g1[0][lx];
+                        w[2] = fxz * g1[1][ly];
+                        w[3] = fxy * g1[2][lz];
                     }
                     if (W2) {
-                        o[((size_t)(O2 + 0) * KC + j) * STRIDE] = fyz * g2[0][lx];
-                        o[((size_t)(O2 + 1) * KC + j) * STRIDE] = fxz * g2[1][ly];
-                        o[((size_t)(O2 + 2) * KC + j) * STRIDE] = fxy * g2[2][lz];
+                        w[O2 + 0] = fyz * g2[0][lx];
+                        w[O2 + 1] = fxz * g2[1][ly];
+                        w[O2 + 2] = fxy * g2[2][lz];
                     }
-                    if (ONLY == 1) o[(size_t)j * STRIDE] = fyz * g1[0][lx];
-                    if (ONLY == 2) o[(size_t)j * STRIDE] = fxz * g1[1][ly];
-                    if (ONLY == 3) o[(size_t)j * STRIDE] = fxy * g1[2][lz];
-                    if (ONLY == 4) o[(size_t)j * STRIDE] = fyz * g2[0][lx];
-                    if (ONLY == 5) o[(size_t)j * STRIDE] = fxz * g2[1][ly];
-                    if (ONLY == 6) o[(size_t)j * STRIDE] = fxy * g2[2][lz];
+                    if (ONLY == 1) w[0] = fyz * g1[0][lx];
+                    if (ONLY == 2) w[0] = fxz * g1[1][ly];
+                    if (ONLY == 3) w[0] = fxy * g1[2][lz];
+                    if (ONLY == 4) w[0] = fyz * g2[0][lx];
+                    if (ONLY == 5) w[0] = fxz * g2[1][ly];
+                    if (ONLY == 6) w[0] = fxy * g2[2][lz];
                 }
+#pragma unroll
+                for (int d = 0; d < D; ++d) o[((size_t)d * KC + j) * STRIDE] = w[d];
+                if (RA::on) ra.row(sh.fn_off + j, q, w);
             }
         } else {
             // Cartesian values stay in registers; the 2L+1 real-spherical rows are the only ones written
@@ -385,6 +398,7 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 });
 #pragma unroll
                 for (int d = 0; d < D; ++d) o[((size_t)d * KC + pos) * STRIDE] = sacc[d];
+                if (RA::on) ra.row(sh.fn_off + pos, q, sacc);
             });
         }
     }
@@ -392,25 +406,26 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
 
 // standard shells of L <= 4 (kind 1: Cartesian rows, kind 2: spherical rows): the straight-line code; returns false for
 // every other shell
-template <int S, int STRIDE, int NP, int ONLY>
+template <int S, int STRIDE, int NP, int ONLY, class RA = NoRem>
 __device__ __forceinline__ bool gen_shell_try_std(const ShellMeta &sh, const double2 *__restrict__ prims,
                                                   const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                                   const double *__restrict__ xs, const double *__restrict__ ys,
-                                                  const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab) {
+                                                  const double *__restrict__ zs, double *__restrict__ tp, const AxTab &tab,
+                                                  const RA &ra = RA()) {
     if (sh.kind == 1) {                  // warp-uniform
         switch (sh.L) {
-            case 0: gen_shell_std<S, 0, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            case 1: gen_shell_std<S, 1, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            case 2: gen_shell_std<S, 2, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            case 3: gen_shell_std<S, 3, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            case 4: gen_shell_std<S, 4, STRIDE, false, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 0: gen_shell_std<S, 0, STRIDE, false, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            case 1: gen_shell_std<S, 1, STRIDE, false, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            case 2: gen_shell_std<S, 2, STRIDE, false, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            case 3: gen_shell_std<S, 3, STRIDE, false, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            case 4: gen_shell_std<S, 4, STRIDE, false, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
             default: return false;
         }
     } else if (sh.kind == 2) {           // spherical output rows (host guarantees 2 <= L <= 4)
         switch (sh.L) {
-            case 2: gen_shell_std<S, 2, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            case 3: gen_shell_std<S, 3, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
-            default: gen_shell_std<S, 4, STRIDE, true, NP, ONLY>(sh, prims, fns, aux, xs, ys, zs, tp, tab); return true;
+            case 2: gen_shell_std<S, 2, STRIDE, true, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            case 3: gen_shell_std<S, 3, STRIDE, true, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
+            default: gen_shell_std<S, 4, STRIDE, true, NP, ONLY, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra); return true;
         }
     }
     return false;
@@ -418,14 +433,14 @@ __device__ __forceinline__ bool gen_shell_try_std(const ShellMeta &sh, const dou
 
 // dispatcher: standard shells of L <= 4 take the specialised code, everything else the generic one.
 // xs/ys/zs point at the coordinates of the thread's first point; its NP points are 32 apart.
-template <int SET, int STRIDE, int NP>
+template <int SET, int STRIDE, int NP, class RA = NoRem>
 __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2 *__restrict__ prims,
                                               const FnMeta *__restrict__ fns, const double *__restrict__ aux,
                                               const double *__restrict__ xs, const double *__restrict__ ys,
                                               const double *__restrict__ zs, double *__restrict__ tp,
-                                              int one_code, int exact, const AxTab &tab) {
+                                              int one_code, int exact, const AxTab &tab, const RA &ra = RA()) {
     if constexpr (SET == SET_VAL || SET == SET_GRAD || SET == SET_LAP || SET == SET_D2 || SET == SET_D2P) {
-        if (gen_shell_try_std<SET, STRIDE, NP, 0>(sh, prims, fns, aux, xs, ys, zs, tp, tab)) return;
+        if (gen_shell_try_std<SET, STRIDE, NP, 0, RA>(sh, prims, fns, aux, xs, ys, zs, tp, tab, ra)) return;
     }
     if constexpr (SET == SET_ONE) {
         // single first or pure second derivatives (ao_creator / mo_creator with drv = x .. zz, cy_core.aocreator with
@@ -446,6 +461,19 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
 #pragma unroll 1
     for (int q = 0; q < NP; ++q)
         gen_shell<SET, STRIDE>(sh, prims, fns, xs[32 * q], ys[32 * q], zs[32 * q], tp + 32 * q, one_code, exact);
+    if constexpr (RA::on) {
+        // generic shells: read the rows back (the thread's own columns of the tile, no synchronisation needed)
+        constexpr int D = set_ncodes(SET);
+#pragma unroll 1
+        for (int k = sh.fn_off; k < sh.fn_off + sh.nfn; ++k)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = tp[((size_t)d * KC + k) * STRIDE + 32 * q];
+                ra.row(k, q, w);
+            }
+    }
 }
 
 }  // namespace okb

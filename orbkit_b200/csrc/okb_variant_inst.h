@@ -29,18 +29,23 @@ template <int SET, int MW, int PT, int NW, int SINK>
 inline size_t smem_variant(int meta_stride) {
     return Cfg<SET, MW, PT, NW, SINK>::smem_bytes(meta_stride);
 }
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK, int REM = 0>
 inline cudaError_t launch_ws(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = okb_ws_kernel<SET, MB, BN, WM, WN, NPW, NST, SINK>;
+    auto kern = okb_ws_kernel<SET, MB, BN, WM, WN, NPW, NST, SINK, REM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, (WM * WN + NPW) * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK, int REM = 0>
 inline size_t smem_ws(int meta_stride) {
-    return WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK>::smem_bytes(meta_stride);
+    return WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK, REM>::smem_bytes(meta_stride);
 }
+// MO tile of 8*MB + REM orbitals: the REM remainder orbitals are contracted by the producer warps (okb_ws.cuh)
+#define OKB_WSR(SET, MB, BN, WM, WN, NPW, NST, SINK, REM)                                                       \
+    Variant { "ws-dmma/" #SET "/" #SINK "/MB" #MB "R" #REM "xBN" #BN "xWM" #WM "xWN" #WN "xNPW" #NPW "xNST" #NST, SET, \
+              SINK, MB, BN, WM * WN, 8 * BN * WN, 8 * MB + REM, smem_ws<SET, MB, BN, WM, WN, NPW, NST, SINK, REM>, \
+              launch_ws<SET, MB, BN, WM, WN, NPW, NST, SINK, REM>, REM }
 #define OKB_WS(SET, MB, BN, WM, WN, NPW, NST, SINK)                                                           \
     Variant { "ws-dmma/" #SET "/" #SINK "/MB" #MB "xBN" #BN "xWM" #WM "xWN" #WN "xNPW" #NPW "xNST" #NST, SET, SINK, \
               MB, BN, WM * WN, 8 * BN * WN, 8 * MB, smem_ws<SET, MB, BN, WM, WN, NPW, NST, SINK>,               \

@@ -41,15 +41,20 @@ namespace okb {
 #endif
 __host__ __device__ constexpr int pad_stride(int n) { return n + ((4 - (n % 16)) + 16) % 16; }
 
-// MB: MO blocks of 8 per CTA tile; WM x WN consumer warps; BN point blocks per warp; NPW producer warps
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
+// MB: MO blocks of 8 per CTA tile; WM x WN consumer warps; BN point blocks per warp; NPW producer warps;
+// REM: remainder orbitals of the tile beyond its MB blocks (MO tile = 8*MB + REM orbitals).  They are contracted by the
+// PRODUCER warps with DFMAs on the AO values they have just written (2 DFMA per AO value and remainder orbital, partial
+// sums per producer warp handed to the consumers once per pass) instead of costing a whole, mostly empty DMMA block:
+// 82 occupied MOs = 10 blocks + 2 run 40 instead of 44 DMMAs per k-step.
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK, int REM = 0>
 struct WsCfg {
     static constexpr int D = set_ncodes(SET);
     static constexpr int NCW = WM * WN;
     static constexpr int AM = (MB + WM - 1) / WM;              // MO blocks per consumer warp
     static constexpr int P = 8 * BN * WN;                      // points per CTA tile
     static constexpr int PT = P / 32;
-    static constexpr int MC = 8 * MB;                          // MOs per CTA tile
+    static constexpr int MC = 8 * MB;                          // MOs per CTA tile contracted by the consumers (DMMA)
+    static constexpr int MCT = MC + REM;                       // MOs per CTA tile
     static constexpr int PS = pad_stride(P);                   // AO tile row stride (doubles)
     static constexpr int CS = pad_stride(MC);                  // coefficient tile row stride (doubles)
     static constexpr int NT = (NCW + NPW) * 32;
@@ -78,9 +83,14 @@ struct WsCfg {
     static constexpr size_t OFF_XYZ = 384;
     static constexpr size_t OFF_IJK = OFF_XYZ + (size_t)3 * P * 8;     // axis indices of the tile's points (regular grids)
     static constexpr size_t OFF_RED = OFF_IJK + (size_t)3 * P * 4;
-    static constexpr size_t OFF_META = OFF_RED + (size_t)(NOUT > 0 ? WM * NOUT * P * 8 : 0);
+    // remainder orbitals: partial sums [NPW][REM][D][P] of one pass, then (behind the chunk tables) a ring of NM
+    // coefficient slots [KC][REM]
+    static constexpr size_t OFF_PART = OFF_RED + (size_t)(NOUT > 0 ? WM * NOUT * P * 8 : 0);
+    static constexpr size_t OFF_META = OFF_PART + (size_t)NPW * REM * D * P * 8;
+    static constexpr uint32_t CREM_BYTES = (uint32_t)KC * REM * 8u;
+    __host__ __device__ static constexpr size_t off_crem(int meta_stride) { return OFF_META + (size_t)NM * meta_stride; }
     __host__ __device__ static constexpr size_t off_cbuf(int meta_stride) {
-        return (OFF_META + (size_t)NM * meta_stride + 127) / 128 * 128;
+        return (off_crem(meta_stride) + (size_t)NM * CREM_BYTES + 127) / 128 * 128;
     }
     __host__ __device__ static constexpr size_t off_tile(int meta_stride) {
         return off_cbuf(meta_stride) + (size_t)NST * CBUF_DOUBLES * 8;
@@ -88,7 +98,8 @@ struct WsCfg {
     __host__ __device__ static constexpr size_t smem_bytes(int meta_stride) {
         return off_tile(meta_stride) + (size_t)NST * TILE_DOUBLES * 8;
     }
-    static_assert(2 * NST + 2 * NM <= 32, "barrier area");
+    static_assert(2 * NST + 2 * NM + 1 <= 32, "barrier area");
+    static_assert(REM == 0 || (REM == 2 && WM == 1 && SINK != SINK_AO), "remainder orbitals: pairs, one consumer warp row");
     static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
     // MO blocks are fetched in pairs (one 16-byte load) when every warp row starts on an even block
     static constexpr bool PAIRED = (WM == 1 || AM % 2 == 0);
@@ -108,6 +119,23 @@ struct WsCfg {
     static constexpr int KSTEP = ROT ? 8 : 4;                  // rows the tile is padded to
     static_assert(P % 32 == 0, "whole warps of points for the producers");
     static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
+};
+
+// Remainder-orbital hook of the AO generators (okb_shell.cuh): the producer thread multiplies every AO value it writes
+// by the two remainder orbitals' coefficients of that row (one warp-uniform 16-byte load) and keeps the partial sums.
+template <int D, int NP>
+struct RemAcc {
+    static constexpr bool on = true;
+    const double2 *cr;                       // [KC] coefficient pairs of the chunk's rows (shared memory)
+    double (&acc)[NP][2][D];                 // [point of the thread][orbital][set]
+    __device__ __forceinline__ void row(int k, int q, const double (&v)[D]) const {
+        const double2 c = cr[k];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            acc[q][0][d] = fma(c.x, v[d], acc[q][0][d]);
+            acc[q][1][d] = fma(c.y, v[d], acc[q][1][d]);
+        }
+    }
 };
 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -158,22 +186,40 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK>
+// one non-blocking probe of a barrier phase (the consumers look at the NEXT chunk's barrier a chunk early, so that the
+// blocking wait -- and the ~40 cycles of its predicate -- only happens when the producers are not ahead)
+__device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <int SET, int MB, int BN, int WM, int WN, int NPW, int NST, int SINK, int REM = 0>
 __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const KParams p) {
-    using C = WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK>;
-    constexpr int D = C::D, P = C::P, PT = C::PT, PS = C::PS, CS = C::CS, MC = C::MC, NCW = C::NCW, AM = C::AM;
+    using C = WsCfg<SET, MB, BN, WM, WN, NPW, NST, SINK, REM>;
+    constexpr int D = C::D, P = C::P, PT = C::PT, PS = C::PS, CS = C::CS, MC = C::MC, MCT = C::MCT, NCW = C::NCW, AM = C::AM;
     constexpr int NPT = NPW * 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     constexpr int NM = C::NM, LAG = C::LAG;
     const uint32_t a_full = sbase + (uint32_t)C::OFF_BAR, a_empty = a_full + 8 * NST, a_mfull = a_empty + 8 * NST,
-                   a_mempty = a_mfull + 8 * NM;
+                   a_mempty = a_mfull + 8 * NM, a_rfree = a_mempty + 8 * NM;
     int *nfn_s = reinterpret_cast<int *>(smem + C::OFF_NFN);
     double *xs = reinterpret_cast<double *>(smem + C::OFF_XYZ);
     double *ys = xs + P, *zs = ys + P;
     int *isx = reinterpret_cast<int *>(smem + C::OFF_IJK), *isy = isx + P, *isz = isy + P;
     double *red = reinterpret_cast<double *>(smem + C::OFF_RED);
+    double *part = reinterpret_cast<double *>(smem + C::OFF_PART);      // [NPW][REM][D][P]
     unsigned char *mbase = smem + C::OFF_META;
+    double *crem_s = reinterpret_cast<double *>(smem + C::off_crem(p.lay.stride));   // [NM][KC][REM]
     double *cbase = reinterpret_cast<double *>(smem + C::off_cbuf(p.lay.stride));
     double *tbase = reinterpret_cast<double *>(smem + C::off_tile(p.lay.stride));
 
@@ -188,12 +234,14 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
             mbar_init(&bars[2 * NST + i], 1);
             mbar_init(&bars[2 * NST + NM + i], NPW);  // one arrival per producer warp that left the chunk
         }
+        mbar_init(&bars[2 * NST + 2 * NM], NCW);      // rfree: the consumers have read the remainder partial sums
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const uint32_t meta_bytes = (uint32_t)p.lay.stride;
     constexpr uint32_t cbuf_bytes = (uint32_t)C::CBUF_DOUBLES * 8u;
+    constexpr uint32_t tile_bytes = (uint32_t)C::TILE_DOUBLES * 8u;
     const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.n_mtile * (uint32_t)p.nchunk;
 
@@ -201,15 +249,21 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
         // ====================================== producers ==========================================
         reg_dec<C::PREG>();
         const int ptid = tid - NCW * 32, pwarp = warp - NCW;
-        const uint32_t a_meta = smem_u32(mbase), a_cbuf = smem_u32(cbase);
+        const uint32_t a_meta = smem_u32(mbase), a_cbuf = smem_u32(cbase), a_crem = smem_u32(crem_s);
         auto issue_meta = [&](uint32_t gc) {
             const uint32_t bar = a_mfull + 8 * (gc % NM);
-            mbar_arrive_expect_tx_a(bar, meta_bytes);
-            bulk_g2s_a(a_meta + (gc % NM) * meta_bytes, p.meta + (size_t)(gc % p.nchunk) * meta_bytes, meta_bytes, bar);
+            const uint32_t c = gc % (uint32_t)p.nchunk;
+            mbar_arrive_expect_tx_a(bar, meta_bytes + C::CREM_BYTES);
+            bulk_g2s_a(a_meta + (gc % NM) * meta_bytes, p.meta + (size_t)c * meta_bytes, meta_bytes, bar);
+            if constexpr (REM > 0) {                  // the remainder orbitals' coefficients of this (MO tile, chunk)
+                const uint32_t mt = (gc / (uint32_t)p.nchunk) % (uint32_t)p.n_mtile;
+                bulk_g2s_a(a_crem + (gc % NM) * C::CREM_BYTES, p.crem + ((size_t)mt * p.nchunk + c) * (KC * REM),
+                           C::CREM_BYTES, bar);
+            }
         };
         if (ptid == 0)
             for (uint32_t i = 0; i < NM && i < total; ++i) issue_meta(i);
-        uint32_t g = 0;
+        uint32_t g = 0, npass = 0;
         for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
             const int q0 = tile_id * P;
             named_bar(1, NPT);                        // previous tile's items no longer read xs/ys/zs
@@ -219,7 +273,24 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 grid_point(p, p.p0 + q, xs[e], ys[e], zs[e], isx[e], isy[e], isz[e]);
             }
             named_bar(1, NPT);
-            for (int mt = 0; mt < p.n_mtile; ++mt)
+            // a thread evaluates NP points (32 apart) of one shell at a time (independent dependency
+            // chains); warps take items round-robin, rotated per chunk so that the same warp is not
+            // always the one with the extra item
+            constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
+            for (int mt = 0; mt < p.n_mtile; ++mt, ++npass) {
+                // remainder orbitals: this thread's partial sums over the shells its warp evaluates in this pass,
+                // per point group / point / orbital / derivative set
+                double racc[PG][NP][REM > 0 ? REM : 1][D];
+                if constexpr (REM > 0) {
+#pragma unroll
+                    for (int a = 0; a < PG; ++a)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q)
+#pragma unroll
+                            for (int r = 0; r < REM; ++r)
+#pragma unroll
+                                for (int d = 0; d < D; ++d) racc[a][q][r][d] = 0.0;
+                }
                 for (int c = 0; c < p.nchunk; ++c, ++g) {
                     const int s = g % NST;
                     // The producer warps are NOT synchronised per chunk: a warp that is done with its items
@@ -245,10 +316,6 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     const FnMeta *fns = reinterpret_cast<const FnMeta *>(mb + p.lay.off_fn);
                     const double *aux = reinterpret_cast<const double *>(mb + p.lay.off_aux);
                     double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
-                    // a thread evaluates NP points (32 apart) of one shell at a time (independent dependency
-                    // chains); warps take items round-robin, rotated per chunk so that the same warp is not
-                    // always the one with the extra item
-                    constexpr int NP = (PT % 2 == 0 && SET != SET_LAP && SET != SET_ALL) ? 2 : 1, PG = PT / NP;
                     // the host sorts the shells of a chunk by descending cost; items are dealt to the warps in
                     // boustrophedon order (0..NPW-1, NPW-1..0, ...), rotated per chunk
                     const int nitems = hdr.nshell * PG, wrot = (pwarp + g) % NPW;
@@ -257,8 +324,20 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         if (item >= nitems) continue;
                         const int sh = item / PG, pt = (item % PG) * (32 * NP) + lane;
                         const AxTab tab{p.tabx, p.taby, p.tabz, p.nx, p.ny, p.nz, isx + pt, isy + pt, isz + pt};
-                        gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
-                                                   p.one_code, p.exact_mixed, tab);
+                        if constexpr (REM > 0) {
+                            // the generators hand every row they write to the remainder orbitals' partial sums
+                            const double2 *cr = reinterpret_cast<const double2 *>(crem_s + (size_t)(g % NM) * (KC * REM));
+                            static_for<0, PG>([&](auto ac) {
+                                constexpr int a = decltype(ac)::value;
+                                if (PG > 1 && (item % PG) != a) return;          // warp-uniform
+                                const RemAcc<D, NP> ra{cr, racc[a]};
+                                gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
+                                                           p.one_code, p.exact_mixed, tab, ra);
+                            });
+                        } else {
+                            gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
+                                                       p.one_code, p.exact_mixed, tab);
+                        }
                     }
                     // zero the rows that pad nfn up to the k-step of the consumer loop (coefficients there are 0,
                     // but stale shared memory could hold NaN/Inf bit patterns)
@@ -268,10 +347,28 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         tile[((size_t)d * KC + k) * PS + pt] = 0.0;
                     }
                     if (ptid == 0) nfn_s[s] = kpad;
-                    mbar_arrive_a(a_full + 8 * s);                       // release: tile + nfn visible
+                    if constexpr (REM > 0) {
+                        if (c == p.nchunk - 1) {
+                            // last chunk of the pass: hand the partial sums over (the arrival on full[s] below
+                            // publishes them); the consumers must have read those of the previous pass
+                            mbar_wait_a(a_rfree, (npass & 1) ^ 1);
+#pragma unroll
+                            for (int a = 0; a < PG; ++a)
+#pragma unroll
+                                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                                    for (int r = 0; r < REM; ++r)
+#pragma unroll
+                                        for (int d = 0; d < D; ++d)
+                                            part[(((size_t)pwarp * REM + r) * D + d) * P + a * (32 * NP) + 32 * q + lane] =
+                                                racc[a][q][r][d];
+                        }
+                    }
+                    mbar_arrive_a(a_full + 8 * s);                       // release: tile + nfn (+ partial sums) visible
                     __syncwarp();
                     if (lane == 0) mbar_arrive_a(a_mempty + 8 * (g % NM));   // this warp no longer reads the chunk table
                 }
+            }
         }
     } else {
         // ====================================== consumers ==========================================
@@ -282,7 +379,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
         const int pt_w = wn * BN * 8;                       // first point of this warp inside the tile
         // number of MO blocks this warp really owns (the last warp row may own fewer: MB % WM != 0)
         const int nblk = (MB - wm * AM) < AM ? (MB - wm * AM) : AM;
-        uint32_t g = 0;
+        // Stage bookkeeping carried from chunk to chunk: stage index, phase parity and this lane's fragment
+        // addresses in the stage.  (Recomputing them from the chunk counter per chunk cost ~140 cycles per chunk:
+        // ptxas rematerialised the lane offsets from %tid every time -- profiles/r02_ws_grad_loop.txt.)
+        // coefficient rows hold the MO blocks in pairs (okb200.cu: mo_blob): block b, row r at (b/2)*16 + 2r + (b&1);
+        // an odd first block (WM > 1 with odd AM) starts in the second slot of its pair
+        uint32_t st = 0, ph = 0;
+        uint32_t a_st = smem_u32(cbase + (size_t)tc * CS + ((mo_w >> 3) >> 1) * 16 + ((mo_w >> 3) & 1) + 2 * tr);
+        uint32_t b_st = smem_u32(tbase + (size_t)tc * PS + pt_w + tr);
+        auto advance = [&](uint32_t &s_, uint32_t &h_, uint32_t &a_, uint32_t &b_) {
+            if (s_ + 1 == NST) {
+                s_ = 0; h_ ^= 1u;
+                a_ -= (uint32_t)(NST - 1) * cbuf_bytes; b_ -= (uint32_t)(NST - 1) * tile_bytes;
+            } else {
+                ++s_; a_ += cbuf_bytes; b_ += tile_bytes;
+            }
+        };
+        uint32_t npass = 0;
         for (int tile_id = blockIdx.x; tile_id < p.ntiles; tile_id += gridDim.x) {
             const int q0 = tile_id * P;
             double osum[C::NOUT > 0 ? C::NOUT : 1][BN][2];
@@ -292,7 +405,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
 #pragma unroll
                     for (int ib = 0; ib < BN; ++ib) osum[o][ib][0] = osum[o][ib][1] = 0.0;
             }
-            for (int mt = 0; mt < p.n_mtile; ++mt) {
+            for (int mt = 0; mt < p.n_mtile; ++mt, ++npass) {
                 double acc[AM][BN][D][2];
 #pragma unroll
                 for (int ia = 0; ia < AM; ++ia)
@@ -309,16 +422,6 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                 // Register use is explicit: A fragments afr[AM], ONE set of B fragments bfr[D][BN]; a fragment
                 // register is refilled right after the last DMMA of the step that reads it.
                 double afr[AM], bfr[D][BN];
-                auto frag_addr = [&](uint32_t gg, uint32_t &aa, uint32_t &bb) {
-                    const int st = gg % NST;
-                    // coefficient rows hold the MO blocks in pairs (okb200.cu: mo_blob): block b, row r at
-                    // (b/2)*16 + 2r + (b&1); this lane's row of the warp's first pair:
-                    // (mo_w = 8 * first block of the warp row; an odd first block -- WM > 1 with odd AM -- starts in
-                    // the second slot of its pair)
-                    const int fb = mo_w >> 3;
-                    aa = smem_u32(cbase + (size_t)st * C::CBUF_DOUBLES + (size_t)tc * CS + (fb >> 1) * 16 + (fb & 1) + 2 * tr);
-                    bb = smem_u32(tbase + (size_t)st * C::TILE_DOUBLES + (size_t)tc * PS + pt_w + tr);
-                };
                 // One k-step = NB*AM DMMAs (NB = D*BN B fragments outermost, AM MO blocks innermost) on the fragments
                 // in registers; a fragment register is refilled behind the last DMMA of the step that reads it:
                 // B[j] behind pass j (needed again (NB-1)*AM DMMAs later), A[ia] during the last pass (needed again
@@ -373,37 +476,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         for (int ia = 0; ia < AM; ++ia) afr[ia] = lds64(ca + aoff(ia));
                     }
                 };
-                uint32_t a_ap, a_bp;
-                frag_addr(g, a_ap, a_bp);
-                mbar_wait_a(a_full + 8 * (g % NST), (g / NST) & 1);      // AO tile + coefficient tile landed
-                int nk = nfn_s[g % NST];                                 // multiple of KSTEP, >= KSTEP
+                uint32_t a_ap = a_st, a_bp = b_st;
+                mbar_wait_a(a_full + 8 * st, ph);                        // AO tile + coefficient tile landed
+                int nk = nfn_s[st];                                      // multiple of KSTEP, >= KSTEP
                 if constexpr (C::ROT) {
                     // ---- rotating-register double step ----------------------------------------------------------------
                     // ncu (profiles/r01_ws_grad_v3_regions.txt, source page): in the one-set scheme above every fragment
                     // load overwrites a register that the DMMA right in front of it reads; the DMMA collects its operands
                     // over several cycles, the load waits for that (short scoreboard) and with it the in-order warp:
-                    // ~7 cycles per load, 10 loads per 704-cycle k-step.  ptxas moves loads and DMMAs freely (only register
-                    // dependencies hold them), merges fragment registers as it likes and puts a load right behind the
-                    // last reader of whatever register it picked, so source order and register naming alone achieve
-                    // nothing.  What does hold is a data dependency, so:
-                    //   * the A fragments of a k-step are no longer all resident: the k-step walks the MO block PAIRS
-                    //     (slot = one pair x all B fragments, 4-8 DMMAs) and the pair of slot q + 1 is fetched during
-                    //     slot q into a small ring of register buffers; the B fragments are double buffered (the k-step
-                    //     of half h reads set h and fetches set h ^ 1);
-                    //   * every fetch address depends on the RESULT of a DMMA of the current slot (`+ lo32(acc) * zero`,
-                    //     one IMAD; zero is a kernel argument that is always 0): the load cannot issue before that DMMA
-                    //     has completed, by which time every register that is free was last read at least a DMMA latency
-                    //     ago, and it is still early enough for its first use one slot later.
+                    // ~7 cycles per load, 10 loads per 704-cycle k-step.  Here the A fragments of a k-step are no longer
+                    // all resident: the k-step walks the MO block PAIRS (slot = one pair x all B fragments, 4-8 DMMAs) and
+                    // the pair of slot q + 1 is fetched during slot q into a small ring of register buffers; the B
+                    // fragments are double buffered (the k-step of half h reads set h and fetches set h ^ 1).
                     // Order per accumulator is unchanged (k-steps in sequence), so the results are bit-identical.
                     constexpr int NPAIR = C::NPAIR, NP2 = C::NP2, NBUF = C::NBUF, PD = C::PD;
                     double abuf[NBUF][2], bset[2][NB];
                     constexpr uint32_t A_HALF = (uint32_t)(4 * CS) * 8u, B_HALF = (uint32_t)(4 * PS) * 8u;
                     auto b_off = [](int j) -> uint32_t { return (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u; };
-                    const int zero = p.zero;
-                    auto tie = [&](const uint32_t addr, const double anchor) -> uint32_t {
-                        return addr + (uint32_t)(__double2loint(anchor) * zero);
-                    };
-                    constexpr int BSLOT = NPAIR >= 2 ? NPAIR - 2 : 0;          // the slot whose DMMAs anchor the B fetches
                     auto dstep = [&](const uint32_t ca, const uint32_t cb, const uint32_t na, const uint32_t nb) {
                         static_for<0, NP2>([&](auto qc) {
                             constexpr int q = decltype(qc)::value;
@@ -440,8 +529,13 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         });
                     };
                     load_first(a_ap, a_bp);
-                    for (int c = 0; c < p.nchunk; ++c, ++g) {
-                        const int s = g % NST;
+                    for (int c = 0; c < p.nchunk; ++c) {
+                        // the next stage of the ring; its barrier is probed now and only waited for (behind the k-steps
+                        // of this chunk) if the producers were not a chunk ahead
+                        uint32_t st_n = st, ph_n = ph, a_n = a_st, b_n = b_st;
+                        advance(st_n, ph_n, a_n, b_n);
+                        const bool more = c + 1 < p.nchunk;
+                        const bool ready = more && mbar_test_a(a_full + 8 * st_n, ph_n);
 #pragma unroll 1
                         for (int k0 = 8; k0 < nk; k0 += 8) {
                             dstep(a_ap, a_bp, a_ap + 2 * A_HALF, a_bp + 2 * B_HALF);
@@ -450,20 +544,22 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         }
                         uint32_t n_ap = a_ap, n_bp = a_bp;               // behind the last chunk: harmless reloads
                         int nk_next = nk;
-                        if (c + 1 < p.nchunk) {
-                            mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
-                            nk_next = nfn_s[(g + 1) % NST];
-                            frag_addr(g + 1, n_ap, n_bp);
+                        if (more) {
+                            if (!ready) mbar_wait_a(a_full + 8 * st_n, ph_n);
+                            nk_next = nfn_s[st_n];
+                            n_ap = a_n; n_bp = b_n;
                         }
                         dstep(a_ap, a_bp, n_ap, n_bp);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_a(a_empty + 8 * s);   // every read of this stage has returned
+                        if (lane == 0) mbar_arrive_a(a_empty + 8 * st);  // every read of this stage has returned
                         a_ap = n_ap; a_bp = n_bp; nk = nk_next;
+                        st = st_n; ph = ph_n; a_st = a_n; b_st = b_n;
                     }
                 } else {
                 load_all(a_ap, a_bp);
-                for (int c = 0; c < p.nchunk; ++c, ++g) {
-                    const int s = g % NST;
+                for (int c = 0; c < p.nchunk; ++c) {
+                    uint32_t st_n = st, ph_n = ph, a_n = a_st, b_n = b_st;
+                    advance(st_n, ph_n, a_n, b_n);
 #pragma unroll 1
                     for (int k0 = 4; k0 < nk; k0 += 4)                   // steps 0 .. nk/4-2: next step in this chunk
                         step(a_ap + (uint32_t)(k0 * CS) * 8u, a_bp + (uint32_t)(k0 * PS) * 8u);
@@ -476,106 +572,136 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     // the pipeline is seamless only for NST >= 3.
                     constexpr bool SEAMLESS = (NST >= 3);
                     if (SEAMLESS && c + 1 < p.nchunk) {
-                        mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
-                        nk_next = nfn_s[(g + 1) % NST];
-                        frag_addr(g + 1, n_ap, n_bp);
+                        mbar_wait_a(a_full + 8 * st_n, ph_n);
+                        nk_next = nfn_s[st_n];
+                        n_ap = a_n; n_bp = b_n;
                     }
                     step(n_ap, n_bp);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_a(a_empty + 8 * s);       // every read of this stage has returned
+                    if (lane == 0) mbar_arrive_a(a_empty + 8 * st);      // every read of this stage has returned
                     if (!SEAMLESS && c + 1 < p.nchunk) {
-                        mbar_wait_a(a_full + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
-                        nk_next = nfn_s[(g + 1) % NST];
-                        frag_addr(g + 1, n_ap, n_bp);
+                        mbar_wait_a(a_full + 8 * st_n, ph_n);
+                        nk_next = nfn_s[st_n];
+                        n_ap = a_n; n_bp = b_n;
                         load_all(n_ap, n_bp);
                     }
                     a_ap = n_ap; a_bp = n_bp; nk = nk_next;
+                    st = st_n; ph = ph_n; a_st = a_n; b_st = b_n;
                 }
                 }   // !ROT
+                // ---- remainder orbitals: sum the producers' partial sums (lane (tr, tc) of warp row 0 takes orbital
+                // tr < REM at its two points per point block, the layout of an accumulator block) ----------------------
+                double rv[BN][D][2];
+                const bool ract = REM > 0 && wm == 0 && tr < REM;
+                if constexpr (REM > 0) {
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) rv[ib][d][0] = rv[ib][d][1] = 0.0;
+                    if (ract) {
+#pragma unroll
+                        for (int w = 0; w < NPW; ++w)                    // fixed order: results are reproducible
+#pragma unroll
+                            for (int d = 0; d < D; ++d)
+#pragma unroll
+                                for (int ib = 0; ib < BN; ++ib) {
+                                    const double2 v = *reinterpret_cast<const double2 *>(
+                                        part + (((size_t)w * REM + tr) * D + d) * P + pt_w + ib * 8 + 2 * tc);
+                                    rv[ib][d][0] += v.x;
+                                    rv[ib][d][1] += v.y;
+                                }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(a_rfree);               // the producers may write the next pass' sums
+                }
                 // ---- per-MO-tile epilogues: lane holds MO row tr of each block, points 2*tc + {0,1} -----
-                if (SINK == SINK_MO) {
+                // act: the lane holds an orbital (always for the DMMA blocks; lanes tr < REM for the remainder orbitals)
+                auto mo_store = [&](const int mo, const bool act, const double (&a)[BN][D][2]) {
+                    if (!act || mo >= p.n_mo) return;
 #pragma unroll
-                    for (int ia = 0; ia < AM; ++ia) {
-                        const int mo = mt * MC + mo_w + ia * 8 + tr;
-                        if (ia >= nblk || mo >= p.n_mo) continue;
+                    for (int d = 0; d < D; ++d) {
+                        const int code = (SET == SET_ONE) ? p.one_code : d;
+                        const int sl = p.slot[code];
+                        if (sl < 0) continue;
+                        double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)mo * p.ld + q0;
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            const int code = (SET == SET_ONE) ? p.one_code : d;
-                            const int sl = p.slot[code];
-                            if (sl < 0) continue;
-                            double *orow = p.out + (size_t)sl * p.slot_stride + (size_t)mo * p.ld + q0;
-#pragma unroll
-                            for (int ib = 0; ib < BN; ++ib) {
-                                const int pt = pt_w + ib * 8 + 2 * tc;
-                                if (q0 + pt < p.npts) orow[pt] = acc[ia][ib][d][0];
-                                if (q0 + pt + 1 < p.npts) orow[pt + 1] = acc[ia][ib][d][1];
-                            }
+                        for (int ib = 0; ib < BN; ++ib) {
+                            const int pt = pt_w + ib * 8 + 2 * tc;
+                            if (q0 + pt < p.npts) orow[pt] = a[ib][d][0];
+                            if (q0 + pt + 1 < p.npts) orow[pt + 1] = a[ib][d][1];
                         }
                     }
+                };
+                auto rho_block = [&](const int mo, const bool act, const double (&a)[BN][D][2]) {
+                    const double oc = act ? p.occ[mo] : 0.0;             // zero for padding MOs
+                    const double o2 = oc * 2.0;
+                    double nrm = 0.0;
+#pragma unroll
+                    for (int ib = 0; ib < BN; ++ib)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            if (SET == SET_D2P) {
+                                // second pass of rho + laplacian on the MO values the first pass left in HBM:
+                                // sum_i 2 occ phi d2phi
+                                const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
+                                const double phi = (act && q < p.npts && mo < p.n_mo) ? __ldg(p.phi + (size_t)mo * p.ldp + q) : 0.0;
+#pragma unroll
+                                for (int d = 0; d < D; ++d) osum[d][ib][e] += o2 * (a[ib][d][e] * phi);
+                                continue;
+                            }
+                            const double phi = a[ib][0][e];
+                            if ((q0 + pt_w + ib * 8 + 2 * tc + e) < p.npts) nrm += phi * phi;
+                            if (SET == SET_GRAD && p.epi == 3) {
+                                const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
+                                if (act && q < p.npts && mo < p.n_mo) p.phi[(size_t)mo * p.ldp + q] = phi;
+                            }
+                            osum[0][ib][e] += oc * (phi * phi);
+                            if (SET == SET_D2) {
+                                // second pass of rho + laplacian: sum_i 2 occ phi d2phi (the first pass added
+                                // sum_i 2 occ (d phi)^2 and wrote rho)
+                                osum[1][ib][e] += o2 * (a[ib][1][e] * phi);
+                                osum[2][ib][e] += o2 * (a[ib][2][e] * phi);
+                                osum[3][ib][e] += o2 * (a[ib][3][e] * phi);
+                            } else if (D >= 4) {
+                                const double gx = a[ib][1][e], gy = a[ib][2][e], gz = a[ib][3][e];
+                                if (SET == SET_GRAD && p.epi != 0) {         // first pass of rho + laplacian
+                                    osum[1][ib][e] += o2 * (gx * gx);
+                                    osum[2][ib][e] += o2 * (gy * gy);
+                                    osum[3][ib][e] += o2 * (gz * gz);
+                                } else {
+                                    osum[1][ib][e] += o2 * (gx * phi);
+                                    osum[2][ib][e] += o2 * (gy * phi);
+                                    osum[3][ib][e] += o2 * (gz * phi);
+                                }
+                                if (D >= 7) {
+                                    osum[4][ib][e] += o2 * (a[ib][4][e] * phi + gx * gx);
+                                    osum[5][ib][e] += o2 * (a[ib][5][e] * phi + gy * gy);
+                                    osum[6][ib][e] += o2 * (a[ib][6][e] * phi + gz * gz);
+                                }
+                                if (D >= 10) {
+                                    osum[7][ib][e] += o2 * (a[ib][7][e] * phi + gx * gy);
+                                    osum[8][ib][e] += o2 * (a[ib][8][e] * phi + gx * gz);
+                                    osum[9][ib][e] += o2 * (a[ib][9][e] * phi + gy * gz);
+                                }
+                            }
+                        }
+                    if (p.mo_norm != nullptr) {
+                        nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);     // over the 4 lanes of a row
+                        nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
+                        if (act && tc == 0 && mo < p.n_mo) atomicAdd(p.mo_norm + mo, nrm);
+                    }
+                };
+                if (SINK == SINK_MO) {
+#pragma unroll
+                    for (int ia = 0; ia < AM; ++ia)
+                        if (ia < nblk) mo_store(mt * MCT + mo_w + ia * 8 + tr, true, acc[ia]);
+                    if constexpr (REM > 0) mo_store(mt * MCT + MC + (ract ? tr : 0), ract, rv);
                 }
                 if (SINK == SINK_RHO) {
 #pragma unroll
-                    for (int ia = 0; ia < AM; ++ia) {
-                        if (ia >= nblk) continue;                        // warp-uniform
-                        const int mo = mt * MC + mo_w + ia * 8 + tr;
-                        const double oc = p.occ[mo];                     // zero for padding MOs
-                        const double o2 = oc * 2.0;
-                        double nrm = 0.0;
-#pragma unroll
-                        for (int ib = 0; ib < BN; ++ib)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                if (SET == SET_D2P) {
-                                    // second pass of rho + laplacian on the MO values the first pass left in HBM:
-                                    // sum_i 2 occ phi d2phi
-                                    const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
-                                    const double phi = (q < p.npts && mo < p.n_mo) ? __ldg(p.phi + (size_t)mo * p.ldp + q) : 0.0;
-#pragma unroll
-                                    for (int d = 0; d < D; ++d) osum[d][ib][e] += o2 * (acc[ia][ib][d][e] * phi);
-                                    continue;
-                                }
-                                const double phi = acc[ia][ib][0][e];
-                                if ((q0 + pt_w + ib * 8 + 2 * tc + e) < p.npts) nrm += phi * phi;
-                                if (SET == SET_GRAD && p.epi == 3) {
-                                    const int q = q0 + pt_w + ib * 8 + 2 * tc + e;
-                                    if (q < p.npts && mo < p.n_mo) p.phi[(size_t)mo * p.ldp + q] = phi;
-                                }
-                                osum[0][ib][e] += oc * (phi * phi);
-                                if (SET == SET_D2) {
-                                    // second pass of rho + laplacian: sum_i 2 occ phi d2phi (the first pass added
-                                    // sum_i 2 occ (d phi)^2 and wrote rho)
-                                    osum[1][ib][e] += o2 * (acc[ia][ib][1][e] * phi);
-                                    osum[2][ib][e] += o2 * (acc[ia][ib][2][e] * phi);
-                                    osum[3][ib][e] += o2 * (acc[ia][ib][3][e] * phi);
-                                } else if (D >= 4) {
-                                    const double gx = acc[ia][ib][1][e], gy = acc[ia][ib][2][e], gz = acc[ia][ib][3][e];
-                                    if (SET == SET_GRAD && p.epi != 0) {         // first pass of rho + laplacian
-                                        osum[1][ib][e] += o2 * (gx * gx);
-                                        osum[2][ib][e] += o2 * (gy * gy);
-                                        osum[3][ib][e] += o2 * (gz * gz);
-                                    } else {
-                                        osum[1][ib][e] += o2 * (gx * phi);
-                                        osum[2][ib][e] += o2 * (gy * phi);
-                                        osum[3][ib][e] += o2 * (gz * phi);
-                                    }
-                                    if (D >= 7) {
-                                        osum[4][ib][e] += o2 * (acc[ia][ib][4][e] * phi + gx * gx);
-                                        osum[5][ib][e] += o2 * (acc[ia][ib][5][e] * phi + gy * gy);
-                                        osum[6][ib][e] += o2 * (acc[ia][ib][6][e] * phi + gz * gz);
-                                    }
-                                    if (D >= 10) {
-                                        osum[7][ib][e] += o2 * (acc[ia][ib][7][e] * phi + gx * gy);
-                                        osum[8][ib][e] += o2 * (acc[ia][ib][8][e] * phi + gx * gz);
-                                        osum[9][ib][e] += o2 * (acc[ia][ib][9][e] * phi + gy * gz);
-                                    }
-                                }
-                            }
-                        if (p.mo_norm != nullptr) {
-                            nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);     // over the 4 lanes of a row
-                            nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
-                            if (tc == 0 && mo < p.n_mo) atomicAdd(p.mo_norm + mo, nrm);
-                        }
-                    }
+                    for (int ia = 0; ia < AM; ++ia)
+                        if (ia < nblk) rho_block(mt * MCT + mo_w + ia * 8 + tr, true, acc[ia]);   // nblk is warp-uniform
+                    if constexpr (REM > 0) rho_block(mt * MCT + MC + (ract ? tr : 0), ract, rv);
                 }
             }   // mt
             if (SINK == SINK_RHO) {

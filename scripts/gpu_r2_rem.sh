@@ -1,0 +1,7 @@
+#!/bin/bash
+# parity tests + A/B of the remainder-orbital tiles
+set -u
+mkdir -p gpurun_out
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+echo "== n_mo A/B"; bash scripts/gpu_ab_nmo.sh 80 82 2>&1 | tee gpurun_out/ab_nmo.txt
+echo "== forced MB11 for 82"; OKB_VARIANT=MB11x bash scripts/gpu_ab_nmo.sh 82 2>&1 | tee -a gpurun_out/ab_nmo.txt
