@@ -109,8 +109,13 @@ struct WsCfg {
     // buffers (a divisor of NP2), prefetch distance PD = NBUF - 2 slots.
     static constexpr int NPAIR = (AM + 1) / 2;
     static constexpr int NP2 = 2 * NPAIR;
+#ifdef OKB_NBUF
+    static constexpr int NBUF = OKB_NBUF, PD = OKB_PD;          // A/B builds
+#else
     static constexpr int NBUF = (NP2 % 3 == 0) ? 3 : 2;         // ring buffers (a divisor of NP2)
     static constexpr int PD = 1;                                // the pair of slot q + 1 is fetched during slot q
+#endif
+    static_assert(NP2 % NBUF == 0 && PD >= 1 && PD < NP2, "ring");
 #ifdef OKB_NO_ROT
     static constexpr bool ROT = false;
 #else
