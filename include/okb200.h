@@ -193,6 +193,24 @@ int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long lon
                 const int *drv_codes, int n_terms, const double *coef, const int *ia,
                 const int *ib, double *out, unsigned flags);
 
+/* Time-dependent detCI contractions (orbkit/detci/cy_ci.pyx:101-122 get_rho_full, 126-151 get_j_full -- the reference's
+ * OpenMP prange loops):  out[t][x] = sum_k w[t][k] * in[k][x],  t < nt, k < nk, x < n.
+ *   get_rho_full(ReS[nt][ns][ns], rho[npair][npts]): in = rho, w[t][count] = ReS[t,m,m] (m == n) or 2 ReS[t,m,n] for the
+ *     pairs count = (n, m >= n) in the reference's order;
+ *   get_j_full(ImS[nt][ns][ns], j[npair][3][npts]): in = j read as rows of n = 3 npts entries, w[t][count] = -2 ImS[t,n,m]
+ *     (0 on the diagonal pairs); out = tdj[nt][3][npts].
+ * w is a HOST array [nt][nk]; in / out are host rows (staged in slabs) or device rows (OKB_FLAG_IN_DEVICE /
+ * OKB_FLAG_OUT_DEVICE) of stride ld_in / ld_out >= n.  FP64 tensor cores (DMMA), k in the reference's order: agrees with
+ * the reference to rounding (a few ulp of the largest term), not bit for bit. */
+int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double *w, const double *in, long long ld_in,
+              double *out, long long ld_out, unsigned flags);
+/* cy_ci.get_jab_full (cy_ci.pyx:186-202):
+ *   out[c][x] = sum_n sum_{m<n} ImS[n][m] / mu * (chi[n][x] dchi[c][m][x] - chi[m][x] dchi[c][n][x]),  c < ncomp <= 3
+ * ImS: HOST [nbasis][nbasis]; chi[nbasis][ld_in], dchi[ncomp][nbasis][ld_in], out[ncomp][ld_out] host or device as above.
+ * Sequential sums in the reference's order without fused multiply-add: bit-identical to the reference. */
+int okb_ci_jab_full(okb_ctx *ctx, int nbasis, int ncomp, long long npts, long long ld_in, const double *ImS,
+                    const double *chi, const double *dchi, double mu, double *out, long long ld_out, unsigned flags);
+
 /* ---- output sink: Gaussian cube text (orbkit/output/cube.py:5-101, cube_creator) ------------------------------
  * The data loop of cube_creator (cube.py:86-96) on the device: data[n_sets][nx][ny][nz] (C order, float64) becomes
  * the text the reference writes -- per (x, y) row the nz * n_sets values ('%.5E' right-justified in 13 columns, the

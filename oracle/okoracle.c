@@ -304,6 +304,70 @@ void okor_ci_a_nabla_b(double *out, long i0, long i1, long npts, long n_mo, cons
     }
 }
 
+/* ---- time-dependent detCI contractions (orbkit/detci/cy_ci.pyx:101-151, 186-202) ---------------------------
+ * get_rho_full: tdrho[t,r] = sum over the state pairs count = (n, m >= n) of ReS[t,m,m] rho[count,r] (m == n) or
+ * 2 ReS[t,m,n] rho[count,r]; the sum runs n outer, m inner, one rounding per product and per addition. */
+void okor_ci_rho_full(double *tdrho, const double *ReS, const double *rho, long nt, long nstate, long npts)
+{
+    long r, t, n, m, count;
+    for (r = 0; r < npts; ++r)
+        for (t = 0; t < nt; ++t) {
+            double tmp = 0.0;
+            count = 0;
+            for (n = 0; n < nstate; ++n)
+                for (m = n; m < nstate; ++m) {
+                    if (m == n) tmp = tmp + ReS[(t * nstate + m) * nstate + m] * rho[count * npts + r];
+                    else tmp = tmp + 2.0 * ReS[(t * nstate + m) * nstate + n] * rho[count * npts + r];
+                    ++count;
+                }
+            tdrho[t * npts + r] = tmp;
+        }
+}
+
+/* get_j_full, cy_ci.pyx:126-151: tdj[t,d,r] = - sum over the pairs m > n of 2 ImS[t,n,m] j[count,d,r]
+ * (count also runs over the diagonal pairs, which are skipped) */
+void okor_ci_j_full(double *tdj, const double *ImS, const double *j, long nt, long nstate, long npts)
+{
+    long r, t, n, m, count;
+    for (r = 0; r < npts; ++r)
+        for (t = 0; t < nt; ++t) {
+            double tx = 0.0, ty = 0.0, tz = 0.0;
+            count = 0;
+            for (n = 0; n < nstate; ++n)
+                for (m = n; m < nstate; ++m) {
+                    if (m != n) {
+                        const double s = ImS[(t * nstate + n) * nstate + m];
+                        tx = tx - (2.0 * s * j[(count * 3 + 0) * npts + r]);
+                        ty = ty - (2.0 * s * j[(count * 3 + 1) * npts + r]);
+                        tz = tz - (2.0 * s * j[(count * 3 + 2) * npts + r]);
+                    }
+                    ++count;
+                }
+            tdj[(t * 3 + 0) * npts + r] = tx;
+            tdj[(t * 3 + 1) * npts + r] = ty;
+            tdj[(t * 3 + 2) * npts + r] = tz;
+        }
+}
+
+/* get_jab_full, cy_ci.pyx:186-202: j[c,r] = sum_n sum_{m<n} f ImS[n,m] (chi[n,r] dchi[c,m,r] - chi[m,r] dchi[c,n,r]),
+ * f = 1/mu */
+void okor_ci_jab_full(double *out, const double *ImS, const double *chi, const double *dchi, double mu,
+                      long nbasis, long ncomp, long npts)
+{
+    long c, r, n, m;
+    const double f = 1. / mu;
+    for (c = 0; c < ncomp; ++c)
+        for (r = 0; r < npts; ++r) {
+            double tmp = 0.0;
+            for (n = 0; n < nbasis; ++n)
+                for (m = 0; m < n; ++m)
+                    tmp = tmp + f * ImS[n * nbasis + m] *
+                                    (chi[n * npts + r] * dchi[(c * nbasis + m) * npts + r] -
+                                     chi[m * npts + r] * dchi[(c * nbasis + n) * npts + r]);
+            out[c * npts + r] = tmp;
+        }
+}
+
 /* ---- non-Cartesian product grids (orbkit/cy_grid.pyx:58-97) ------------------------------
  * xyz is [3][n0*n1*n2], first axis slowest; same expressions, same multiplication order. */
 void okor_sph2cart(double *xyz, const double *r, long nr, const double *theta, long nt,

@@ -30,7 +30,8 @@ def _port():
     global _lib
     if _lib is None:
         _lib = ctypes.CDLL(os.path.join(_HERE, 'libokoracle.so'))
-        for name in ('okor_ci_rho', 'okor_ci_jab', 'okor_ci_a_nabla_b'):
+        for name in ('okor_ci_rho', 'okor_ci_jab', 'okor_ci_a_nabla_b', 'okor_ci_rho_full', 'okor_ci_j_full',
+                     'okor_ci_jab_full'):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -126,6 +127,45 @@ def jab(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
 
 def a_nabla_b(zero, sing, molist, molistdrv, slice_length=1e4, kind='port'):
     return _vec('get_a_nabla_b', 'okor_ci_a_nabla_b', zero, sing, molist, molistdrv, slice_length, kind)
+
+
+# ---- time-dependent contractions (cy_ci.pyx:101-151, 186-202) -----------------------------------------------
+def get_rho_full(ReS, rho, kind='port'):
+    """tdrho[t, r] = sum_{n <= m} (1 or 2) ReS[t, m, n] rho[count, r]   (cy_ci.get_rho_full)"""
+    ReS = np.require(ReS, dtype=np.float64, requirements='CA')
+    rho = np.require(rho, dtype=np.float64, requirements='CA')
+    if kind == 'ref':
+        return _ref().get_rho_full(ReS, rho)
+    nt, ns, npts = ReS.shape[0], ReS.shape[1], rho.shape[1]
+    out = np.zeros((nt, npts))
+    _port().okor_ci_rho_full(_dp(out), _dp(ReS), _dp(rho), ctypes.c_long(nt), ctypes.c_long(ns), ctypes.c_long(npts))
+    return out
+
+
+def get_j_full(ImS, j, kind='port'):
+    """tdj[t, d, r] = - sum_{n < m} 2 ImS[t, n, m] j[count, d, r]   (cy_ci.get_j_full)"""
+    ImS = np.require(ImS, dtype=np.float64, requirements='CA')
+    j = np.require(j, dtype=np.float64, requirements='CA')
+    if kind == 'ref':
+        return _ref().get_j_full(ImS, j)
+    nt, ns, npts = ImS.shape[0], ImS.shape[1], j.shape[2]
+    out = np.zeros((nt, 3, npts))
+    _port().okor_ci_j_full(_dp(out), _dp(ImS), _dp(j), ctypes.c_long(nt), ctypes.c_long(ns), ctypes.c_long(npts))
+    return out
+
+
+def get_jab_full(ImS, chi_n, nabla_chi_n, mu, kind='port'):
+    """j[c, r] = sum_n sum_{m < n} ImS[n, m] / mu (chi[n] d_c chi[m] - chi[m] d_c chi[n])   (cy_ci.get_jab_full)"""
+    ImS = np.require(ImS, dtype=np.float64, requirements='CA')
+    chi = np.require(chi_n, dtype=np.float64, requirements='CA')
+    dchi = np.require(nabla_chi_n, dtype=np.float64, requirements='CA')
+    if kind == 'ref':
+        return _ref().get_jab_full(ImS, chi, dchi, float(mu))
+    nb, npts, nc = ImS.shape[0], chi.shape[1], dchi.shape[0]
+    out = np.zeros((nc, npts))
+    _port().okor_ci_jab_full(_dp(out), _dp(ImS), _dp(chi), _dp(dchi), ctypes.c_double(mu), ctypes.c_long(nb),
+                             ctypes.c_long(nc), ctypes.c_long(npts))
+    return out
 
 
 # ---- core.calc_mo_matrix / extras.calc_jmo ------------------------------------------------------------------

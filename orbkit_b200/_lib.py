@@ -84,6 +84,11 @@ SIGNATURES = {
     'okb_eval_rho_ld': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ll, ll, c_int_p,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ll, ctypes.c_void_p,
                                        ctypes.c_uint]),
+    'okb_ci_td': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, c_double_p, ctypes.c_void_p, ll,
+                                 ctypes.c_void_p, ll, ctypes.c_uint]),
+    'okb_ci_jab_full': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, c_double_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ll,
+                                       ctypes.c_uint]),
     'okb_ci_contract': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, c_double_p, c_int_p, c_int_p,
                                        ctypes.c_void_p, ll, ctypes.c_uint]),

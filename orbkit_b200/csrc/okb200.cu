@@ -31,6 +31,7 @@
 #include "okb_ao_zrun.cuh" // ZR_MAXL
 #include "okb_misc.cuh"
 #include "okb_ci.cuh"
+#include "okb_td.cuh"
 #include "okb_text.cuh"
 
 using namespace okb;
@@ -1493,7 +1494,7 @@ extern "C" int okb_eval_rho(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long 
 
 // ---- detCI grid contractions ------------------------------------------------------------------------------------
 static int ci_ncomp(int mode, int n_terms, int nd) {
-    return mode == CI_RHO ? 1 : mode == CI_PAIRS ? n_terms : mode == CI_JPAIRS ? nd * n_terms : 3;
+    return mode == CI_RHO ? 1 : mode == CI_PAIRS ? n_terms : mode == CI_JPAIRS ? nd * n_terms : mode == CI_JABF ? nd : 3;
 }
 
 static int ci_reserve(okb_ctx *ctx, size_t bytes) {
@@ -1509,7 +1510,7 @@ static int ci_reserve(okb_ctx *ctx, size_t bytes) {
 static int ci_check(okb_ctx *ctx, int mode, int n_mo, int n_terms, const double *coef, const int *ia, const int *ib,
                     const double *out) {
     if (!ctx) return fail(OKB_ERR_ARG, "ci: null context");
-    if (mode < CI_RHO || mode > CI_JPAIRS) return fail(OKB_ERR_ARG, "ci: unknown mode %d", mode);
+    if (mode < CI_RHO || mode > CI_JABF) return fail(OKB_ERR_ARG, "ci: unknown mode %d", mode);
     if (n_mo <= 0) return fail(OKB_ERR_ARG, "ci: n_mo must be positive");
     if (n_terms < 0) return fail(OKB_ERR_ARG, "ci: negative term count");
     if (n_terms > 0 && (!ia || !ib || (mode != CI_PAIRS && mode != CI_JPAIRS && !coef)))
@@ -1547,30 +1548,33 @@ static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
         case CI_JAB: okb_ci_kernel<CI_JAB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         case CI_ANB: okb_ci_kernel<CI_ANB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         case CI_JPAIRS: okb_ci_kernel<CI_JPAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        case CI_JABF: okb_ci_kernel<CI_JABF><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
         default: okb_ci_kernel<CI_PAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "ci kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
     ctx->last_kernel = mode == CI_RHO ? "ci/rho" : mode == CI_JAB ? "ci/jab" : mode == CI_ANB ? "ci/a_nabla_b"
-                       : mode == CI_JPAIRS ? "ci/jpairs" : "ci/pairs";
+                       : mode == CI_JPAIRS ? "ci/jpairs" : mode == CI_JABF ? "ci/jab_full" : "ci/pairs";
     return OKB_OK;
 }
 
-extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
-                               const double *molist, const double *molistdrv, int n_terms, const double *coef,
-                               const int *ia, const int *ib, double *out, long long ld_out, unsigned flags) {
+// ncomp_in: JABF only -- the number of derivative components in molistdrv (1..3); the other modes fix it
+static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
+                            const double *molist, const double *molistdrv, int ncomp_in, int n_terms, const double *coef,
+                            const int *ia, const int *ib, double *out, long long ld_out, unsigned flags) {
     int rc = ci_check(ctx, mode, n_mo, n_terms, coef, ia, ib, out);
     if (rc != OKB_OK) return rc;
     if (npts < 0) return fail(OKB_ERR_ARG, "okb_ci_contract: negative point count");
     if (ld_in < npts || ld_out < npts) return fail(OKB_ERR_ARG, "okb_ci_contract: row stride smaller than the point count");
     if (npts == 0) return OKB_OK;
     // derivative / second-factor sets that come with molistdrv: 3 for JAB, A_NABLA_B and JPAIRS, 1 (optional) for PAIRS
-    const int nd = (mode == CI_JAB || mode == CI_ANB || mode == CI_JPAIRS) ? 3 : (mode == CI_PAIRS && molistdrv) ? 1 : 0;
+    const int nd = (mode == CI_JAB || mode == CI_ANB || mode == CI_JPAIRS) ? 3 : mode == CI_JABF ? ncomp_in
+                   : (mode == CI_PAIRS && molistdrv) ? 1 : 0;
     const bool need_drv = nd > 0;
-    if (!molist || (nd == 3 && !molistdrv)) return fail(OKB_ERR_ARG, "okb_ci_contract: null MO array");
+    if (!molist || (need_drv && mode != CI_PAIRS && !molistdrv)) return fail(OKB_ERR_ARG, "okb_ci_contract: null MO array");
     const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
-    const int nsets = 1 + nd, ncomp = ci_ncomp(mode, n_terms, 3);
+    const int nsets = 1 + nd, ncomp = ci_ncomp(mode, n_terms, nd);
     CU(cudaSetDevice(ctx->device));
     // slab geometry: device-resident inputs and outputs need no staging at all
     const size_t per_pt = (in_dev ? 0 : (size_t)nsets * n_mo * 8) + (out_dev ? 0 : (size_t)ncomp * 8);
@@ -1608,7 +1612,7 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
         }
         p.dstride = (long long)n_mo * p.ld;
         p.npts = sn;
-        p.ncomp = 3;
+        p.ncomp = mode == CI_JABF ? nd : 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? ld_out : sn;
         rc = ci_launch(ctx, mode, p);
@@ -1621,6 +1625,112 @@ extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts,
         }
     }
     if (!out_dev || !in_dev) CU(cudaStreamSynchronize(ctx->stream));
+    return OKB_OK;
+}
+
+extern "C" int okb_ci_contract(okb_ctx *ctx, int mode, int n_mo, long long npts, long long ld_in,
+                               const double *molist, const double *molistdrv, int n_terms, const double *coef,
+                               const int *ia, const int *ib, double *out, long long ld_out, unsigned flags) {
+    if (mode == CI_JABF) return fail(OKB_ERR_ARG, "okb_ci_contract: use okb_ci_jab_full for mode %d", mode);
+    return ci_contract_impl(ctx, mode, n_mo, npts, ld_in, molist, molistdrv, 3, n_terms, coef, ia, ib, out, ld_out, flags);
+}
+
+// cy_ci.get_jab_full (cy_ci.pyx:186-202): the pairs n > m of the state basis in the reference's loop order as terms
+// (f ImS[n,m], n, m) of the pair kernel; the sums are bit-identical to the reference's
+extern "C" int okb_ci_jab_full(okb_ctx *ctx, int nbasis, int ncomp, long long npts, long long ld_in, const double *ImS,
+                               const double *chi, const double *dchi, double mu, double *out, long long ld_out,
+                               unsigned flags) {
+    if (!ctx) return fail(OKB_ERR_ARG, "okb_ci_jab_full: null context");
+    if (nbasis <= 0 || ncomp < 1 || ncomp > 3) return fail(OKB_ERR_ARG, "okb_ci_jab_full: nbasis > 0 and 1 <= ncomp <= 3 expected");
+    if (!ImS || !chi || !dchi || !out) return fail(OKB_ERR_ARG, "okb_ci_jab_full: null array");
+    const double f = 1. / mu;
+    std::vector<double> coef;
+    std::vector<int> ia, ib;
+    for (int n = 0; n < nbasis; ++n)
+        for (int m = 0; m < n; ++m) {
+            coef.push_back(f * ImS[(size_t)n * nbasis + m]);
+            ia.push_back(n);
+            ib.push_back(m);
+        }
+    if (coef.empty()) {                                       // a single state: the sum is empty
+        if (flags & OKB_FLAG_OUT_DEVICE) {
+            CU(cudaSetDevice(ctx->device));
+            CU(cudaMemset2DAsync(out, (size_t)ld_out * 8, 0, (size_t)npts * 8, ncomp, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            for (int c = 0; c < ncomp; ++c) std::fill(out + (size_t)c * ld_out, out + (size_t)c * ld_out + npts, 0.0);
+        }
+        return OKB_OK;
+    }
+    return ci_contract_impl(ctx, CI_JABF, nbasis, npts, ld_in, chi, dchi, ncomp, (int)coef.size(), coef.data(), ia.data(),
+                            ib.data(), out, ld_out, flags);
+}
+
+// Time-dependent contraction out[t][x] = sum_k w[t][k] in[k][x] (okb_td.cuh; cy_ci.get_rho_full / get_j_full with the
+// weights packed by the caller).  w: HOST [nt][nk]; in / out: host (staged in slabs) or device (OKB_FLAG_IN_DEVICE /
+// OKB_FLAG_OUT_DEVICE) rows of stride ld_in / ld_out >= n.
+extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double *w, const double *in, long long ld_in,
+                         double *out, long long ld_out, unsigned flags) {
+    if (!ctx) return fail(OKB_ERR_ARG, "okb_ci_td: null context");
+    if (nt < 0 || nk < 0 || n < 0) return fail(OKB_ERR_ARG, "okb_ci_td: negative extent");
+    if (nt == 0 || n == 0) return OKB_OK;
+    if (!out || (nk > 0 && (!w || !in))) return fail(OKB_ERR_ARG, "okb_ci_td: null array");
+    if (ld_in < n || ld_out < n) return fail(OKB_ERR_ARG, "okb_ci_td: row stride smaller than the point count");
+    const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
+    CU(cudaSetDevice(ctx->device));
+    const int kp = std::max(4, (nk + 3) / 4 * 4), ntp = (nt + TD_MT - 1) / TD_MT * TD_MT;
+    std::vector<double> wp((size_t)ntp * kp, 0.0);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < nk; ++k) wp[(size_t)t * kp + k] = w[(size_t)t * nk + k];
+    const size_t wbytes = (wp.size() * 8 + 255) / 256 * 256;
+    const size_t per_pt = (in_dev ? 0 : (size_t)nk * 8) + (out_dev ? 0 : (size_t)nt * 8);
+    long long slab = n;
+    if (per_pt > 0) {
+        slab = (long long)(((size_t)1 << 30) / per_pt) / 1024 * 1024;
+        slab = std::max<long long>(1024, std::min(slab, n));
+    }
+    const long long lds = (slab + 1) & ~1LL;
+    const size_t in_bytes = in_dev ? 0 : ((size_t)nk * lds * 8 + 255) / 256 * 256;
+    int rc = ci_reserve(ctx, wbytes + in_bytes + (out_dev ? 0 : (size_t)nt * lds * 8));
+    if (rc != OKB_OK) return rc;
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
+    double *d_w = reinterpret_cast<double *>(base), *d_in = reinterpret_cast<double *>(base + wbytes),
+           *d_out = reinterpret_cast<double *>(base + wbytes + in_bytes);
+    CU(cudaMemcpyAsync(d_w, wp.data(), wp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)wp.size() * 8;
+    CU(cudaFuncSetAttribute(okb_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TD_SMEM));
+    for (long long s0 = 0; s0 < n; s0 += slab) {
+        const long long sn = std::min(slab, n - s0);
+        TdParams p{};
+        p.w = d_w;
+        p.nt = nt; p.nk = nk; p.kp = kp; p.n = sn;
+        if (in_dev || nk == 0) {
+            p.in = in ? in + s0 : nullptr;
+            p.ldi = ld_in;
+        } else {
+            CU(cudaMemcpy2DAsync(d_in, (size_t)lds * 8, in + s0, (size_t)ld_in * 8, (size_t)sn * 8, nk, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+            ctx->h2d_bytes += (long long)nk * sn * 8;
+            p.in = d_in;
+            p.ldi = lds;
+        }
+        p.out = out_dev ? out + s0 : d_out;
+        p.ldo = out_dev ? ld_out : lds;
+        p.vec_ok = (reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.ldo % 2 == 0) ? 1 : 0;
+        const unsigned grid = (unsigned)((sn + TD_P - 1) / TD_P);
+        okb_td_kernel<<<grid, TD_NT, TD_SMEM, ctx->stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "okb_td_kernel launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ctx->last_kernel = "ci/td-dmma";
+        if (!out_dev) {
+            CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)lds * 8, (size_t)sn * 8, nt, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+            ctx->d2h_bytes += (long long)nt * sn * 8;
+            CU(cudaStreamSynchronize(ctx->stream));          // the staging buffers are reused by the next slab
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
     return OKB_OK;
 }
 

@@ -8,6 +8,9 @@
 //                                                                     second array is given: core.calc_mo_matrix, core.py:925-941)
 //   CI_JPAIRS out[d][t][x] = -1/2 (mo[a_t] dmo[d][b_t] - mo[b_t] dmo[d][a_t])   per pair, d < ncomp (extras.calc_jmo,
 //                                                                     extras.py:441-493, only the requested pairs)
+//   CI_JABF   out[d][x] = sum_t c_t (mo[a_t][x] dmo[d][b_t][x] - mo[b_t][x] dmo[d][a_t][x]),  d < ncomp
+//                                                                    (cy_ci.get_jab_full, cy_ci.pyx:186-202: the terms are
+//                                                                     the pairs n > m of the state basis, c = ImS[n,m] / mu)
 //
 // One thread owns one grid point and walks the term list in the caller's order with the reference's
 // expression order and NO fused multiply-add (__dmul_rn / __dadd_rn), so for the same MO arrays the
@@ -20,7 +23,7 @@
 
 namespace okb {
 
-enum { CI_RHO = 0, CI_JAB = 1, CI_ANB = 2, CI_PAIRS = 3, CI_JPAIRS = 4 };
+enum { CI_RHO = 0, CI_JAB = 1, CI_ANB = 2, CI_PAIRS = 3, CI_JPAIRS = 4, CI_JABF = 5 };
 
 struct CiParams {
     const double *mo;          // [n_mo][ld]
@@ -33,7 +36,7 @@ struct CiParams {
     const int *ta, *tb;        // term orbital indices
     double *out;
     long long ldo;             // row stride of out in points
-    int ncomp;                 // JPAIRS: number of derivative components (1..3)
+    int ncomp;                 // JPAIRS, JABF: number of derivative components (1..3)
 };
 
 constexpr int CI_NT = 128;     // threads per CTA = points per CTA
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     const bool live = x < p.npts;
     const long long xc = live ? x : p.npts - 1;              // clamp: every thread takes part in the staging
     const double *mo = p.mo + xc;
-    const double *d0 = (MODE == CI_JAB || MODE == CI_ANB || MODE == CI_JPAIRS) ? p.dmo + xc
+    const double *d0 = (MODE == CI_JAB || MODE == CI_ANB || MODE == CI_JPAIRS || MODE == CI_JABF) ? p.dmo + xc
                        : (MODE == CI_PAIRS && p.dmo != nullptr)                 ? p.dmo + xc
                                                                                 : mo;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -79,6 +82,20 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
                         p.out[((long long)d * p.n_terms + t0 + e) * p.ldo + x] =
                             __dmul_rn(-0.5, __dadd_rn(__dmul_rn(ma, db), -__dmul_rn(mb, da)));
                 }
+            } else if (MODE == CI_JABF) {
+                // tmp = tmp + f*ImS[n,m]*(chi_n[n,r]*nabla_chi_n[c,m,r] - chi_n[m,r]*nabla_chi_n[c,n,r])   (cy_ci.pyx:199-201)
+                // with a = n, b = m, c = f*ImS[n,m] (the product the reference forms first)
+                const double ma = __ldg(mo + ra), mb = __ldg(mo + rb);
+                double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    if (d < p.ncomp) {
+                        const double db = __ldg(d0 + d * p.dstride + rb), da = __ldg(d0 + d * p.dstride + ra);
+                        v[d] = __dmul_rn(c, __dadd_rn(__dmul_rn(ma, db), -__dmul_rn(mb, da)));
+                    }
+                acc0 = __dadd_rn(acc0, v[0]);
+                acc1 = __dadd_rn(acc1, v[1]);
+                acc2 = __dadd_rn(acc2, v[2]);
             } else {
                 const double ma = __ldg(mo + ra), mb = (MODE == CI_JAB) ? __ldg(mo + rb) : 0.0;
                 double v[3];
@@ -102,7 +119,10 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     }
     if (!live || MODE == CI_PAIRS || MODE == CI_JPAIRS) return;
     p.out[x] = acc0;
-    if (MODE != CI_RHO) {
+    if (MODE == CI_JABF) {
+        if (p.ncomp > 1) p.out[p.ldo + x] = acc1;
+        if (p.ncomp > 2) p.out[2 * p.ldo + x] = acc2;
+    } else if (MODE != CI_RHO) {
         p.out[p.ldo + x] = acc1;
         p.out[2 * p.ldo + x] = acc2;
     }

@@ -1,0 +1,107 @@
+// okb_td.cuh -- time-dependent detCI contractions (replaces the OpenMP loops of orbkit/detci/cy_ci.pyx:101-122
+// get_rho_full and 126-151 get_j_full):
+//
+//   out[t][x] = sum_k w[t][k] * in[k][x]        t < nt time steps, k < nk state pairs, x < n points
+//
+// get_rho_full: in = the transition densities rho[count][x] of the state pairs count = (n, m >= n), w[t][count] =
+// ReS[t,m,m] (m == n) or 2 ReS[t,m,n]; get_j_full: in = j[count][3][x] read as rows of 3*npts entries, w[t][count] =
+// -2 ImS[t,n,m] (0 for m == n).  The weights are packed by the caller (nt x nk doubles); 2 * S is exact, so the packed
+// products are the reference's.
+//
+// A dense (nt x nk) . (nk x n) product with small nk (3 .. a few hundred) and huge n: between the HBM roofline (8 (nk + nt)
+// bytes per point; store bound below nk ~ 23) and the FP64 one.  FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA; tcgen05 has
+// no f64 kind), the k-steps of 4 state pairs in the reference's order -- the sum runs in the reference's order up to the
+// fused rounding inside a DMMA, so the results agree to a few ulp of the largest term, not bit for bit (stated tolerance
+// in tests/test_gpu_ci.py).
+//
+//   CTA = 4 warps, tile = TD_P = 128 points (warp w: points [32 w, 32 w + 32) = 4 point blocks) x all time steps in
+//   passes of TD_MT = 32 (4 blocks of 8): 16 accumulator blocks = 64 registers per thread.
+//   The `in` tile [kc][TD_P] is staged ONCE per point tile (whole k range when nk <= TD_KC, else per pass and chunk),
+//   the weights of a pass [32][kc] per pass; both row strides = 4 (mod 16) doubles: conflict-free fragment loads.
+//   HBM traffic = `in` once + `out` once (the weights, nt x nk doubles, stay in L2).
+#pragma once
+#include "okb_ws.cuh"
+
+namespace okb {
+
+constexpr int TD_P = 128, TD_MT = 32, TD_KC = 64, TD_NT = 128;
+constexpr int TD_PS = TD_P + 4;                 // 132 = 4 (mod 16)
+constexpr int TD_WS = TD_KC + 4;                // 68  = 4 (mod 16)
+constexpr size_t TD_SMEM = ((size_t)TD_KC * TD_PS + (size_t)TD_MT * TD_WS) * 8;
+
+struct TdParams {
+    const double *w;       // [ntp][kp] device: nt rows padded to a multiple of TD_MT, nk to a multiple of 4, zero filled
+    const double *in;      // [nk][ldi]
+    double *out;           // [nt][ldo]
+    long long ldi, ldo, n;
+    int nt, nk, kp;
+    int vec_ok;            // out rows 16-byte aligned: paired stores
+};
+
+__global__ void __launch_bounds__(TD_NT, 2) okb_td_kernel(const TdParams p) {
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    double *rt = reinterpret_cast<double *>(td_smem);           // [TD_KC][TD_PS]
+    double *wt = rt + (size_t)TD_KC * TD_PS;                    // [TD_MT][TD_WS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tr = lane >> 2, tc = lane & 3;
+    const long long x0 = (long long)blockIdx.x * TD_P;
+    const int nchunk = (p.kp + TD_KC - 1) / TD_KC;
+    auto stage_in = [&](int k0, int kc) {                       // rows [k0, k0 + kc) of `in`, zero beyond nk / n
+        for (int e = tid; e < kc * TD_P; e += TD_NT) {
+            const int k = e / TD_P, pt = e - k * TD_P;
+            const long long x = x0 + pt;
+            rt[(size_t)k * TD_PS + pt] = (k0 + k < p.nk && x < p.n) ? __ldg(p.in + (size_t)(k0 + k) * p.ldi + x) : 0.0;
+        }
+    };
+    if (nchunk == 1) stage_in(0, p.kp);
+    const uint32_t a_rt = smem_u32(rt) + (uint32_t)((tc * TD_PS + warp * 32 + tr) * 8);
+    const uint32_t a_wt = smem_u32(wt) + (uint32_t)((tr * TD_WS + tc) * 8);
+    for (int t0 = 0; t0 < p.nt; t0 += TD_MT) {
+        double acc[4][4][2];
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+        for (int c = 0; c < nchunk; ++c) {
+            const int k0 = c * TD_KC, kc = min(TD_KC, p.kp - k0);
+            __syncthreads();                                    // previous pass / chunk no longer reads wt (rt)
+            if (nchunk > 1) stage_in(k0, kc);
+            for (int e = tid; e < TD_MT * kc; e += TD_NT) {     // weights of the pass (rows beyond nt are zero padded)
+                const int t = e / kc, k = e - t * kc;
+                wt[(size_t)t * TD_WS + k] = __ldg(p.w + (size_t)(t0 + t) * p.kp + k0 + k);
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int ks = 0; ks < kc; ks += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) a[mb] = lds64(a_wt + (uint32_t)((mb * 8 * TD_WS + ks) * 8));
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) b[nb] = lds64(a_rt + (uint32_t)((ks * TD_PS + nb * 8) * 8));
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+            }
+        }
+        // lane holds out[t0 + 8 mb + tr][x0 + 32 warp + 8 nb + 2 tc + {0, 1}]
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int t = t0 + mb * 8 + tr;
+            if (t >= p.nt) continue;
+            double *orow = p.out + (size_t)t * p.ldo;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const long long x = x0 + warp * 32 + nb * 8 + 2 * tc;
+                if (p.vec_ok && x + 1 < p.n) {
+                    *reinterpret_cast<double2 *>(orow + x) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                } else {
+                    if (x < p.n) orow[x] = acc[mb][nb][0];
+                    if (x + 1 < p.n) orow[x + 1] = acc[mb][nb][1];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace okb

@@ -348,6 +348,38 @@ class Engine:
             npts, flags))
         return out
 
+    def ci_td(self, w, data, out=None, nk=None, n=None, ld_in=None, ld_out=None, flags=0):
+        """out[t, x] = sum_k w[t, k] data[k, x] (okb_ci_td: the time-dependent detCI contractions).  w: NumPy (nt, nk);
+        data (nk, n) / out (nt, n): NumPy arrays, or device pointers (ints) with OKB_FLAG_IN_DEVICE / OKB_FLAG_OUT_DEVICE
+        and explicit extents."""
+        w = _lib.f64(w)
+        nt = w.shape[0]
+        in_dev = bool(flags & _lib.OKB_FLAG_IN_DEVICE)
+        out_dev = bool(flags & _lib.OKB_FLAG_OUT_DEVICE)
+        if not in_dev:
+            data = _lib.f64(data)
+            nk, n = data.shape
+            ld_in = n
+        if w.shape[1] != nk:
+            raise ValueError('weights (%d, %d) do not match %d rows' % (w.shape + (nk,)))
+        if out is None:
+            out = self.host_array((nt, n))
+        ld_out = n if ld_out is None else ld_out
+        _lib.check(self.lib.okb_ci_td(self.ctx, nt, nk, n, _lib.dptr(w), data if in_dev else data.ctypes.data,
+                                      ld_in if ld_in is not None else n, out if out_dev else out.ctypes.data, ld_out, flags))
+        return out
+
+    def ci_jab_full(self, ImS, chi, dchi, mu, out=None):
+        """cy_ci.get_jab_full on NumPy arrays (okb_ci_jab_full)"""
+        ImS, chi, dchi = _lib.f64(ImS), _lib.f64(chi), _lib.f64(dchi)
+        nb, npts = chi.shape
+        ncomp = dchi.shape[0]
+        if out is None:
+            out = self.host_array((ncomp, npts))
+        _lib.check(self.lib.okb_ci_jab_full(self.ctx, nb, ncomp, npts, npts, _lib.dptr(ImS), chi.ctypes.data,
+                                            dchi.ctypes.data, float(mu), out.ctypes.data, npts, 0))
+        return out
+
     def eval_ci(self, mode, terms, mo, grid, drv_codes=(1, 2, 3), p0=0, p1=None, out=None, flags=0):
         """fused: MOs of `mo` evaluated on the device slab by slab and contracted there (okb_eval_ci)"""
         coef, ia, ib = _lib.f64(terms[0]), _lib.i32(terms[1]), _lib.i32(terms[2])

@@ -217,3 +217,36 @@ def test_calc_mo_matrix_and_calc_jmo(ok, oci):
         ok.extras.calc_jmo(qc, ij, drv=[None, 'x', 'y'])
     with pytest.raises(NotImplementedError):
         ok.extras.calc_jmo(qc, ij, otype='am')
+
+
+def test_time_dependent_contractions(ok, oci):
+    """cy_ci.get_rho_full / get_j_full on the FP64 tensor cores against the oracle (the reference's own module when
+    oracle/_ref is built).  The DMMA k-steps run in the reference's order but round once per fused step, so the stated
+    tolerance is |d| <= 1e-10 |ref| + 1e-13 max|ref| (measured: a few 1e-16 max|ref|).  get_jab_full walks the pairs with
+    the sequential pair kernel: bit for bit."""
+    from orbkit_b200.detci import cy_ci
+    kind = 'ref' if oci.have_ref() else 'port'
+    rng = numpy.random.default_rng(17)
+    # (nt, nstate, npts): one pair; ragged everything; more pairs than one k chunk (nstate 12 -> 78 pairs); many time steps
+    for nt, ns, npts in ((1, 1, 1), (5, 2, 127), (33, 4, 1000), (70, 12, 257), (300, 3, 4099)):
+        npair = ns * (ns + 1) // 2
+        ReS, ImS = rng.normal(size=(nt, ns, ns)), rng.normal(size=(nt, ns, ns))
+        rho, j = rng.normal(size=(npair, npts)), rng.normal(size=(npair, 3, npts))
+        for got, ref in ((cy_ci.get_rho_full(ReS, rho), oci.get_rho_full(ReS, rho, kind=kind)),
+                         (cy_ci.get_j_full(ImS, j), oci.get_j_full(ImS, j, kind=kind))):
+            assert got.shape == ref.shape and got.dtype == numpy.float64
+            tol = 1e-10 * numpy.abs(ref) + 1e-13 * numpy.abs(ref).max()
+            assert (numpy.abs(got - ref) <= tol).all(), (nt, ns, npts, numpy.abs(got - ref).max())
+    for nb, nc, npts in ((1, 3, 9), (2, 1, 33), (7, 3, 1025), (25, 2, 300)):
+        S, chi, dchi = rng.normal(size=(nb, nb)), rng.normal(size=(nb, npts)), rng.normal(size=(nc, nb, npts))
+        assert numpy.array_equal(cy_ci.get_jab_full(S, chi, dchi, 1836.15), oci.get_jab_full(S, chi, dchi, 1836.15, kind=kind))
+    # linearity in the weights at a larger size (size-independent property): tdrho(a S1 + S2) = a tdrho(S1) + tdrho(S2)
+    nt, ns, npts = 64, 6, 200000
+    npair = ns * (ns + 1) // 2
+    S1, S2, rho = rng.normal(size=(nt, ns, ns)), rng.normal(size=(nt, ns, ns)), rng.normal(size=(npair, npts))
+    lhs = cy_ci.get_rho_full(2.0 * S1 + S2, rho)
+    rhs = 2.0 * cy_ci.get_rho_full(S1, rho) + cy_ci.get_rho_full(S2, rho)
+    assert numpy.abs(lhs - rhs).max() <= 1e-12 * numpy.abs(rhs).max()
+    sub = rng.integers(0, npts, size=64)
+    ref = oci.get_rho_full(S1, numpy.ascontiguousarray(rho[:, sub]), kind=kind)
+    assert numpy.abs(cy_ci.get_rho_full(S1, rho)[:, sub] - ref).max() <= 1e-13 * numpy.abs(ref).max()

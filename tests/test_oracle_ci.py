@@ -121,3 +121,47 @@ def test_mo_matrix_and_jmo_golden_reproduced(oci, oracle_mod):
         assert numpy.array_equal(oci.calc_jmo(qc, g['ij'], x, y, z, drv=['z', 'x'], kind=kind), g['jmo_zx'])
         assert numpy.array_equal(oci.calc_jmo(qc, [4, 1], x, y, z, kind=kind), g['jmo_one'])
     assert g['jmo'].shape == (3, 5, 5, 6, 7) and (g['jmo'][:, 3] == 0.0).all()     # the pair (3, 3) has no flux
+
+
+def _td_case(rng, nt, ns, npts):
+    npair = ns * (ns + 1) // 2
+    return (rng.normal(size=(nt, ns, ns)), rng.normal(size=(nt, ns, ns)), rng.normal(size=(npair, npts)),
+            rng.normal(size=(npair, 3, npts)))
+
+
+def test_time_dependent_port_equals_reference_bitwise(oci):
+    """get_rho_full / get_j_full / get_jab_full (cy_ci.pyx:101-151, 186-202): the C restatement against the reference's
+    own compiled module"""
+    if not oci.have_ref():
+        pytest.skip('oracle/_ref/cy_ci not built')
+    rng = numpy.random.default_rng(5)
+    for nt, ns, npts in ((1, 1, 1), (3, 2, 17), (9, 5, 130), (40, 3, 64)):
+        ReS, ImS, rho, j = _td_case(rng, nt, ns, npts)
+        assert numpy.array_equal(oci.get_rho_full(ReS, rho), oci.get_rho_full(ReS, rho, kind='ref'))
+        assert numpy.array_equal(oci.get_j_full(ImS, j), oci.get_j_full(ImS, j, kind='ref'))
+    for nb, nc, npts in ((1, 3, 5), (2, 1, 33), (6, 3, 129), (11, 2, 40)):
+        S, chi, dchi = rng.normal(size=(nb, nb)), rng.normal(size=(nb, npts)), rng.normal(size=(nc, nb, npts))
+        assert numpy.array_equal(oci.get_jab_full(S, chi, dchi, 1836.15), oci.get_jab_full(S, chi, dchi, 1836.15, kind='ref'))
+
+
+def test_time_dependent_host_logic(oci):
+    """orbkit_b200.detci.cy_ci: the packed pair weights reproduce the reference's loops as a plain matrix product
+    (to rounding: the product sums in another order), and the typed-buffer argument checks of the compiled module"""
+    from orbkit_b200.detci import cy_ci
+    rng = numpy.random.default_rng(6)
+    ReS, ImS, rho, j = _td_case(rng, 7, 4, 50)
+    ref = oci.get_rho_full(ReS, rho)
+    got = cy_ci.pair_weights_rho(ReS) @ rho
+    assert numpy.abs(got - ref).max() <= 1e-13 * numpy.abs(ref).max()
+    ref = oci.get_j_full(ImS, j)
+    got = (cy_ci.pair_weights_j(ImS) @ j.reshape(j.shape[0], -1)).reshape(ref.shape)
+    assert numpy.abs(got - ref).max() <= 1e-13 * numpy.abs(ref).max()
+    with pytest.raises(ValueError):
+        cy_ci.get_rho_full(ReS.astype(numpy.float32), rho)
+    with pytest.raises(ValueError):
+        cy_ci.get_rho_full(ReS, rho.T)                       # not C-contiguous
+    with pytest.raises(ValueError):
+        cy_ci.get_j_full(ImS, j[:, 0])                       # wrong number of dimensions
+    with pytest.raises(TypeError):
+        cy_ci.get_jab_full(None, rho, j, 1.0)
+    assert cy_ci.get_rho_full(ReS[:0], rho).shape == (0, 50)
