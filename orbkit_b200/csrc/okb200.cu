@@ -1698,7 +1698,8 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
            *d_out = reinterpret_cast<double *>(base + wbytes + in_bytes);
     CU(cudaMemcpyAsync(d_w, wp.data(), wp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += (long long)wp.size() * 8;
-    CU(cudaFuncSetAttribute(okb_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TD_SMEM));
+    const size_t td_bytes = td_smem(kp);
+    CU(cudaFuncSetAttribute(okb_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC)));
     for (long long s0 = 0; s0 < n; s0 += slab) {
         const long long sn = std::min(slab, n - s0);
         TdParams p{};
@@ -1718,7 +1719,7 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
         p.ldo = out_dev ? ld_out : lds;
         p.vec_ok = (reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.ldo % 2 == 0) ? 1 : 0;
         const unsigned grid = (unsigned)((sn + TD_P - 1) / TD_P);
-        okb_td_kernel<<<grid, TD_NT, TD_SMEM, ctx->stream>>>(p);
+        okb_td_kernel<<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "okb_td_kernel launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;

@@ -225,8 +225,37 @@ __device__ __forceinline__ double mixed2(const AxisQ &a, const AxisQ &b, int la,
     return 4.0 * R2 * a.qp1 * b.qp1 + R0 * B;
 }
 
+// ---- AO tile layouts ------------------------------------------------------------------------------------
+// STRIDE > 0: tile[d][k][pt], row stride STRIDE doubles; the points of a thread are 32 doubles apart.
+// STRIDE < 0: derivative sets interleaved in pairs, tile[d/2][k][pt][d%2], row stride -STRIDE doubles (okb_ws.cuh: the
+//             consumer fetches the B fragments of two sets with one 16-byte load, the producers store two sets with one
+//             16-byte store); the points of a thread are 64 doubles apart and tp points at tile[0][0][pt][0].
+template <int STRIDE>
+struct TileLay {
+    static constexpr bool IL = STRIDE < 0;
+    static constexpr int RS = IL ? -STRIDE : STRIDE;
+    static constexpr int PQ = IL ? 64 : 32;
+    __host__ __device__ static constexpr size_t off(int d, int k) {
+        return IL ? ((size_t)(d >> 1) * KC + k) * RS + (d & 1) : ((size_t)d * KC + k) * RS;
+    }
+    // store the D values of row k (relative to o = tile row 0 of the thread's point)
+    template <int D>
+    __device__ __forceinline__ static void store(double *__restrict__ o, int k, const double (&w)[D]) {
+        if constexpr (IL) {
+#pragma unroll
+            for (int dp = 0; 2 * dp < D; ++dp) {
+                if (2 * dp + 1 < D) *reinterpret_cast<double2 *>(o + off(2 * dp, k)) = make_double2(w[2 * dp], w[2 * dp + 1]);
+                else o[off(2 * dp, k)] = w[2 * dp];
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) o[off(d, k)] = w[d];
+        }
+    }
+};
+
 // ---- phase A: one (shell, point) item -------------------------------------------------------------
-// tp points at tile[0][0][pt]; element (d, k) lives at tp[(d*KC + k) * P].
+// tp points at the thread's point of tile row 0, set 0; element (d, k) lives at tp[TileLay<P>::off(d, k)].
 template <int SET, int P>
 __device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__restrict__ prims,
                                           const FnMeta *__restrict__ fns, double x, double y, double z,
@@ -257,7 +286,7 @@ __device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__
         const FnMeta fm = ff[j];
         const int lx = fm.lxyz & 0xff, ly = (fm.lxyz >> 8) & 0xff, lz = (fm.lxyz >> 16) & 0xff;
         const AxisQ ax = axis_q<LEVEL>(X, lx), ay = axis_q<LEVEL>(Y, ly), az = axis_q<LEVEL>(Z, lz);
-        double *o = tp + (size_t)(sh.fn_off + j) * P;
+        double *o = tp + TileLay<P>::off(0, sh.fn_off + j);
         const double f = fm.f;
         if (SET == SET_ONE) {
             double v;
@@ -279,31 +308,31 @@ __device__ __forceinline__ void gen_shell(const ShellMeta &sh, const double2 *__
         const double yz = ay.q0 * az.q0, xz = ax.q0 * az.q0, xy = ax.q0 * ay.q0;
         if (SET == SET_D2P) {
             o[0] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
-            o[(size_t)1 * KC * P] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
-            o[(size_t)2 * KC * P] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
+            o[TileLay<P>::off(1, 0)] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
+            o[TileLay<P>::off(2, 0)] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
             continue;
         }
         o[0] = f * (R0 * ax.q0 * yz);
         if (SET == SET_D2) {
-            o[(size_t)1 * KC * P] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
-            o[(size_t)2 * KC * P] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
-            o[(size_t)3 * KC * P] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
+            o[TileLay<P>::off(1, 0)] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
+            o[TileLay<P>::off(2, 0)] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
+            o[TileLay<P>::off(3, 0)] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
             continue;
         }
         if (N1) {
-            o[(size_t)1 * KC * P] = f * (yz * (ax.qm1 * R0 - 2.0 * ax.qp1 * R1));
-            o[(size_t)2 * KC * P] = f * (xz * (ay.qm1 * R0 - 2.0 * ay.qp1 * R1));
-            o[(size_t)3 * KC * P] = f * (xy * (az.qm1 * R0 - 2.0 * az.qp1 * R1));
+            o[TileLay<P>::off(1, 0)] = f * (yz * (ax.qm1 * R0 - 2.0 * ax.qp1 * R1));
+            o[TileLay<P>::off(2, 0)] = f * (xz * (ay.qm1 * R0 - 2.0 * ay.qp1 * R1));
+            o[TileLay<P>::off(3, 0)] = f * (xy * (az.qm1 * R0 - 2.0 * az.qp1 * R1));
         }
         if (SET == SET_LAP || SET == SET_ALL) {
-            o[(size_t)4 * KC * P] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
-            o[(size_t)5 * KC * P] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
-            o[(size_t)6 * KC * P] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
+            o[TileLay<P>::off(4, 0)] = f * (yz * (ax.q0 * (4.0 * X * X * R2 - (double)(4 * lx + 2) * R1) + ax.qm2 * R0));
+            o[TileLay<P>::off(5, 0)] = f * (xz * (ay.q0 * (4.0 * Y * Y * R2 - (double)(4 * ly + 2) * R1) + ay.qm2 * R0));
+            o[TileLay<P>::off(6, 0)] = f * (xy * (az.q0 * (4.0 * Z * Z * R2 - (double)(4 * lz + 2) * R1) + az.qm2 * R0));
         }
         if (SET == SET_ALL) {
-            o[(size_t)7 * KC * P] = f * (az.q0 * mixed2(ax, ay, lx, ly, R0, R1, R2, exact));
-            o[(size_t)8 * KC * P] = f * (ay.q0 * mixed2(ax, az, lx, lz, R0, R1, R2, exact));
-            o[(size_t)9 * KC * P] = f * (ax.q0 * mixed2(ay, az, ly, lz, R0, R1, R2, exact));
+            o[TileLay<P>::off(7, 0)] = f * (az.q0 * mixed2(ax, ay, lx, ly, R0, R1, R2, exact));
+            o[TileLay<P>::off(8, 0)] = f * (ay.q0 * mixed2(ax, az, lx, lz, R0, R1, R2, exact));
+            o[TileLay<P>::off(9, 0)] = f * (ax.q0 * mixed2(ay, az, ly, lz, R0, R1, R2, exact));
         }
     }
 }

@@ -313,7 +313,8 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                 }
             }
         }
-        double *o = tp + 32 * q + (size_t)sh.fn_off * STRIDE;
+        using TL = TileLay<STRIDE>;
+        double *o = tp + TL::PQ * q + TL::off(0, sh.fn_off);
         if constexpr (!SPH) {
             const FnMeta *ff = fns + sh.fn_off;
 #pragma unroll
@@ -345,8 +346,7 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
                     if (ONLY == 5) w[0] = fxz * g2[1][ly];
                     if (ONLY == 6) w[0] = fxy * g2[2][lz];
                 }
-#pragma unroll
-                for (int d = 0; d < D; ++d) o[((size_t)d * KC + j) * STRIDE] = w[d];
+                TL::template store<D>(o, j, w);
                 if (RA::on) ra.row(sh.fn_off + j, q, w);
             }
         } else {
@@ -396,8 +396,7 @@ __device__ __forceinline__ void gen_shell_std(const ShellMeta &sh, const double2
 #pragma unroll
                     for (int d = 0; d < D; ++d) sacc[d] = (t == 0) ? c * v[cj][d] : fma(c, v[cj][d], sacc[d]);
                 });
-#pragma unroll
-                for (int d = 0; d < D; ++d) o[((size_t)d * KC + pos) * STRIDE] = sacc[d];
+                TL::template store<D>(o, pos, sacc);
                 if (RA::on) ra.row(sh.fn_off + pos, q, sacc);
             });
         }
@@ -460,7 +459,8 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
     }
 #pragma unroll 1
     for (int q = 0; q < NP; ++q)
-        gen_shell<SET, STRIDE>(sh, prims, fns, xs[32 * q], ys[32 * q], zs[32 * q], tp + 32 * q, one_code, exact);
+        gen_shell<SET, STRIDE>(sh, prims, fns, xs[32 * q], ys[32 * q], zs[32 * q], tp + TileLay<STRIDE>::PQ * q, one_code,
+                               exact);
     if constexpr (RA::on) {
         // generic shells: read the rows back (the thread's own columns of the tile, no synchronisation needed)
         constexpr int D = set_ncodes(SET);
@@ -470,7 +470,7 @@ __device__ __forceinline__ void gen_shell_any(const ShellMeta &sh, const double2
             for (int q = 0; q < NP; ++q) {
                 double w[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) w[d] = tp[((size_t)d * KC + k) * STRIDE + 32 * q];
+                for (int d = 0; d < D; ++d) w[d] = tp[TileLay<STRIDE>::off(d, k) + TileLay<STRIDE>::PQ * q];
                 ra.row(k, q, w);
             }
     }

@@ -27,7 +27,10 @@ namespace okb {
 constexpr int TD_P = 128, TD_MT = 32, TD_KC = 64, TD_NT = 128;
 constexpr int TD_PS = TD_P + 4;                 // 132 = 4 (mod 16)
 constexpr int TD_WS = TD_KC + 4;                // 68  = 4 (mod 16)
-constexpr size_t TD_SMEM = ((size_t)TD_KC * TD_PS + (size_t)TD_MT * TD_WS) * 8;
+// dynamic shared memory: the `in` tile takes only the rows it needs (few state pairs -> more CTAs per SM)
+__host__ __device__ constexpr size_t td_smem(int kp) {
+    return ((size_t)(kp < TD_KC ? kp : TD_KC) * TD_PS + (size_t)TD_MT * TD_WS) * 8;
+}
 
 struct TdParams {
     const double *w;       // [ntp][kp] device: nt rows padded to a multiple of TD_MT, nk to a multiple of 4, zero filled
@@ -38,10 +41,10 @@ struct TdParams {
     int vec_ok;            // out rows 16-byte aligned: paired stores
 };
 
-__global__ void __launch_bounds__(TD_NT, 2) okb_td_kernel(const TdParams p) {
-    extern __shared__ __align__(16) unsigned char td_smem[];
-    double *rt = reinterpret_cast<double *>(td_smem);           // [TD_KC][TD_PS]
-    double *wt = rt + (size_t)TD_KC * TD_PS;                    // [TD_MT][TD_WS]
+__global__ void __launch_bounds__(TD_NT, 4) okb_td_kernel(const TdParams p) {
+    extern __shared__ __align__(16) unsigned char td_smem_raw[];
+    double *rt = reinterpret_cast<double *>(td_smem_raw);       // [min(kp, TD_KC)][TD_PS]
+    double *wt = rt + (size_t)(p.kp < TD_KC ? p.kp : TD_KC) * TD_PS;   // [TD_MT][TD_WS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane >> 2, tc = lane & 3;
     const long long x0 = (long long)blockIdx.x * TD_P;

@@ -58,7 +58,25 @@ struct WsCfg {
     static constexpr int PS = pad_stride(P);                   // AO tile row stride (doubles)
     static constexpr int CS = pad_stride(MC);                  // coefficient tile row stride (doubles)
     static constexpr int NT = (NCW + NPW) * 32;
-    static constexpr int TILE_DOUBLES = D * KC * PS;
+    // ROT: the consumer walks TWO k-steps (8 rows) per loop iteration with the A fragments in a small ring of register
+    // buffers and the B fragments double buffered (see the consumer loop).
+#ifdef OKB_NO_ROT
+    static constexpr bool ROT = false;
+#else
+    static constexpr bool ROT = (WM == 1 && NST >= 3 && D <= 4 && (((MB + WM - 1) / WM + 1) / 2) >= 2);
+#endif
+    // IL: derivative sets interleaved in pairs in the AO tile (TileLay<-RS>): one 16-byte load fetches the B fragments of
+    // two sets, one 16-byte store of a producer writes two sets.  RS = row stride; RS/2 = 2 (mod 8) makes the 16-byte
+    // fragment loads of a quarter warp (2 point rows x 4 k rows) hit all 8 16-byte slots of a 128-byte line.
+#ifdef OKB_NO_IL
+    static constexpr bool IL = false;
+#else
+    static constexpr bool IL = ROT && D >= 2;
+#endif
+    static constexpr int DP = (D + 1) / 2;                     // set pairs
+    static constexpr int RS = 2 * (P + ((2 - (P % 8)) + 8) % 8);
+    static constexpr int STR = IL ? -RS : PS;                  // TileLay parameter of the generators
+    static constexpr int TILE_DOUBLES = IL ? DP * KC * RS : D * KC * PS;
     static constexpr int CBUF_DOUBLES = KC * CS;
     static constexpr int NOUT = (SINK == SINK_RHO) ? D : 0;
     // register budget: NT threads are launched with 65536/NT registers each; after setmaxnreg
@@ -103,10 +121,7 @@ struct WsCfg {
     static_assert(NCW % 4 == 0 && NPW % 4 == 0, "whole warpgroups (setmaxnreg)");
     // MO blocks are fetched in pairs (one 16-byte load) when every warp row starts on an even block
     static constexpr bool PAIRED = (WM == 1 || AM % 2 == 0);
-    // ROT: the consumer walks TWO k-steps (8 rows) per loop iteration with the A fragments in a small ring of register
-    // buffers and the B fragments double buffered, so that no fragment load overwrites a register a neighbouring DMMA
-    // still reads (see the consumer loop).  NPAIR block pairs per k-step, NP2 pair slots per double step, NBUF ring
-    // buffers (a divisor of NP2), prefetch distance PD = NBUF - 2 slots.
+    // NPAIR block pairs per k-step, NP2 pair slots per double step, NBUF ring buffers (a divisor of NP2)
     static constexpr int NPAIR = (AM + 1) / 2;
     static constexpr int NP2 = 2 * NPAIR;
 #ifdef OKB_NBUF
@@ -116,11 +131,6 @@ struct WsCfg {
     static constexpr int PD = 1;                                // the pair of slot q + 1 is fetched during slot q
 #endif
     static_assert(NP2 % NBUF == 0 && PD >= 1 && PD < NP2, "ring");
-#ifdef OKB_NO_ROT
-    static constexpr bool ROT = false;
-#else
-    static constexpr bool ROT = (WM == 1 && NST >= 3 && D <= 4 && NPAIR >= 2);
-#endif
     static constexpr int KSTEP = ROT ? 8 : 4;                  // rows the tile is padded to
     static_assert(P % 32 == 0, "whole warps of points for the producers");
     static_assert(PREG >= 56 && CREG >= LAUNCH_REGS && PREG <= LAUNCH_REGS, "register split");
@@ -336,12 +346,12 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                                 constexpr int a = decltype(ac)::value;
                                 if (PG > 1 && (item % PG) != a) return;          // warp-uniform
                                 const RemAcc<D, NP> ra{cr, racc[a]};
-                                gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
-                                                           p.one_code, p.exact_mixed, tab, ra);
+                                gen_shell_any<SET, C::STR, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt,
+                                                               tile + (C::IL ? 2 : 1) * pt, p.one_code, p.exact_mixed, tab, ra);
                             });
                         } else {
-                            gen_shell_any<SET, PS, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt, tile + pt,
-                                                       p.one_code, p.exact_mixed, tab);
+                            gen_shell_any<SET, C::STR, NP>(shells[sh], prims, fns, aux, xs + pt, ys + pt, zs + pt,
+                                                           tile + (C::IL ? 2 : 1) * pt, p.one_code, p.exact_mixed, tab);
                         }
                     }
                     // zero the rows that pad nfn up to the k-step of the consumer loop (coefficients there are 0,
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     const int kpad = (hdr.nfn + C::KSTEP - 1) & ~(C::KSTEP - 1);
                     for (int e = ptid; e < (kpad - hdr.nfn) * D * P; e += NPT) {
                         const int pt = e % P, r = e / P, d = r % D, k = hdr.nfn + r / D;
-                        tile[((size_t)d * KC + k) * PS + pt] = 0.0;
+                        tile[TileLay<C::STR>::off(d, k) + (C::IL ? 2 : 1) * pt] = 0.0;
                     }
                     if (ptid == 0) nfn_s[s] = kpad;
                     if constexpr (REM > 0) {
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
         // an odd first block (WM > 1 with odd AM) starts in the second slot of its pair
         uint32_t st = 0, ph = 0;
         uint32_t a_st = smem_u32(cbase + (size_t)tc * CS + ((mo_w >> 3) >> 1) * 16 + ((mo_w >> 3) & 1) + 2 * tr);
-        uint32_t b_st = smem_u32(tbase + (size_t)tc * PS + pt_w + tr);
+        uint32_t b_st = C::IL ? smem_u32(tbase + (size_t)tc * C::RS + 2 * (pt_w + tr)) : smem_u32(tbase + (size_t)tc * PS + pt_w + tr);
         auto advance = [&](uint32_t &s_, uint32_t &h_, uint32_t &a_, uint32_t &b_) {
             if (s_ + 1 == NST) {
                 s_ = 0; h_ ^= 1u;
@@ -496,8 +506,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     // Order per accumulator is unchanged (k-steps in sequence), so the results are bit-identical.
                     constexpr int NPAIR = C::NPAIR, NP2 = C::NP2, NBUF = C::NBUF, PD = C::PD;
                     double abuf[NBUF][2], bset[2][NB];
-                    constexpr uint32_t A_HALF = (uint32_t)(4 * CS) * 8u, B_HALF = (uint32_t)(4 * PS) * 8u;
-                    auto b_off = [](int j) -> uint32_t { return (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u; };
+                    constexpr uint32_t A_HALF = (uint32_t)(4 * CS) * 8u, B_HALF = (uint32_t)(4 * (C::IL ? C::RS : PS)) * 8u;
+                    // the B fragments (set d, point block ib) = bset[.][d * BN + ib] of one k-step from the tile rows at `base`
+                    auto load_b = [&](double (&dst)[NB], const uint32_t base) {
+                        if constexpr (C::IL) {
+#pragma unroll
+                            for (int dp = 0; dp < C::DP; ++dp)
+#pragma unroll
+                                for (int ib = 0; ib < BN; ++ib) {
+                                    const uint32_t a = base + (uint32_t)(dp * KC * C::RS + ib * 16) * 8u;
+                                    if (2 * dp + 1 < D) lds128(a, dst[(2 * dp) * BN + ib], dst[(2 * dp + 1) * BN + ib]);
+                                    else dst[(2 * dp) * BN + ib] = lds64(a);
+                                }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NB; ++j) dst[j] = lds64(base + (uint32_t)((j / BN) * KC * PS + (j % BN) * 8) * 8u);
+                        }
+                    };
                     auto dstep = [&](const uint32_t ca, const uint32_t cb, const uint32_t na, const uint32_t nb) {
                         static_for<0, NP2>([&](auto qc) {
                             constexpr int q = decltype(qc)::value;
@@ -505,9 +530,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                             // the B fragments of the next k-step first: issued while set h is still needed by every
                             // DMMA of this half, so the two sets cannot share registers
                             if constexpr (pq == 0) {
-                                const uint32_t bbase = (h == 0) ? cb + B_HALF : nb;
-#pragma unroll
-                                for (int j = 0; j < NB; ++j) bset[h ^ 1][j] = lds64(bbase + b_off(j));
+                                load_b(bset[h ^ 1], (h == 0) ? cb + B_HALF : nb);
                             }
                             // the pair of slot q + 1
                             constexpr int t = q + PD, tt = t % NP2, th = tt / NPAIR, tp = tt % NPAIR;
@@ -524,8 +547,7 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         });
                     };
                     auto load_first = [&](const uint32_t ca, const uint32_t cb) {
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) bset[0][j] = lds64(cb + b_off(j));
+                        load_b(bset[0], cb);
                         static_for<0, PD>([&](auto tc_) {
                             constexpr int t = decltype(tc_)::value, th = t / NPAIR, tp = t % NPAIR;
                             const uint32_t abase = ca + (uint32_t)th * A_HALF + (uint32_t)tp * 128u;
