@@ -1290,9 +1290,21 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     }
     zrun_ok = zrun_ok && tabx != nullptr;
 
-    int slab_idx = 0;
-    for (long long s0 = 0; s0 < ntot; s0 += slab_pts, ++slab_idx) {
+    // Slab boundaries.  Host outputs: the device -> host copy of a slab overlaps the evaluation of the next one, so only the
+    // LAST slab's copy is exposed; the last slab is therefore cut short (1/8 of the final stretch, >= 64 K points): a rank of
+    // an 8-GPU job that evaluates 1e6 points (32 MB of rho + grad rho) waits for a 4 MB copy instead of the whole 32 MB.
+    std::vector<long long> cut;                               // slab start offsets, then ntot
+    for (long long s0 = 0; s0 < ntot; s0 += slab_pts) {
+        cut.push_back(s0);
         const long long sn = std::min(slab_pts, ntot - s0);
+        if (!dev_out && s0 + sn == ntot) {
+            const long long tail = std::max<long long>(sn / 8 / 1024 * 1024, 65536);
+            if (sn >= 4 * tail) cut.push_back(s0 + sn - tail);
+        }
+    }
+    cut.push_back(ntot);
+    for (int slab_idx = 0; slab_idx + 1 < (int)cut.size(); ++slab_idx) {
+        const long long s0 = cut[slab_idx], sn = cut[slab_idx + 1] - s0;
         const int buf = slab_idx & 1;
         double *dbase;          // device output base for this slab
         long long ld;
@@ -1678,7 +1690,9 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
     if (ld_in < n || ld_out < n) return fail(OKB_ERR_ARG, "okb_ci_td: row stride smaller than the point count");
     const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
     CU(cudaSetDevice(ctx->device));
-    const int kp = std::max(4, (nk + 3) / 4 * 4), ntp = (nt + TD_MT - 1) / TD_MT * TD_MT;
+    const int kp = std::max(4, (nk + 3) / 4 * 4), ntp = (nt + 63) / 64 * 64;
+    // several k chunks: every pass over 8 MTB time steps re-reads `in`, so take the taller pass
+    const int mtb = (kp > TD_KC && nt > 32) ? 8 : 4;
     std::vector<double> wp((size_t)ntp * kp, 0.0);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < nk; ++k) wp[(size_t)t * kp + k] = w[(size_t)t * nk + k];
@@ -1698,8 +1712,9 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
            *d_out = reinterpret_cast<double *>(base + wbytes + in_bytes);
     CU(cudaMemcpyAsync(d_w, wp.data(), wp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += (long long)wp.size() * 8;
-    const size_t td_bytes = td_smem(kp);
-    CU(cudaFuncSetAttribute(okb_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC)));
+    const size_t td_bytes = td_smem(kp, mtb);
+    CU(cudaFuncSetAttribute(okb_td_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 4)));
+    CU(cudaFuncSetAttribute(okb_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 8)));
     for (long long s0 = 0; s0 < n; s0 += slab) {
         const long long sn = std::min(slab, n - s0);
         TdParams p{};
@@ -1719,11 +1734,12 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
         p.ldo = out_dev ? ld_out : lds;
         p.vec_ok = (reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.ldo % 2 == 0) ? 1 : 0;
         const unsigned grid = (unsigned)((sn + TD_P - 1) / TD_P);
-        okb_td_kernel<<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
+        if (mtb == 8) okb_td_kernel<8><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
+        else okb_td_kernel<4><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "okb_td_kernel launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;
-        ctx->last_kernel = "ci/td-dmma";
+        ctx->last_kernel = mtb == 8 ? "td-dmma/MT64" : "td-dmma/MT32";
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)lds * 8, (size_t)sn * 8, nt, cudaMemcpyDeviceToHost,
                                  ctx->stream));
@@ -1906,45 +1922,13 @@ extern "C" int okb_lcreator(okb_ctx *ctx, double *ao_list, long long row_stride,
     return OKB_OK;
 }
 
+// cy_core.mocreator (cy_core.pyx:82-101): mo[i][x] = sum_j coeffs[i][j] ao[j][x] -- the dense contraction of okb_td.cuh
+// (FP64 tensor cores, AOs in the reference's order) on host arrays staged in slabs
 extern "C" int okb_mocreator(okb_ctx *ctx, const double *ao, const double *coeffs, int n_ao, long long npts,
                              int n_mo, double *mo) {
     if (!ctx || !ao || !coeffs || !mo) return fail(OKB_ERR_ARG, "okb_mocreator: null argument");
     if (n_ao <= 0 || n_mo <= 0 || npts <= 0) return fail(OKB_ERR_ARG, "okb_mocreator: empty operand");
-    CU(cudaSetDevice(ctx->device));
-    double *d_c = nullptr, *d_ao = nullptr, *d_mo = nullptr;
-    CU(cudaMalloc(&d_c, sizeof(double) * (size_t)n_mo * n_ao));
-    CU(cudaMemcpyAsync(d_c, coeffs, sizeof(double) * (size_t)n_mo * n_ao, cudaMemcpyHostToDevice, ctx->stream));
-    // stream the point dimension through the device in slabs
-    const long long per_pt = (long long)(n_ao + n_mo) * sizeof(double);
-    long long slab = std::max<long long>(((long long)(512ll << 20) / per_pt) / 64 * 64, 64);
-    slab = std::min(slab, npts);
-    cudaError_t e1 = cudaMalloc(&d_ao, sizeof(double) * (size_t)n_ao * slab);
-    cudaError_t e2 = cudaMalloc(&d_mo, sizeof(double) * (size_t)n_mo * slab);
-    int rc = OKB_OK;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(OKB_ERR_NOMEM, "okb_mocreator: device allocation failed");
-    for (long long s0 = 0; rc == OKB_OK && s0 < npts; s0 += slab) {
-        const long long sn = std::min(slab, npts - s0);
-        cudaError_t e = cudaMemcpy2DAsync(d_ao, sizeof(double) * sn, ao + s0, sizeof(double) * npts,
-                                          sizeof(double) * sn, n_ao, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) {
-            dim3 grid((unsigned)((sn + 63) / 64), (unsigned)((n_mo + 63) / 64));
-            okb_mocreator_kernel<<<grid, 256, 0, ctx->stream>>>(d_ao, d_c, d_mo, n_mo, n_ao, sn);
-            e = cudaGetLastError();
-            ctx->launches++;
-            ctx->last_kernel = "okb_mocreator_kernel";
-        }
-        if (e == cudaSuccess)
-            e = cudaMemcpy2DAsync(mo + s0, sizeof(double) * npts, d_mo, sizeof(double) * sn, sizeof(double) * sn,
-                                  n_mo, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        ctx->h2d_bytes += (long long)sizeof(double) * sn * n_ao;
-        ctx->d2h_bytes += (long long)sizeof(double) * sn * n_mo;
-        if (e != cudaSuccess) rc = fail(OKB_ERR_CUDA, "okb_mocreator: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d_c);
-    if (d_ao) cudaFree(d_ao);
-    if (d_mo) cudaFree(d_mo);
-    return rc;
+    return okb_ci_td(ctx, n_mo, n_ao, npts, coeffs, ao, npts, mo, npts, 0);
 }
 
 // ---- FP64 peak measurement (the roofline denominator MEASURED_PEAKS.json does not carry) --------------

@@ -19,58 +19,6 @@ __global__ void __launch_bounds__(256) okb_axis_table_kernel(const double *__res
     out[idx] = axis == 0 ? q[1] * e : e;
 }
 
-// ---- plain FP64 GEMM for the cy_core.mocreator drop-in: mo[M][N] = Cm[M][K] * ao[K][N] -----------
-// 64 x 64 output tile per CTA (256 threads, 4x4 register tile), K stepped by 16 through smem.
-__global__ void __launch_bounds__(256) okb_mocreator_kernel(const double *__restrict__ ao,
-                                                            const double *__restrict__ cm,
-                                                            double *__restrict__ mo, int M, int K,
-                                                            long long N) {
-    __shared__ double sa[16][64 + 1];   // ao tile  [k][n]
-    __shared__ double sc[16][64 + 1];   // coef tile [k][m]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const long long n0 = (long long)blockIdx.x * 64;
-    const int m0 = blockIdx.y * 64;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            const int kk = e >> 6, nn = e & 63;
-            const long long n = n0 + nn;
-            sa[kk][nn] = (k0 + kk < K && n < N) ? ao[(size_t)(k0 + kk) * N + n] : 0.0;
-            const int mm = e >> 4, k2 = e & 15;
-            sc[k2][mm] = (m0 + mm < M && k0 + k2 < K) ? cm[(size_t)(m0 + mm) * K + k0 + k2] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double a[4], c[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = sa[kk][tx + 16 * j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) c[i] = sc[kk][ty + 16 * i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(c[i], a[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty + 16 * i;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long n = n0 + tx + 16 * j;
-            if (n < N) mo[(size_t)m * N + n] = acc[i][j];
-        }
-    }
-}
-
-
 // ---- FP64 peak microbenchmarks (roofline denominators measured on the box) ------------
 // kind 0: DFMA issue-bound (8 independent chains per thread)
 // kind 1: DMMA mma.sync.m8n8k4.f64 (8 independent accumulator tiles per warp)

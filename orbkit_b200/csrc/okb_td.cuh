@@ -15,7 +15,9 @@
 // in tests/test_gpu_ci.py).
 //
 //   CTA = 4 warps, tile = TD_P = 128 points (warp w: points [32 w, 32 w + 32) = 4 point blocks) x all time steps in
-//   passes of TD_MT = 32 (4 blocks of 8): 16 accumulator blocks = 64 registers per thread.
+//   passes of 8 MTB rows (MTB = 4 blocks of 8: 16 accumulator blocks = 64 registers per thread; MTB = 8 when the k range
+//   needs several chunks, i.e. when every pass re-reads `in`: half the passes).  Also the cy_core.mocreator drop-in
+//   (okb_mocreator: t = MO, k = AO).
 //   The `in` tile [kc][TD_P] is staged ONCE per point tile (whole k range when nk <= TD_KC, else per pass and chunk),
 //   the weights of a pass [32][kc] per pass; both row strides = 4 (mod 16) doubles: conflict-free fragment loads.
 //   HBM traffic = `in` once + `out` once (the weights, nt x nk doubles, stay in L2).
@@ -24,16 +26,16 @@
 
 namespace okb {
 
-constexpr int TD_P = 128, TD_MT = 32, TD_KC = 64, TD_NT = 128;
+constexpr int TD_P = 128, TD_KC = 64, TD_NT = 128;
 constexpr int TD_PS = TD_P + 4;                 // 132 = 4 (mod 16)
 constexpr int TD_WS = TD_KC + 4;                // 68  = 4 (mod 16)
 // dynamic shared memory: the `in` tile takes only the rows it needs (few state pairs -> more CTAs per SM)
-__host__ __device__ constexpr size_t td_smem(int kp) {
-    return ((size_t)(kp < TD_KC ? kp : TD_KC) * TD_PS + (size_t)TD_MT * TD_WS) * 8;
+__host__ __device__ constexpr size_t td_smem(int kp, int mtb) {
+    return ((size_t)(kp < TD_KC ? kp : TD_KC) * TD_PS + (size_t)(8 * mtb) * TD_WS) * 8;
 }
 
 struct TdParams {
-    const double *w;       // [ntp][kp] device: nt rows padded to a multiple of TD_MT, nk to a multiple of 4, zero filled
+    const double *w;       // [ntp][kp] device: nt rows padded to a multiple of 64, nk to a multiple of 4, zero filled
     const double *in;      // [nk][ldi]
     double *out;           // [nt][ldo]
     long long ldi, ldo, n;
@@ -41,7 +43,9 @@ struct TdParams {
     int vec_ok;            // out rows 16-byte aligned: paired stores
 };
 
-__global__ void __launch_bounds__(TD_NT, 4) okb_td_kernel(const TdParams p) {
+template <int MTB>
+__global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const TdParams p) {
+    constexpr int TD_MT = 8 * MTB;
     extern __shared__ __align__(16) unsigned char td_smem_raw[];
     double *rt = reinterpret_cast<double *>(td_smem_raw);       // [min(kp, TD_KC)][TD_PS]
     double *wt = rt + (size_t)(p.kp < TD_KC ? p.kp : TD_KC) * TD_PS;   // [TD_MT][TD_WS]
@@ -60,9 +64,9 @@ __global__ void __launch_bounds__(TD_NT, 4) okb_td_kernel(const TdParams p) {
     const uint32_t a_rt = smem_u32(rt) + (uint32_t)((tc * TD_PS + warp * 32 + tr) * 8);
     const uint32_t a_wt = smem_u32(wt) + (uint32_t)((tr * TD_WS + tc) * 8);
     for (int t0 = 0; t0 < p.nt; t0 += TD_MT) {
-        double acc[4][4][2];
+        double acc[MTB][4][2];
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb)
+        for (int mb = 0; mb < MTB; ++mb)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
         for (int c = 0; c < nchunk; ++c) {
@@ -76,20 +80,20 @@ __global__ void __launch_bounds__(TD_NT, 4) okb_td_kernel(const TdParams p) {
             __syncthreads();
 #pragma unroll 2
             for (int ks = 0; ks < kc; ks += 4) {
-                double a[4], b[4];
+                double a[MTB], b[4];
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb) a[mb] = lds64(a_wt + (uint32_t)((mb * 8 * TD_WS + ks) * 8));
+                for (int mb = 0; mb < MTB; ++mb) a[mb] = lds64(a_wt + (uint32_t)((mb * 8 * TD_WS + ks) * 8));
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) b[nb] = lds64(a_rt + (uint32_t)((ks * TD_PS + nb * 8) * 8));
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb)
+                for (int mb = 0; mb < MTB; ++mb)
 #pragma unroll
                     for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
             }
         }
         // lane holds out[t0 + 8 mb + tr][x0 + 32 warp + 8 nb + 2 tc + {0, 1}]
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
+        for (int mb = 0; mb < MTB; ++mb) {
             const int t = t0 + mb * 8 + tr;
             if (t >= p.nt) continue;
             double *orow = p.out + (size_t)t * p.ldo;
