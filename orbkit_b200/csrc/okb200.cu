@@ -1555,14 +1555,24 @@ static int ci_upload_terms(okb_ctx *ctx, int n_terms, const double *coef, const 
 static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
     if (p.npts <= 0) return OKB_OK;
     const unsigned grid = (unsigned)((p.npts + CI_NT - 1) / CI_NT);
+    // A/B measurements only: OKB_CI_SMEM = bytes of (unused) dynamic shared memory per CTA, i.e. a cap on the resident CTAs
+    // per SM (does the working set of fewer CTAs stay in L2?  profiles/r02_ci_occupancy.txt)
+    static const char *occ_env = getenv("OKB_CI_SMEM");
+    const size_t dsm = occ_env ? (size_t)atol(occ_env) : 0;
+#define OKB_CI_LAUNCH(M)                                                                                                  \
+    do {                                                                                                                  \
+        if (dsm) cudaFuncSetAttribute(okb_ci_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);           \
+        okb_ci_kernel<M><<<grid, CI_NT, dsm, ctx->stream>>>(p);                                                           \
+    } while (0)
     switch (mode) {
-        case CI_RHO: okb_ci_kernel<CI_RHO><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
-        case CI_JAB: okb_ci_kernel<CI_JAB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
-        case CI_ANB: okb_ci_kernel<CI_ANB><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
-        case CI_JPAIRS: okb_ci_kernel<CI_JPAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
-        case CI_JABF: okb_ci_kernel<CI_JABF><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
-        default: okb_ci_kernel<CI_PAIRS><<<grid, CI_NT, 0, ctx->stream>>>(p); break;
+        case CI_RHO: OKB_CI_LAUNCH(CI_RHO); break;
+        case CI_JAB: OKB_CI_LAUNCH(CI_JAB); break;
+        case CI_ANB: OKB_CI_LAUNCH(CI_ANB); break;
+        case CI_JPAIRS: OKB_CI_LAUNCH(CI_JPAIRS); break;
+        case CI_JABF: OKB_CI_LAUNCH(CI_JABF); break;
+        default: OKB_CI_LAUNCH(CI_PAIRS); break;
     }
+#undef OKB_CI_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "ci kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;

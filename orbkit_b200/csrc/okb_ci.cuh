@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     }
 }
 
-// Measured alternative (not kept): a tiled kernel that stages all n_mo row segments of a 24-32 point tile in shared
-// memory (bulk-async copies) so that HBM delivers every MO value exactly once.  Bit-identical results require the
-// sequential term order per point, i.e. parallelism only ACROSS points, and shared memory caps the points in flight
-// at ~48 per SM for 500 MOs: the kernel was latency bound and 2x (rho) to 4x (jab) SLOWER than this gather kernel
-// (7.6 / 63.8 ms against 3.8 / 16.4 ms for 1.5e6 points, 1000 pairs).  Splitting the term list over warps would fix
-// that at the price of a different summation order.  The gather kernel runs at 85% of the HBM bandwidth but moves
-// 3.5x the algorithmic bytes (ncu: 12.5 GB read for 3.5 GB of MO values; L1/L2 hit rates 1% / 8%): the MO rows are
-// re-fetched per term because n_mo KB per CTA times the resident CTAs exceeds the L2.  In the fused path
+// Measured alternatives (not kept).  Round 1: a tiled kernel that stages all n_mo row segments of a 24-32 point tile in
+// shared memory so that HBM delivers every MO value exactly once was 2x (rho) to 4x (jab) SLOWER than the gather kernel.
+// Round 2 (profiles/r02_ci_staged_vs_gather.txt): the same idea with one private tile per WARP, bulk-async copies issued by
+// all lanes and the warps of a CTA in different phases (loading / summing): bit-identical, DRAM traffic = algorithmic, but
+// 5.55 ms against 2.25 ms (rho) and 59.7 against 9.5 ms (jab) for 884 736 points, 500 MOs, 1000 pairs.  Bit-identical results
+// require the sequential term order per point, i.e. parallelism only ACROSS points, and shared memory caps the points in
+// flight at ~48 per SM (rho; 12 for the four sets of jab): ~90 cycles per term of exposed load + FP64 latency cannot be hidden
+// by three warps, while the gather kernel keeps 2048 points per SM in flight.  The gather kernel runs at 85% of the HBM
+// bandwidth but moves 3.5x the algorithmic bytes (ncu: 12.5 GB read for 3.5 GB of MO values; L1/L2 hit rates 1% / 8%): the
+// MO rows are re-fetched per term because n_mo KB per CTA times the resident CTAs exceeds the L2.  In the fused path
 // (okb_eval_ci) this kernel is < 8% of the time, the MO evaluation dominates.
 
 }  // namespace okb
