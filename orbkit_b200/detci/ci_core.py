@@ -97,8 +97,15 @@ def _given(mode, zero, sing, molist, molistdrv=None, slice_length=1e4):
     ncomp = 1 if mode == OKB_CI_RHO else 3
     if mo2.shape[1] == 0:
         return numpy.zeros(((ncomp,) if ncomp > 1 else ()) + shape[1:])
-    out = get_engine().ci_contract(mode, _terms(zero, sing, shape[0], mode), mo2, drv3,
-                                   n_eval=_n_visited(mo2.shape[1], slice_length))
+    n_eval = _n_visited(mo2.shape[1], slice_length)
+    if n_eval < mo2.shape[1]:
+        # parity with the reference's slice driver (ci_core.py:123-125: arange(0, N+1, slice_length) never reaches the
+        # points behind the last full slice); say so, the fused *_from_qc variants evaluate every point
+        from ..display import display
+        display('detci.ci_core: like the reference, the last %d of %d points (behind the last full slice of %d) are not '
+                'evaluated and stay 0; pass a slice_length that divides the number of points' %
+                (mo2.shape[1] - n_eval, mo2.shape[1], abs(int(min(mo2.shape[1], slice_length)))))
+    out = get_engine().ci_contract(mode, _terms(zero, sing, shape[0], mode), mo2, drv3, n_eval=n_eval)
     return out.reshape(shape[1:]) if ncomp == 1 else out.reshape((3,) + shape[1:])
 
 

@@ -404,11 +404,33 @@ class MOClass(UserList):
     def get_indices(self):
         return self.selected_mo if self.selected_mo is not None else list(range(len(self.data)))
 
+    @property
+    def is_energy_sorted(self):
+        return bool(numpy.all(numpy.diff(self.get_eig()) >= 0))
+
+    def sort_by_energy(self):
+        """orbitals.py:649-659: the MO list itself is reordered (stable argsort of the energies), with a warning"""
+        if self.is_energy_sorted:
+            return
+        import warnings
+        warnings.warn('MOs are not sorted by energy. Sorting them...', UserWarning)
+        order = numpy.argsort(self.get_eig())
+        self.data = [self.data[i] for i in order]
+        self._up_to_date = False
+        self.update()
+
     def get_homo(self, tol=1e-5, sort=True):
+        """index of the highest occupied MO; like the reference (orbitals.py:566-576) `sort=True` first sorts the MO
+        list by energy IN PLACE -- for an unrestricted set read with all_mo=True (alpha block, then beta block) homo and
+        lumo would otherwise straddle the two blocks"""
+        if sort:
+            self.sort_by_energy()
         occ = numpy.nonzero(self.get_occ() > tol)[0]
         return None if not len(occ) else occ[-1]
 
     def get_lumo(self, tol=1e-5, sort=True):
+        if sort:
+            self.sort_by_energy()
         un = numpy.nonzero(self.get_occ() < tol)[0]
         return None if not len(un) else un[0]
 

@@ -113,6 +113,33 @@ def test_set_lm_dict_order_and_mo_selection():
         bad.update()
 
 
+def test_homo_lumo_on_an_unrestricted_mo_list():
+    """orbitals.py:566-588: get_homo / get_lumo first sort the MO list by energy IN PLACE (with a warning).  For an
+    unrestricted set stored as alpha block + beta block (fchk / molden with all_mo=True) the unsorted list would put
+    the first alpha virtual in front of the occupied beta orbitals."""
+    import warnings
+    from orbkit_b200 import synth
+    qc = synth.to_qcinfo(synth.make_molecule(n_heavy=1, n_light=0, n_mo=8, seed=2))
+    mo = qc.mo_spec
+    #            alpha: 2 occupied, 2 virtual          beta: 1 occupied, 3 virtual
+    energies = [-1.0, -0.5, 0.2, 0.9, -0.9, 0.1, 0.3, 1.1]
+    occ = [1.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+    for i in range(8):
+        mo[i]['energy'], mo[i]['occ_num'], mo[i]['sym'] = energies[i], occ[i], '%d.%s' % (i % 4 + 1, 'ab'[i // 4])
+    mo.update()
+    assert not mo.is_energy_sorted
+    assert mo.get_homo(sort=False) == 4 and mo.get_lumo(sort=False) == 2       # straddling the two blocks
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        homo = mo.get_homo()
+    assert any('not sorted by energy' in str(x.message) for x in w)
+    # sorted energies: -1.0 -0.9 -0.5 | 0.1 0.2 0.3 0.9 1.1
+    assert mo.is_energy_sorted and homo == 2 and mo.get_lumo() == 3
+    assert [m['sym'] for m in mo] == ['1.a', '1.b', '2.a', '2.b', '3.a', '3.b', '4.a', '4.b']
+    assert list(mo.select('homo-1:lumo+1').get_indices()) == [1, 2, 3]
+    assert numpy.allclose(mo.get_eig(), sorted(energies)) and numpy.allclose(mo.get_occ(), [1, 1, 1, 0, 0, 0, 0, 0])
+
+
 def test_validate_drv_and_tables():
     from orbkit_b200.tools import validate_drv, exp, cart2sph, get_cart2sph, l_deg
     expect = {None: 0, 'None': 0, '': 0, 'x': 1, 'y': 2, 'z': 3, 'xx': 4, 'x2': 4, 'yy': 5, 'y2': 5, 'zz': 6,
