@@ -211,6 +211,15 @@ int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double *w, const 
 int okb_ci_jab_full(okb_ctx *ctx, int nbasis, int ncomp, long long npts, long long ld_in, const double *ImS,
                     const double *chi, const double *dchi, double mu, double *out, long long ld_out, unsigned flags);
 
+/* ---- analytic overlap matrix (orbkit/cy_overlap.pyx:75-156 aooverlap; c_non-grid-based.c:9-52) --------------------
+ * The argument list of cy_overlap.aooverlap: contraction i has assign[i] Cartesian functions (rows of lxlylz_a / _b, bra /
+ * ket exponents) x pnum_list[i] primitives (rows of ao_coeffs: exponent, coefficient) on atom atom_indices[i] of geo_a
+ * (bra) / geo_b (ket), [n_atom][3].  drv 0: overlap; 1..3: <a| d/dx b>, d/dy, d/dz.  aoom: HOST [ao_num][ao_num].
+ * Used by main_read (Molden renormalisation, check_norm) through orbkit_b200.analytical_integrals.get_ao_overlap. */
+int okb_aooverlap(okb_ctx *ctx, const double *geo_a, const double *geo_b, int n_atom, const int *lxlylz_a,
+                  const int *lxlylz_b, int ao_num, const int *assign, const double *ao_coeffs, const int *pnum_list,
+                  const int *atom_indices, int n_cont, int drv, int is_normalized, double *aoom);
+
 /* ---- output sink: Gaussian cube text (orbkit/output/cube.py:5-101, cube_creator) ------------------------------
  * The data loop of cube_creator (cube.py:86-96) on the device: data[n_sets][nx][ny][nz] (C order, float64) becomes
  * the text the reference writes -- per (x, y) row the nz * n_sets values ('%.5E' right-justified in 13 columns, the

@@ -1,8 +1,8 @@
-"""Cythonize the reference's own cy_core.pyx / cy_grid.pyx / detci/cy_ci.pyx into oracle/_ref/.
+"""Cythonize the reference's own cy_core.pyx / cy_grid.pyx / cy_overlap.pyx / detci/cy_ci.pyx into oracle/_ref/.
 
 TEST INFRASTRUCTURE ONLY.  The .pyx/.c sources are read where they lie under the
 reference tree (argv[1], default /root/reference); generated C and objects go to a
-scratch directory; only the resulting extension modules (`cy_core`, `cy_grid`, `cy_ci`) are
+scratch directory; only the resulting extension modules (`cy_core`, `cy_grid`, `cy_overlap`, `cy_ci`) are
 written to oracle/_ref/ (git-ignored).  The reference's own setup.py is not used.
 """
 import os, sys, shutil, tempfile, glob
@@ -24,6 +24,11 @@ def main():
         Extension('cy_core', [os.path.join(src, 'cy_core.pyx'),
                               os.path.join(src, 'c_grid-based.c'),
                               os.path.join(src, 'c_support.c')],
+                  include_dirs=[numpy.get_include(), src]),
+        # analytic overlap integrals (read/molden.py:378-398 renormalisation, check_mo_norm)
+        Extension('cy_overlap', [os.path.join(src, 'cy_overlap.pyx'),
+                                 os.path.join(src, 'c_non-grid-based.c'),
+                                 os.path.join(src, 'c_support.c')],
                   include_dirs=[numpy.get_include(), src]),
         # detCI grid contractions (prange loops: OpenMP, as in the reference's setup.py)
         Extension('cy_ci', [os.path.join(src, 'detci', 'cy_ci.pyx')],

@@ -368,6 +368,116 @@ void okor_ci_jab_full(double *out, const double *ImS, const double *chi, const d
         }
 }
 
+/* ---- analytic overlap integrals (orbkit/c_non-grid-based.c:9-52, orbkit/cy_overlap.pyx:24-156) -----------------
+ * Primitive Cartesian Gaussians: S = E_AB (pi/(a+b))^(3/2) prod_i s_i(la_i, lb_i) with the Obara-Saika-type recursion of
+ * c_non-grid-based.c:36-52 (initial conditions, recurrence in a, transfer equation). */
+typedef struct { double alpha; int l[3]; double R[3]; } okor_prim;
+
+static double okor_s(int i, int a, int b, const okor_prim *A, const okor_prim *B)
+{
+    if (a == 0 && b == 0) return 1.;
+    else if (a == 1 && b == 0)
+        return -(A->R[i] - ((A->alpha * A->R[i] + B->alpha * B->R[i]) / (A->alpha + B->alpha)));
+    else if (b == 0)
+        return -(A->R[i] - (A->alpha * A->R[i] + B->alpha * B->R[i]) / (A->alpha + B->alpha)) * okor_s(i, a - 1, 0, A, B) +
+               ((a - 1) / (2. * (A->alpha + B->alpha))) * okor_s(i, a - 2, 0, A, B);
+    else
+        return okor_s(i, a + 1, b - 1, A, B) + (A->R[i] - B->R[i]) * okor_s(i, a, b - 1, A, B);
+}
+
+static double okor_prim_overlap(const okor_prim *A, const okor_prim *B)
+{
+    double rr = 0., EAB, ov;
+    int i;
+    for (i = 0; i < 3; ++i) rr += (A->R[i] - B->R[i]) * (A->R[i] - B->R[i]);
+    EAB = exp(-((A->alpha * B->alpha) / (A->alpha + B->alpha)) * rr);
+    ov = EAB * pow((M_PI / (A->alpha + B->alpha)), 3. / 2.);
+    for (i = 0; i < 3; ++i) ov *= okor_s(i, A->l[i], B->l[i], A, B);
+    return ov;
+}
+
+/* cy_overlap.aooverlap (cy_overlap.pyx:75-156).  The contractions are expanded to (primitive, function) entries in the
+ * order contraction -> function -> primitive; aoom[fn_i][fn_j] accumulates over all entry pairs, i outer, j inner.
+ * drv 0: overlap; 1..3: <a| d/dx_drv b> through the exponents of the ket (lxlylz_b). */
+void okor_aooverlap(double *aoom, const double *geo_a, const double *geo_b, const int *lxlylz_a, const int *lxlylz_b,
+                    long ao_num, const int *assign, const double *ao_coeffs, const int *pnum_list,
+                    const int *atom_indices, long ncont, int drv, int is_normalized)
+{
+    long nindex = 0, i, j, c = 0, c_ao = 0, c_p = 0;
+    int i_ao, i_p, rr;
+    for (i = 0; i < ncont; ++i) nindex += (long)pnum_list[i] * assign[i];
+    double *norm = (double *)malloc(sizeof(double) * (nindex > 0 ? nindex : 1));
+    long *ip = (long *)malloc(sizeof(long) * 3 * (nindex > 0 ? nindex : 1));
+    for (i = 0; i < ao_num * ao_num; ++i) aoom[i] = 0.;
+    for (i = 0; i < ncont; ++i) {
+        for (i_ao = 0; i_ao < assign[i]; ++i_ao)
+            for (i_p = 0; i_p < pnum_list[i]; ++i_p) {
+                const int *l = lxlylz_a + 3 * (c_ao + i_ao);
+                norm[c] = okor_ao_norm(l[0], l[1], l[2], ao_coeffs[2 * (c_p + i_p)], is_normalized);
+                ip[3 * c] = c_p + i_p;
+                ip[3 * c + 1] = c_ao + i_ao;
+                ip[3 * c + 2] = atom_indices[i];
+                ++c;
+            }
+        c_ao += assign[i];
+        c_p += pnum_list[i];
+    }
+    for (i = 0; i < nindex; ++i)
+        for (j = 0; j < nindex; ++j) {
+            const long i_l = ip[3 * i + 1], j_l = ip[3 * j + 1];
+            const double *pa = ao_coeffs + 2 * ip[3 * i], *pb = ao_coeffs + 2 * ip[3 * j];
+            okor_prim A, B;
+            double *dst = aoom + i_l * ao_num + j_l;
+            for (rr = 0; rr < 3; ++rr) {
+                A.R[rr] = geo_a[3 * ip[3 * i + 2] + rr];
+                B.R[rr] = geo_b[3 * ip[3 * j + 2] + rr];
+                A.l[rr] = lxlylz_a[3 * i_l + rr];
+                B.l[rr] = lxlylz_b[3 * j_l + rr];
+            }
+            A.alpha = pa[0];
+            B.alpha = pb[0];
+            if (drv <= 0) {
+                *dst += (pa[1] * pb[1] * norm[i] * norm[j] * okor_prim_overlap(&A, &B));
+            } else if (B.l[drv - 1] == 0) {
+                B.l[drv - 1] = lxlylz_b[3 * j_l + drv - 1] + 1;
+                *dst += ((-2 * B.alpha) * pa[1] * pb[1] * norm[i] * norm[j] * okor_prim_overlap(&A, &B));
+            } else {
+                const int lb = lxlylz_b[3 * j_l + drv - 1];
+                B.l[drv - 1] = lb - 1;
+                *dst += (lb * pa[1] * pb[1] * norm[i] * norm[j] * okor_prim_overlap(&A, &B));
+                B.l[drv - 1] = lb + 1;
+                *dst += ((-2 * B.alpha) * pa[1] * pb[1] * norm[i] * norm[j] * okor_prim_overlap(&A, &B));
+            }
+        }
+    free(norm);
+    free(ip);
+}
+
+/* cy_overlap.ommited_cca_norm (cy_overlap.pyx:24-52) / tmol_aomix_norm (54-72) */
+void okor_cca_norm(double *norm, const int *lxlylz, long ao_num, int with_divisor)
+{
+    long i;
+    for (i = 0; i < ao_num; ++i) {
+        const int *l = lxlylz + 3 * i;
+        const double num = (double)(okor_dfact(2 * l[0] - 1) * okor_dfact(2 * l[1] - 1) * okor_dfact(2 * l[2] - 1));
+        norm[i] = with_divisor ? sqrt(num / (double)okor_dfact(2 * (l[0] + l[1] + l[2]) - 1)) : sqrt(num);
+    }
+}
+
+/* cy_overlap.mooverlapmatrix (cy_overlap.pyx:177-205): moom[i][j] = sum_k sum_l mo_a[i,k] mo_b[j,l] aoom[k,l] */
+void okor_mooverlapmatrix(double *moom, const double *mo_a, const double *mo_b, const double *aoom, long nmo_a,
+                          long nmo_b, long nao)
+{
+    long i, j, k, l;
+    for (i = 0; i < nmo_a; ++i)
+        for (j = 0; j < nmo_b; ++j) {
+            double t = 0.0;
+            for (k = 0; k < nao; ++k)
+                for (l = 0; l < nao; ++l) t += mo_a[i * nao + k] * mo_b[j * nao + l] * aoom[k * nao + l];
+            moom[i * nmo_b + j] = t;
+        }
+}
+
 /* ---- non-Cartesian product grids (orbkit/cy_grid.pyx:58-97) ------------------------------
  * xyz is [3][n0*n1*n2], first axis slowest; same expressions, same multiplication order. */
 void okor_sph2cart(double *xyz, const double *r, long nr, const double *theta, long nt,

@@ -89,6 +89,9 @@ SIGNATURES = {
     'okb_ci_jab_full': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, c_double_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ll,
                                        ctypes.c_uint]),
+    'okb_aooverlap': (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int, c_int_p, c_int_p,
+                                     ctypes.c_int, c_int_p, c_double_p, c_int_p, c_int_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, c_double_p]),
     'okb_ci_contract': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ll, ll, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, c_double_p, c_int_p, c_int_p,
                                        ctypes.c_void_p, ll, ctypes.c_uint]),

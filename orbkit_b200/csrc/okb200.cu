@@ -32,6 +32,7 @@
 #include "okb_misc.cuh"
 #include "okb_ci.cuh"
 #include "okb_td.cuh"
+#include "okb_overlap.cuh"
 #include "okb_text.cuh"
 
 using namespace okb;
@@ -1939,6 +1940,94 @@ extern "C" int okb_mocreator(okb_ctx *ctx, const double *ao, const double *coeff
     if (!ctx || !ao || !coeffs || !mo) return fail(OKB_ERR_ARG, "okb_mocreator: null argument");
     if (n_ao <= 0 || n_mo <= 0 || npts <= 0) return fail(OKB_ERR_ARG, "okb_mocreator: empty operand");
     return okb_ci_td(ctx, n_mo, n_ao, npts, coeffs, ao, npts, mo, npts, 0);
+}
+
+// ---- analytic overlap matrix (cy_overlap.aooverlap, cy_overlap.pyx:75-156) ---------------------------------------
+// Same argument list as the Cython function (contractions: assign[i] functions x pnum_list[i] primitives on atom
+// atom_indices[i]); aoom is a HOST array [ao_num][ao_num].
+extern "C" int okb_aooverlap(okb_ctx *ctx, const double *geo_a, const double *geo_b, int n_atom, const int *lxlylz_a,
+                             const int *lxlylz_b, int ao_num, const int *assign, const double *ao_coeffs,
+                             const int *pnum_list, const int *atom_indices, int n_cont, int drv, int is_normalized,
+                             double *aoom) {
+    if (!ctx) return fail(OKB_ERR_ARG, "okb_aooverlap: null context");
+    if (!geo_a || !geo_b || !lxlylz_a || !lxlylz_b || !assign || !ao_coeffs || !pnum_list || !atom_indices || !aoom)
+        return fail(OKB_ERR_ARG, "okb_aooverlap: null argument");
+    if (drv < 0 || drv > 3) return fail(OKB_ERR_ARG, "okb_aooverlap: drv must be 0..3 (only first derivatives)");
+    if (ao_num <= 0 || n_cont <= 0 || n_atom <= 0) return fail(OKB_ERR_ARG, "okb_aooverlap: empty basis");
+    std::vector<int> fn_atom, fn_e0, fn_ne;
+    std::vector<double> e_alpha, e_c, e_n;
+    int c_ao = 0, c_p = 0;
+    for (int i = 0; i < n_cont; ++i) {
+        if (assign[i] < 0 || pnum_list[i] < 0) return fail(OKB_ERR_ARG, "okb_aooverlap: negative count in contraction %d", i);
+        if (atom_indices[i] < 0 || atom_indices[i] >= n_atom) return fail(OKB_ERR_ARG, "okb_aooverlap: atom index of contraction %d", i);
+        for (int f = 0; f < assign[i]; ++f) {
+            if (c_ao + f >= ao_num) return fail(OKB_ERR_ARG, "okb_aooverlap: assign does not match the %d functions", ao_num);
+            const int *l = lxlylz_a + 3 * (c_ao + f);
+            for (int r = 0; r < 3; ++r) {
+                const int lb = lxlylz_b[3 * (c_ao + f) + r];
+                if (l[r] < 0 || lb < 0 || l[r] + lb + 1 > 15) return fail(OKB_ERR_UNSUPPORTED, "okb_aooverlap: exponents of function %d", c_ao + f);
+            }
+            fn_atom.push_back(atom_indices[i]);
+            fn_e0.push_back((int)e_alpha.size());
+            fn_ne.push_back(pnum_list[i]);
+            for (int q = 0; q < pnum_list[i]; ++q) {
+                const double alpha = ao_coeffs[2 * (size_t)(c_p + q)];
+                e_alpha.push_back(alpha);
+                e_c.push_back(ao_coeffs[2 * (size_t)(c_p + q) + 1]);
+                e_n.push_back(okb_aonorm(l[0], l[1], l[2], alpha, is_normalized));
+            }
+        }
+        c_ao += assign[i];
+        c_p += pnum_list[i];
+    }
+    if (c_ao != ao_num) return fail(OKB_ERR_ARG, "okb_aooverlap: assign sums to %d functions, %d given", c_ao, ao_num);
+    CU(cudaSetDevice(ctx->device));
+    const size_t nf = (size_t)ao_num, ne = std::max<size_t>(e_alpha.size(), 1);
+    // one scratch allocation: [geo_a | geo_b | e_alpha | e_c | e_n | aoom | la | lb | fn_atom | fn_e0 | fn_ne]
+    const size_t nd = 6 * (size_t)n_atom + 3 * ne + nf * nf, ni = 6 * nf + 3 * nf;
+    unsigned char *buf = nullptr;
+    CU(cudaMalloc(&buf, nd * 8 + ni * 4));
+    double *d = reinterpret_cast<double *>(buf);
+    int *di = reinterpret_cast<int *>(buf + nd * 8);
+    OvParams p{};
+    auto up_d = [&](const double *src, size_t n, const double **dst) {
+        cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        *dst = d;
+        d += n;
+    };
+    auto up_i = [&](const int *src, size_t n, const int **dst) {
+        cudaMemcpyAsync(di, src, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        *dst = di;
+        di += n;
+    };
+    up_d(geo_a, 3 * (size_t)n_atom, &p.geo_a);
+    up_d(geo_b, 3 * (size_t)n_atom, &p.geo_b);
+    up_d(e_alpha.data(), e_alpha.size(), &p.e_alpha);
+    d = const_cast<double *>(p.e_alpha) + ne;
+    up_d(e_c.data(), e_c.size(), &p.e_c);
+    d = const_cast<double *>(p.e_c) + ne;
+    up_d(e_n.data(), e_n.size(), &p.e_n);
+    d = const_cast<double *>(p.e_n) + ne;
+    p.aoom = d;
+    up_i(lxlylz_a, 3 * nf, &p.la);
+    up_i(lxlylz_b, 3 * nf, &p.lb);
+    up_i(fn_atom.data(), nf, &p.fn_atom);
+    up_i(fn_e0.data(), nf, &p.fn_e0);
+    up_i(fn_ne.data(), nf, &p.fn_ne);
+    p.n_fn = ao_num;
+    p.drv = drv;
+    const long long total = (long long)ao_num * ao_num;
+    okb_overlap_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(aoom, p.aoom, nf * nf * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "okb_aooverlap: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ctx->last_kernel = "okb_overlap_kernel";
+    ctx->h2d_bytes += (long long)(nd * 8 + ni * 4 - nf * nf * 8);
+    ctx->d2h_bytes += (long long)(nf * nf * 8);
+    return OKB_OK;
 }
 
 // ---- FP64 peak measurement (the roofline denominator MEASURED_PEAKS.json does not carry) --------------

@@ -387,8 +387,12 @@ def read_molden(fname, all_mo=False, spin=None, i_md=-1, interactive=False, **kw
         else:
             qc.ao_spec[0]['N'] = 1 / numpy.sqrt(norm[:, numpy.newaxis])
         if cart_flags:
-            raise NotImplementedError('renormalisation of Cartesian d/f/g shells with omitted CCA factors '
-                                      '(cy_overlap.ommited_cca_norm) is not built; use the reference reader')
+            # explicit Cartesian flags ([6D], [10F], ...): the CCA standard omits the Cartesian normalisation
+            # sqrt((2lx-1)!!(2ly-1)!!(2lz-1)!!/(2l-1)!!) of every function (molden.py:394-398, cy_overlap.pyx:24-52)
+            from .cy_overlap import ommited_cca_norm
+            cca = ommited_cca_norm(numpy.require(qc.ao_spec.get_lxlylz(), dtype=numpy.intc, requirements='CA'))
+            for mo in mos:
+                mo['coeffs'] *= cca
     qc.mo_spec = MOClass(mos)
     qc.mo_spec.update()
     qc.ao_spec.update()
@@ -428,8 +432,12 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
             raise NotImplementedError('orbkit_b200 reads Gaussian .fchk and Molden files; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
-    if check_norm:
-        raise NotImplementedError('check_norm needs the analytical overlap integrals (out of scope)')
     display('Loading data from {0} type file {1}\n'.format(itype, fname if isinstance(fname, str)
                                                            else getattr(fname, 'name', '<stream>')))
-    return readers[itype](fname, all_mo=all_mo, spin=spin, **kwargs)
+    qc = readers[itype](fname, all_mo=all_mo, spin=spin, **kwargs)
+    if check_norm:                               # read/high_level.py:74-77; the overlap integrals run on the device
+        from .analytical_integrals import check_mo_norm
+        deviation = check_mo_norm(qc)
+        if deviation >= 1e-5:
+            raise ValueError('Bad molecular orbital norm: {0:.4e}'.format(deviation))
+    return qc
