@@ -62,7 +62,8 @@ def test_get_ao_overlap_and_check_norm_vs_reference_goldens(tmp_path):
     assert abs(ai.check_mo_norm(qc) - float(gold['h2o_cart.dev'])) <= 1e-11
     assert abs(ai.get_mo_overlap(qc.mo_spec[0], qc.mo_spec[1], gold['h2o_cart.S']) - gold['h2o_cart.moom'][0, 1]) <= 1e-12
     with pytest.raises(ValueError):
-        ai.get_ao_overlap(qc.geo_spec, qc.geo_spec, qc.ao_spec, drv='xx')
+        ai.get_ao_overlap(qc.geo_spec, qc.geo_spec, qc.ao_spec, drv=4)      # only first derivatives (code > 3)
+    assert len(ai.get_ao_overlap(qc.geo_spec, qc.geo_spec, qc.ao_spec, drv='xz')) == 2   # a string of letters is a list
     with pytest.raises(TypeError):
         ai.get_ao_overlap(qc.geo_spec, qc.geo_spec, list(qc.ao_spec))
     # real-spherical d and f shells: T S T^T
