@@ -399,8 +399,11 @@ def read_molden(fname, all_mo=False, spin=None, i_md=-1, interactive=False, **kw
     return qc
 
 
-readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden}
-_OTHER = ('aomix', 'gamess', 'gaussian.log', 'gaussian_log', 'wfn', 'wfx', 'cclib', 'native')
+from .read_wf import read_wfn, read_wfx          # noqa: E402  (primitive-based wave-function files)
+
+readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden,
+           'wfn': read_wfn, 'wfx': read_wfx}
+_OTHER = ('aomix', 'gamess', 'gaussian.log', 'gaussian_log', 'cclib', 'native')
 
 
 def find_itype(fname):
@@ -429,7 +432,7 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
         itype = find_itype(fname)
     if itype not in readers:
         if itype in _OTHER:
-            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk and Molden files; use the reference\'s reader for %r and pass '
+            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk, Molden, .wfn and .wfx files; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
     display('Loading data from {0} type file {1}\n'.format(itype, fname if isinstance(fname, str)

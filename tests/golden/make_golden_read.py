@@ -11,6 +11,7 @@ and tests/golden/reader_inputs.npz: the bytes of the quantum-chemistry program o
 (`file.<name>`; Gaussian fchk, Molpro / Psi4 Molden files from the reference's test data orbkit/test/outputs_for_testing) --
 the tests write them to a scratch directory and read them with orbkit_b200.read.
 The spherical restricted / unrestricted cases are pinned by h2o_gaussian_sph*.npz / h2o_gaussian_uhf.npz (make_golden.py).
+tests/golden/read_wf.npz: `wfx_beta.<flat QCinfo arrays>` of orca/1.wfx read with spin='beta'.
 """
 import os
 import sys
@@ -41,9 +42,18 @@ def main():
         print(name, len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
     numpy.savez_compressed(os.path.join(HERE, 'read_fchk.npz'), **out)
     odir = os.path.join(scratch, 'orbkit', 'test', 'outputs_for_testing')
+    # primitive-based wave-function files: the unrestricted ORCA .wfx file restricted to one spin (the full reads are
+    # pinned by water_gamess_wfn.npz / h2o_orca_wfx.npz, make_golden.py)
+    out = {}
+    qc = read.main_read(os.path.join(odir, 'orca', '1.wfx'), all_mo=True, spin='beta')
+    for k, v in mg.qc_arrays(qc).items():
+        out['wfx_beta.' + k] = v
+    print('wfx_beta', len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
+    numpy.savez_compressed(os.path.join(HERE, 'read_wf.npz'), **out)
     files = {}
     for rel in ['gaussian/h2o_rhf_sph.fchk', 'gaussian/h2o_uhf_sph.fchk', 'gaussian/h2o_rhf_cart.fchk',
-                'molpro/h2o_rhf_sph.molden', 'molpro/nh3.mold', 'psi4/lih_cis_aug-cc-pVTZ.out.default.molden']:
+                'molpro/h2o_rhf_sph.molden', 'molpro/nh3.mold', 'psi4/lih_cis_aug-cc-pVTZ.out.default.molden',
+                'gamess/water_gamess-us.wfn', 'orca/1.wfx']:
         with open(os.path.join(odir, rel), 'rb') as f:
             files['file.' + os.path.basename(rel)] = numpy.frombuffer(f.read(), dtype=numpy.uint8)
     numpy.savez_compressed(os.path.join(HERE, 'reader_inputs.npz'), **files)

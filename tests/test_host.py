@@ -392,7 +392,36 @@ def test_fchk_reader_equals_reference_reader(tmp_path):
     with pytest.raises(IOError):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
     with pytest.raises(NotImplementedError):
-        read.main_read('something.wfn')
+        read.main_read('something.log')
+
+
+def test_wfn_and_wfx_readers_equal_reference_readers(tmp_path):
+    """read_wfn / read_wfx == the reference's readers on its GAMESS .wfn and ORCA .wfx test outputs: every flat QCinfo array
+    identical (primitive-based inputs: pnum = -1, explicit lxlylz rows; goldens written by running the reference)"""
+    import io
+    import os
+    from conftest import load_golden, reader_input
+    from orbkit_b200 import read, options
+    options.quiet = True
+    inputs = str(tmp_path)
+    wfn, wfx = reader_input('water_gamess-us.wfn', inputs), reader_input('1.wfx', inputs)
+    cases = [(load_golden('water_gamess_wfn'), '', wfn, dict(all_mo=True)),
+             (load_golden('h2o_orca_wfx'), '', wfx, dict(all_mo=True)),
+             (load_golden('read_wf'), 'wfx_beta.', wfx, dict(all_mo=True, spin='beta'))]
+    for g, prefix, path, kw in cases:
+        qc = read.main_read(path, **kw)
+        for k, v in _flat_qc(qc).items():
+            ref = g[prefix + k]
+            assert v.shape == ref.shape and (v == ref).all(), (path, kw, k)
+        assert qc.ao_spec.get_normalized() and not qc.ao_spec.spherical
+    with open(wfx, 'rb') as f:
+        assert read.main_read(io.BytesIO(f.read()), itype='wfx', all_mo=True) == read.main_read(wfx)
+    with pytest.raises(IOError):
+        read.main_read(wfn, spin='alpha')                    # not supported by the .wfn reader
+    with pytest.raises(IOError):
+        read.main_read(wfx, spin='gamma')
+    with pytest.raises(IOError):
+        read.read_wfx(io.StringIO('<Keywords>\n STO\n</Keywords>\n'))
 
 
 def test_molden_reader_equals_reference_reader(tmp_path):
