@@ -562,12 +562,23 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                         uint32_t st_n = st, ph_n = ph, a_n = a_st, b_n = b_st;
                         advance(st_n, ph_n, a_n, b_n);
                         const bool more = c + 1 < p.nchunk;
-                        const bool ready = more && mbar_test_a(a_full + 8 * st_n, ph_n);
-#pragma unroll 1
-                        for (int k0 = 8; k0 < nk; k0 += 8) {
+                        // (the probe sits in ONE basic block with the chunk's first double step, peeled out of the loop: its
+                        // S2UR / SYNCS / predicate latencies, ~75 cycles, overlap with DMMAs instead of stalling the warp
+                        // in front of the loop)
+                        bool ready = false;
+                        if (nk > 8) {
+                            ready = more && mbar_test_a(a_full + 8 * st_n, ph_n);
                             dstep(a_ap, a_bp, a_ap + 2 * A_HALF, a_bp + 2 * B_HALF);
                             a_ap += 2 * A_HALF;
                             a_bp += 2 * B_HALF;
+#pragma unroll 1
+                            for (int k0 = 16; k0 < nk; k0 += 8) {
+                                dstep(a_ap, a_bp, a_ap + 2 * A_HALF, a_bp + 2 * B_HALF);
+                                a_ap += 2 * A_HALF;
+                                a_bp += 2 * B_HALF;
+                            }
+                        } else {
+                            ready = more && mbar_test_a(a_full + 8 * st_n, ph_n);
                         }
                         uint32_t n_ap = a_ap, n_bp = a_bp;               // behind the last chunk: harmless reloads
                         int nk_next = nk;
