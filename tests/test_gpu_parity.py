@@ -471,3 +471,54 @@ def test_calc_ao_zrun_kernel_regular_grids(ok, oracle_mod, name):
     # ao_creator (core.py:38-105) takes the same route
     got = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, x=ax[0], y=ax[1], z=ax[2], is_vector=False)
     assert numpy.array_equal(got.reshape(full[0].shape), full[0])
+
+
+_REM_WORKER = r'''
+import os, sys, numpy
+sys.path.insert(0, %(repo)r)
+sys.path.insert(0, os.path.join(%(repo)r, 'tests'))
+import orbkit_b200 as ok
+from orbkit_b200.engine import get_engine
+from conftest import golden_qc, assert_close
+ok.options.quiet = True
+seen = set()
+for name in %(names)r:
+    qc, a = golden_qc(name)
+    ok.grid.set_grid(a['rx'], a['ry'], a['rz'], is_vector=False)
+    r, d = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    seen.add(get_engine().last_kernel())
+    assert_close(r, a['reg.rho'], name + ' reg.rho')
+    assert_close(d, a['reg.drho'], name + ' reg.drho')
+    r, d, l = ok.rho_compute(qc, laplacian=True)
+    seen.add(get_engine().last_kernel())
+    assert_close(d, a['reg.d2rho'], name + ' reg.d2rho')
+    assert_close(l, a['reg.lap'], name + ' reg.lap', afloor=3e-14)
+    ok.grid.set_grid(a['vx'], a['vy'], a['vz'], is_vector=True)
+    r, d = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert_close(d, a['vec.drho'], name + ' vec.drho')
+    m = ok.rho_compute(qc, calc_mo=True, drv=['z'])[0]
+    assert_close(m, a['vec.mo10'][3] if 'vec.mo10' in a.files else a['vec.mo_z'], name + ' mo_z')
+    # mo_norm path (want_norm): regular grid, no derivative -> the displayed norms are accumulated
+    # two rho_compute calls with the same inputs are bit-identical (the remainder partial sums are added in a fixed order)
+    r2, d2 = ok.rho_compute(qc, drv=['x', 'y', 'z'])
+    assert numpy.array_equal(d, d2) and numpy.array_equal(r, r2)
+print('kernels', sorted(seen))
+assert any('MB10R2' in k for k in seen), seen
+'''
+
+
+def test_remainder_orbital_tiles_forced_on_small_molecules(tmp_path):
+    """The 8 MB + 2 tiles (two remainder orbitals contracted by the producer warps, okb_ws.cuh REM) are chosen by the
+    cost model only for MO counts such as 82 or 246; here they are FORCED (OKB_VARIANT, read once per process) on the
+    small fixture molecules: one chunk per pass (the producers run several tiles ahead of the consumers, so the hand-over
+    of the partial sums is exercised across tiles), fewer MOs than one tile, ragged point counts, both laplacian passes,
+    the SINK_MO epilogue, vector and regular grids."""
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    script = tmp_path / 'rem_worker.py'
+    script.write_text(_REM_WORKER % {'repo': REPO, 'names': ['h2o_gaussian_sph', 'lih_psi4_sph_f', 'synth_small_cart_g']})
+    env = dict(os.environ, OKB_VARIANT='MB10R2')
+    p = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0, p.stdout.decode()[-3000:]
