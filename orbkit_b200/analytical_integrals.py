@@ -4,7 +4,7 @@ check_mo_norm.  Dipole moments, nuclear-attraction and kinetic-energy integrals 
 import numpy
 
 from . import cy_overlap
-from .engine import build_cart2sph_csr
+from .engine import cart2sph_dense
 from .orbitals import AOClass
 from .tools import require, validate_drv
 
@@ -48,12 +48,7 @@ def get_ao_overlap(coord_a, coord_b, ao_spec, lxlylz_b=None, drv=None):
 def cartesian2spherical_aoom(ao_overlap_matrix, ao_spec):
     """T S T^T with T the Cartesian -> real-spherical table of core.cartesian2spherical
     (analytical_integrals.py:118-183, a quadruple Python loop there)"""
-    ptr, col, val = build_cart2sph_csr(ao_spec)
-    n_sph, n_cart = len(ptr) - 1, ao_overlap_matrix.shape[0]
-    t = numpy.zeros((n_sph, n_cart))
-    for i in range(n_sph):
-        for k in range(ptr[i], ptr[i + 1]):
-            t[i, col[k]] += val[k]
+    t = cart2sph_dense(ao_spec, ao_overlap_matrix.shape[0])
     return t.dot(ao_overlap_matrix).dot(t.T)
 
 

@@ -22,7 +22,7 @@ from . import cy_core, cy_grid, grid, options
 from . import dist as okdist
 from ._lib import OKB_FLAG_EXACT_MIXED
 from .display import display
-from .engine import get_engine, build_cart2sph_csr
+from .engine import get_engine, build_cart2sph_csr, cart2sph_dense
 from .qcinfo import QCinfo
 from .tools import require, validate_drv, convert, zeros, reshape
 
@@ -103,13 +103,9 @@ def mo_creator(ao_list, mo_spec):
 
 def cartesian2spherical(ao_list, ao_spec):
     """Cartesian -> real spherical AOs for a given AO array (core.py:135-176; table tools.cart2sph).
-    Runs as T[n_sph,n_cart] x ao[n_cart,N] on the device GEMM."""
+    Runs as T[n_sph,n_cart] x ao[n_cart,N] on the device (the DMMA contraction behind cy_core.mocreator)."""
     ao_list = require(ao_list, dtype='f')
-    ptr, col, val = build_cart2sph_csr(ao_spec)
-    T = numpy.zeros((len(ptr) - 1, ao_list.shape[0]))
-    for j in range(len(ptr) - 1):
-        for t in range(ptr[j], ptr[j + 1]):
-            T[j, col[t]] += val[t]
+    T = cart2sph_dense(ao_spec, ao_list.shape[0])
     out = cy_core.mocreator(ao_list.reshape((ao_list.shape[0], -1)), T)
     return out.reshape((T.shape[0],) + ao_list.shape[1:])
 

@@ -55,6 +55,16 @@ def build_cart2sph_csr(ao_spec):
             numpy.asarray(val, dtype=numpy.float64))
 
 
+def cart2sph_dense(ao_spec, n_cart=None):
+    """dense T[n_sph, n_cart] of the CSR table above (terms that hit the same Cartesian row add up)"""
+    ptr, col, val = build_cart2sph_csr(ao_spec)
+    n_sph = len(ptr) - 1
+    n_cart = int(col.max()) + 1 if n_cart is None and len(col) else (n_cart or 0)
+    t = numpy.zeros((n_sph, n_cart))
+    numpy.add.at(t, (numpy.repeat(numpy.arange(n_sph), numpy.diff(ptr)), col), val)
+    return t
+
+
 def _stamped_key(obj, slot, compute):
     """`compute()` (a digest of the object's flat arrays), cached on the object for as long as the arrays it was taken
     from are the ones the getters hand out: AOClass / MOClass rebuild them in update() and stamp every rebuild
