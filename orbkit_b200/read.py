@@ -400,30 +400,41 @@ def read_molden(fname, all_mo=False, spin=None, i_md=-1, interactive=False, **kw
 
 
 from .read_wf import read_wfn, read_wfx          # noqa: E402  (primitive-based wave-function files)
+from .read_aomix import read_aomix               # noqa: E402
+from .read_gamess import read_gamess             # noqa: E402
 
 readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden,
-           'wfn': read_wfn, 'wfx': read_wfx}
-_OTHER = ('aomix', 'gamess', 'gaussian.log', 'gaussian_log', 'cclib', 'native')
+           'wfn': read_wfn, 'wfx': read_wfx, 'aomix': read_aomix, 'gamess': read_gamess}
+_OTHER = ('gaussian.log', 'gaussian_log', 'cclib', 'native')
 
 
-def find_itype(fname):
-    """file type from the name or the content (read/tools.py:find_itype, reduced to what is told apart here)"""
+_MAGIC = (('molden', re.compile(r'\[[ ]{,}[Mm]olden[ ]+[Ff]ormat[ ]{,}\]')),
+          ('gamess', re.compile(r'[Gg][Aa][Mm][Ee][Ss][Ss]')),
+          ('gaussian_log', re.compile(r'[Cc]opyright[,\s\(\)c0-9]+[Gg]aussian\s{,},\s+Inc.')),
+          ('aomix', re.compile(r'\[[ ]{,}[Aa][Oo][Mm]ix[ ]+[Ff]ormat[ ]{,}\]')))
+
+
+def find_itype(fname, extension=None):
+    """file type from the extension (fchk, wfx, wfn, native containers) or from magic strings in the content, tried in
+    the reference's order: Molden, GAMESS-US, Gaussian log, AOMix (read/tools.py:71-145)"""
     name = fname if isinstance(fname, str) else getattr(fname, 'name', '')
-    low = name.lower()
-    if low.endswith(('.fchk', '.fch')):
-        return 'fchk'
-    for ext, t in (('.molden', 'molden'), ('.mold', 'molden'), ('.wfn', 'wfn'), ('.wfx', 'wfx'), ('.log', 'gaussian.log'),
-                   ('.in', 'aomix'), ('.npz', 'native'), ('.hdf5', 'native'), ('.h5', 'native')):
-        if low.endswith(ext):
-            return t
+    ext = (extension or name.split('.')[-1]).lower()
+    if ext in ('fchk', 'wfx', 'wfn'):
+        return ext
+    if ext in ('numpy', 'npz', 'hdf5', 'h5'):
+        return 'native'
     if isinstance(fname, str):
-        with open(fname, 'r', encoding='iso-8859-1') as f:
-            head = f.read(4096)
-        if 'Number of atoms' in head and re.search(r'^.{40} {3}[IR] ', head, re.M):
-            return 'fchk'
-        if _RE_MOLDEN.search(head):
-            return 'molden'
-    raise NotImplementedError('cannot determine the type of %r; pass itype=' % (name,))
+        with open(fname, 'rb') as f:
+            text = f.read().decode('iso-8859-1')
+    else:
+        text = fname.read()
+        fname.seek(0)
+        if isinstance(text, bytes):
+            text = text.decode('iso-8859-1')
+    for itype, rex in _MAGIC:
+        if rex.search(text):
+            return itype
+    raise NotImplementedError('File format not reccognized or reader not implemented!')
 
 
 def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **kwargs):
@@ -432,7 +443,7 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
         itype = find_itype(fname)
     if itype not in readers:
         if itype in _OTHER:
-            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk, Molden, .wfn and .wfx files; use the reference\'s reader for %r and pass '
+            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk, Molden, .wfn, .wfx, GAMESS-US and AOMix files; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
     display('Loading data from {0} type file {1}\n'.format(itype, fname if isinstance(fname, str)

@@ -53,7 +53,8 @@ def main():
     files = {}
     for rel in ['gaussian/h2o_rhf_sph.fchk', 'gaussian/h2o_uhf_sph.fchk', 'gaussian/h2o_rhf_cart.fchk',
                 'molpro/h2o_rhf_sph.molden', 'molpro/nh3.mold', 'psi4/lih_cis_aug-cc-pVTZ.out.default.molden',
-                'gamess/water_gamess-us.wfn', 'orca/1.wfx']:
+                'gamess/water_gamess-us.wfn', 'orca/1.wfx', 'gamess/formaldehyde.log',
+                'turbomole/h2o_rhf_sph/aomix.in']:
         with open(os.path.join(odir, rel), 'rb') as f:
             files['file.' + os.path.basename(rel)] = numpy.frombuffer(f.read(), dtype=numpy.uint8)
     numpy.savez_compressed(os.path.join(HERE, 'reader_inputs.npz'), **files)

@@ -391,8 +391,12 @@ def test_fchk_reader_equals_reference_reader(tmp_path):
         read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), spin='alpha')        # restricted file
     with pytest.raises(IOError):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
+    glog = os.path.join(inputs, 'run.log')                    # a Gaussian log file is recognised but has no reader here
+    with open(glog, 'w') as f:
+        f.write(' Copyright (c) 1988,1990,1992,1993,1995,1998,2003,2009,2013,\n            Gaussian, Inc.  All Rights Reserved.\n')
+    assert read.find_itype(glog) == 'gaussian_log'
     with pytest.raises(NotImplementedError):
-        read.main_read('something.log')
+        read.main_read(glog)
 
 
 def test_wfn_and_wfx_readers_equal_reference_readers(tmp_path):
@@ -422,6 +426,31 @@ def test_wfn_and_wfx_readers_equal_reference_readers(tmp_path):
         read.main_read(wfx, spin='gamma')
     with pytest.raises(IOError):
         read.read_wfx(io.StringIO('<Keywords>\n STO\n</Keywords>\n'))
+
+
+def test_gamess_and_aomix_readers_equal_reference_readers(tmp_path):
+    """read_gamess / read_aomix == the reference's readers on its GAMESS-US (formaldehyde, f functions, explicit lxlylz) and
+    Turbomole tm2aomix test outputs; the file type is found from the content like the reference does (magic strings)"""
+    import os
+    from conftest import load_golden, reader_input
+    from orbkit_b200 import read, options
+    options.quiet = True
+    inputs = str(tmp_path)
+    log, aomix = reader_input('formaldehyde.log', inputs), reader_input('aomix.in', inputs)
+    assert read.find_itype(log) == 'gamess' and read.find_itype(aomix) == 'aomix'
+    assert read.find_itype(reader_input('nh3.mold', inputs)) == 'molden'
+    for g, path in ((load_golden('formaldehyde_gamess'), log), (load_golden('h2o_turbomole_aomix'), aomix)):
+        qc = read.main_read(path, all_mo=True)
+        for k, v in _flat_qc(qc).items():
+            assert v.shape == g[k].shape and (v == g[k]).all(), (path, k)
+    occ = read.main_read(log)                                  # all_mo=False: occupied orbitals only
+    assert len(occ.mo_spec) == 8 and (occ.mo_spec.get_occ() == 2.0).all()
+    with pytest.raises(IOError):
+        read.main_read(log, spin='alpha')                      # restricted calculation
+    with pytest.raises(NotImplementedError):
+        read.read_gamess(log, read_properties=True)
+    with pytest.raises(IOError):
+        read.read_aomix(log)                                   # no [AOMix Format] keyword
 
 
 def test_molden_reader_equals_reference_reader(tmp_path):
