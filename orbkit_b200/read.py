@@ -1,8 +1,9 @@
 """Readers -> QCinfo for the grid path (orbkit/read/high_level.py:33-79).
 
-Only the formats BASELINE configs[0] names are built: Gaussian formatted checkpoint files
-(read_gaussian_fchk, orbkit/read/gaussian_fchk.py:11-324) and Molden files (read_molden, orbkit/read/molden.py:47-402).
-The other readers of the reference stay with the reference; `main_read` raises NotImplementedError for them.
+This module: Gaussian formatted checkpoint files (read_gaussian_fchk, orbkit/read/gaussian_fchk.py:11-324), Molden files
+(read_molden, orbkit/read/molden.py:47-402), `find_itype` and `main_read`.  The other formats live in read_wf.py (.wfn, .wfx),
+read_gamess.py, read_aomix.py and read_glog.py (Gaussian .log); the cclib bridge and the `native` containers are not built
+(`main_read` raises NotImplementedError for them).
 
 Mechanism: an fchk file is a sequence of named sections (`<name, 40 columns> <type I/R/C> [N=] <value or count>` followed,
 for arrays, by the values).  The file is cut into sections once, the arrays are converted by NumPy, and the QCinfo is
@@ -402,10 +403,12 @@ def read_molden(fname, all_mo=False, spin=None, i_md=-1, interactive=False, **kw
 from .read_wf import read_wfn, read_wfx          # noqa: E402  (primitive-based wave-function files)
 from .read_aomix import read_aomix               # noqa: E402
 from .read_gamess import read_gamess             # noqa: E402
+from .read_glog import read_gaussian_log         # noqa: E402
 
 readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden,
-           'wfn': read_wfn, 'wfx': read_wfx, 'aomix': read_aomix, 'gamess': read_gamess}
-_OTHER = ('gaussian.log', 'gaussian_log', 'cclib', 'native')
+           'wfn': read_wfn, 'wfx': read_wfx, 'aomix': read_aomix, 'gamess': read_gamess,
+           'gaussian.log': read_gaussian_log, 'gaussian_log': read_gaussian_log}
+_OTHER = ('cclib', 'native')
 
 
 _MAGIC = (('molden', re.compile(r'\[[ ]{,}[Mm]olden[ ]+[Ff]ormat[ ]{,}\]')),
@@ -443,7 +446,7 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
         itype = find_itype(fname)
     if itype not in readers:
         if itype in _OTHER:
-            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk, Molden, .wfn, .wfx, GAMESS-US and AOMix files; use the reference\'s reader for %r and pass '
+            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk / .log, Molden, .wfn, .wfx, GAMESS-US and AOMix files; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
     display('Loading data from {0} type file {1}\n'.format(itype, fname if isinstance(fname, str)

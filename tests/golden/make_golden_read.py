@@ -50,10 +50,24 @@ def main():
         out['wfx_beta.' + k] = v
     print('wfx_beta', len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
     numpy.savez_compressed(os.path.join(HERE, 'read_wf.npz'), **out)
+    # Gaussian .log files (GFINPUT + POP=FULL): restricted spherical, unrestricted Cartesian, the occupied orbitals of the unrestricted
+    # spherical file, occupied orbitals only
+    out = {}
+    for name, fn, kw in [('rhf_sph', 'h2o_rhf_sph.inp.log', dict(all_mo=True)),
+                         ('uhf_cart', 'h2o_uhf_cart.inp.log', dict(all_mo=True)),
+                         ('uhf_sph_occ', 'h2o_uhf_sph.inp.log', dict(all_mo=False)),
+                         ('rhf_cart_occ', 'h2o_rhf_cart.inp.log', dict(all_mo=False))]:
+        qc = read.main_read(os.path.join(gdir, fn), interactive=False, **kw)
+        for k, v in mg.qc_arrays(qc).items():
+            out[name + '.' + k] = v
+        out[name + '.etot'] = numpy.array(qc.etot)
+        print('glog', name, len(qc.mo_spec), 'MOs', qc.ao_spec.get_ao_num(), 'AOs')
+    numpy.savez_compressed(os.path.join(HERE, 'read_glog.npz'), **out)
     files = {}
     for rel in ['gaussian/h2o_rhf_sph.fchk', 'gaussian/h2o_uhf_sph.fchk', 'gaussian/h2o_rhf_cart.fchk',
                 'molpro/h2o_rhf_sph.molden', 'molpro/nh3.mold', 'psi4/lih_cis_aug-cc-pVTZ.out.default.molden',
-                'gamess/water_gamess-us.wfn', 'orca/1.wfx', 'gamess/formaldehyde.log',
+                'gaussian/h2o_rhf_sph.inp.log', 'gaussian/h2o_uhf_cart.inp.log', 'gaussian/h2o_uhf_sph.inp.log',
+                'gaussian/h2o_rhf_cart.inp.log', 'gamess/water_gamess-us.wfn', 'orca/1.wfx', 'gamess/formaldehyde.log',
                 'turbomole/h2o_rhf_sph/aomix.in']:
         with open(os.path.join(odir, rel), 'rb') as f:
             files['file.' + os.path.basename(rel)] = numpy.frombuffer(f.read(), dtype=numpy.uint8)

@@ -391,12 +391,40 @@ def test_fchk_reader_equals_reference_reader(tmp_path):
         read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), spin='alpha')        # restricted file
     with pytest.raises(IOError):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
-    glog = os.path.join(inputs, 'run.log')                    # a Gaussian log file is recognised but has no reader here
-    with open(glog, 'w') as f:
-        f.write(' Copyright (c) 1988,1990,1992,1993,1995,1998,2003,2009,2013,\n            Gaussian, Inc.  All Rights Reserved.\n')
-    assert read.find_itype(glog) == 'gaussian_log'
     with pytest.raises(NotImplementedError):
-        read.main_read(glog)
+        read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), itype='cclib')     # cclib is not in the image
+
+
+def test_gaussian_log_reader_equals_reference_reader(tmp_path):
+    """read_gaussian_log == the reference's reader on its four Gaussian .log test outputs (GFINPUT + POP=FULL): restricted /
+    unrestricted, pure-spherical (the (l, m) labels come from the coefficient rows) / Cartesian, all / occupied orbitals"""
+    import os
+    from conftest import load_golden, reader_input
+    from orbkit_b200 import read, options
+    options.quiet = True
+    inputs = str(tmp_path)
+    g = load_golden('read_glog')
+    for name, fn, kw in [('rhf_sph', 'h2o_rhf_sph.inp.log', dict(all_mo=True)),
+                         ('uhf_cart', 'h2o_uhf_cart.inp.log', dict(all_mo=True)),
+                         ('uhf_sph_occ', 'h2o_uhf_sph.inp.log', dict(all_mo=False)),
+                         ('rhf_cart_occ', 'h2o_rhf_cart.inp.log', dict(all_mo=False))]:
+        path = reader_input(fn, inputs)
+        assert read.find_itype(path) == 'gaussian_log'
+        qc = read.main_read(path, **kw)
+        for k, v in _flat_qc(qc).items():
+            ref = g[name + '.' + k]
+            assert v.shape == ref.shape and (v == ref).all(), (fn, kw, k)
+        assert qc.etot == float(g[name + '.etot'])
+    # the fchk file of the same calculation holds the same basis and (to the printed digits) the same orbitals
+    fq = read.main_read(reader_input('h2o_rhf_sph.fchk', inputs), all_mo=True)
+    lq = read.main_read(os.path.join(inputs, 'h2o_rhf_sph.inp.log'), all_mo=True)
+    assert numpy.abs(numpy.abs(fq.mo_spec.get_coeffs()) - numpy.abs(lq.mo_spec.get_coeffs())).max() < 1e-5
+    with pytest.raises(IOError):                               # like the reference: no per-orbital spin with symmetries
+        read.main_read(os.path.join(inputs, 'h2o_uhf_sph.inp.log'), spin='beta')
+    with pytest.raises(IOError):
+        read.main_read(os.path.join(inputs, 'h2o_uhf_sph.inp.log'), spin='gamma')
+    with pytest.raises(IOError):
+        read.read_gaussian_log(reader_input('nh3.mold', inputs))                  # no `Entering Link 1`
 
 
 def test_wfn_and_wfx_readers_equal_reference_readers(tmp_path):
