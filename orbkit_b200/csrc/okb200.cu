@@ -1703,7 +1703,10 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
     CU(cudaSetDevice(ctx->device));
     const int kp = std::max(4, (nk + 3) / 4 * 4), ntp = (nt + 63) / 64 * 64;
     // several k chunks: every pass over 8 MTB time steps re-reads `in`, so take the taller pass
-    const int mtb = (kp > TD_KC && nt > 32) ? 8 : 4;
+    // (A/B: OKB_TD_MTB=4|8 forces one)
+    static const char *force_mtb = getenv("OKB_TD_MTB");
+    int mtb = (kp > TD_KC && nt > 32) ? 8 : 4;
+    if (force_mtb && force_mtb[0]) mtb = atoi(force_mtb) == 8 ? 8 : 4;
     std::vector<double> wp((size_t)ntp * kp, 0.0);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < nk; ++k) wp[(size_t)t * kp + k] = w[(size_t)t * nk + k];
