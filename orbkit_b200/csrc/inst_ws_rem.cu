@@ -9,6 +9,9 @@ namespace okb {
 static const Variant table[] = {
     OKB_WSR(SET_GRAD, 10, 1, 1, 4, 8, 3, SINK_RHO, 2), OKB_WSR(SET_GRAD, 10, 1, 1, 4, 8, 3, SINK_MO, 2),
     OKB_WSR(SET_D2P, 10, 1, 1, 4, 8, 3, SINK_RHO, 2),
+    // 74-wide tile = 9 blocks + 2: 222 MOs (benzene def2-TZVP, BASELINE configs[1]) = 3 x 74 instead of 3 x 80
+    OKB_WSR(SET_GRAD, 9, 1, 1, 4, 8, 3, SINK_RHO, 2), OKB_WSR(SET_GRAD, 9, 1, 1, 4, 8, 3, SINK_MO, 2),
+    OKB_WSR(SET_D2P, 9, 1, 1, 4, 8, 3, SINK_RHO, 2),
 };
 OKB_TABLE(okb_variants_rem, table);
 
