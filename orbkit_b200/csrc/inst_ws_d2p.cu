@@ -7,6 +7,7 @@ namespace okb {
 
 static const Variant table[] = {
     OKB_WS(SET_D2P, 11, 1, 1, 4, 8, 3, SINK_RHO), OKB_WS(SET_D2P, 12, 1, 1, 4, 8, 3, SINK_RHO),
+    // (12 producer warps with the 88-wide tile: second pass 146 instead of 143 ms -- not kept)
     OKB_WS(SET_D2P, 3, 1, 1, 4, 12, 3, SINK_RHO), OKB_WS(SET_D2P, 3, 1, 1, 4, 8, 3, SINK_RHO),
     // 80-wide tile: less padding for MO counts such as 222 (3 x 80 instead of 3 x 88) or 160
     OKB_WS(SET_D2P, 10, 1, 1, 4, 8, 3, SINK_RHO),

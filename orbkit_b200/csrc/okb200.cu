@@ -1076,7 +1076,11 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         // Remainder orbitals (v.rem of the v.MC, contracted by the producer warps) are charged 3 DMMA columns each:
         // 82 MOs go to the 80 + 2 tile (86) instead of the 88-wide one, 83..88 MOs stay on the latter.
         const long long n_tiles = (n_mo + v.MC - 1) / v.MC;
-        const long long cost = n_tiles * std::max(v.MC + 2 * v.rem, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
+        // (The second laplacian pass, SET_D2P, has 3 sets per row for the consumers but the heaviest generators: there the
+        // producers bound the kernel and a remainder orbital costs more than its DMMA columns -- 82 MOs: 88-wide 144 ms,
+        // 80 + 2 148 ms, profiles/r02_lap_passes_ab.txt -- so it is charged 5 columns.)
+        const int rem_cols = set == SET_D2P ? 5 : 3;
+        const long long cost = n_tiles * std::max(v.MC - v.rem + rem_cols * v.rem, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;
