@@ -333,7 +333,10 @@ __global__ void __launch_bounds__((WM * WN + NPW) * 32, 1) okb_ws_kernel(const K
                     double *tile = tbase + (size_t)s * C::TILE_DOUBLES;
                     // the host sorts the shells of a chunk by descending cost; items are dealt to the warps in
                     // boustrophedon order (0..NPW-1, NPW-1..0, ...), rotated per chunk
-                    const int nitems = hdr.nshell * PG, wrot = (pwarp + g) % NPW;
+                    // (rotated by the chunk's index IN THE PASS, not by the CTA's running chunk counter: which warp
+                    // evaluates which shell of a tile must not depend on how a request is cut into launches -- the remainder
+                    // orbitals' partial sums are grouped by warp, and results stay bit-identical across slabs and shards)
+                    const int nitems = hdr.nshell * PG, wrot = (pwarp + c) % NPW;
                     for (int r = 0; r * NPW < nitems; ++r) {
                         const int item = r * NPW + ((r & 1) ? NPW - 1 - wrot : wrot);
                         if (item >= nitems) continue;

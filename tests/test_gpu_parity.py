@@ -502,6 +502,21 @@ for name in %(names)r:
     # two rho_compute calls with the same inputs are bit-identical (the remainder partial sums are added in a fixed order)
     r2, d2 = ok.rho_compute(qc, drv=['x', 'y', 'z'])
     assert numpy.array_equal(d, d2) and numpy.array_equal(r, r2)
+# results do not depend on how the points are cut into launches (slabs of a big request, shards of a multi-GPU job): the
+# remainder orbitals' partial sums are grouped by producer warp, and which warp takes which shell is fixed per tile
+qc, a = golden_qc('lih_psi4_sph_f')
+eng = get_engine()
+ax = numpy.linspace(-4.0, 4.0, 40)
+basis = eng.basis(qc.geo_spec, qc.ao_spec)
+mo = eng.mos(basis, qc.mo_spec.get_coeffs(), qc.mo_spec.get_occ())
+g = eng.grid_regular(ax, ax, ax)
+n = 40 ** 3
+whole = eng.eval_rho(mo, g, [1, 2, 3])
+for cut in (128, 4096, 33920):
+    lo = eng.eval_rho(mo, g, [1, 2, 3], 0, cut)
+    hi = eng.eval_rho(mo, g, [1, 2, 3], cut, n)
+    assert numpy.array_equal(numpy.concatenate([lo[0], hi[0]]), whole[0]), cut
+    assert numpy.array_equal(numpy.concatenate([lo[1], hi[1]], axis=1), whole[1]), cut
 print('kernels', sorted(seen))
 assert any('MB10R2' in k for k in seen), seen
 '''
