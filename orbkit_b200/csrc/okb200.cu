@@ -1284,10 +1284,15 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
     static const bool no_zrun = getenv("OKB_NO_ZRUN") != nullptr;          // A/B measurements only
     bool zrun_ok = rq.sink == SINK_AO && g->kind == 0 && !no_zrun;
     if (zrun_ok) {
-        bool all_values = true;
-        for (const Pass &ps : passes) all_values &= (ps.set == SET_VAL);
-        for (const DevShell &sh : b->shells) all_values &= (sh.L <= ZR_MAXL);
-        zrun_ok = all_values;
+        // values and the derivative codes 1..6 (one launch per code); the mixed second derivatives 7..9 keep the
+        // kernels that reproduce the reference's formulas
+        bool all_ok = true;
+        for (int i = 0; i < rq.n_codes; ++i) all_ok &= (rq.codes[i] >= 0 && rq.codes[i] <= 6);
+        for (const DevShell &sh : b->shells) all_ok &= (sh.L <= ZR_MAXL);
+        static const bool no_zrun_drv = getenv("OKB_NO_ZRUN_DRV") != nullptr;   // A/B measurements only
+        if (no_zrun_drv)
+            for (int i = 0; i < rq.n_codes; ++i) all_ok &= (rq.codes[i] == 0);
+        zrun_ok = all_ok;
     }
     if (rq.sink != SINK_AO || ao_tables || zrun_ok) {
         rc = ensure_axis_tables(ctx, b, g, &tabx, &taby, &tabz);
@@ -1364,12 +1369,17 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                 p.ld = ld;
                 p.slot_stride = (long long)n_rows * ld;
                 for (int k = 0; k < 10; ++k) p.slot[k] = ps.slot[k];
-                p.one_code = 0;
                 p.out = (dev_out ? rq.out + s0 : dbase) + u0;
-                cudaError_t e = okb_launch_ao_zrun(p, ctx->sm_count, ctx->stream);
-                if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "launch of %s failed: %s", okb_ao_zrun_name(), cudaGetErrorString(e));
-                ctx->launches++;
-                ctx->last_kernel = okb_ao_zrun_name();
+                for (int code = 0; code <= 6; ++code) {      // every code this pass writes: its own launch
+                    const bool in_pass = ps.set == SET_ONE ? code == ps.one_code : ps.slot[code] >= 0;
+                    if (!in_pass || ps.slot[code] < 0) continue;
+                    p.one_code = code;
+                    cudaError_t e = okb_launch_ao_zrun(p, ctx->sm_count, ctx->stream);
+                    if (e != cudaSuccess)
+                        return fail(OKB_ERR_CUDA, "launch of %s failed: %s", okb_ao_zrun_code_name(code), cudaGetErrorString(e));
+                    ctx->launches++;
+                    ctx->last_kernel = okb_ao_zrun_code_name(code);
+                }
                 continue;
             }
             const bool use_mix = !b->mix_is_cart &&

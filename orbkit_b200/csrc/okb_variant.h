@@ -23,5 +23,6 @@ extern const VariantTable okb_variants_tile, okb_variants_val, okb_variants_grad
 // z-run SINK_AO kernel for regular grids (inst_ao_zrun.cu)
 cudaError_t okb_launch_ao_zrun(const KParams &p, int sm_count, cudaStream_t st);
 const char *okb_ao_zrun_name();
+const char *okb_ao_zrun_code_name(int code);     // kernel name of a launch for derivative code 0..6
 
 }  // namespace okb

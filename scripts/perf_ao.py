@@ -25,7 +25,8 @@ def timed(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 for name, heavy, light, sph, codes in (('c3 sph', 24, 20, True, [0]), ('c3 cart', 24, 20, False, [0]), ('c2-like', 6, 6, True, [0]),
-                                       ('c3 sph d/dx', 24, 20, True, [1]), ('c3 sph grad', 24, 20, True, [1, 2, 3]), ('c3 sph 7 sets', 24, 20, True, [0, 1, 2, 3, 4, 5, 6]),
+                                       ('c3 sph d/dx', 24, 20, True, [1]), ('c3 sph d/dz', 24, 20, True, [3]), ('c3 sph d2/dx2', 24, 20, True, [4]),
+                                       ('c3 sph d2/dz2', 24, 20, True, [6]), ('c3 sph grad', 24, 20, True, [1, 2, 3]), ('c3 sph 7 sets', 24, 20, True, [0, 1, 2, 3, 4, 5, 6]),
                                        ('c3 sph 10 sets', 24, 20, True, list(range(10)))):
     qc = synth.to_qcinfo(synth.make_molecule(n_heavy=heavy, n_light=light, n_mo=8, seed=0, spherical=sph))
     n_ao = qc.ao_spec.get_ao_num()

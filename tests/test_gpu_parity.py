@@ -471,6 +471,22 @@ def test_calc_ao_zrun_kernel_regular_grids(ok, oracle_mod, name):
     # ao_creator (core.py:38-105) takes the same route
     got = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, x=ax[0], y=ax[1], z=ax[2], is_vector=False)
     assert numpy.array_equal(got.reshape(full[0].shape), full[0])
+    # first and pure second derivatives (codes 1..6): one launch per code, A(Z) R0 + B(Z) R1 [+ C(Z) R2]
+    for shape in ((3, 4, 5), (2, 3, 37), (2, 2, 130)):
+        ax = [numpy.sort(rng.uniform(-3.5, 3.5, n)) for n in shape]
+        set_regular(ok, *ax)
+        drv = ['x', 'y', 'z', 'xx', 'yy', 'zz']
+        got = ok.rho_compute(qc, calc_ao=True, drv=drv)
+        assert eng.last_kernel().startswith('zrun/ONE6'), eng.last_kernel()
+        for i, d in enumerate(drv):
+            ref = oracle_mod.ao_creator(qc.geo_spec, qc.ao_spec, drv=d, x=ax[0], y=ax[1], z=ax[2], is_vector=False)
+            assert_close(got[i], ref.reshape(got[i].shape), '%s zrun d/d%s %s' % (name, d, shape), afloor=1e-13)
+        one = ok.core.ao_creator(qc.geo_spec, qc.ao_spec, drv='y', x=ax[0], y=ax[1], z=ax[2], is_vector=False)
+        assert eng.last_kernel().startswith('zrun/ONE2')
+        assert numpy.array_equal(one.reshape(got[1].shape), got[1])
+        mixed = ok.rho_compute(qc, calc_ao=True, drv=[None, 'z', 'xy'])          # a mixed code: not the z-run kernel
+        assert not eng.last_kernel().startswith('zrun/')
+        assert_close(mixed[1], got[2], '%s zrun vs tile kernel d/dz' % name, afloor=1e-13)
 
 
 _REM_WORKER = r'''
