@@ -231,12 +231,15 @@ def run_b200(args):
         aobuf = torch.empty((1, N_AO, n_sub), dtype=torch.float64, device=dev)
         ms_ao = timed(lambda: eng.eval_ao(basis, g, [0], p0, p0 + n_sub, out=aobuf.data_ptr(), flags=OKB_FLAG_OUT_DEVICE))
         ao_kernel = eng.last_kernel()
+        ms_ao_dx = timed(lambda: eng.eval_ao(basis, g, [1], p0, p0 + n_sub, out=aobuf.data_ptr(), flags=OKB_FLAG_OUT_DEVICE))
+        ao_dx_kernel = eng.last_kernel()
         del aobuf
         also = {'rho_ms': round(ms_rho, 3), 'rho_tflops_alg': round(2.0 * N_MO * N_AO * n_loc / ms_rho / 1e9, 2),
                 'rho_laplacian_ms': round(ms_lap, 3),
                 'rho_laplacian_tflops_alg': round(2.0 * N_MO * N_AO * 7 * n_loc / ms_lap / 1e9, 2),
                 'calc_ao_ms_per_1e6_points': round(ms_ao * 1e6 / n_sub, 3),
                 'calc_ao_gbs_stored': round(8.0 * N_AO * n_sub / ms_ao / 1e6, 1), 'calc_ao_kernel': ao_kernel,
+                'calc_ao_ddx_gbs_stored': round(8.0 * N_AO * n_sub / ms_ao_dx / 1e6, 1), 'calc_ao_ddx_kernel': ao_dx_kernel,
                 'note': 'per GPU, device resident, same molecule; algorithmic flops 2*n_mo*n_ao*D per point (D = 1, 7)'}
 
     # ---- end to end through the public API: QCinfo + grid in, NumPy out, every step ------------------
