@@ -22,6 +22,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
 OKB_FLAG_EXACT_MIXED = 1
 OKB_FLAG_OUT_DEVICE = 2
 OKB_FLAG_IN_DEVICE = 4
+OKB_FLAG_CI_FAST = 8
 OKB_CI_RHO, OKB_CI_JAB, OKB_CI_A_NABLA_B, OKB_CI_PAIRS, OKB_CI_JAB_PAIRS = 0, 1, 2, 3, 4
 
 c_int_p = ctypes.POINTER(ctypes.c_int)

@@ -82,6 +82,8 @@ struct okb_ctx {
     size_t norm_cap = 0;
     void *ci_buf = nullptr;                  // detCI: term arrays + MO slab + output slab
     size_t ci_bytes = 0;
+    void *rdm_buf = nullptr;                 // detCI, OKB_FLAG_CI_FAST: dense orbital-pair matrix + row list
+    size_t rdm_bytes = 0;
     double *phi_buf = nullptr;               // rho + laplacian: MO values between the two passes
     size_t phi_bytes = 0;
     // Recycled device buffers of destroyed handles (chunk tables, coefficient tiles, axes, axis tables).
@@ -237,6 +239,7 @@ extern "C" int okb_ctx_destroy(okb_ctx *c) {
     }
     if (c->norm_dev) cudaFree(c->norm_dev);
     if (c->ci_buf) cudaFree(c->ci_buf);
+    if (c->rdm_buf) cudaFree(c->rdm_buf);
     if (c->phi_buf) cudaFree(c->phi_buf);
     for (auto &e : c->pool) cudaFree(e.first);
     cudaStreamDestroy(c->stream);
@@ -1567,6 +1570,161 @@ static int ci_upload_terms(okb_ctx *ctx, int n_terms, const double *coef, const 
     return OKB_OK;
 }
 
+static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p);
+
+// OKB_FLAG_CI_FAST, many terms per orbital pair (the usual shape of a CI expansion: 1e4 .. 1e6 determinant pairs over a few
+// dozen active orbitals): the terms are summed on the host into the dense matrix of the orbital pairs,
+//   RHO   M = D             out    = sum_a phi_a (M phi)_a          D[a][b] = sum of the c_t with (a_t, b_t) = (a, b)
+//   ANB   M = D             out[d] = sum_a phi_a (M d_d phi)_a
+//   JAB   M = -(D - D^T)/2, JABF: M = D - D^T  (same form as ANB)
+// and the grid work becomes n_act^2 fused multiply-adds per point on the FP64 tensor path (okb_td_kernel<MTB, true>)
+// instead of n_terms gathers.  Taken when r n_terms >= n_act^2, r = the measured cost of a term of the split kernel in
+// matrix entries of the DMMA kernel (rho 4.5, jab 3.8, a_nabla_b 2.5: profiles/r02_ci_fast.txt; OKB_CI_DENSE=0|1 forces
+// either).
+struct CiDensePlan {
+    bool on = false;
+    int n_act = 0, kp = 0;
+    const double *d_w = nullptr;
+    const int *d_rows = nullptr;
+};
+
+static int ci_dense_plan(okb_ctx *ctx, int mode, int n_mo, int n_terms, const double *coef, const int *ia, const int *ib,
+                         CiDensePlan *pl) {
+    pl->on = false;
+    if (!(mode == CI_RHO || mode == CI_JAB || mode == CI_ANB || mode == CI_JABF) || n_terms == 0) return OKB_OK;
+    std::vector<int> idx(n_mo, -1), rows;
+    for (int t = 0; t < n_terms; ++t) {
+        if (idx[ia[t]] < 0) idx[ia[t]] = 1;
+        if (idx[ib[t]] < 0) idx[ib[t]] = 1;
+    }
+    for (int m = 0; m < n_mo; ++m)
+        if (idx[m] > 0) {
+            idx[m] = (int)rows.size();
+            rows.push_back(m);
+        }
+    const int n_act = (int)rows.size();
+    static const char *force = getenv("OKB_CI_DENSE");
+    const double r = mode == CI_RHO ? 4.5 : mode == CI_ANB ? 2.5 : 3.8;
+    bool dense = (double)n_terms * r >= (double)n_act * n_act;
+    if (force && force[0]) dense = atoi(force) != 0;
+    if (!dense || n_act > 4096) return OKB_OK;
+    const int kp = std::max(4, (n_act + 3) / 4 * 4), ntp = (n_act + 63) / 64 * 64;
+    std::vector<double> d((size_t)n_act * n_act, 0.0), w((size_t)ntp * kp, 0.0);
+    for (int t = 0; t < n_terms; ++t) d[(size_t)idx[ia[t]] * n_act + idx[ib[t]]] += coef[t];
+    for (int a = 0; a < n_act; ++a)
+        for (int b = 0; b < n_act; ++b) {
+            const double dab = d[(size_t)a * n_act + b], dba = d[(size_t)b * n_act + a];
+            w[(size_t)a * kp + b] = mode == CI_JAB ? -0.5 * (dab - dba) : mode == CI_JABF ? dab - dba : dab;
+        }
+    const size_t wbytes = (w.size() * 8 + 255) / 256 * 256, need = wbytes + (size_t)n_act * 4;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->rdm_bytes < need) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->rdm_buf) CU(cudaFree(ctx->rdm_buf));
+        ctx->rdm_buf = nullptr;
+        ctx->rdm_bytes = 0;
+        CU(cudaMalloc(&ctx->rdm_buf, need));
+        ctx->rdm_bytes = need;
+    }
+    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->rdm_buf);
+    // pageable sources: the copies return after the host vectors were read
+    CU(cudaMemcpyAsync(base, w.data(), w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + wbytes, rows.data(), (size_t)n_act * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h2d_bytes += (long long)(w.size() * 8 + (size_t)n_act * 4);
+    pl->on = true;
+    pl->n_act = n_act;
+    pl->kp = kp;
+    pl->d_w = reinterpret_cast<const double *>(base);
+    pl->d_rows = reinterpret_cast<const int *>(base + wbytes);
+    return OKB_OK;
+}
+
+static int ci_launch_dense(okb_ctx *ctx, int mode, const CiParams &p, const CiDensePlan &pl) {
+    TdParams t{};
+    t.w = pl.d_w;
+    t.rows = pl.d_rows;
+    t.phi = p.mo;
+    t.in = mode == CI_RHO ? p.mo : p.dmo;
+    t.dstride_in = p.dstride;
+    t.ncomp = mode == CI_RHO ? 1 : mode == CI_JABF ? p.ncomp : 3;
+    t.out = p.out;
+    t.ldi = p.ld; t.ldo = p.ldo; t.n = p.npts;
+    t.nt = t.nk = pl.n_act;
+    t.kp = pl.kp;
+    t.vec_ok = (reinterpret_cast<uintptr_t>(p.mo) % 16 == 0 && p.ld % 2 == 0) ? 1 : 0;
+    const int mtb = (pl.kp > TD_KC && pl.n_act > 32) ? 8 : 4;
+    const long long tiles = (p.npts + TD_P - 1) / TD_P;
+    if (tiles * t.ncomp > 0x7fffffffLL) return fail(OKB_ERR_ARG, "ci: too many points for one launch");
+    const unsigned grid = (unsigned)(tiles * t.ncomp);
+    CU(cudaFuncSetAttribute(okb_td_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 4)));
+    CU(cudaFuncSetAttribute(okb_td_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 8)));
+    if (mtb == 8) okb_td_kernel<8, true><<<grid, TD_NT, td_smem(pl.kp, 8), ctx->stream>>>(t);
+    else okb_td_kernel<4, true><<<grid, TD_NT, td_smem(pl.kp, 4), ctx->stream>>>(t);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "dense ci kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ctx->last_kernel = mode == CI_RHO ? "ci-dense/rho" : mode == CI_JAB ? "ci-dense/jab" : mode == CI_ANB ? "ci-dense/a_nabla_b"
+                                                                                                     : "ci-dense/jab_full";
+    return OKB_OK;
+}
+
+// OKB_FLAG_CI_FAST: the term list split over the warps of a CTA, every MO row staged once (okb_ci_fast_kernel).  Needs
+// 16-byte aligned row segments and at least two points per tile in shared memory; everything else (and the ragged rest of
+// the points) goes to the bit-identical gather kernel.
+static int ci_launch_fast(okb_ctx *ctx, int mode, const CiParams &p, int n_mo, int nsets, const CiDensePlan &pl) {
+    if (pl.on) return ci_launch_dense(ctx, mode, p, pl);
+    const bool summed = mode == CI_RHO || mode == CI_JAB || mode == CI_ANB || mode == CI_JABF;
+    // tile width: 32 points when all row segments fit twice per SM (two resident CTAs: one stages while the other sums),
+    // else 16.  Narrower tiles lose: row segments under 128 bytes waste DRAM pages (500 MOs x 4 sets, 96^3 points: jab
+    // 11.6 ms at 4 points, 7.5 ms at 8 points in one CTA per SM, 9.5 ms gather kernel; a_nabla_b 11.2 / 6.4 / 5.0 ms --
+    // profiles/r02_ci_fast.txt), so wider row sets stay with the gather kernel.  A/B: OKB_CIF_PW = log2(points).
+    const size_t row_bytes = (size_t)n_mo * nsets * 8;
+    static const char *force_pw = getenv("OKB_CIF_PW");
+    int lpw = CIF_FIXED + (row_bytes << 5) <= (size_t)112 * 1024 ? 5 : 4;
+    const bool forced = force_pw && force_pw[0];
+    if (forced) lpw = std::max(1, std::min(5, atoi(force_pw)));
+    const int pw = 1 << lpw;
+    const size_t smem = CIF_FIXED + row_bytes * pw;
+    const bool aligned = reinterpret_cast<uintptr_t>(p.mo) % 16 == 0 && p.ld % 2 == 0 &&
+                         (nsets == 1 || (reinterpret_cast<uintptr_t>(p.dmo) % 16 == 0 && p.dstride % 2 == 0));
+    if (!summed || smem > (size_t)(forced ? 224 : 112) * 1024 || !aligned || p.npts < pw || p.n_terms == 0)
+        return ci_launch(ctx, mode, p);
+    CiFastParams q{};
+    q.p = p;
+    q.n_mo = n_mo; q.nsets = nsets; q.pw = pw; q.lpw = lpw;
+    q.ntiles = p.npts / pw;
+    const int per_sm = smem <= (size_t)112 * 1024 ? 2 : 1;
+    const unsigned grid = (unsigned)std::min<long long>(q.ntiles, (long long)ctx->sm_count * per_sm);
+    cudaError_t e = cudaSuccess;
+#define OKB_CIF_LAUNCH(M)                                                                                            \
+    e = cudaFuncSetAttribute(okb_ci_fast_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e == cudaSuccess) okb_ci_fast_kernel<M><<<grid, CIF_NW * 32, smem, ctx->stream>>>(q)
+    switch (mode) {
+        case CI_RHO: OKB_CIF_LAUNCH(CI_RHO); break;
+        case CI_JAB: OKB_CIF_LAUNCH(CI_JAB); break;
+        case CI_ANB: OKB_CIF_LAUNCH(CI_ANB); break;
+        default: OKB_CIF_LAUNCH(CI_JABF); break;
+    }
+#undef OKB_CIF_LAUNCH
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "fast ci kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    const long long done = q.ntiles * pw;
+    if (done < p.npts) {                                      // ragged rest: fewer than pw points
+        CiParams r = p;
+        r.mo = p.mo + done;
+        r.dmo = p.dmo ? p.dmo + done : nullptr;
+        r.out = p.out + done;
+        r.npts = p.npts - done;
+        const int rc = ci_launch(ctx, mode, r);
+        if (rc != OKB_OK) return rc;
+    }
+    ctx->last_kernel = mode == CI_RHO ? "ci-fast/rho" : mode == CI_JAB ? "ci-fast/jab" : mode == CI_ANB ? "ci-fast/a_nabla_b"
+                                                                                                    : "ci-fast/jab_full";
+    return OKB_OK;
+}
+
 static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
     if (p.npts <= 0) return OKB_OK;
     const unsigned grid = (unsigned)((p.npts + CI_NT - 1) / CI_NT);
@@ -1626,8 +1784,17 @@ static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, lo
     rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
     if (rc != OKB_OK) return rc;
     CiParams p{};
-    rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
-    if (rc != OKB_OK) return rc;
+    CiDensePlan dense;
+    if (flags & OKB_FLAG_CI_FAST) {
+        rc = ci_dense_plan(ctx, mode, n_mo, n_terms, coef, ia, ib, &dense);
+        if (rc != OKB_OK) return rc;
+    }
+    if (dense.on) {                                           // the dense form needs no term list on the device
+        p.n_terms = n_terms;
+    } else {
+        rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
+        if (rc != OKB_OK) return rc;
+    }
     unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
     double *d_in = reinterpret_cast<double *>(base + tbytes), *d_out = reinterpret_cast<double *>(base + tbytes + in_bytes);
     for (long long s0 = 0; s0 < npts; s0 += slab) {
@@ -1652,7 +1819,7 @@ static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, lo
         p.ncomp = mode == CI_JABF ? nd : 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? ld_out : sn;
-        rc = ci_launch(ctx, mode, p);
+        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch(ctx, mode, p);
         if (rc != OKB_OK) return rc;
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,
@@ -1816,8 +1983,17 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
     rc = ci_reserve(ctx, tbytes + in_bytes + (out_dev ? 0 : (size_t)ncomp * slab * 8));
     if (rc != OKB_OK) return rc;
     CiParams p{};
-    rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
-    if (rc != OKB_OK) return rc;
+    CiDensePlan dense;
+    if (flags & OKB_FLAG_CI_FAST) {
+        rc = ci_dense_plan(ctx, mode, n_mo, n_terms, coef, ia, ib, &dense);
+        if (rc != OKB_OK) return rc;
+    }
+    if (dense.on) {                                           // the dense form needs no term list on the device
+        p.n_terms = n_terms;
+    } else {
+        rc = ci_upload_terms(ctx, n_terms, coef, ia, ib, &p);
+        if (rc != OKB_OK) return rc;
+    }
     unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
     double *d_in = reinterpret_cast<double *>(base + tbytes), *d_out = reinterpret_cast<double *>(base + tbytes + in_bytes);
     for (long long s0 = 0; s0 < npts; s0 += slab) {
@@ -1835,7 +2011,7 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
         p.ncomp = 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? npts : sn;
-        rc = ci_launch(ctx, mode, p);
+        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch(ctx, mode, p);
         if (rc != OKB_OK) return rc;
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)npts * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,

@@ -128,6 +128,97 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
     }
 }
 
+// ---- fast variant: terms split over the warps of a CTA (OKB_FLAG_CI_FAST) ----------------------------------------------
+// The bit-identical kernel above is bound by re-fetched MO rows (3.5x the algorithmic DRAM bytes).  When the caller does not
+// need the reference's summation order -- the fused *_from_qc paths, whose MO values come from the device anyway -- the sum
+// over the term list is split: a CTA stages ALL n_mo x nsets row segments of a tile of PW points (a power of two <= 32) in
+// shared memory with 16-byte async copies (every MO value comes from HBM exactly once; bulk copies of these 32..256-byte
+// segments were measured at ~16 cycles per copy, TMA-issue bound), a warp is split into 32 / PW term slots, slot s of warp w
+// sums the terms (w 32/PW + s), + NW 32/PW, ... for the tile's points; the slots are added by shuffles, the warps in warp
+// order.  Deterministic (the grouping depends on nothing but the term list and PW), agreement with the sequential sum to
+// rounding.  Two CTAs per SM: one stages while the other sums.  HBM bound: 8 n_mo nsets bytes per point in, the results out.
+struct CiFastParams {
+    CiParams p;
+    int n_mo, nsets;           // rows per set; sets staged: 1 (rho) or 1 + ncomp (mo + derivative blocks)
+    int pw, lpw;               // points per tile = 1 << lpw
+    long long ntiles;          // full tiles; the ragged rest of the points is left to the kernel above
+};
+
+constexpr int CIF_NW = 16;     // warps per CTA
+constexpr size_t CIF_FIXED = (size_t)CIF_NW * 3 * 32 * 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(CIF_NW * 32, 2) okb_ci_fast_kernel(const CiFastParams q) {
+    extern __shared__ __align__(128) unsigned char cif_smem[];
+    const CiParams &p = q.p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PW = q.pw, nrow = q.n_mo * q.nsets;
+    double *part = reinterpret_cast<double *>(cif_smem);                       // [NW][3][PW]
+    double *buf = part + CIF_NW * 3 * 32;                                      // [set][mo][PW]
+    const uint32_t a_buf = smem_u32(buf);
+    const int ncomp = MODE == CI_RHO ? 1 : MODE == CI_JABF ? p.ncomp : 3;
+    const int nslot = 32 >> q.lpw, slot = lane >> q.lpw, pt = lane & (PW - 1);
+    const int seg16 = PW >> 1;                           // 16-byte pieces of a row segment
+    const int ncopy = nrow * seg16;
+    const size_t dstr = (size_t)q.n_mo * PW;
+    const double *mo = buf + pt, *d0 = mo + dstr;
+    for (long long tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x) {
+        const long long x0 = tile * PW;
+        __syncthreads();                                 // the previous tile (buf, part) is no longer read
+        for (int e = tid; e < ncopy; e += CIF_NW * 32) {
+            const int r = e >> (q.lpw - 1), piece = e & (seg16 - 1);
+            const int sset = r / q.n_mo, m = r - sset * q.n_mo;
+            const double *src = (sset == 0 ? p.mo : p.dmo + (size_t)(sset - 1) * p.dstride) + (size_t)m * p.ld + x0 + 2 * piece;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a_buf + (uint32_t)e * 16u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+#pragma unroll 2
+        for (int e = warp * nslot + slot; e < p.n_terms; e += CIF_NW * nslot) {
+            const double c = __ldg(p.tc + e);
+            const int ra = __ldg(p.ta + e) * PW, rb = __ldg(p.tb + e) * PW;
+            const double ma = mo[ra];
+            if (MODE == CI_RHO) {
+                acc0 = fma(c * ma, mo[rb], acc0);
+            } else if (MODE == CI_ANB) {
+                const double cm = c * ma;
+                acc0 = fma(cm, d0[rb], acc0);
+                acc1 = fma(cm, d0[dstr + rb], acc1);
+                acc2 = fma(cm, d0[2 * dstr + rb], acc2);
+            } else {
+                // JAB: -1/2 c (ma db - mb da);  JABF: c (ma db - mb da)
+                const double mb = mo[rb];
+                const double f = MODE == CI_JAB ? -0.5 * c : c;
+                acc0 = fma(f, fma(ma, d0[rb], -(mb * d0[ra])), acc0);
+                if (ncomp > 1) acc1 = fma(f, fma(ma, d0[dstr + rb], -(mb * d0[dstr + ra])), acc1);
+                if (ncomp > 2) acc2 = fma(f, fma(ma, d0[2 * dstr + rb], -(mb * d0[2 * dstr + ra])), acc2);
+            }
+        }
+        for (int off = 16; off >= PW; off >>= 1) {       // the term slots of the warp
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+            if (MODE != CI_RHO) {
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+                acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+            }
+        }
+        if (lane < PW) {
+            part[(warp * 3 + 0) * 32 + lane] = acc0;
+            if (MODE != CI_RHO) {
+                part[(warp * 3 + 1) * 32 + lane] = acc1;
+                part[(warp * 3 + 2) * 32 + lane] = acc2;
+            }
+        }
+        __syncthreads();
+        if (warp < ncomp && lane < PW) {                 // warp d adds the partial sums of component d in warp order
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < CIF_NW; ++w) sum += part[(w * 3 + warp) * 32 + lane];
+            p.out[(size_t)warp * p.ldo + x0 + lane] = sum;
+        }
+    }
+}
+
 // Measured alternatives (not kept).  Round 1: a tiled kernel that stages all n_mo row segments of a 24-32 point tile in
 // shared memory so that HBM delivers every MO value exactly once was 2x (rho) to 4x (jab) SLOWER than the gather kernel.
 // Round 2 (profiles/r02_ci_staged_vs_gather.txt): the same idea with one private tile per WARP, bulk-async copies issued by

@@ -41,9 +41,17 @@ struct TdParams {
     long long ldi, ldo, n;
     int nt, nk, kp;
     int vec_ok;            // out rows 16-byte aligned: paired stores
+    // RDM form (dense one-particle-matrix contraction of the detCI sums, OKB_FLAG_CI_FAST with many terms per orbital pair):
+    //   out[d][x] = sum_a phi[rows[a]][x] * sum_b w[a][b] in_d[rows[b]][x],   in_d = in + d * dstride_in, d < ncomp
+    // nt = nk = the number of orbitals the term list refers to; CTA (tile, d) = blockIdx.x = tile * ncomp + d, so the
+    // CTAs that share a phi tile run back to back (L2).
+    const double *phi;     // [*][ldi]
+    const int *rows;       // [nk] row of orbital k in phi / in
+    long long dstride_in;  // distance of the derivative blocks of `in`
+    int ncomp;
 };
 
-template <int MTB>
+template <int MTB, bool RDM = false>
 __global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const TdParams p) {
     constexpr int TD_MT = 8 * MTB;
     extern __shared__ __align__(16) unsigned char td_smem_raw[];
@@ -51,15 +59,22 @@ __global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const T
     double *wt = rt + (size_t)(p.kp < TD_KC ? p.kp : TD_KC) * TD_PS;   // [TD_MT][TD_WS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane >> 2, tc = lane & 3;
-    const long long x0 = (long long)blockIdx.x * TD_P;
+    const int comp = RDM ? (int)(blockIdx.x % (unsigned)p.ncomp) : 0;
+    const long long x0 = (long long)(RDM ? blockIdx.x / (unsigned)p.ncomp : blockIdx.x) * TD_P;
+    const double *in = RDM ? p.in + (size_t)comp * p.dstride_in : p.in;
     const int nchunk = (p.kp + TD_KC - 1) / TD_KC;
     auto stage_in = [&](int k0, int kc) {                       // rows [k0, k0 + kc) of `in`, zero beyond nk / n
         for (int e = tid; e < kc * TD_P; e += TD_NT) {
             const int k = e / TD_P, pt = e - k * TD_P;
             const long long x = x0 + pt;
-            rt[(size_t)k * TD_PS + pt] = (k0 + k < p.nk && x < p.n) ? __ldg(p.in + (size_t)(k0 + k) * p.ldi + x) : 0.0;
+            double v = 0.0;
+            if (k0 + k < p.nk && x < p.n) v = __ldg(in + (size_t)(RDM ? __ldg(p.rows + k0 + k) : k0 + k) * p.ldi + x);
+            rt[(size_t)k * TD_PS + pt] = v;
         }
     };
+    double red[4][2];                                           // RDM: sum over the orbitals a of phi_a (w in)_a
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) red[nb][0] = red[nb][1] = 0.0;
     if (nchunk == 1) stage_in(0, p.kp);
     const uint32_t a_rt = smem_u32(rt) + (uint32_t)((tc * TD_PS + warp * 32 + tr) * 8);
     const uint32_t a_wt = smem_u32(wt) + (uint32_t)((tr * TD_WS + tc) * 8);
@@ -92,21 +107,62 @@ __global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const T
             }
         }
         // lane holds out[t0 + 8 mb + tr][x0 + 32 warp + 8 nb + 2 tc + {0, 1}]
+        if constexpr (RDM) {
 #pragma unroll
-        for (int mb = 0; mb < MTB; ++mb) {
-            const int t = t0 + mb * 8 + tr;
-            if (t >= p.nt) continue;
-            double *orow = p.out + (size_t)t * p.ldo;
+            for (int mb = 0; mb < MTB; ++mb) {
+                const int t = t0 + mb * 8 + tr;
+                if (t >= p.nt) continue;
+                const double *prow = p.phi + (size_t)__ldg(p.rows + t) * p.ldi;
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const long long x = x0 + warp * 32 + nb * 8 + 2 * tc;
-                if (p.vec_ok && x + 1 < p.n) {
-                    *reinterpret_cast<double2 *>(orow + x) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-                } else {
-                    if (x < p.n) orow[x] = acc[mb][nb][0];
-                    if (x + 1 < p.n) orow[x + 1] = acc[mb][nb][1];
+                for (int nb = 0; nb < 4; ++nb) {
+                    const long long x = x0 + warp * 32 + nb * 8 + 2 * tc;
+                    double f0 = 0.0, f1 = 0.0;
+                    if (p.vec_ok && x + 1 < p.n) {
+                        const double2 f = __ldg(reinterpret_cast<const double2 *>(prow + x));
+                        f0 = f.x; f1 = f.y;
+                    } else {
+                        if (x < p.n) f0 = __ldg(prow + x);
+                        if (x + 1 < p.n) f1 = __ldg(prow + x + 1);
+                    }
+                    red[nb][0] = fma(acc[mb][nb][0], f0, red[nb][0]);
+                    red[nb][1] = fma(acc[mb][nb][1], f1, red[nb][1]);
                 }
             }
+        } else {
+#pragma unroll
+            for (int mb = 0; mb < MTB; ++mb) {
+                const int t = t0 + mb * 8 + tr;
+                if (t >= p.nt) continue;
+                double *orow = p.out + (size_t)t * p.ldo;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const long long x = x0 + warp * 32 + nb * 8 + 2 * tc;
+                    if (p.vec_ok && x + 1 < p.n) {
+                        *reinterpret_cast<double2 *>(orow + x) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                    } else {
+                        if (x < p.n) orow[x] = acc[mb][nb][0];
+                        if (x + 1 < p.n) orow[x + 1] = acc[mb][nb][1];
+                    }
+                }
+            }
+        }
+    }
+    if (RDM) {                                                  // the eight row groups of the lanes, fixed order
+        double *orow = p.out + (size_t)comp * p.ldo;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double v = red[nb][h];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                red[nb][h] = v;
+            }
+            const long long x = x0 + warp * 32 + nb * 8 + 2 * tc;
+            if (tr != 0) continue;
+            if (x < p.n) orow[x] = red[nb][0];
+            if (x + 1 < p.n) orow[x + 1] = red[nb][1];
         }
     }
 }

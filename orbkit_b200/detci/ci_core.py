@@ -25,7 +25,7 @@ With `options.ci_merge_terms = True` duplicate orbital pairs are merged on the h
 import numpy
 
 from .. import grid, options
-from .._lib import OKB_CI_RHO, OKB_CI_JAB, OKB_CI_A_NABLA_B, OKB_CI_PAIRS
+from .._lib import OKB_CI_RHO, OKB_CI_JAB, OKB_CI_A_NABLA_B, OKB_CI_PAIRS, OKB_FLAG_CI_FAST
 from ..engine import get_engine
 from ..tools import require, validate_drv
 
@@ -105,7 +105,8 @@ def _given(mode, zero, sing, molist, molistdrv=None, slice_length=1e4):
         display('detci.ci_core: like the reference, the last %d of %d points (behind the last full slice of %d) are not '
                 'evaluated and stay 0; pass a slice_length that divides the number of points' %
                 (mo2.shape[1] - n_eval, mo2.shape[1], abs(int(min(mo2.shape[1], slice_length)))))
-    out = get_engine().ci_contract(mode, _terms(zero, sing, shape[0], mode), mo2, drv3, n_eval=n_eval)
+    out = get_engine().ci_contract(mode, _terms(zero, sing, shape[0], mode), mo2, drv3, n_eval=n_eval,
+                                   flags=OKB_FLAG_CI_FAST if getattr(options, 'ci_fast', None) else 0)
     return out.reshape(shape[1:]) if ncomp == 1 else out.reshape((3,) + shape[1:])
 
 
@@ -146,7 +147,18 @@ def _from_qc(mode, qc, zero, sing, drv, x, y, z, is_vector):
     x, y, z, is_vector, N = _resolve_grid(x, y, z, is_vector)
     eng = get_engine()
     basis = eng.basis(require(qc.geo_spec, dtype='f'), qc.ao_spec)
-    mo = eng.mos_of(basis, qc.mo_spec)
+    terms = _terms(zero, sing, len(qc.mo_spec), mode)
+    # only the orbitals the term lists refer to are evaluated (a CI expansion over a few dozen active orbitals of a
+    # few hundred MOs: the AO -> MO contraction, the dominant cost, shrinks by that factor); the order of the terms
+    # and hence of the sums is untouched
+    act = numpy.unique(numpy.concatenate((terms[1], terms[2])))
+    if 0 < len(act) < len(qc.mo_spec):
+        mo = eng.mos(basis, numpy.ascontiguousarray(qc.mo_spec.get_coeffs()[act]),
+                     numpy.ascontiguousarray(qc.mo_spec.get_occ()[act]))
+        terms = (terms[0], numpy.searchsorted(act, terms[1]).astype(numpy.intc),
+                 numpy.searchsorted(act, terms[2]).astype(numpy.intc))
+    else:
+        mo = eng.mos_of(basis, qc.mo_spec)
     ncomp = 1 if mode == OKB_CI_RHO else 3
     lead = () if ncomp == 1 else (3,)
     if int(numpy.prod(N)) == 0:
@@ -155,7 +167,9 @@ def _from_qc(mode, qc, zero, sing, drv, x, y, z, is_vector):
     if len(codes) != 3 or any(c == 0 for c in codes):
         raise ValueError('`drv` must name three derivatives, e.g. ["x","y","z"] or ["xx","yy","zz"]')
     g = _grid_handle(eng, x, y, z, is_vector)
-    out = eng.eval_ci(mode, _terms(zero, sing, mo.n_mo, mode), mo, g, drv_codes=codes)
+    fast = getattr(options, 'ci_fast', None)
+    out = eng.eval_ci(mode, terms, mo, g, drv_codes=codes,
+                      flags=OKB_FLAG_CI_FAST if (fast is None or fast) else 0)
     return out.reshape(lead + N)
 
 

@@ -15,6 +15,8 @@ kernels of the same module, are reached through `ci_core.rho / jab / a_nabla_b`.
 """
 import numpy
 
+from .. import options
+from .._lib import OKB_FLAG_CI_FAST
 from ..engine import get_engine
 
 
@@ -82,5 +84,6 @@ def get_jab_full(ImS, chi_n, nabla_chi_n, mu):
     out = numpy.empty((nc, npts))
     # okb_ci_jab_full takes up to three components per call
     for c0 in range(0, nc, 3):
-        get_engine().ci_jab_full(ImS, chi_n, nabla_chi_n[c0:c0 + 3], mu, out=out[c0:c0 + 3])
+        get_engine().ci_jab_full(ImS, chi_n, nabla_chi_n[c0:c0 + 3], mu, out=out[c0:c0 + 3],
+                                 flags=OKB_FLAG_CI_FAST if getattr(options, 'ci_fast', None) else 0)
     return out

@@ -379,7 +379,7 @@ class Engine:
                                       ld_in if ld_in is not None else n, out if out_dev else out.ctypes.data, ld_out, flags))
         return out
 
-    def ci_jab_full(self, ImS, chi, dchi, mu, out=None):
+    def ci_jab_full(self, ImS, chi, dchi, mu, out=None, flags=0):
         """cy_ci.get_jab_full on NumPy arrays (okb_ci_jab_full)"""
         ImS, chi, dchi = _lib.f64(ImS), _lib.f64(chi), _lib.f64(dchi)
         nb, npts = chi.shape
@@ -387,7 +387,7 @@ class Engine:
         if out is None:
             out = self.host_array((ncomp, npts))
         _lib.check(self.lib.okb_ci_jab_full(self.ctx, nb, ncomp, npts, npts, _lib.dptr(ImS), chi.ctypes.data,
-                                            dchi.ctypes.data, float(mu), out.ctypes.data, npts, 0))
+                                            dchi.ctypes.data, float(mu), out.ctypes.data, npts, flags))
         return out
 
     def eval_ci(self, mode, terms, mo, grid, drv_codes=(1, 2, 3), p0=0, p1=None, out=None, flags=0):

@@ -15,3 +15,8 @@ exact_mixed_derivatives = False  #: opt-in analytically correct xy/xz/yz AO deri
                                  #  (the reference drops cross terms, c_support.c:121-168)
 ci_merge_terms = False           #: detci.ci_core: merge duplicate orbital pairs before the launch (faster;
                                  #  summation order then differs from the reference at the 1e-16 level)
+ci_fast = None                   #: detci.ci_core summed contractions (rho, jab, a_nabla_b): None = the fused *_from_qc calls
+                                 #  use the re-ordered device sums (OKB_FLAG_CI_FAST: dense orbital-pair matrix on the FP64
+                                 #  tensor path when there are many terms per pair, terms split over warps otherwise;
+                                 #  agreement ~1e-15 of the largest term) and rho()/jab()/a_nabla_b() on given MO arrays keep
+                                 #  the reference's summation order bit for bit; True / False force one for both

@@ -110,6 +110,69 @@ def test_merged_terms_and_pair_products(ok, oci):
     assert numpy.array_equal(prod, mo[pairs[:, 0]] * mo[pairs[:, 1]])
 
 
+def test_fast_sums_dense_and_split(ok, oci):
+    """options.ci_fast = True (OKB_FLAG_CI_FAST): the re-ordered device sums -- dense orbital-pair matrix on the FP64
+    tensor path when there are many terms per orbital pair, terms split over the warps of a CTA otherwise -- against the
+    bit-exact path.  Tolerance: 1e-12 of the largest result (sums of up to 2500 terms of O(1) products, re-associated);
+    repeated calls are bit-identical (fixed grouping)."""
+    import os
+    from orbkit_b200.detci import ci_core, cy_ci
+    from orbkit_b200.engine import get_engine
+    rng = numpy.random.default_rng(23)
+    cases = ((12, (777,), 40, 900, 'ci-dense'),          # many terms per pair, ragged point count
+             (64, (4099,), 100, 2500, 'ci-dense'),
+             (7, (2, 65), 4, 19, 'ci-'),                  # dense for rho and jab, split for a_nabla_b
+             (150, (1500,), 0, 300, 'ci-fast'),           # few terms over many orbitals: split over warps + ragged tail
+             (600, (257,), 10, 500, 'ci/'),               # row sets too wide for the split kernel: gather kernel
+             (3, (1,), 0, 1, None))                        # a single point
+    for n_mo, shape, n_det, n_sing, kernel in cases:
+        zero, sing = random_lists(rng, n_mo, n_det, n_sing)
+        mo = rng.normal(size=(n_mo,) + shape)
+        dmo = rng.normal(size=(3, n_mo) + shape)
+        n = mo[0].size
+        exact = (ci_core.rho(zero, sing, mo, slice_length=n), ci_core.jab(zero, sing, mo, dmo, slice_length=n),
+                 ci_core.a_nabla_b(zero, sing, mo, dmo, slice_length=n))
+        ok.options.ci_fast = True
+        try:
+            fast = (ci_core.rho(zero, sing, mo, slice_length=n), ci_core.jab(zero, sing, mo, dmo, slice_length=n),
+                    ci_core.a_nabla_b(zero, sing, mo, dmo, slice_length=n))
+            if kernel:
+                assert get_engine().last_kernel().startswith(kernel), (n_mo, get_engine().last_kernel())
+            again = ci_core.jab(zero, sing, mo, dmo, slice_length=n)
+        finally:
+            ok.options.ci_fast = None
+        for f, e, name in zip(fast, exact, ('rho', 'jab', 'a_nabla_b')):
+            assert f.shape == e.shape
+            assert numpy.abs(f - e).max() <= 1e-12 * max(numpy.abs(e).max(), 1e-300), (n_mo, name)
+        assert numpy.array_equal(again, fast[1])
+    # cy_ci.get_jab_full: the state-pair sum is a dense antisymmetric matrix by construction
+    nb, npts = 9, 1111
+    ImS = rng.normal(size=(nb, nb)); chi = rng.normal(size=(nb, npts)); dchi = rng.normal(size=(2, nb, npts))
+    exact = cy_ci.get_jab_full(ImS, chi, dchi, 1.7)
+    assert numpy.array_equal(exact, oci.get_jab_full(ImS, chi, dchi, 1.7))
+    ok.options.ci_fast = True
+    try:
+        fast = cy_ci.get_jab_full(ImS, chi, dchi, 1.7)
+        assert get_engine().last_kernel() == 'ci-dense/jab_full'
+    finally:
+        ok.options.ci_fast = None
+    assert numpy.abs(fast - exact).max() <= 1e-12 * numpy.abs(exact).max()
+    # ci_fast = False: the fused call keeps the reference's order as well
+    g = load_golden('h3p_detci')
+    qc = ok.QCinfo.from_arrays(g)
+    ok.grid.set_grid(g['x'], g['y'], g['z'], is_vector=False)
+    zero, sing = lists_from_golden(g, 0)
+    a = ci_core.rho_from_qc(qc, zero, sing)
+    assert get_engine().last_kernel().startswith('ci-')
+    ok.options.ci_fast = False
+    try:
+        b = ci_core.rho_from_qc(qc, zero, sing)
+        assert get_engine().last_kernel() == 'ci/rho'
+    finally:
+        ok.options.ci_fast = None
+    assert numpy.abs(a - b).max() <= 1e-12 * max(numpy.abs(b).max(), 1e-300)
+
+
 def test_config5_scale_properties(ok):
     """500 AOs / 500 MOs, 1000 random pairs on 32^3 points of the Config-5 generator: the fused device
     path against (a) the two-step path through host MOs, (b) linearity, (c) sum of per-pair products"""
