@@ -13,6 +13,7 @@ eng = get_engine(); dev = torch.device('cuda', eng.device)
 stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
 hbm = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))['hbm_gbs']
 n = 96 ** 3
+REPS = int(os.environ.get("REPS", "5"))
 ax = numpy.linspace(-10, 10, 96)
 for n_mo, n_terms in ((500, 1000), (40, 20000), (120, 5000)):
     qc = synth.to_qcinfo(synth.make_molecule(n_heavy=12, n_light=10, n_mo=n_mo, seed=5, spherical=True))
@@ -31,9 +32,9 @@ for n_mo, n_terms in ((500, 1000), (40, 20000), (120, 5000)):
             f(); eng.sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
-                e0.record(stream); [f() for _ in range(5)]; e1.record(stream)
+                e0.record(stream); [f() for _ in range(REPS)]; e1.record(stream)
             eng.sync()
-            ms = e0.elapsed_time(e1) / 5
+            ms = e0.elapsed_time(e1) / REPS
             nc = 1 if sets == 1 else 3
             by = 8.0 * n_mo * sets * n + 8.0 * nc * n
             res[(name, fast)] = out[:nc].clone()
