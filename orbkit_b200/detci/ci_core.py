@@ -152,13 +152,10 @@ def _from_qc(mode, qc, zero, sing, drv, x, y, z, is_vector):
     # few hundred MOs: the AO -> MO contraction, the dominant cost, shrinks by that factor); the order of the terms
     # and hence of the sums is untouched
     act = numpy.unique(numpy.concatenate((terms[1], terms[2])))
-    if 0 < len(act) < len(qc.mo_spec):
-        mo = eng.mos(basis, numpy.ascontiguousarray(qc.mo_spec.get_coeffs()[act]),
-                     numpy.ascontiguousarray(qc.mo_spec.get_occ()[act]))
+    subset = 0 < len(act) < len(qc.mo_spec)
+    if subset:
         terms = (terms[0], numpy.searchsorted(act, terms[1]).astype(numpy.intc),
                  numpy.searchsorted(act, terms[2]).astype(numpy.intc))
-    else:
-        mo = eng.mos_of(basis, qc.mo_spec)
     ncomp = 1 if mode == OKB_CI_RHO else 3
     lead = () if ncomp == 1 else (3,)
     if int(numpy.prod(N)) == 0:
@@ -168,9 +165,35 @@ def _from_qc(mode, qc, zero, sing, drv, x, y, z, is_vector):
         raise ValueError('`drv` must name three derivatives, e.g. ["x","y","z"] or ["xx","yy","zz"]')
     g = _grid_handle(eng, x, y, z, is_vector)
     fast = getattr(options, 'ci_fast', None)
-    out = eng.eval_ci(mode, terms, mo, g, drv_codes=codes,
-                      flags=OKB_FLAG_CI_FAST if (fast is None or fast) else 0)
+    fast = fast is None or bool(fast)
+    if mode == OKB_CI_RHO and fast and 0 < len(act) <= NATURAL_MAX:
+        return _rho_natural(eng, basis, qc, act, terms, g).reshape(N)
+    if subset:
+        mo = eng.mos(basis, numpy.ascontiguousarray(require(qc.mo_spec.get_coeffs(), dtype='f')[act]),
+                     numpy.ascontiguousarray(require(qc.mo_spec.get_occ(), dtype='f')[act]))
+    else:                                  # every orbital is referred to (act = 0..n_mo-1) or there are no terms
+        mo = eng.mos_of(basis, qc.mo_spec)
+    out = eng.eval_ci(mode, terms, mo, g, drv_codes=codes, flags=OKB_FLAG_CI_FAST if fast else 0)
     return out.reshape(lead + N)
+
+
+NATURAL_MAX = 256    #: largest active space whose pair matrix is diagonalised on the host (eigh of 256^2: ~10 ms)
+
+
+def _rho_natural(eng, basis, qc, act, terms, g):
+    """rho = sum_ab D_ab phi_a phi_b depends on the symmetric part of D only: with D_s = U diag(lam) U^T it is
+    sum_k lam_k psi_k^2 over the natural (transition) orbitals psi = U^T phi -- ONE launch of the fused
+    AO -> MO -> rho kernel with n_act orbitals and signed weights, no MO slab and no second kernel.  `terms` index
+    into `act`.  Eigenvalues below 1e-15 of the largest are dropped (transition matrices are of low rank)."""
+    n = len(act)
+    d = numpy.bincount(terms[1].astype(numpy.int64) * n + terms[2], weights=terms[0], minlength=n * n).reshape((n, n))
+    lam, u = numpy.linalg.eigh(0.5 * (d + d.T))
+    keep = numpy.abs(lam) > 1e-15 * max(numpy.abs(lam).max(), 1e-300)
+    if not keep.any():
+        return numpy.zeros(g.npts)
+    coeffs = numpy.ascontiguousarray(u[:, keep].T @ require(qc.mo_spec.get_coeffs(), dtype='f')[act])
+    mo = eng.mos(basis, coeffs, numpy.ascontiguousarray(lam[keep]))
+    return eng.eval_rho(mo, g, [])[0]
 
 
 def rho_from_qc(qc, zero, sing, x=None, y=None, z=None, is_vector=None):

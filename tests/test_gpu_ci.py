@@ -162,15 +162,20 @@ def test_fast_sums_dense_and_split(ok, oci):
     qc = ok.QCinfo.from_arrays(g)
     ok.grid.set_grid(g['x'], g['y'], g['z'], is_vector=False)
     zero, sing = lists_from_golden(g, 0)
-    a = ci_core.rho_from_qc(qc, zero, sing)
+    a = ci_core.rho_from_qc(qc, zero, sing)          # natural orbitals of the pair matrix: one fused rho launch
+    assert not get_engine().last_kernel().startswith('ci')
+    j = ci_core.jab_from_qc(qc, zero, sing)
     assert get_engine().last_kernel().startswith('ci-')
     ok.options.ci_fast = False
     try:
         b = ci_core.rho_from_qc(qc, zero, sing)
         assert get_engine().last_kernel() == 'ci/rho'
+        jb = ci_core.jab_from_qc(qc, zero, sing)
+        assert get_engine().last_kernel() == 'ci/jab'
     finally:
         ok.options.ci_fast = None
     assert numpy.abs(a - b).max() <= 1e-12 * max(numpy.abs(b).max(), 1e-300)
+    assert numpy.abs(j - jb).max() <= 1e-12 * max(numpy.abs(jb).max(), 1e-300)
 
 
 def test_config5_scale_properties(ok):
