@@ -1043,7 +1043,10 @@ extern "C" int okb_grid_destroy(okb_grid *g) {
 // (SINK_AO: the first matching entry is the default: the warp-specialised "aows/" kernels for the derivative sets -- twice
 // the throughput of the tile kernel there -- and the tile kernel for plain values, where both measure the same because the
 // AO generators, not the stores, bound calc_ao)
-static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants_tile, &okb_variants_val, &okb_variants_grad,
+// (ties of the cost model go to the table listed first: the narrow-tile variants with wide point tiles come before the
+// older narrow variants of the per-set tables)
+static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants_tile, &okb_variants_narrow_a,
+                                               &okb_variants_narrow_b, &okb_variants_val, &okb_variants_grad,
                                                &okb_variants_lap, &okb_variants_all, &okb_variants_d2, &okb_variants_d2p,
                                                &okb_variants_rem};
 
@@ -1072,9 +1075,11 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
         if (meta_stride > 0 && v.smem(meta_stride) > 227 * 1024) continue;
-        // Every MO tile regenerates the AO tiles, and the producers run beside the consumers: a pass over one
-        // MO tile costs max(contraction ~ MC, generation).  Measured on the 1000-AO molecule the two balance at
-        // MC ~ 45-60 for every set (profiles/r01_perf_matrix.txt), so narrow tiles are charged as 48 wide.
+        // Every MO tile regenerates the AO tiles, and the producers run beside the consumers.  Measured per pass over one
+        // MO tile on the Config-2 shape (222 AOs; 24- / 48- / 80-wide tiles, profiles/r02_c2_narrow.txt) the time is affine
+        // in the tile width MC: rho 3.0 / 3.55 / 4.5 ms, rho + grad 8.7 / 11.3 / 17.4 ms, second laplacian pass
+        // 7.8 / 9.55 / 14.4 ms, i.e. ~ MC + K with K = 100 / 35 / 42 orbitals' worth of AO generation per tile.  (The
+        // other sets keep the older rule: narrow tiles charged as 48 wide, 24 for SET_ALL.)
         // Prefer the wider tile on ties (fewer AO regenerations).
         // Remainder orbitals (v.rem of the v.MC, contracted by the producer warps) are charged 3 DMMA columns each:
         // 82 MOs go to the 80 + 2 tile (86) instead of the 88-wide one, 83..88 MOs stay on the latter.
@@ -1083,7 +1088,9 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         // producers bound the kernel and a remainder orbital costs more than its DMMA columns -- 82 MOs: 88-wide 144 ms,
         // 80 + 2 148 ms, profiles/r02_lap_passes_ab.txt -- so it is charged 5 columns.)
         const int rem_cols = set == SET_D2P ? 5 : 3;
-        const long long cost = n_tiles * std::max(v.MC - v.rem + rem_cols * v.rem, set == SET_ALL ? 24 : 48) * 1000 - v.MC;
+        const int width = v.MC - v.rem + rem_cols * v.rem;
+        const int gen = set == SET_VAL ? 100 : set == SET_GRAD ? 35 : set == SET_D2P ? 42 : 0;
+        const long long cost = n_tiles * (gen > 0 ? width + gen : std::max(width, set == SET_ALL ? 24 : 48)) * 1000 - v.MC;
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;

@@ -16,9 +16,9 @@ struct Variant {
 };
 struct VariantTable { const Variant *v; int n; };
 
-// defined in inst_ao_ws.cu, inst_tile.cu, inst_ws_val.cu, inst_ws_grad.cu, inst_ws_lap.cu, inst_ws_all.cu, inst_ws_d2.cu, inst_ws_d2p.cu, inst_ws_rem.cu
+// defined in inst_ao_ws.cu, inst_tile.cu, inst_ws_val.cu, inst_ws_grad.cu, inst_ws_lap.cu, inst_ws_all.cu, inst_ws_d2.cu, inst_ws_d2p.cu, inst_ws_rem.cu, inst_ws_narrow_a.cu, inst_ws_narrow_b.cu
 extern const VariantTable okb_variants_tile, okb_variants_val, okb_variants_grad, okb_variants_lap, okb_variants_all,
-    okb_variants_d2, okb_variants_d2p, okb_variants_aows, okb_variants_rem;
+    okb_variants_d2, okb_variants_d2p, okb_variants_aows, okb_variants_rem, okb_variants_narrow_a, okb_variants_narrow_b;
 
 // z-run SINK_AO kernel for regular grids (inst_ao_zrun.cu)
 cudaError_t okb_launch_ao_zrun(const KParams &p, int sm_count, cudaStream_t st);
