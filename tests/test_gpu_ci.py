@@ -145,6 +145,29 @@ def test_fast_sums_dense_and_split(ok, oci):
             assert f.shape == e.shape
             assert numpy.abs(f - e).max() <= 1e-12 * max(numpy.abs(e).max(), 1e-300), (n_mo, name)
         assert numpy.array_equal(again, fast[1])
+    # device-resident rows with an odd row stride (unaligned: scalar loads in the dense kernel, gather kernel instead of
+    # the split kernel) and 16-byte aligned ones, results left on the device
+    import torch
+    from orbkit_b200 import _lib
+    eng = get_engine()
+    dev = torch.device('cuda', eng.device)
+    fl = _lib.OKB_FLAG_IN_DEVICE | _lib.OKB_FLAG_OUT_DEVICE
+    for n_mo, n_terms, ld, npts in ((9, 400, 1001, 999), (9, 400, 1002, 1000), (90, 60, 1001, 1001), (90, 60, 1000, 1000)):
+        pairs = rng.integers(0, n_mo, size=(n_terms, 2))
+        terms = (rng.normal(size=n_terms), pairs[:, 0].astype(numpy.intc), pairs[:, 1].astype(numpy.intc))
+        buf = torch.from_numpy(rng.normal(size=(4, n_mo, ld))).to(dev)
+        for mode, nc in ((_lib.OKB_CI_RHO, 1), (_lib.OKB_CI_JAB, 3), (_lib.OKB_CI_A_NABLA_B, 3)):
+            outs = []
+            for fast in (0, _lib.OKB_FLAG_CI_FAST):
+                out = torch.full((3 * npts + 8,), 7.0, dtype=torch.float64, device=dev)     # rows of stride npts + guard
+                eng.ci_contract(mode, terms, buf[0].data_ptr(), buf[1:].data_ptr(), n_mo=n_mo, npts=npts, ld=ld,
+                                out=out.data_ptr(), flags=fl | fast)
+                eng.sync()
+                outs.append(out.cpu().numpy())
+            e, f = outs
+            assert (f[nc * npts:] == 7.0).all() and (e[nc * npts:] == 7.0).all()    # nothing written outside the result
+            e, f = e[:nc * npts], f[:nc * npts]
+            assert numpy.abs(f - e).max() <= 1e-12 * numpy.abs(e).max(), (n_mo, ld, mode)
     # cy_ci.get_jab_full: the state-pair sum is a dense antisymmetric matrix by construction
     nb, npts = 9, 1111
     ImS = rng.normal(size=(nb, nb)); chi = rng.normal(size=(nb, npts)); dchi = rng.normal(size=(2, nb, npts))
