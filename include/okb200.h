@@ -179,10 +179,14 @@ int okb_eval_rho_ld(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p0, long
 #define OKB_CI_PAIRS 3
 #define OKB_CI_JAB_PAIRS 4
 #define OKB_FLAG_IN_DEVICE 4u    /* okb_ci_contract: molist / molistdrv are DEVICE pointers */
-#define OKB_FLAG_CI_FAST   8u    /* okb_ci_contract / okb_eval_ci, summed modes: the term list is split over the warps of a
-                                  * CTA and every MO row is staged in shared memory once (HBM roofline instead of 3.5x
-                                  * re-fetched rows).  Deterministic, equal to the sequential sum to rounding -- NOT bit for
-                                  * bit with the reference's loops; without the flag the sums keep the reference's order. */
+#define OKB_FLAG_CI_FAST   8u    /* okb_ci_contract / okb_eval_ci / okb_ci_jab_full, summed modes: re-ordered sums.  Many terms
+                                  * per orbital pair (r n_terms >= n_act^2): the terms are summed on the host into the dense
+                                  * orbital-pair matrix and the grid work runs on the FP64 tensor path (n_act^2 fused
+                                  * multiply-adds per point instead of n_terms gathers); otherwise the term list is split
+                                  * over the warps of a CTA and every MO row is staged in shared memory once (DRAM traffic =
+                                  * algorithmic instead of 3.5x).  Deterministic, equal to the sequential sum to rounding
+                                  * (~1e-15 of the largest value) -- NOT bit for bit with the reference's loops; without the
+                                  * flag the sums keep the reference's order. */
 /* Level 1: given MO arrays molist[n_mo][ld_in] and (JAB, A_NABLA_B) molistdrv[3][n_mo][ld_in]; the first
  * npts points of every row are contracted into the first npts entries of the rows of out[.][ld_out]
  * (ld_* = row strides in points, >= npts). */

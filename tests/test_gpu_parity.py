@@ -202,6 +202,40 @@ def test_edge_sizes_and_point_ranges(ok, oracle_mod):
     assert_close(nrm, (mo_ref.reshape(9, -1) ** 2).sum(axis=1), 'mo_norm', rtol=1e-12)
 
 
+def test_documented_limits_of_the_chunk_tables(ok, oracle_mod):
+    """DESIGN 7 'known limits': a contraction of up to 96 primitives and shells of up to 28 functions (L = 6, i shells --
+    beyond every published basis set) are evaluated; 97 primitives or an L = 7 shell (36 functions) are refused with a
+    message, never silently truncated."""
+    from orbkit_b200._lib import OkbError
+    rng = numpy.random.default_rng(12)
+    port = oracle_mod.backend('port')
+    geo = numpy.zeros((1, 3)); atoms = numpy.zeros(1, dtype=numpy.intc)
+    x, y, z = rng.uniform(-2, 2, size=(3, 77))
+
+    def shell(L):
+        return numpy.array([(a, b, L - a - b) for a in range(L, -1, -1) for b in range(L - a, -1, -1)], dtype=numpy.intc)
+    s_fn = shell(0)
+    for npr, fine in ((96, True), (97, False)):
+        coeffs = numpy.stack([10 ** rng.uniform(-1, 3, npr), rng.uniform(-1, 1, npr)], axis=1)
+        args = (s_fn, numpy.array([1], dtype=numpy.intc), coeffs, numpy.array([npr], dtype=numpy.intc), geo, atoms, x, y, z)
+        if fine:
+            for drv in (0, 1, 4):
+                assert_close(ok.cy_core.aocreator(*args, drv, 0), port.aocreator(*args, drv, 0), '96 primitives drv %d' % drv)
+        else:
+            with pytest.raises(OkbError, match='primitives'):
+                ok.cy_core.aocreator(*args, 0, 0)
+    coeffs = numpy.array([[0.7, 1.0], [0.2, 0.5]])
+    for L, fine in ((6, True), (7, False)):
+        fn = shell(L)
+        args = (fn, numpy.array([len(fn)], dtype=numpy.intc), coeffs, numpy.array([2], dtype=numpy.intc), geo, atoms, x, y, z)
+        if fine:
+            for drv in (0, 2, 6):
+                assert_close(ok.cy_core.aocreator(*args, drv, 0), port.aocreator(*args, drv, 0), 'L = 6 drv %d' % drv)
+        else:
+            with pytest.raises(OkbError, match='functions'):
+                ok.cy_core.aocreator(*args, 0, 0)
+
+
 def test_many_mos_multiple_mo_tiles(ok, oracle_mod):
     """n_mo larger than one MO tile (MC<=96): AO tiles are regenerated per MO tile"""
     from orbkit_b200 import synth
