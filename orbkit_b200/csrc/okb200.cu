@@ -1778,6 +1778,33 @@ static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, lo
     const bool in_dev = (flags & OKB_FLAG_IN_DEVICE) != 0, out_dev = (flags & OKB_FLAG_OUT_DEVICE) != 0;
     const int nsets = 1 + nd, ncomp = ci_ncomp(mode, n_terms, nd);
     CU(cudaSetDevice(ctx->device));
+    // Host inputs: only the rows the term list refers to are staged -- a CI expansion over a few dozen active orbitals of
+    // a few hundred MOs moves n_act / n_mo of the bytes over PCIe (the reference's callers pass the MOs of the whole
+    // calculation, ci_core.py:85-136).  The terms keep their order and the rows their values: the sums are unchanged.
+    std::vector<int> rows, ia2, ib2;
+    const int n_all = n_mo;                                   // rows per set of the caller's arrays
+    if (!in_dev && n_terms > 0) {
+        std::vector<int> idx(n_mo, -1);
+        for (int t = 0; t < n_terms; ++t) idx[ia[t]] = idx[ib[t]] = 0;
+        for (int m = 0; m < n_mo; ++m)
+            if (idx[m] == 0) {
+                idx[m] = (int)rows.size();
+                rows.push_back(m);
+            }
+        if (rows.size() * 4 <= (size_t)n_mo * 3) {            // worth one copy per row instead of one strided copy
+            ia2.resize(n_terms);
+            ib2.resize(n_terms);
+            for (int t = 0; t < n_terms; ++t) {
+                ia2[t] = idx[ia[t]];
+                ib2[t] = idx[ib[t]];
+            }
+            ia = ia2.data();
+            ib = ib2.data();
+            n_mo = (int)rows.size();                          // from here on: rows per set of the staged arrays
+        } else {
+            rows.clear();
+        }
+    }
     // slab geometry: device-resident inputs and outputs need no staging at all
     const size_t per_pt = (in_dev ? 0 : (size_t)nsets * n_mo * 8) + (out_dev ? 0 : (size_t)ncomp * 8);
     long long slab = npts;
@@ -1811,11 +1838,20 @@ static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, lo
             p.dmo = need_drv ? molistdrv + s0 : nullptr;
             p.ld = ld_in;
         } else {
-            CU(cudaMemcpy2DAsync(d_in, (size_t)lds * 8, molist + s0, (size_t)ld_in * 8, (size_t)sn * 8, n_mo,
-                                 cudaMemcpyHostToDevice, ctx->stream));
-            if (need_drv)
-                CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * lds, (size_t)lds * 8, molistdrv + s0, (size_t)ld_in * 8,
-                                     (size_t)sn * 8, (size_t)nd * n_mo, cudaMemcpyHostToDevice, ctx->stream));
+            if (!rows.empty()) {
+                for (int st = 0; st < nsets; ++st) {
+                    const double *src = st == 0 ? molist : molistdrv + (size_t)(st - 1) * n_all * ld_in;
+                    for (int r = 0; r < n_mo; ++r)
+                        CU(cudaMemcpyAsync(d_in + ((size_t)st * n_mo + r) * lds, src + (size_t)rows[r] * ld_in + s0,
+                                           (size_t)sn * 8, cudaMemcpyHostToDevice, ctx->stream));
+                }
+            } else {
+                CU(cudaMemcpy2DAsync(d_in, (size_t)lds * 8, molist + s0, (size_t)ld_in * 8, (size_t)sn * 8, n_mo,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+                if (need_drv)
+                    CU(cudaMemcpy2DAsync(d_in + (size_t)n_mo * lds, (size_t)lds * 8, molistdrv + s0, (size_t)ld_in * 8,
+                                         (size_t)sn * 8, (size_t)nd * n_mo, cudaMemcpyHostToDevice, ctx->stream));
+            }
             ctx->h2d_bytes += (long long)nsets * n_mo * sn * 8;
             p.mo = d_in;
             p.dmo = need_drv ? d_in + (size_t)n_mo * lds : nullptr;

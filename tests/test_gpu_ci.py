@@ -80,6 +80,21 @@ def test_random_terms_bitwise_vs_oracle(ok, oci):
                                      oci.a_nabla_b(zero, sing, mo, dmo, sl))
         # the caller's arrays keep their shape (the reference reshapes them in place and restores, ci_core.py:112-135)
         assert mo.shape == (n_mo,) + shape and dmo.shape == (3, n_mo) + shape
+    # few active orbitals among many MOs: only the rows the lists refer to cross PCIe, same bits out
+    act = numpy.array([3, 17, 18, 40, 41, 59])
+    zero, sing = random_lists(rng, len(act), 5, 300)
+    zero = [zero[0], [[int(act[i]) for i in idx] for idx in zero[1]]]
+    sing = [sing[0], [[int(act[a]), int(act[b])] for a, b in sing[1]]]
+    mo = rng.normal(size=(60, 1501)); dmo = rng.normal(size=(3, 60, 1501))
+    from orbkit_b200.engine import get_engine
+    h0 = get_engine().traffic()[0]
+    got = ci_core.rho(zero, sing, mo, slice_length=1501)
+    assert get_engine().traffic()[0] - h0 < 8 * 1501 * (len(act) + 1) + 16 * 400          # 6 of the 60 rows + the terms
+    assert numpy.array_equal(got, oci.rho(zero, sing, mo, 1501))
+    assert numpy.array_equal(ci_core.jab(zero, sing, mo, dmo, slice_length=1501), oci.jab(zero, sing, mo, dmo, 1501))
+    assert numpy.array_equal(ci_core.a_nabla_b(zero, sing, mo, dmo, slice_length=1501), oci.a_nabla_b(zero, sing, mo, dmo, 1501))
+    prod = ci_core.pair_products(numpy.array([[3, 41], [59, 59]]), mo)
+    assert numpy.array_equal(prod, numpy.stack([mo[3] * mo[41], mo[59] * mo[59]]))
     # empty grid, error conventions
     assert ci_core.rho([[], []], [[], []], numpy.zeros((4, 0))).shape == (0,)
     assert (ci_core.rho([[], []], [[], []], numpy.ones((4, 9))) == 0.0).all()
