@@ -8,6 +8,7 @@ compute entry point raises.  The library is built in-tree by `__graft_entry__.bu
 """
 import ctypes
 import os
+import re
 import subprocess
 import threading
 
@@ -125,6 +126,26 @@ def build(force=False, verbose=False, jobs=None):
     objdir = os.path.join(csrc, 'build')
     os.makedirs(objdir, exist_ok=True)
     hdr_time = max(os.path.getmtime(h) for h in headers)
+    inc_re = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+    def deps_time(path, seen):
+        """newest modification time of `path` and the project headers it includes (recursively); a header that
+        cannot be found next to the sources counts as 'any header changed'"""
+        if path in seen:
+            return 0.0
+        seen.add(path)
+        t = os.path.getmtime(path)
+        with open(path) as f:
+            text = f.read()
+        for name in inc_re.findall(text):
+            for d in (os.path.dirname(path), csrc, os.path.join(os.path.dirname(_HERE), 'include')):
+                cand = os.path.join(d, name)
+                if os.path.exists(cand):
+                    t = max(t, deps_time(cand, seen))
+                    break
+            else:
+                t = max(t, hdr_time)
+        return t
     nvcc = os.environ.get('NVCC', 'nvcc')
     extra = os.environ.get('OKB_NVCC_EXTRA', '').split()        # A/B builds, e.g. -DOKB_REFILL_DEP
 
@@ -133,7 +154,7 @@ def build(force=False, verbose=False, jobs=None):
 
     def stale(u):
         o = obj_of(u)
-        return force or not os.path.exists(o) or os.path.getmtime(o) < max(hdr_time, os.path.getmtime(u))
+        return force or not os.path.exists(o) or os.path.getmtime(o) < deps_time(u, set())
 
     todo = [u for u in units if stale(u)]
 

@@ -1732,6 +1732,70 @@ static int ci_launch_fast(okb_ctx *ctx, int mode, const CiParams &p, int n_mo, i
     return OKB_OK;
 }
 
+// Bit-identical sums from shared memory (okb_ci_seq_kernel): many terms over rows that fit.  Returns false when the
+// request is not of that shape (the caller then takes the gather kernel).  OKB_CI_SEQ=0|1 forces either (A/B).
+static bool ci_seq_wanted(const CiParams &p, int mode, int n_mo, int nsets, int *nwp) {
+    const bool summed = mode == CI_RHO || mode == CI_JAB || mode == CI_ANB || mode == CI_JABF;
+    if (!summed || p.n_terms == 0) return false;
+    static const char *force = getenv("OKB_CI_SEQ");
+    if (force && force[0] && atoi(force) == 0) return false;
+    if (!(force && force[0]) && nsets == 1) return false;     // rho: the gather kernel's rows stay in L1
+    const size_t row_bytes = (size_t)n_mo * nsets * 8;
+    const bool aligned = reinterpret_cast<uintptr_t>(p.mo) % 16 == 0 && p.ld % 2 == 0 &&
+                         (nsets == 1 || (reinterpret_cast<uintptr_t>(p.dmo) % 16 == 0 && p.dstride % 2 == 0));
+    if (!aligned || row_bytes * 32 > (size_t)72 * 1024 || p.npts < 32) return false;
+    // staging costs ~ the rows, the sums ~ the terms: wins from 6 terms per staged row on (the smallest ratio measured,
+    // 2x there: profiles/r02_ci_seq.txt); below 2 the gather kernel is kept
+    if (!(force && force[0]) && (long long)p.n_terms < 2LL * n_mo * nsets) return false;
+    int w = 4;                                                // 32-point groups per tile: three CTAs per SM if possible
+    while (w > 1 && row_bytes * 32 * w > (size_t)72 * 1024) w >>= 1;
+    *nwp = w;
+    return true;
+}
+
+static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p);
+static int ci_launch_seq(okb_ctx *ctx, int mode, const CiParams &p, int n_mo, int nsets, int nwp) {
+    CiSeqParams q{};
+    q.p = p;
+    q.n_mo = n_mo; q.nsets = nsets; q.nwp = nwp;
+    q.ncw = mode == CI_RHO ? 1 : mode == CI_JABF ? p.ncomp : 3;
+    const int tp = 32 * nwp;
+    q.ntiles = p.npts / tp;
+    const size_t smem = (size_t)n_mo * nsets * 8 * tp;
+    const int threads = 32 * nwp * q.ncw;
+    cudaError_t e = cudaSuccess;
+    int per_sm = 1;
+#define OKB_CIS_LAUNCH(M)                                                                                            \
+    e = cudaFuncSetAttribute(okb_ci_seq_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, okb_ci_seq_kernel<M>, threads, smem); \
+    if (e == cudaSuccess)                                                                                            \
+        okb_ci_seq_kernel<M><<<(unsigned)std::min<long long>(q.ntiles, (long long)ctx->sm_count * std::max(per_sm, 1)), \
+                               threads, smem, ctx->stream>>>(q)
+    switch (mode) {
+        case CI_RHO: OKB_CIS_LAUNCH(CI_RHO); break;
+        case CI_JAB: OKB_CIS_LAUNCH(CI_JAB); break;
+        case CI_ANB: OKB_CIS_LAUNCH(CI_ANB); break;
+        default: OKB_CIS_LAUNCH(CI_JABF); break;
+    }
+#undef OKB_CIS_LAUNCH
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "sequential ci kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    const long long done = q.ntiles * tp;
+    if (done < p.npts) {                                      // ragged rest: fewer than one tile of points
+        CiParams r = p;
+        r.mo = p.mo + done;
+        r.dmo = p.dmo ? p.dmo + done : nullptr;
+        r.out = p.out + done;
+        r.npts = p.npts - done;
+        const int rc = ci_launch(ctx, mode, r);
+        if (rc != OKB_OK) return rc;
+    }
+    ctx->last_kernel = mode == CI_RHO ? "ci-seq/rho" : mode == CI_JAB ? "ci-seq/jab" : mode == CI_ANB ? "ci-seq/a_nabla_b"
+                                                                                                  : "ci-seq/jab_full";
+    return OKB_OK;
+}
+
 static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
     if (p.npts <= 0) return OKB_OK;
     const unsigned grid = (unsigned)((p.npts + CI_NT - 1) / CI_NT);
@@ -1759,6 +1823,13 @@ static int ci_launch(okb_ctx *ctx, int mode, const CiParams &p) {
     ctx->last_kernel = mode == CI_RHO ? "ci/rho" : mode == CI_JAB ? "ci/jab" : mode == CI_ANB ? "ci/a_nabla_b"
                        : mode == CI_JPAIRS ? "ci/jpairs" : mode == CI_JABF ? "ci/jab_full" : "ci/pairs";
     return OKB_OK;
+}
+
+// reference summation order: shared-memory kernel when the request has its shape, else the gather kernel
+static int ci_launch_exact(okb_ctx *ctx, int mode, const CiParams &p, int n_mo, int nsets) {
+    int nwp = 1;
+    if (ci_seq_wanted(p, mode, n_mo, nsets, &nwp)) return ci_launch_seq(ctx, mode, p, n_mo, nsets, nwp);
+    return ci_launch(ctx, mode, p);
 }
 
 // ncomp_in: JABF only -- the number of derivative components in molistdrv (1..3); the other modes fix it
@@ -1862,7 +1933,7 @@ static int ci_contract_impl(okb_ctx *ctx, int mode, int n_mo, long long npts, lo
         p.ncomp = mode == CI_JABF ? nd : 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? ld_out : sn;
-        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch(ctx, mode, p);
+        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch_exact(ctx, mode, p, n_mo, nsets);
         if (rc != OKB_OK) return rc;
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,
@@ -2054,7 +2125,7 @@ extern "C" int okb_eval_ci(okb_ctx *ctx, okb_mo *mo, okb_grid *grid, long long p
         p.ncomp = 3;
         p.out = out_dev ? out + s0 : d_out;
         p.ldo = out_dev ? npts : sn;
-        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch(ctx, mode, p);
+        rc = (flags & OKB_FLAG_CI_FAST) ? ci_launch_fast(ctx, mode, p, n_mo, nsets, dense) : ci_launch_exact(ctx, mode, p, n_mo, nsets);
         if (rc != OKB_OK) return rc;
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)npts * 8, d_out, (size_t)sn * 8, (size_t)sn * 8, ncomp,

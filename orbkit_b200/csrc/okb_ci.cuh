@@ -219,6 +219,64 @@ __global__ void __launch_bounds__(CIF_NW * 32, 2) okb_ci_fast_kernel(const CiFas
     }
 }
 
+// ---- sequential sums from shared memory: the bit-identical path for MANY terms over FEW rows of several sets -------------
+// With thousands of terms per point tile the gather kernel re-reads its rows from L1 / L2 / DRAM over and over (40 MOs x 4
+// sets, 20 000 terms: 740 GB of DRAM reads for 1.1 GB of MO values).  When all rows of a tile of 32 NWP points fit in
+// shared memory they are staged ONCE (16-byte async copies) and every lane walks the whole term list for its point with the
+// reference's expression order -- the same __dmul_rn / __dadd_rn sequence as okb_ci_kernel, so the same bits.  The three
+// components of jab / a_nabla_b are independent sums: component d runs on its own warp (NCW = 3 warps per 32 points; one
+// warp for all three was measured at 151 instead of 85 ms: too few warps per SM).  Several CTAs per SM: one stages while
+// the others sum.  Used for the derivative modes only: for rho (one set) the gather kernel's rows stay in L1 and it is the
+// faster one (15.6 against 18.3 ms), as it is for few terms over many rows (see below).
+struct CiSeqParams {
+    CiParams p;
+    int n_mo, nsets, nwp, ncw;  // rows per set, sets staged, 32-point groups per tile, component warps per group
+    long long ntiles;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(384) okb_ci_seq_kernel(const CiSeqParams q) {
+    extern __shared__ __align__(128) unsigned char cis_smem[];
+    const CiParams &p = q.p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    const int TP = 32 * q.nwp, nrow = q.n_mo * q.nsets;
+    double *buf = reinterpret_cast<double *>(cis_smem);                       // [set][mo][TP]
+    const uint32_t a_buf = smem_u32(buf);
+    const int seg16 = TP >> 1, ncopy = nrow * seg16;
+    const int grp = warp / q.ncw, comp = warp - grp * q.ncw;                  // 32-point group, component of this warp
+    const size_t dstr = (size_t)q.n_mo * TP;
+    const double *mo = buf + grp * 32 + lane;
+    const double *dd = mo + dstr + (size_t)comp * dstr;                       // derivative block of this warp's component
+    for (long long tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x) {
+        const long long x0 = tile * TP;
+        __syncthreads();
+        for (int e = tid; e < ncopy; e += nthr) {
+            const int r = e / seg16, piece = e - r * seg16;
+            const int sset = r / q.n_mo, m = r - sset * q.n_mo;
+            const double *src = (sset == 0 ? p.mo : p.dmo + (size_t)(sset - 1) * p.dstride) + (size_t)m * p.ld + x0 + 2 * piece;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a_buf + (uint32_t)e * 16u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double acc = 0.0;
+#pragma unroll 4
+        for (int e = 0; e < p.n_terms; ++e) {
+            const double c = __ldg(p.tc + e);
+            const int ra = __ldg(p.ta + e) * TP, rb = __ldg(p.tb + e) * TP;
+            if (MODE == CI_RHO) {
+                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(c, mo[ra]), mo[rb]));                        // cy_ci.pyx:88,95
+            } else if (MODE == CI_ANB) {
+                acc = __dadd_rn(acc, __dmul_rn(c, __dmul_rn(mo[ra], dd[rb])));                        // cy_ci.pyx:236-238
+            } else {
+                const double t = __dadd_rn(__dmul_rn(mo[ra], dd[rb]), -__dmul_rn(mo[rb], dd[ra]));
+                if (MODE == CI_JAB) acc = __dadd_rn(acc, -__dmul_rn(0.5, __dmul_rn(c, t)));           // cy_ci.pyx:181-184
+                else acc = __dadd_rn(acc, __dmul_rn(c, t));                                           // cy_ci.pyx:199-201
+            }
+        }
+        p.out[(size_t)comp * p.ldo + x0 + grp * 32 + lane] = acc;
+    }
+}
+
 // Measured alternatives (not kept).  Round 1: a tiled kernel that stages all n_mo row segments of a 24-32 point tile in
 // shared memory so that HBM delivers every MO value exactly once was 2x (rho) to 4x (jab) SLOWER than the gather kernel.
 // Round 2 (profiles/r02_ci_staged_vs_gather.txt): the same idea with one private tile per WARP, bulk-async copies issued by

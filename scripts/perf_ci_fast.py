@@ -15,7 +15,8 @@ hbm = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))['hbm_gbs']
 n = 96 ** 3
 REPS = int(os.environ.get("REPS", "5"))
 ax = numpy.linspace(-10, 10, 96)
-for n_mo, n_terms in ((500, 1000), (40, 20000), (120, 5000)):
+CASES = [tuple(int(v) for v in c.split(':')) for c in os.environ.get('CASES', '500:1000,40:20000,120:5000').split(',')]
+for n_mo, n_terms in CASES:
     qc = synth.to_qcinfo(synth.make_molecule(n_heavy=12, n_light=10, n_mo=n_mo, seed=5, spherical=True))
     rng = numpy.random.default_rng(5)
     pairs = rng.integers(0, n_mo, size=(n_terms, 2))

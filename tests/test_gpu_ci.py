@@ -209,7 +209,7 @@ def test_fast_sums_dense_and_split(ok, oci):
         b = ci_core.rho_from_qc(qc, zero, sing)
         assert get_engine().last_kernel() == 'ci/rho'
         jb = ci_core.jab_from_qc(qc, zero, sing)
-        assert get_engine().last_kernel() == 'ci/jab'
+        assert get_engine().last_kernel() in ('ci/jab', 'ci-seq/jab')          # reference order, either kernel
     finally:
         ok.options.ci_fast = None
     assert numpy.abs(a - b).max() <= 1e-12 * max(numpy.abs(b).max(), 1e-300)
