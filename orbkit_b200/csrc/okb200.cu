@@ -1559,21 +1559,25 @@ static int ci_check(okb_ctx *ctx, int mode, int n_mo, int n_terms, const double 
     return OKB_OK;
 }
 
-// term arrays at the head of ctx->ci_buf: [coef n_terms doubles | ia | ib], padded to 256 bytes
+// term records at the head of ctx->ci_buf: [n_terms] x {coefficient, (a, b)} of 16 bytes, padded to 256 bytes
 static size_t ci_terms_bytes(int n_terms) { return (((size_t)n_terms * 16 + 255) / 256 + 1) * 256; }
 static int ci_upload_terms(okb_ctx *ctx, int n_terms, const double *coef, const int *ia, const int *ib, CiParams *p) {
-    unsigned char *base = reinterpret_cast<unsigned char *>(ctx->ci_buf);
-    double *tc = reinterpret_cast<double *>(base);
-    int *ta = reinterpret_cast<int *>(base + (size_t)n_terms * 8), *tb = ta + n_terms;
+    double2 *tp = reinterpret_cast<double2 *>(ctx->ci_buf);
     if (n_terms > 0) {
-        if (coef) CU(cudaMemcpyAsync(tc, coef, (size_t)n_terms * 8, cudaMemcpyHostToDevice, ctx->stream));
-        else CU(cudaMemsetAsync(tc, 0, (size_t)n_terms * 8, ctx->stream));
-        CU(cudaMemcpyAsync(ta, ia, (size_t)n_terms * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(tb, ib, (size_t)n_terms * 4, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<double2> rec(n_terms);
+        for (int t = 0; t < n_terms; ++t) {
+            const long long bits = (long long)(unsigned)ia[t] | ((long long)(unsigned)ib[t] << 32);
+            double y;
+            memcpy(&y, &bits, 8);
+            rec[t] = make_double2(coef ? coef[t] : 0.0, y);
+        }
+        // pageable source: the copy returns after the vector was read
+        CU(cudaMemcpyAsync(tp, rec.data(), (size_t)n_terms * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
         ctx->h2d_bytes += (long long)n_terms * 16;
     }
     p->n_terms = n_terms;
-    p->tc = tc; p->ta = ta; p->tb = tb;
+    p->tp = tp;
     return OKB_OK;
 }
 

@@ -32,8 +32,8 @@ struct CiParams {
     long long dstride;         // n_mo * ld: distance between the three derivative blocks
     long long npts;
     int n_terms;
-    const double *tc;          // term coefficients
-    const int *ta, *tb;        // term orbital indices
+    const double2 *tp;         // term records: x = coefficient, y = the two orbital indices (low word a, high word b) --
+                               // one 16-byte load per term instead of three (every kernel here is bound by the load pipe)
     double *out;
     long long ldo;             // row stride of out in points
     int ncomp;                 // JPAIRS, JABF: number of derivative components (1..3)
@@ -44,8 +44,7 @@ constexpr int CI_TB = 1024;    // terms per shared-memory batch
 
 template <int MODE>
 __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
-    __shared__ double s_c[CI_TB];
-    __shared__ int s_a[CI_TB], s_b[CI_TB];
+    __shared__ double2 s_t[CI_TB];
     const long long x = (long long)blockIdx.x * CI_NT + threadIdx.x;
     const bool live = x < p.npts;
     const long long xc = live ? x : p.npts - 1;              // clamp: every thread takes part in the staging
@@ -58,15 +57,14 @@ __global__ void __launch_bounds__(CI_NT) okb_ci_kernel(const CiParams p) {
         const int nb = min(CI_TB, p.n_terms - t0);
         __syncthreads();
         for (int e = threadIdx.x; e < nb; e += CI_NT) {
-            s_c[e] = p.tc[t0 + e];
-            s_a[e] = p.ta[t0 + e];
-            s_b[e] = p.tb[t0 + e];
+            s_t[e] = p.tp[t0 + e];
         }
         __syncthreads();
 #pragma unroll 4
         for (int e = 0; e < nb; ++e) {
-            const double c = s_c[e];
-            const long long ra = (long long)s_a[e] * p.ld, rb = (long long)s_b[e] * p.ld;
+            const double2 rec = s_t[e];
+            const double c = rec.x;
+            const long long ra = (long long)__double2loint(rec.y) * p.ld, rb = (long long)__double2hiint(rec.y) * p.ld;
             if (MODE == CI_RHO) {
                 // rho[x] += citmp*molist[sta,x]*molist[stb,x]        (cy_ci.pyx:88,95)
                 acc0 = __dadd_rn(acc0, __dmul_rn(__dmul_rn(c, __ldg(mo + ra)), __ldg(mo + rb)));
@@ -176,8 +174,9 @@ __global__ void __launch_bounds__(CIF_NW * 32, 2) okb_ci_fast_kernel(const CiFas
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
 #pragma unroll 2
         for (int e = warp * nslot + slot; e < p.n_terms; e += CIF_NW * nslot) {
-            const double c = __ldg(p.tc + e);
-            const int ra = __ldg(p.ta + e) * PW, rb = __ldg(p.tb + e) * PW;
+            const double2 rec = __ldg(p.tp + e);
+            const double c = rec.x;
+            const int ra = __double2loint(rec.y) * PW, rb = __double2hiint(rec.y) * PW;
             const double ma = mo[ra];
             if (MODE == CI_RHO) {
                 acc0 = fma(c * ma, mo[rb], acc0);
@@ -259,10 +258,12 @@ __global__ void __launch_bounds__(384) okb_ci_seq_kernel(const CiSeqParams q) {
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         double acc = 0.0;
+        const double *trec = reinterpret_cast<const double *>(p.tp);
 #pragma unroll 4
         for (int e = 0; e < p.n_terms; ++e) {
-            const double c = __ldg(p.tc + e);
-            const int ra = __ldg(p.ta + e) * TP, rb = __ldg(p.tb + e) * TP;
+            // two 8-byte loads: a warp-uniform 16-byte load was measured slower here (jab 96 against 85 ms)
+            const double c = __ldg(trec + 2 * e), ab = __ldg(trec + 2 * e + 1);
+            const int ra = __double2loint(ab) * TP, rb = __double2hiint(ab) * TP;
             if (MODE == CI_RHO) {
                 acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(c, mo[ra]), mo[rb]));                        // cy_ci.pyx:88,95
             } else if (MODE == CI_ANB) {
