@@ -2,7 +2,7 @@
 
 This module: Gaussian formatted checkpoint files (read_gaussian_fchk, orbkit/read/gaussian_fchk.py:11-324), Molden files
 (read_molden, orbkit/read/molden.py:47-402), `find_itype` and `main_read`.  The other formats live in read_wf.py (.wfn, .wfx),
-read_gamess.py, read_aomix.py and read_glog.py (Gaussian .log); the cclib bridge and the `native` containers are not built
+read_gamess.py, read_aomix.py, read_glog.py (Gaussian .log) and read_cclib.py (cclib bridge); the `native` containers are not built
 (`main_read` raises NotImplementedError for them).
 
 Mechanism: an fchk file is a sequence of named sections (`<name, 40 columns> <type I/R/C> [N=] <value or count>` followed,
@@ -405,10 +405,12 @@ from .read_aomix import read_aomix               # noqa: E402
 from .read_gamess import read_gamess             # noqa: E402
 from .read_glog import read_gaussian_log         # noqa: E402
 
+from .read_cclib import read_with_cclib, convert_cclib   # noqa: E402  (cclib itself is imported on use only)
+
 readers = {'gaussian.fchk': read_gaussian_fchk, 'fchk': read_gaussian_fchk, 'molden': read_molden,
            'wfn': read_wfn, 'wfx': read_wfx, 'aomix': read_aomix, 'gamess': read_gamess,
-           'gaussian.log': read_gaussian_log, 'gaussian_log': read_gaussian_log}
-_OTHER = ('cclib', 'native')
+           'gaussian.log': read_gaussian_log, 'gaussian_log': read_gaussian_log, 'cclib': read_with_cclib}
+_OTHER = ('native',)
 
 
 _MAGIC = (('molden', re.compile(r'\[[ ]{,}[Mm]olden[ ]+[Ff]ormat[ ]{,}\]')),
@@ -446,7 +448,7 @@ def main_read(fname, all_mo=False, spin=None, itype='auto', check_norm=False, **
         itype = find_itype(fname)
     if itype not in readers:
         if itype in _OTHER:
-            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk / .log, Molden, .wfn, .wfx, GAMESS-US and AOMix files; use the reference\'s reader for %r and pass '
+            raise NotImplementedError('orbkit_b200 reads Gaussian .fchk / .log, Molden, .wfn, .wfx, GAMESS-US and AOMix files and cclib data; use the reference\'s reader for %r and pass '
                                       'its QCinfo (or QCinfo(qc.todict())) to orbkit_b200' % itype)
         raise KeyError(itype)
     display('Loading data from {0} type file {1}\n'.format(itype, fname if isinstance(fname, str)

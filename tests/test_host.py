@@ -392,7 +392,7 @@ def test_fchk_reader_equals_reference_reader(tmp_path):
     with pytest.raises(IOError):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.fchk'), spin='gamma')
     with pytest.raises(NotImplementedError):
-        read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), itype='cclib')     # cclib is not in the image
+        read.main_read(os.path.join(inputs, 'h2o_rhf_sph.fchk'), itype='native')    # the reference's npz / hdf5 containers
 
 
 def test_gaussian_log_reader_equals_reference_reader(tmp_path):
@@ -425,6 +425,56 @@ def test_gaussian_log_reader_equals_reference_reader(tmp_path):
         read.main_read(os.path.join(inputs, 'h2o_uhf_sph.inp.log'), spin='gamma')
     with pytest.raises(IOError):
         read.read_gaussian_log(reader_input('nh3.mold', inputs))                  # no `Entering Link 1`
+
+
+def test_cclib_bridge_equals_reference_conversion():
+    """read_cclib.convert_cclib == the reference's convert_cclib (read/cclib_parser.py:56-219) on cclib-shaped inputs
+    (tests/cclib_cases.py; golden written by running the reference, make_golden_cclib.py): Cartesian / spherical AO labels,
+    restricted / unrestricted / restricted open shell, natural orbitals, data without `aonames`"""
+    import cclib_cases as cases
+    from conftest import load_golden
+    from orbkit_b200 import read, options
+    from orbkit_b200.read_cclib import convert_cclib
+    options.quiet = True
+    g = load_golden('read_cclib')
+    for name, kw in cases.CASES:
+        k = cases.key(name, kw)
+        qc = convert_cclib(cases.case(name), **kw)
+        flat = _flat_qc(qc)
+        for kk, v in flat.items():
+            ref = g[k + '.' + kk]
+            if v.dtype.kind == 'f':
+                assert v.shape == ref.shape and (v == ref).all(), (k, kk)
+            else:
+                assert v.shape == ref.shape and (v == ref).all(), (k, kk)
+    # the reference raises IOError for `spin` on restricted data ...
+    assert str(g['rhf_cart_all_alpha.error']) == 'OSError'
+    with pytest.raises(IOError):
+        convert_cclib(cases.case('rhf_cart'), all_mo=True, spin='alpha')
+    with pytest.raises(IOError):
+        convert_cclib(cases.case('uhf_sph'), spin='gamma')
+    # ... and crashes on a typo for unrestricted data (AttributeError, cclib_parser.py:157); here the selection it was
+    # about to make is carried out: the orbitals of that spin of the all-orbital conversion, in order
+    assert str(g['uhf_sph_all_beta.error']) == 'AttributeError'
+    both = convert_cclib(cases.case('uhf_sph'), all_mo=True)
+    beta = convert_cclib(cases.case('uhf_sph'), all_mo=True, spin='beta')
+    pick = [i for i, s in enumerate(both.mo_spec.get_spin()) if s == 'beta'] if hasattr(both.mo_spec, 'get_spin') else \
+        [i for i, mo in enumerate(both.mo_spec) if mo['spin'] == 'beta']
+    assert len(beta.mo_spec) == len(pick) == 23
+    assert (beta.mo_spec.get_coeffs() == both.mo_spec.get_coeffs()[pick]).all()
+    assert [mo['sym'] for mo in beta.mo_spec] == [both.mo_spec[i]['sym'] for i in pick]
+    # natural orbitals need their occupation numbers; main_read routes itype='cclib' to the parser front end
+    cc = cases.case('natorb')
+    del cc.nooccnos
+    with pytest.raises(IOError):
+        convert_cclib(cc)
+    with pytest.raises(IOError):
+        read.main_read('some.log', itype='cclib')                       # no parser named
+    try:
+        import cclib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            read.main_read('some.log', itype='cclib', cclib_parser='Gaussian')
 
 
 def test_wfn_and_wfx_readers_equal_reference_readers(tmp_path):
