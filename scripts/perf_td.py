@@ -16,7 +16,7 @@ hbm = peaks['hbm_gbs']
 fp64 = 37.0                                   # TFLOP/s, DMMA issue bound measured by bench.py (okb_measure_fp64)
 npts = 128 ** 3
 rng = numpy.random.default_rng(0)
-cases = [(64, 2), (64, 4), (256, 4), (256, 7), (512, 10), (128, 16)]
+cases = [(64, 2), (64, 4), (256, 4), (256, 7), (512, 10), (128, 16), (512, 13), (512, 17), (64, 15), (82, 44)]
 if len(sys.argv) > 1 and sys.argv[1] == 'one':
     cases = [(512, 10)]
 for nt, ns in cases:

@@ -334,7 +334,8 @@ def test_time_dependent_contractions(ok, oci):
     kind = 'ref' if oci.have_ref() else 'port'
     rng = numpy.random.default_rng(17)
     # (nt, nstate, npts): one pair; ragged everything; more pairs than one k chunk (nstate 12 -> 78 pairs); many time steps
-    for nt, ns, npts in ((1, 1, 1), (5, 2, 127), (33, 4, 1000), (70, 12, 257), (300, 3, 4099)):
+    # (70, 12), (130, 17), (40, 13): 78 / 153 / 91 pairs, several k chunks
+    for nt, ns, npts in ((1, 1, 1), (5, 2, 127), (33, 4, 1000), (70, 12, 257), (300, 3, 4099), (130, 17, 515), (40, 13, 300)):
         npair = ns * (ns + 1) // 2
         ReS, ImS = rng.normal(size=(nt, ns, ns)), rng.normal(size=(nt, ns, ns))
         rho, j = rng.normal(size=(npair, npts)), rng.normal(size=(npair, 3, npts))
