@@ -1668,6 +1668,18 @@ static int ci_launch_dense(okb_ctx *ctx, int mode, const CiParams &p, const CiDe
     const long long tiles = (p.npts + TD_P - 1) / TD_P;
     if (tiles * t.ncomp > 0x7fffffffLL) return fail(OKB_ERR_ARG, "ci: too many points for one launch");
     const unsigned grid = (unsigned)(tiles * t.ncomp);
+    static const char *no_pipe = getenv("OKB_TD_NOPIPE");       // A/B
+    const bool in_ok = reinterpret_cast<uintptr_t>(t.in) % 16 == 0 && t.ldi % 2 == 0 && t.dstride_in % 2 == 0;
+    if (pl.kp > TD_KC && in_ok && !(no_pipe && no_pipe[0] == '1')) {      // several k chunks: pipelined variant
+        CU(cudaFuncSetAttribute(okb_td2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TD2_SMEM));
+        okb_td2_kernel<true><<<grid, TD2_NT, TD2_SMEM, ctx->stream>>>(t);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return fail(OKB_ERR_CUDA, "dense ci kernel launch failed: %s", cudaGetErrorString(e2));
+        ctx->launches++;
+        ctx->last_kernel = mode == CI_RHO ? "ci-dense/rho" : mode == CI_JAB ? "ci-dense/jab" : mode == CI_ANB ? "ci-dense/a_nabla_b"
+                                                                                                         : "ci-dense/jab_full";
+        return OKB_OK;
+    }
     CU(cudaFuncSetAttribute(okb_td_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 4)));
     CU(cudaFuncSetAttribute(okb_td_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem(TD_KC, 8)));
     if (mtb == 8) okb_td_kernel<8, true><<<grid, TD_NT, td_smem(pl.kp, 8), ctx->stream>>>(t);
@@ -2047,12 +2059,23 @@ extern "C" int okb_ci_td(okb_ctx *ctx, int nt, int nk, long long n, const double
         p.ldo = out_dev ? ld_out : lds;
         p.vec_ok = (reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && p.ldo % 2 == 0) ? 1 : 0;
         const unsigned grid = (unsigned)((sn + TD_P - 1) / TD_P);
-        if (mtb == 8) okb_td_kernel<8><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
-        else okb_td_kernel<4><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
+        static const char *no_pipe = getenv("OKB_TD_NOPIPE");   // A/B
+        static const char *pipe_k = getenv("OKB_TD_PIPE_K");    // A/B: smallest k range that takes the pipelined variant
+        const int kmin = pipe_k && pipe_k[0] ? atoi(pipe_k) : TD_KC;
+        const bool pipe = kp > kmin && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && p.ldi % 2 == 0 &&
+                          !(no_pipe && no_pipe[0] == '1');
+        if (pipe) {                                             // several k chunks: pipelined variant
+            CU(cudaFuncSetAttribute(okb_td2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TD2_SMEM));
+            okb_td2_kernel<false><<<grid, TD2_NT, TD2_SMEM, ctx->stream>>>(p);
+        } else if (mtb == 8) {
+            okb_td_kernel<8><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
+        } else {
+            okb_td_kernel<4><<<grid, TD_NT, td_bytes, ctx->stream>>>(p);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(OKB_ERR_CUDA, "okb_td_kernel launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;
-        ctx->last_kernel = mtb == 8 ? "td-dmma/MT64" : "td-dmma/MT32";
+        ctx->last_kernel = pipe ? "td-dmma/pipe" : mtb == 8 ? "td-dmma/MT64" : "td-dmma/MT32";
         if (!out_dev) {
             CU(cudaMemcpy2DAsync(out + s0, (size_t)ld_out * 8, d_out, (size_t)lds * 8, (size_t)sn * 8, nt, cudaMemcpyDeviceToHost,
                                  ctx->stream));

@@ -167,4 +167,190 @@ __global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const T
     }
 }
 
+// ---- k ranges of several chunks (more than TD_KC state pairs; cy_core.mocreator: k = AO): pipelined variant -------------
+// The kernel above re-stages the `in` chunk and the weights synchronously for every (pass, chunk): with several chunks the
+// DMMA pipe idles during the staging (990 functions x 82 rows: 0.21 of the FP64 peak).  Here EIGHT DMMA warps (two per
+// sub-partition: 2 warp rows x 4 point groups; a warp row takes every other block of 8 rows of the pass, x 32 points) walk
+// the flattened (pass of 64 rows, chunk of 32 k) sequence through a three-stage ring that a NINTH warp fills with 16-byte
+// cp.async copies two iterations ahead: one __syncthreads per iteration, staging hidden behind the 128 DMMAs a warp issues
+// per chunk.  Row blocks beyond nt are skipped (82 rows: 11
+// instead of 16 blocks).  Needs 16-byte aligned `in` rows (else the kernel above).
+constexpr int TD2_NT = 288, TD2_KC = 32, TD2_NS = 3, TD2_MT = 64;   // 8 DMMA warps + 1 staging warp
+constexpr int TD2_WS = TD2_KC + 4;                              // 36 = 4 (mod 16)
+constexpr size_t TD2_STAGE = ((size_t)TD2_KC * TD_PS + (size_t)TD2_MT * TD2_WS) * 8;
+constexpr size_t TD2_SMEM = TD2_NS * TD2_STAGE;
+
+template <bool RDM>
+__global__ void __launch_bounds__(TD2_NT, 1) okb_td2_kernel(const TdParams p) {
+    extern __shared__ __align__(16) unsigned char td2_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tr = lane >> 2, tc = lane & 3, wr = warp >> 2, wc = warp & 3;
+    const int comp = RDM ? (int)(blockIdx.x % (unsigned)p.ncomp) : 0;
+    const long long x0 = (long long)(RDM ? blockIdx.x / (unsigned)p.ncomp : blockIdx.x) * TD_P;
+    const double *in = RDM ? p.in + (size_t)comp * p.dstride_in : p.in;
+    const int nchunk = (p.kp + TD2_KC - 1) / TD2_KC, npass = (p.nt + TD2_MT - 1) / TD2_MT, nit = npass * nchunk;
+    const uint32_t a_raw = smem_u32(td2_raw);
+    if (warp == 8) {
+        // ---- staging warp: all copies of the ring (ncu of the first version, in which the eight DMMA warps staged their
+        // own share after the barrier: half of all instructions were staging, issued while the DMMA pipe idled).
+        // Lane slots, the same in every iteration: `in` row r (r < kc), 16-byte pieces lane and lane + 32; weight rows
+        // (lane >> 4) + 2 j (j < 32) at piece lane & 15.
+        const uint32_t xb0 = x0 + 2 * lane + 1 < p.n ? 16u : x0 + 2 * lane < p.n ? 8u : 0u;
+        const uint32_t xb1 = x0 + 2 * lane + 65 < p.n ? 16u : x0 + 2 * lane + 64 < p.n ? 8u : 0u;
+        const double *in_x = in + x0 + 2 * lane;
+        const int sw = lane >> 4, pw = lane & 15;
+        auto stage = [&](int it) {                              // copies of iteration `it` into stage it % NS, one group
+            const int ps = it / nchunk, c = it - ps * nchunk, k0 = c * TD2_KC, kc = min(TD2_KC, p.kp - k0), t0 = ps * TD2_MT;
+            const uint32_t a_rt = a_raw + (uint32_t)((it % TD2_NS) * TD2_STAGE) + (uint32_t)(2 * lane * 8);
+            const uint32_t a_wt = a_raw + (uint32_t)((it % TD2_NS) * TD2_STAGE) + (uint32_t)(TD2_KC * TD_PS * 8) +
+                                  (uint32_t)((sw * TD2_WS + 2 * pw) * 8);
+#pragma unroll 4
+            for (int k = 0; k < kc; ++k) {                      // `in`: zero filled beyond nk / n
+                const int row = k0 + k;
+                const bool live = row < p.nk;
+                const double *src = live ? in_x + (size_t)(RDM ? __ldg(p.rows + row) : row) * p.ldi : in;
+                const uint32_t b0 = live ? xb0 : 0u, b1 = live ? xb1 : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_rt + (uint32_t)(k * TD_PS * 8)),
+                             "l"(b0 ? src : in), "r"(b0)
+                             : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_rt + (uint32_t)((k * TD_PS + 64) * 8)),
+                             "l"(b1 ? src + 64 : in), "r"(b1)
+                             : "memory");
+            }
+            if (2 * pw < kc) {                                  // weights: 64 rows (zero padded beyond nt) x kc / 2 pieces
+                const double *wsrc = p.w + (size_t)(t0 + sw) * p.kp + k0 + 2 * pw;
+#pragma unroll 8
+                for (int j = 0; j < TD2_MT / 2; ++j)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a_wt + (uint32_t)(2 * j * TD2_WS * 8)),
+                                 "l"(wsrc + (size_t)2 * j * p.kp)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage(0);
+        if (nit > 1) stage(1);
+        for (int it = 0; it < nit; ++it) {
+            if (it + 1 < nit) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                    // stage `it` complete; the DMMA warps left stage it - 1
+            if (it + 2 < nit) stage(it + 2);
+        }
+        if (RDM) {
+            __syncthreads();
+            __syncthreads();
+        }
+        return;
+    }
+    double acc[4][4][2], red[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        red[nb][0] = red[nb][1] = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    }
+    for (int it = 0; it < nit; ++it) {
+        __syncthreads();                                        // stage `it` complete (staging warp waited for its group)
+        const int ps = it / nchunk, c = it - ps * nchunk, kc = min(TD2_KC, p.kp - c * TD2_KC), t0 = ps * TD2_MT;
+        const uint32_t a_rt = a_raw + (uint32_t)((it % TD2_NS) * TD2_STAGE) + (uint32_t)((tc * TD_PS + wc * 32 + tr) * 8);
+        // the row blocks of a pass alternate between the two warp rows (block 2 mb + wr): a ragged last pass is shared
+        const uint32_t a_wt = a_raw + (uint32_t)((it % TD2_NS) * TD2_STAGE) + (uint32_t)(TD2_KC * TD_PS * 8) +
+                              (uint32_t)(((wr * 8 + tr) * TD2_WS + tc) * 8);
+        const int nblk = min(8, (p.nt - t0 + 7) >> 3);          // row blocks of this pass that exist
+        const int nmbv = (nblk - wr + 1) >> 1;                  // ... of this warp row (warp-uniform)
+        auto kstep = [&](int ks) {
+            double b[4];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) b[nb] = lds64(a_rt + (uint32_t)((ks * TD_PS + nb * 8) * 8));
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                if (mb >= nmbv) continue;
+                const double a = lds64(a_wt + (uint32_t)((mb * 16 * TD2_WS + ks) * 8));
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+            }
+        };
+        if (kc == TD2_KC && nmbv == 4) {                        // full chunk of a full pass: straight-line code, all
+#pragma unroll                                                  // fragment loads of a k-step in front of its 16 DMMAs
+            for (int ks = 0; ks < TD2_KC; ks += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) b[nb] = lds64(a_rt + (uint32_t)((ks * TD_PS + nb * 8) * 8));
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) a[mb] = lds64(a_wt + (uint32_t)((mb * 16 * TD2_WS + ks) * 8));
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+            }
+        } else {
+            for (int ks = 0; ks < kc; ks += 4) kstep(ks);
+        }
+        if (c != nchunk - 1) continue;
+        // end of a pass: lane holds out[t0 + 8 (2 mb + wr) + tr][x0 + 32 wc + 8 nb + 2 tc + {0, 1}]
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int t = t0 + (2 * mb + wr) * 8 + tr;
+            if (t < p.nt) {
+                const double *prow = RDM ? p.phi + (size_t)__ldg(p.rows + t) * p.ldi : nullptr;
+                double *orow = RDM ? nullptr : p.out + (size_t)t * p.ldo;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const long long x = x0 + wc * 32 + nb * 8 + 2 * tc;
+                    if constexpr (RDM) {
+                        double f0 = 0.0, f1 = 0.0;
+                        if (p.vec_ok && x + 1 < p.n) {
+                            const double2 f = __ldg(reinterpret_cast<const double2 *>(prow + x));
+                            f0 = f.x; f1 = f.y;
+                        } else {
+                            if (x < p.n) f0 = __ldg(prow + x);
+                            if (x + 1 < p.n) f1 = __ldg(prow + x + 1);
+                        }
+                        red[nb][0] = fma(acc[mb][nb][0], f0, red[nb][0]);
+                        red[nb][1] = fma(acc[mb][nb][1], f1, red[nb][1]);
+                    } else {
+                        if (p.vec_ok && x + 1 < p.n) {
+                            *reinterpret_cast<double2 *>(orow + x) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                        } else {
+                            if (x < p.n) orow[x] = acc[mb][nb][0];
+                            if (x + 1 < p.n) orow[x + 1] = acc[mb][nb][1];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+        }
+    }
+    if constexpr (RDM) {                                        // the eight row groups of the lanes, then the two row halves
+        double *scratch = reinterpret_cast<double *>(td2_raw);
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double v = red[nb][h];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                red[nb][h] = v;
+            }
+        __syncthreads();                                        // the stages are no longer read
+        if (wr == 1 && tr == 0)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                scratch[wc * 32 + nb * 8 + 2 * tc] = red[nb][0];
+                scratch[wc * 32 + nb * 8 + 2 * tc + 1] = red[nb][1];
+            }
+        __syncthreads();
+        if (wr == 0 && tr == 0) {
+            double *orow = p.out + (size_t)comp * p.ldo;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const long long x = x0 + wc * 32 + nb * 8 + 2 * tc;
+                if (x < p.n) orow[x] = red[nb][0] + scratch[wc * 32 + nb * 8 + 2 * tc];
+                if (x + 1 < p.n) orow[x + 1] = red[nb][1] + scratch[wc * 32 + nb * 8 + 2 * tc + 1];
+            }
+        }
+    }
+}
+
 }  // namespace okb

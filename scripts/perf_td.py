@@ -18,7 +18,7 @@ npts = 128 ** 3
 rng = numpy.random.default_rng(0)
 cases = [(64, 2), (64, 4), (256, 4), (256, 7), (512, 10), (128, 16), (512, 13), (512, 17), (64, 15), (82, 44)]
 if len(sys.argv) > 1 and sys.argv[1] == 'one':
-    cases = [(512, 10)]
+    cases = [tuple(int(v) for v in os.environ.get('TD_CASE', '512:10').split(':'))]
 for nt, ns in cases:
     nk = ns * (ns + 1) // 2
     n = npts if nt * npts * 8 < 40e9 else npts // 4
