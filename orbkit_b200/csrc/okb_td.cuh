@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(TD_NT, MTB == 4 ? 4 : 2) okb_td_kernel(const T
 // DMMA pipe idles during the staging (990 functions x 82 rows: 0.21 of the FP64 peak).  Here EIGHT DMMA warps (two per
 // sub-partition: 2 warp rows x 4 point groups; a warp row takes every other block of 8 rows of the pass, x 32 points) walk
 // the flattened (pass of 64 rows, chunk of 32 k) sequence through a three-stage ring that a NINTH warp fills with 16-byte
-// cp.async copies two iterations ahead: one __syncthreads per iteration, staging hidden behind the 128 DMMAs a warp issues
+// cp.async copies two iterations ahead, handed over through two named barriers in producer / consumer form, staging hidden behind the 128 DMMAs a warp issues
 // per chunk.  Row blocks beyond nt are skipped (82 rows: 11
 // instead of 16 blocks).  Needs 16-byte aligned `in` rows (else the kernel above).
 constexpr int TD2_NT = 288, TD2_KC = 32, TD2_NS = 3, TD2_MT = 64;   // 8 DMMA warps + 1 staging warp
@@ -227,17 +227,20 @@ __global__ void __launch_bounds__(TD2_NT, 1) okb_td2_kernel(const TdParams p) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // hand-over by two named barriers in producer / consumer form (PTX bar.arrive / bar.sync with the thread count):
+        // FULL (1): this warp arrives when the copies of iteration `it` have landed, the DMMA warps wait on it;
+        // EMPTY (2): the DMMA warps arrive when they are done with an iteration, this warp waits on it before it reuses
+        // that stage -- and before it arrives on FULL again, so no barrier ever sees two phases at once.
         stage(0);
         if (nit > 1) stage(1);
         for (int it = 0; it < nit; ++it) {
+            if (it >= 1) named_bar(2, TD2_NT);                  // the DMMA warps left iteration it - 1
             if (it + 1 < nit) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                    // stage `it` complete; the DMMA warps left stage it - 1
-            if (it + 2 < nit) stage(it + 2);
-        }
-        if (RDM) {
-            __syncthreads();
-            __syncthreads();
+            __threadfence_block();
+            asm volatile("bar.arrive 1, %0;" ::"r"(TD2_NT) : "memory");
+            if (it >= 1 && it + 2 < nit) stage(it + 2);         // into the stage of iteration it - 1
+            else if (it == 0 && nit > 2) stage(2);              // third stage: never used so far
         }
         return;
     }
@@ -249,7 +252,8 @@ __global__ void __launch_bounds__(TD2_NT, 1) okb_td2_kernel(const TdParams p) {
         for (int mb = 0; mb < 4; ++mb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
     }
     for (int it = 0; it < nit; ++it) {
-        __syncthreads();                                        // stage `it` complete (staging warp waited for its group)
+        if (it >= 1) asm volatile("bar.arrive 2, %0;" ::"r"(TD2_NT) : "memory");      // done with iteration it - 1
+        named_bar(1, TD2_NT);                                   // FULL: the copies of iteration `it` have landed
         const int ps = it / nchunk, c = it - ps * nchunk, kc = min(TD2_KC, p.kp - c * TD2_KC), t0 = ps * TD2_MT;
         const uint32_t a_rt = a_raw + (uint32_t)((it % TD2_NS) * TD2_STAGE) + (uint32_t)((tc * TD_PS + wc * 32 + tr) * 8);
         // the row blocks of a pass alternate between the two warp rows (block 2 mb + wr): a ragged last pass is shared
@@ -333,14 +337,14 @@ __global__ void __launch_bounds__(TD2_NT, 1) okb_td2_kernel(const TdParams p) {
                 v += __shfl_xor_sync(0xffffffffu, v, 16);
                 red[nb][h] = v;
             }
-        __syncthreads();                                        // the stages are no longer read
+        named_bar(3, TD2_NT - 32);                                        // the stages are no longer read
         if (wr == 1 && tr == 0)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 scratch[wc * 32 + nb * 8 + 2 * tc] = red[nb][0];
                 scratch[wc * 32 + nb * 8 + 2 * tc + 1] = red[nb][1];
             }
-        __syncthreads();
+        named_bar(3, TD2_NT - 32);
         if (wr == 0 && tr == 0) {
             double *orow = p.out + (size_t)comp * p.ldo;
 #pragma unroll
