@@ -49,6 +49,18 @@ def _m_of_label(label):
     return p - 1 if p != -1 else int(m[-1])
 
 
+def _restricted_occupations(n_el, unpaired, nmo):
+    """occupation pattern of a restricted (open-shell) determinant as the reference assigns it orbital by orbital
+    (cclib_parser.py:177-186): doubly occupied while more electrons are left than unpaired ones, then singly occupied"""
+    occ = numpy.zeros(nmo)
+    for n in range(nmo):
+        if n_el > unpaired:
+            occ[n], n_el = 2.0, n_el - 2.0
+        elif 0.0 < n_el <= unpaired:
+            occ[n], n_el, unpaired = 1.0, n_el - 1.0, unpaired - 1.0
+    return occ
+
+
 def convert_cclib(ccData, all_mo=False, spin=None):
     qc = QCinfo()
     qc.geo_spec = numpy.asarray(ccData.atomcoords[0]) * AA_TO_A0
@@ -71,46 +83,39 @@ def convert_cclib(ccData, all_mo=False, spin=None):
                 ao['lxlylz'] = [(n.lower().count('x'), n.lower().count('y'), n.lower().count('z')) for n in labels]
             else:
                 ao['lm'] = [(lquant[ao['type']], _m_of_label(n)) for n in labels]
-    ele_num = numpy.sum(ccData.atomnos) - numpy.sum(ccData.coreelectrons) - ccData.charge
-    ue = ccData.mult - 1
-    is_natorb = hasattr(ccData, 'nocoeffs')
-    if is_natorb and not hasattr(ccData, 'nooccnos'):
+    natural = hasattr(ccData, 'nocoeffs')
+    if natural and not hasattr(ccData, 'nooccnos'):
         raise IOError('There are natural orbital coefficients (`nocoeffs`) in the cclib ccData, but no natural '
                       'occupation numbers (`nooccnos`)!')
-    restricted = len(ccData.mosyms) == 1
+    nspin = len(ccData.mosyms)                       # 1: restricted (one set of orbitals), 2: alpha and beta sets
     if spin is not None:
         if spin not in ('alpha', 'beta'):
             raise IOError('`spin=%s` is not a valid option' % spin)
-        if restricted:
+        if nspin == 1:
             raise IOError('The keyword `spin` is only supported for unrestricted calculations.')
         display('Converting only molecular orbitals of spin %s.' % spin)
-    add, orb_sym = ([''], [None]) if restricted else (['_a', '_b'], ['alpha', 'beta'])
     nmo = ccData.nmo if hasattr(ccData, 'nmo') else len(ccData.mocoeffs[0])
-    sym, mos = {}, []
-    for ii in range(nmo):
-        for i, j in enumerate(add):
-            a = '%s%s' % (ccData.mosyms[i][ii], j)
-            sym[a] = sym.get(a, 0) + 1
-            if is_natorb:
-                occ = ccData.nooccnos[ii]
-            elif not restricted:
-                occ = 1.0 if ii <= ccData.homos[i] else 0.0
-            elif ele_num > ue:
-                occ = 2.0
-                ele_num -= 2.0
-            elif 0.0 < ele_num <= ue:
-                occ = 1.0
-                ele_num -= 1.0
-                ue -= 1.0
+    tags = [('', None)] if nspin == 1 else [('_a', 'alpha'), ('_b', 'beta')]
+    aufbau = _restricted_occupations(numpy.sum(ccData.atomnos) - numpy.sum(ccData.coreelectrons) - ccData.charge,
+                                     ccData.mult - 1, nmo)
+    seen, mos = {}, []
+    for n in range(nmo):                              # orbital n of every spin set, alpha before beta
+        for s, (suffix, label) in enumerate(tags):
+            irrep = '%s%s' % (ccData.mosyms[s][n], suffix)
+            seen[irrep] = seen.get(irrep, 0) + 1      # counted for both spins even when one of them is dropped
+            if label is not None and spin is not None and spin != label:
+                continue
+            if natural:
+                occ = ccData.nooccnos[n]
+            elif nspin == 2:
+                occ = 1.0 if n <= ccData.homos[s] else 0.0
             else:
-                occ = 0.0
-            mo = {'coeffs': numpy.array((ccData.nocoeffs if is_natorb else ccData.mocoeffs[i])[ii], dtype=float),
-                  'energy': 0.0 if is_natorb else ccData.moenergies[i][ii] * EV_TO_HA,
-                  'occ_num': occ, 'sym': '%d.%s' % (sym[a], a)}
-            if orb_sym[i] is not None:
-                mo['spin'] = orb_sym[i]
-                if spin is not None and spin != orb_sym[i]:
-                    continue
+                occ = aufbau[n]
+            mo = {'coeffs': numpy.array((ccData.nocoeffs if natural else ccData.mocoeffs[s])[n], dtype=float),
+                  'energy': 0.0 if natural else ccData.moenergies[s][n] * EV_TO_HA,
+                  'occ_num': occ, 'sym': '%d.%s' % (seen[irrep], irrep)}
+            if label is not None:
+                mo['spin'] = label
             mos.append(mo)
     qc.ao_spec = AOClass(aos)
     qc.ao_spec.spherical = spherical
