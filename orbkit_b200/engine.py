@@ -102,8 +102,10 @@ class _Handle:
 class Engine:
     """Owns the okb_ctx of one CUDA device and small LRU caches of device handles."""
     CACHE = 8
-    VECTOR_CACHE_POINTS = 1 << 18     # larger vector grids are uploaded per call: hashing 24 B/point to find a cached
-                                      # copy costs as much as the upload, and cached copies would pile up in HBM
+    VECTOR_CACHE_POINTS = 0           # vector grids are uploaded per call: finding a cached copy means hashing 24 B/point
+                                      # (blake2b, ~1 GB/s), which costs several times the upload it would save (1000 points:
+                                      # 37 us of hashing in a 300 us call, scripts/prof_latency.py), and cached copies would
+                                      # pile up in HBM.  (> 0: cache grids of up to that many points by content.)
 
     def __init__(self, device=None):
         self.lib = _lib.load()
