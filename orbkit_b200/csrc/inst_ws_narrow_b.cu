@@ -9,6 +9,10 @@ static const Variant table[] = {
     OKB_WS(SET_VAL, 3, 8, 1, 4, 12, 2, SINK_MO), OKB_WS(SET_VAL, 3, 8, 1, 4, 12, 2, SINK_RHO),
     // (48 orbitals with 256-point tiles: 3.46 against 3.55 ms -- not kept)
     OKB_WS(SET_VAL, 6, 4, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 6, 4, 1, 4, 12, 3, SINK_RHO),
+    // 32-point tiles for SMALL requests only (pick_variant: fewer points than 32 per SM -- the cubature use case, a
+    // thousand new points per call): a 128-point tile would leave all but a few SMs idle and take longer per chunk
+    OKB_WS(SET_VAL, 11, 1, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 11, 1, 1, 4, 12, 3, SINK_RHO),
+    OKB_WS(SET_VAL, 3, 1, 1, 4, 12, 3, SINK_MO), OKB_WS(SET_VAL, 3, 1, 1, 4, 12, 3, SINK_RHO),
 };
 OKB_TABLE(okb_variants_narrow_b, table);
 

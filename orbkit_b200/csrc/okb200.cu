@@ -1052,7 +1052,10 @@ static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants
 
 // ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
 // meta_stride > 0: skip the MO-tile variants whose shared memory does not fit with chunk tables of that size
-static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false, int meta_stride = 0) {
+// npts / n_sm: points of the request and SMs of the device -- value-set variants with 32-point tiles are for requests of
+// fewer than 32 points per SM only (and are preferred there)
+static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false, int meta_stride = 0,
+                                   long long npts = -1, int n_sm = 148) {
     const Variant *best = nullptr;
     long long best_cost = 0;
     for (const VariantTable *tab : g_tables)
@@ -1075,6 +1078,8 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
         if (meta_stride > 0 && v.smem(meta_stride) > 227 * 1024) continue;
+        const bool small = npts >= 0 && npts <= 32LL * n_sm;
+        if (set == SET_VAL && v.P == 32 && !small) continue;
         // Every MO tile regenerates the AO tiles, and the producers run beside the consumers.  Measured per pass over one
         // MO tile on the Config-2 shape (222 AOs; 24- / 48- / 80-wide tiles, profiles/r02_c2_narrow.txt) the time is affine
         // in the tile width MC: rho 3.0 / 3.55 / 4.5 ms, rho + grad 8.7 / 11.3 / 17.4 ms, second laplacian pass
@@ -1090,7 +1095,8 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         const int rem_cols = set == SET_D2P ? 5 : 3;
         const int width = v.MC - v.rem + rem_cols * v.rem;
         const int gen = set == SET_VAL ? 100 : set == SET_GRAD ? 35 : set == SET_D2P ? 42 : 0;
-        const long long cost = n_tiles * (gen > 0 ? width + gen : std::max(width, set == SET_ALL ? 24 : 48)) * 1000 - v.MC;
+        long long cost = n_tiles * (gen > 0 ? width + gen : std::max(width, set == SET_ALL ? 24 : 48)) * 1000 - v.MC;
+        if (small && set == SET_VAL) cost += v.P;               // small request: the narrowest point tile of that width
         if (!best || cost < best_cost) {
             best = &v;
             best_cost = cost;
@@ -1397,7 +1403,7 @@ static int run_eval(okb_ctx *ctx, const EvalReq &rq) {
                                   ps.set == SET_D2P || (ps.set == SET_ONE && ps.one_code >= 1 && ps.one_code <= 6));
             const Layout &lo = use_mix ? b->mix : b->cart;
             const Variant *v = pick_variant(ps.set, rq.sink, rq.sink == SINK_AO ? 1 : rq.mo->n_mo, ao_bulk_ok,
-                                            rq.sink == SINK_AO ? 0 : lo.lay.stride);
+                                            rq.sink == SINK_AO ? 0 : lo.lay.stride, rq.p1 - rq.p0, ctx->sm_count);
             // (a basis with very large chunk tables may not leave the stage ring of an "aows/" kernel enough shared memory)
             if (v && rq.sink == SINK_AO && ao_bulk_ok && v->smem(lo.lay.stride) > 227 * 1024)
                 v = pick_variant(ps.set, rq.sink, 1, false);
