@@ -1053,7 +1053,8 @@ static const VariantTable *const g_tables[] = {&okb_variants_aows, &okb_variants
 // ao_bulk_ok: the SINK_AO output rows start on 16-byte boundaries (the "aows/" kernels store them with bulk copies)
 // meta_stride > 0: skip the MO-tile variants whose shared memory does not fit with chunk tables of that size
 // npts / n_sm: points of the request and SMs of the device -- value-set variants with 32-point tiles are for requests of
-// fewer than 32 points per SM only (and are preferred there)
+// at most 96 points per SM only (and are preferred there: a 128-point tile takes ~4x as long as a 32-point one, so up to
+// three waves of 32-point tiles beat one partial wave of 128-point tiles)
 static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok = false, int meta_stride = 0,
                                    long long npts = -1, int n_sm = 148) {
     const Variant *best = nullptr;
@@ -1078,7 +1079,9 @@ static const Variant *pick_variant(int set, int sink, int n_mo, bool ao_bulk_ok 
         static const char *force = getenv("OKB_VARIANT");
         if (force && force[0] && strstr(v.name, force)) return &v;
         if (meta_stride > 0 && v.smem(meta_stride) > 227 * 1024) continue;
-        const bool small = npts >= 0 && npts <= 32LL * n_sm;
+        static const char *small_env = getenv("OKB_SMALL_PTS_PER_SM");     // A/B
+        static const long long small_per_sm = small_env && small_env[0] ? atoll(small_env) : 96;
+        const bool small = npts >= 0 && npts <= small_per_sm * n_sm;
         if (set == SET_VAL && v.P == 32 && !small) continue;
         // Every MO tile regenerates the AO tiles, and the producers run beside the consumers.  Measured per pass over one
         // MO tile on the Config-2 shape (222 AOs; 24- / 48- / 80-wide tiles, profiles/r02_c2_narrow.txt) the time is affine
