@@ -192,15 +192,23 @@ def _rho_natural(eng, basis, qc, act, terms, g):
     sum_k lam_k psi_k^2 over the natural (transition) orbitals psi = U^T phi -- ONE launch of the fused
     AO -> MO -> rho kernel with n_act orbitals and signed weights, no MO slab and no second kernel.  `terms` index
     into `act`.  Eigenvalues below 1e-15 of the largest are dropped (transition matrices are of low rank)."""
-    n = len(act)
-    d = numpy.bincount(terms[1].astype(numpy.int64) * n + terms[2], weights=terms[0], minlength=n * n).reshape((n, n))
-    lam, u = numpy.linalg.eigh(0.5 * (d + d.T))
-    keep = numpy.abs(lam) > 1e-15 * max(numpy.abs(lam).max(), 1e-300)
-    if not keep.any():
+    lam, u = natural_orbitals(terms, len(act))
+    if len(lam) == 0:
         return numpy.zeros(g.npts)
-    coeffs = numpy.ascontiguousarray(u[:, keep].T @ require(qc.mo_spec.get_coeffs(), dtype='f')[act])
-    mo = eng.mos(basis, coeffs, numpy.ascontiguousarray(lam[keep]))
+    coeffs = numpy.ascontiguousarray(u.T @ require(qc.mo_spec.get_coeffs(), dtype='f')[act])
+    mo = eng.mos(basis, coeffs, numpy.ascontiguousarray(lam))
     return eng.eval_rho(mo, g, [])[0]
+
+
+def natural_orbitals(terms, n):
+    """(lam, U) with sum_t c_t phi_{a_t} phi_{b_t} = sum_k lam_k (sum_a U[a, k] phi_a)^2 for orbital indices below n:
+    eigen-decomposition of the symmetric part of the pair matrix D[a, b] = sum of the c_t with (a_t, b_t) = (a, b);
+    eigenvalues below 1e-15 of the largest are dropped (possibly all of them: an antisymmetric D gives rho = 0)."""
+    d = numpy.bincount(numpy.asarray(terms[1]).astype(numpy.int64) * n + numpy.asarray(terms[2]),
+                       weights=numpy.asarray(terms[0], dtype=float), minlength=n * n).reshape((n, n))
+    lam, u = numpy.linalg.eigh(0.5 * (d + d.T))
+    keep = numpy.abs(lam) > 1e-15 * max(numpy.abs(lam).max() if len(lam) else 0.0, 1e-300)
+    return lam[keep], u[:, keep]
 
 
 def rho_from_qc(qc, zero, sing, x=None, y=None, z=None, is_vector=None):

@@ -427,6 +427,51 @@ def test_gaussian_log_reader_equals_reference_reader(tmp_path):
         read.read_gaussian_log(reader_input('nh3.mold', inputs))                  # no `Entering Link 1`
 
 
+def test_natural_orbitals_of_the_pair_matrix():
+    """detci.ci_core.natural_orbitals: sum_t c_t phi_a phi_b == sum_k lam_k psi_k^2 (the identity behind rho_from_qc's single
+    fused launch), rank reduction, the antisymmetric case"""
+    from orbkit_b200.detci.ci_core import natural_orbitals, flatten_terms
+    rng = numpy.random.default_rng(31)
+    n, nt = 9, 400
+    terms = (rng.normal(size=nt), rng.integers(0, n, size=nt).astype(numpy.intc), rng.integers(0, n, size=nt).astype(numpy.intc))
+    phi = rng.normal(size=(n, 57))
+    ref = numpy.einsum('t,tx,tx->x', terms[0], phi[terms[1]], phi[terms[2]])
+    lam, u = natural_orbitals(terms, n)
+    got = numpy.einsum('k,kx->x', lam, (u.T @ phi) ** 2)
+    assert lam.shape == (n,) and u.shape == (n, n)
+    assert numpy.abs(got - ref).max() <= 1e-12 * numpy.abs(ref).max()
+    # a transition between two determinants differing in one orbital: rank 2 (eigenvalues +c/2, -c/2)
+    lam, u = natural_orbitals((numpy.array([0.7]), numpy.array([2]), numpy.array([5])), 8)
+    assert lam.shape == (2,) and numpy.allclose(sorted(lam), [-0.35, 0.35])
+    # antisymmetric pair matrix: no density at all
+    lam, u = natural_orbitals((numpy.array([1.0, -1.0]), numpy.array([1, 3]), numpy.array([3, 1])), 4)
+    assert lam.shape == (0,) and u.shape == (4, 0)
+    # the host side of rho_from_qc on a stand-in engine (coefficients of the natural orbitals, signed weights)
+    import types
+    from orbkit_b200.detci import ci_core
+    n_mo, n_ao, npts = 12, 7, 33
+    C, chi = rng.normal(size=(n_mo, n_ao)), rng.normal(size=(n_ao, npts))
+    qc = types.SimpleNamespace(mo_spec=types.SimpleNamespace(get_coeffs=lambda: C))
+
+    class Eng:
+        def mos(self, basis, coeffs, occ):
+            return coeffs, occ
+
+        def eval_rho(self, mo, g, codes):
+            return numpy.einsum('k,kx->x', mo[1], (mo[0] @ chi) ** 2), None, None
+    act = numpy.array([1, 4, 5, 9])
+    ia, ib, c = rng.integers(0, 4, size=50).astype(numpy.intc), rng.integers(0, 4, size=50).astype(numpy.intc), rng.normal(size=50)
+    got = ci_core._rho_natural(Eng(), None, qc, act, (c, ia, ib), types.SimpleNamespace(npts=npts))
+    mo_values = C @ chi
+    ref = numpy.einsum('t,tx,tx->x', c, mo_values[act[ia]], mo_values[act[ib]])
+    assert numpy.abs(got - ref).max() <= 1e-12 * numpy.abs(ref).max()
+    # arrays in, no list traffic: same flat terms as the list form
+    zero, sing = [[], []], [[0.5, -1.5], [[0, 1], [2, 2]]]
+    a = flatten_terms(zero, sing)
+    b = flatten_terms(zero, [numpy.array(sing[0]), numpy.array(sing[1])])
+    assert all((x == y).all() and x.dtype == y.dtype for x, y in zip(a, b))
+
+
 def test_cclib_bridge_equals_reference_conversion():
     """read_cclib.convert_cclib == the reference's convert_cclib (read/cclib_parser.py:56-219) on cclib-shaped inputs
     (tests/cclib_cases.py; golden written by running the reference, make_golden_cclib.py): Cartesian / spherical AO labels,
